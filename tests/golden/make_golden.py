@@ -1,0 +1,168 @@
+"""Generates tests/golden/*.npz by running the UNMODIFIED reference in the build container.
+
+Run once here (the GPU box has no /root/reference):
+    python tests/golden/make_golden.py
+It imports /root/reference/main.py (whose model classes are the service's copy of
+train.py:90-170) and scikit-learn's NearestNeighbors exactly as main.py:268-269 builds it,
+feeds them small seeded inputs and stores inputs + state_dict + outputs + gradients.
+Nothing from the reference's source is copied into the repo -- only numeric vectors.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+REF = os.environ.get("REF_DIR", "/root/reference")
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REF)
+import main as ref_main  # noqa: E402  (reference module; import has no side effects beyond logging/seed)
+from sklearn.neighbors import NearestNeighbors  # noqa: E402
+
+
+def _pack_state(sd):
+    return {"sd::" + k: v.detach().cpu().numpy() for k, v in sd.items()}
+
+
+def model_case(name, n_users, n_items, cat_dims, n_num, params, B, seed, emb_scale=1.0, randomize_bn=False):
+    torch.manual_seed(seed)
+    model = ref_main.DCN_RecSys(n_users, n_items, cat_dims, n_num, params)
+    g = torch.Generator().manual_seed(seed + 1)
+    with torch.no_grad():
+        if emb_scale != 1.0:
+            model.user_embedding.weight.mul_(emb_scale)
+            model.item_embedding.weight.mul_(emb_scale)
+            for e in model.cat_embeddings:
+                e.weight.mul_(emb_scale)
+        if randomize_bn:
+            for blk in model.res_blocks:
+                for bn in (blk.bn1, blk.bn2):
+                    bn.weight.copy_(0.5 + torch.rand(bn.weight.shape, generator=g))
+                    bn.bias.copy_(torch.randn(bn.bias.shape, generator=g) * 0.2)
+                    bn.running_mean.copy_(torch.randn(bn.bias.shape, generator=g) * 0.3)
+                    bn.running_var.copy_(0.5 + torch.rand(bn.bias.shape, generator=g))
+            for cl in model.cross_network:
+                cl.b.copy_(torch.randn(cl.b.shape, generator=g) * 0.05)
+    user_ids = torch.randint(0, n_users, (B,), generator=g)
+    item_ids = torch.randint(0, n_items, (B,), generator=g)
+    # duplicate-heavy ids in the second half so the scatter sees long segments
+    user_ids[B // 2:] = user_ids[B // 2:] % max(1, n_users // 8)
+    cat = torch.stack([torch.randint(0, n, (B,), generator=g) for n in cat_dims.values()], dim=1)
+    num = torch.rand(B, n_num, generator=g)
+    labels = (torch.rand(B, generator=g) < 0.3).float()
+    grad_logits = torch.randn(B, generator=g) / B
+
+    sd0 = {k: v.clone() for k, v in model.state_dict().items()}
+
+    # eval-mode forward (the ranking call, main.py:320-322)
+    model.eval()
+    with torch.no_grad():
+        logits_eval = model(user_ids, item_ids, cat, num)
+
+    # train-mode forward + backward with an explicit upstream gradient (train.py:223-225)
+    model.train()
+    model.zero_grad()
+    logits_train = model(user_ids, item_ids, cat, num)
+    logits_train.backward(gradient=grad_logits)
+    grads = {"grad::" + k: p.grad.detach().numpy().copy() for k, p in model.named_parameters()}
+    sd1 = {k: v.clone() for k, v in model.state_dict().items()}   # running stats after one train step
+
+    # same through the loss (train.py:224-225)
+    model.load_state_dict(sd0)
+    model.zero_grad()
+    loss = torch.nn.BCEWithLogitsLoss()(model(user_ids, item_ids, cat, num), labels)
+    loss.backward()
+    grads_loss = {"lossgrad::" + k: p.grad.detach().numpy().copy() for k, p in model.named_parameters()}
+
+    # float64 arbiter
+    model.load_state_dict(sd0)
+    m64 = ref_main.DCN_RecSys(n_users, n_items, cat_dims, n_num, params).double()
+    m64.load_state_dict(sd0)
+    m64.train()
+    logits64 = m64(user_ids, item_ids, cat, num.double())
+
+    out = dict(
+        meta=np.array([n_users, n_items, n_num, B, params["emb_dim"], params["hidden_dim"],
+                       params["n_cross_layers"], params.get("n_res_blocks", 2)], dtype=np.int64),
+        cat_dims=np.array(list(cat_dims.values()), dtype=np.int64),
+        user_ids=user_ids.numpy(), item_ids=item_ids.numpy(), cat=cat.numpy(), num=num.numpy(),
+        labels=labels.numpy(), grad_logits=grad_logits.numpy(),
+        logits_eval=logits_eval.numpy(), logits_train=logits_train.detach().numpy(),
+        logits_train_f64=logits64.detach().numpy(), loss=np.array(loss.item(), dtype=np.float64),
+    )
+    out.update(_pack_state(sd0))
+    out.update({"after::" + k: v.numpy() for k, v in sd1.items() if "running" in k or "num_batches" in k})
+    out.update(grads)
+    if n_users * params['emb_dim'] + params['hidden_dim'] ** 2 < 20000:   # keep the big fixtures small
+        out.update(grads_loss)
+    path = os.path.join(HERE, f"model_{name}.npz")
+    np.savez_compressed(path, **out)
+    print(name, "->", path, os.path.getsize(path) // 1024, "KiB; loss", loss.item())
+
+
+def cross_case():
+    torch.manual_seed(7)
+    layer = ref_main.CrossLayer(57)
+    with torch.no_grad():
+        layer.b.copy_(torch.randn(57) * 0.1)
+    x = torch.randn(33, 57, requires_grad=True)
+    y = layer(x)
+    g = torch.randn(33, 57)
+    y.backward(g)
+    np.savez_compressed(os.path.join(HERE, "cross_layer.npz"), x=x.detach().numpy(), w=layer.w.weight.detach().numpy(),
+                        b=layer.b.detach().numpy(), y=y.detach().numpy(), g=g.numpy(), gx=x.grad.numpy(),
+                        gw=layer.w.weight.grad.numpy(), gb=layer.b.grad.numpy())
+
+
+def resblock_case():
+    torch.manual_seed(11)
+    blk = ref_main.ResBlock(64, 0.0)
+    with torch.no_grad():
+        for bn in (blk.bn1, blk.bn2):
+            bn.weight.copy_(0.5 + torch.rand(64)); bn.bias.copy_(torch.randn(64) * 0.2)
+    x = torch.randn(48, 64, requires_grad=True)
+    blk.train()
+    y = blk(x)
+    g = torch.randn(48, 64)
+    y.backward(g)
+    d = dict(x=x.detach().numpy(), y=y.detach().numpy(), g=g.numpy(), gx=x.grad.numpy())
+    d.update({"sd::" + k: v.numpy() for k, v in blk.state_dict().items()})
+    d.update({"grad::" + k: p.grad.numpy() for k, p in blk.named_parameters()})
+    blk.eval()
+    with torch.no_grad():
+        d["y_eval"] = blk(x.detach()).numpy()
+    np.savez_compressed(os.path.join(HERE, "res_block.npz"), **d)
+
+
+def knn_case(name, n, d, nq, k, seed):
+    rng = np.random.default_rng(seed)
+    E = rng.standard_normal((n, d)).astype(np.float32)
+    q_rows = rng.integers(0, n, size=nq)
+    Q = E[q_rows].copy()                                   # the reference queries with catalog rows (main.py:199,299)
+    nn_model = NearestNeighbors(n_neighbors=16, metric="cosine", algorithm="brute")   # main.py:268
+    nn_model.fit(E)                                                                      # main.py:269
+    dists, inds = [], []
+    for i in range(nq):                                    # one [1,d] query per call, as main.py:200,300
+        dd, ii = nn_model.kneighbors(Q[i].reshape(1, -1), n_neighbors=k)
+        dists.append(dd[0]); inds.append(ii[0])
+    np.savez_compressed(os.path.join(HERE, f"knn_{name}.npz"), E=E, Q=Q, q_rows=q_rows, k=np.array(k),
+                        dist=np.stack(dists), ind=np.stack(inds))
+    print("knn", name, "dist dtype", dists[0].dtype, "ind dtype", inds[0].dtype)
+
+
+if __name__ == "__main__":
+    P0 = dict(emb_dim=16, hidden_dim=256, n_cross_layers=3, n_res_blocks=2, dropout=0.0,
+              lr=1e-3, batch_size=512)   # extra keys must be ignored (train.py:186-192)
+    model_case("p0", 300, 120, {"city": 100, "hotel_type": 6}, 11, P0, B=96, seed=42)
+    model_case("p0_trained", 300, 120, {"city": 100, "hotel_type": 6}, 11, P0, B=96, seed=43,
+               emb_scale=0.1, randomize_bn=True)
+    PODD = dict(emb_dim=24, hidden_dim=96, n_cross_layers=5, n_res_blocks=3, dropout=0.0)
+    model_case("odd", 50, 31, {"city": 17, "hotel_type": 3, "extra": 40}, 7, PODD, B=37, seed=44,
+               emb_scale=0.3, randomize_bn=True)
+    PMIN = dict(emb_dim=16, hidden_dim=32, n_cross_layers=1, dropout=0.0)  # n_res_blocks default 2 (train.py:134)
+    model_case("min", 10, 9, {"city": 4, "hotel_type": 2}, 11, PMIN, B=5, seed=45, emb_scale=0.5)
+    cross_case()
+    resblock_case()
+    knn_case("small", 3000, 16, 8, 11, 5)
+    knn_case("k51", 5000, 16, 4, 51, 6)
+    knn_case("d64", 2000, 64, 4, 11, 7)
