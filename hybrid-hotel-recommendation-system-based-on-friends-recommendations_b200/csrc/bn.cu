@@ -1,0 +1,438 @@
+// Train-mode BatchNorm1d statistics / normalise+ReLU(+dropout, +residual) forward and backward,
+// BN folding for eval, column sums, row padding.  All are HBM-bound passes over [m, n] fp32.
+//
+// Reference lines: ResBlock.forward train.py:112-122 (main.py:83-90); BatchNorm1d defaults
+// (eps 1e-5, momentum 0.1, biased variance for normalisation, unbiased into running_var).
+//
+// Thread mapping for every column-wise kernel: the CTA owns a fixed chunk of kChunkRows rows;
+// threads are (ty, tx) with tx walking float4 column quads (coalesced 16-byte accesses) and ty
+// walking rows.  Every reduction is chunk-local in a fixed order, written as one partial row per
+// chunk and finalised in chunk order, so results are bit-reproducible run to run.
+#include "kernels.cuh"
+
+namespace dcnr {
+
+constexpr int kT = 256;
+
+struct ColMap {
+    int tx_n, ty_n;   // threads along columns (power of two) and rows
+};
+static inline ColMap col_map(int n) {
+    int cq = n / 4, tx = 8;
+    while (tx < cq && tx < kT) tx <<= 1;
+    return ColMap{tx, kT / tx};
+}
+
+// ------------------------------------------------------------------------------------ statistics
+// Per thread: shifted sums around the first value it sees (no catastrophic cancellation), turned
+// into (count, mean, M2); threads of a chunk and then chunks are merged with Chan's formula in
+// double, always in the same order.
+__global__ void __launch_bounds__(kT)
+k_bn_stats_partial(const float *__restrict__ z, int64_t ldz, int64_t m, int n, int tx_n, int ty_n,
+                   double *__restrict__ pmean, double *__restrict__ pm2) {
+    extern __shared__ __align__(16) float sm[];   // [ty_n][n] mean, [ty_n][n] m2, [ty_n] counts
+    float *s_mean = sm, *s_m2 = sm + (size_t)ty_n * n;
+    int *s_cnt = reinterpret_cast<int *>(s_m2 + (size_t)ty_n * n);
+    const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
+    const int64_t r0 = (int64_t)blockIdx.x * kChunkRows;
+    const int64_t r1 = min(r0 + kChunkRows, m);
+    const int cq = n >> 2;
+    for (int q = tx; q < cq; q += tx_n) {
+        float4 piv = make_float4(0.f, 0.f, 0.f, 0.f), s1 = piv, s2 = piv;
+        int cnt = 0;
+        for (int64_t r = r0 + ty; r < r1; r += ty_n) {
+            float4 v = ldg4(z + r * ldz + 4 * q);
+            if (cnt == 0) piv = v;
+            float dx = v.x - piv.x, dy = v.y - piv.y, dz = v.z - piv.z, dw = v.w - piv.w;
+            s1.x += dx; s1.y += dy; s1.z += dz; s1.w += dw;
+            s2.x = fmaf(dx, dx, s2.x); s2.y = fmaf(dy, dy, s2.y); s2.z = fmaf(dz, dz, s2.z); s2.w = fmaf(dw, dw, s2.w);
+            ++cnt;
+        }
+        const float inv = cnt > 0 ? 1.f / (float)cnt : 0.f;
+        float *pm = s_mean + (size_t)ty * n + 4 * q, *pv = s_m2 + (size_t)ty * n + 4 * q;
+        pm[0] = piv.x + s1.x * inv; pm[1] = piv.y + s1.y * inv; pm[2] = piv.z + s1.z * inv; pm[3] = piv.w + s1.w * inv;
+        pv[0] = s2.x - s1.x * s1.x * inv; pv[1] = s2.y - s1.y * s1.y * inv;
+        pv[2] = s2.z - s1.z * s1.z * inv; pv[3] = s2.w - s1.w * s1.w * inv;
+        if (q == tx) s_cnt[ty] = cnt;
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += kT) {
+        double cn = 0.0, mean = 0.0, m2 = 0.0;
+        for (int t = 0; t < ty_n; ++t) {
+            const double nb = (double)s_cnt[t];
+            if (nb == 0.0) continue;
+            const double mb = (double)s_mean[(size_t)t * n + c], vb = (double)s_m2[(size_t)t * n + c];
+            const double tot = cn + nb, delta = mb - mean;
+            mean += delta * nb / tot;
+            m2 += vb + delta * delta * cn * nb / tot;
+            cn = tot;
+        }
+        pmean[(int64_t)blockIdx.x * n + c] = mean;
+        pm2[(int64_t)blockIdx.x * n + c] = m2;
+    }
+}
+
+__global__ void k_bn_stats_finalize(const double *__restrict__ pmean, const double *__restrict__ pm2, int64_t chunks,
+                                    int64_t m, int n, float eps, float momentum, float *__restrict__ mean_out,
+                                    float *__restrict__ rstd_out, float *running_mean, float *running_var,
+                                    int64_t *nbt) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c == 0 && nbt != nullptr) *nbt += 1;
+    if (c >= n) return;
+    double cn = 0.0, mean = 0.0, m2 = 0.0;
+    for (int64_t k = 0; k < chunks; ++k) {
+        const double nb = (double)min((int64_t)kChunkRows, m - k * kChunkRows);
+        const double mb = pmean[k * n + c], vb = pm2[k * n + c];
+        const double tot = cn + nb, delta = mb - mean;
+        mean += delta * nb / tot;
+        m2 += vb + delta * delta * cn * nb / tot;
+        cn = tot;
+    }
+    const double var_b = m2 / (double)m;
+    mean_out[c] = (float)mean;
+    rstd_out[c] = (float)(1.0 / sqrt(var_b + (double)eps));
+    if (running_mean != nullptr) {
+        const double var_u = m > 1 ? m2 / (double)(m - 1) : var_b;
+        running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * mean);
+        running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * var_u);
+    }
+}
+
+int64_t bn_scratch_floats(int64_t m, int32_t n) {
+    const int64_t chunks = std::max<int64_t>(ceil_div(m, kChunkRows), 1);
+    return chunks * 4 * (int64_t)n + 4 * (int64_t)n + 64;   // two double rows per chunk, then 2 float rows of sums
+}
+
+int launch_bn_stats(const float *z, int64_t ldz, int64_t m, int32_t n, float eps, float momentum, float *mean,
+                    float *rstd, float *running_mean, float *running_var, int64_t *nbt, float *scratch,
+                    cudaStream_t stream) {
+    DCNR_REQUIRE(n % 4 == 0 && n >= 4 && (ldz & 3) == 0, "bn: n=%d / ld must be multiples of 4", n);
+    DCNR_REQUIRE(m >= 1, "bn: empty batch");
+    const int64_t chunks = ceil_div(m, kChunkRows);
+    double *pmean = reinterpret_cast<double *>(scratch);
+    double *pm2 = pmean + chunks * n;
+    const ColMap cm = col_map(n);
+    const size_t smem = (size_t)cm.ty_n * n * 2 * sizeof(float) + cm.ty_n * sizeof(int);
+    if (smem > 48 * 1024)
+        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_bn_stats_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bn_stats_partial<<<(unsigned)chunks, kT, smem, stream>>>(z, ldz, m, n, cm.tx_n, cm.ty_n, pmean, pm2);
+    DCNR_LAUNCHED();
+    k_bn_stats_finalize<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(pmean, pm2, chunks, m, n, eps, momentum, mean,
+                                                                      rstd, running_mean, running_var, nbt);
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}
+
+// ------------------------------------------------------------------------------------ Philox4x32-10
+__device__ __forceinline__ uint4 philox4x32_10(uint4 ctr, uint2 key) {
+    const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(M0, ctr.x), lo0 = M0 * ctr.x;
+        const uint32_t hi1 = __umulhi(M1, ctr.z), lo1 = M1 * ctr.z;
+        ctr = make_uint4(hi1 ^ ctr.y ^ key.x, lo1, hi0 ^ ctr.w ^ key.y, lo0);
+        key.x += W0;
+        key.y += W1;
+    }
+    return ctr;
+}
+__device__ __forceinline__ float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); }
+
+// ------------------------------------------------------------------------------------ forward apply
+__global__ void __launch_bounds__(kT)
+k_bn_act_fwd(const float *__restrict__ z, int64_t ldz, const float *__restrict__ mean,
+             const float *__restrict__ rstd, const float *__restrict__ gamma, const float *__restrict__ beta,
+             const float *__restrict__ residual, int64_t ldr, const uint8_t *__restrict__ keep, float drop_p,
+             uint64_t seed, uint32_t layer_tag, float *__restrict__ out, int64_t ldo, int64_t m, int n, int tx_n,
+             int ty_n) {
+    const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
+    const int64_t r0 = (int64_t)blockIdx.x * kChunkRows;
+    const int64_t r1 = min(r0 + kChunkRows, m);
+    const int cq = n >> 2;
+    const bool philox = keep == nullptr && drop_p > 0.f;
+    const float post = (keep != nullptr || philox) ? 1.f / (1.f - drop_p) : 1.f;
+    const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
+    for (int q = tx; q < cq; q += tx_n) {
+        const float4 mu = ldg4(mean + 4 * q), rs = ldg4(rstd + 4 * q), ga = ldg4(gamma + 4 * q), be = ldg4(beta + 4 * q);
+        for (int64_t r = r0 + ty; r < r1; r += ty_n) {
+            float4 v = ldg4(z + r * ldz + 4 * q);
+            v.x = fmaf((v.x - mu.x) * rs.x, ga.x, be.x);
+            v.y = fmaf((v.y - mu.y) * rs.y, ga.y, be.y);
+            v.z = fmaf((v.z - mu.z) * rs.z, ga.z, be.z);
+            v.w = fmaf((v.w - mu.w) * rs.w, ga.w, be.w);
+            if (residual != nullptr) {
+                const float4 rr = ldg4(residual + r * ldr + 4 * q);
+                v.x += rr.x; v.y += rr.y; v.z += rr.z; v.w += rr.w;
+            }
+            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+            if (keep != nullptr) {
+                const uchar4 k4 = *reinterpret_cast<const uchar4 *>(keep + r * (int64_t)n + 4 * q);
+                v.x = k4.x ? v.x * post : 0.f; v.y = k4.y ? v.y * post : 0.f;
+                v.z = k4.z ? v.z * post : 0.f; v.w = k4.w ? v.w * post : 0.f;
+            } else if (philox) {
+                const uint4 rnd = philox4x32_10(make_uint4((uint32_t)r, (uint32_t)((uint64_t)r >> 32), (uint32_t)q, layer_tag), key);
+                v.x = u01(rnd.x) >= drop_p ? v.x * post : 0.f; v.y = u01(rnd.y) >= drop_p ? v.y * post : 0.f;
+                v.z = u01(rnd.z) >= drop_p ? v.z * post : 0.f; v.w = u01(rnd.w) >= drop_p ? v.w * post : 0.f;
+            }
+            st4(out + r * ldo + 4 * q, v);
+        }
+    }
+}
+
+int launch_bn_act_fwd(const float *z, int64_t ldz, const float *mean, const float *rstd, const float *gamma,
+                      const float *beta, const float *residual, int64_t ldr, const uint8_t *keep, float drop_p,
+                      uint64_t seed, uint32_t layer_tag, float *out, int64_t ldo, int64_t m, int32_t n,
+                      cudaStream_t stream) {
+    DCNR_REQUIRE(n % 4 == 0 && (ldz & 3) == 0 && (ldo & 3) == 0 && (residual == nullptr || (ldr & 3) == 0),
+                 "bn_act: n / ld must be multiples of 4");
+    DCNR_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout p must be in [0,1)");
+    if (m <= 0) return DCNR_OK;
+    const ColMap cm = col_map(n);
+    k_bn_act_fwd<<<(unsigned)ceil_div(m, kChunkRows), kT, 0, stream>>>(z, ldz, mean, rstd, gamma, beta, residual, ldr,
+                                                                     keep, drop_p, seed, layer_tag, out, ldo, m, n,
+                                                                     cm.tx_n, cm.ty_n);
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}
+
+// ------------------------------------------------------------------------------------ backward
+// pass 1: partial[chunk][0][c] = sum dy, partial[chunk][1][c] = sum dy*xhat over the chunk's rows
+__global__ void __launch_bounds__(kT)
+k_bn_bwd_reduce(const float *__restrict__ g, int64_t ldg, const float *__restrict__ out, int64_t ldo,
+                const float *__restrict__ z, int64_t ldz, const float *__restrict__ mean,
+                const float *__restrict__ rstd, float post_scale, int64_t m, int n, int tx_n, int ty_n,
+                float *__restrict__ partials) {
+    extern __shared__ __align__(16) float sm[];   // [ty_n][2][n]
+    const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
+    const int64_t r0 = (int64_t)blockIdx.x * kChunkRows;
+    const int64_t r1 = min(r0 + kChunkRows, m);
+    const int cq = n >> 2;
+    for (int q = tx; q < cq; q += tx_n) {
+        const float4 mu = ldg4(mean + 4 * q), rs = ldg4(rstd + 4 * q);
+        float4 a = make_float4(0.f, 0.f, 0.f, 0.f), b = a;
+        for (int64_t r = r0 + ty; r < r1; r += ty_n) {
+            const float4 gv = ldg4(g + r * ldg + 4 * q), ov = ldg4(out + r * ldo + 4 * q), zv = ldg4(z + r * ldz + 4 * q);
+            const float dx = ov.x > 0.f ? gv.x * post_scale : 0.f, dy = ov.y > 0.f ? gv.y * post_scale : 0.f;
+            const float dzv = ov.z > 0.f ? gv.z * post_scale : 0.f, dw = ov.w > 0.f ? gv.w * post_scale : 0.f;
+            a.x += dx; a.y += dy; a.z += dzv; a.w += dw;
+            b.x = fmaf(dx, (zv.x - mu.x) * rs.x, b.x); b.y = fmaf(dy, (zv.y - mu.y) * rs.y, b.y);
+            b.z = fmaf(dzv, (zv.z - mu.z) * rs.z, b.z); b.w = fmaf(dw, (zv.w - mu.w) * rs.w, b.w);
+        }
+        st4(sm + ((size_t)ty * 2 + 0) * n + 4 * q, a);
+        st4(sm + ((size_t)ty * 2 + 1) * n + 4 * q, b);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * n; c += kT) {
+        float s = 0.f;
+        for (int t = 0; t < ty_n; ++t) s += sm[(size_t)t * 2 * n + c];
+        partials[(int64_t)blockIdx.x * 2 * n + c] = s;
+    }
+}
+
+// pass 2: dz = gamma*rstd*(dy - sum_dy/m - xhat*sum_dyx/m); optional dy_out; per-chunk column sums of dz
+__global__ void __launch_bounds__(kT)
+k_bn_bwd_apply(const float *g, int64_t ldg, const float *__restrict__ out, int64_t ldo,
+               const float *__restrict__ z, int64_t ldz, const float *__restrict__ mean,
+               const float *__restrict__ rstd, const float *__restrict__ gamma, const float *__restrict__ sums,
+               float post_scale, float *dz, int64_t lddz, float *dy_out, int64_t lddy, int64_t m, int n, int tx_n,
+               int ty_n, float *__restrict__ partials) {
+    extern __shared__ __align__(16) float sm[];   // [ty_n][n]
+    const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
+    const int64_t r0 = (int64_t)blockIdx.x * kChunkRows;
+    const int64_t r1 = min(r0 + kChunkRows, m);
+    const int cq = n >> 2;
+    const float inv_m = 1.f / (float)m;
+    for (int q = tx; q < cq; q += tx_n) {
+        const float4 mu = ldg4(mean + 4 * q), rs = ldg4(rstd + 4 * q), ga = ldg4(gamma + 4 * q);
+        const float4 sa = ldg4(sums + 4 * q), sb = ldg4(sums + n + 4 * q);
+        const float4 k = make_float4(ga.x * rs.x, ga.y * rs.y, ga.z * rs.z, ga.w * rs.w);
+        const float4 ma = make_float4(sa.x * inv_m, sa.y * inv_m, sa.z * inv_m, sa.w * inv_m);
+        const float4 mb = make_float4(sb.x * inv_m, sb.y * inv_m, sb.z * inv_m, sb.w * inv_m);
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t r = r0 + ty; r < r1; r += ty_n) {
+            const float4 gv = *reinterpret_cast<const float4 *>(g + r * ldg + 4 * q);
+            const float4 ov = ldg4(out + r * ldo + 4 * q), zv = ldg4(z + r * ldz + 4 * q);
+            float4 dy;
+            dy.x = ov.x > 0.f ? gv.x * post_scale : 0.f; dy.y = ov.y > 0.f ? gv.y * post_scale : 0.f;
+            dy.z = ov.z > 0.f ? gv.z * post_scale : 0.f; dy.w = ov.w > 0.f ? gv.w * post_scale : 0.f;
+            float4 d;
+            d.x = k.x * (dy.x - ma.x - (zv.x - mu.x) * rs.x * mb.x);
+            d.y = k.y * (dy.y - ma.y - (zv.y - mu.y) * rs.y * mb.y);
+            d.z = k.z * (dy.z - ma.z - (zv.z - mu.z) * rs.z * mb.z);
+            d.w = k.w * (dy.w - ma.w - (zv.w - mu.w) * rs.w * mb.w);
+            if (dy_out != nullptr) st4(dy_out + r * lddy + 4 * q, dy);
+            st4(dz + r * lddz + 4 * q, d);
+            acc.x += d.x; acc.y += d.y; acc.z += d.z; acc.w += d.w;
+        }
+        st4(sm + (size_t)ty * n + 4 * q, acc);
+    }
+    if (partials == nullptr) return;
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += kT) {
+        float s = 0.f;
+        for (int t = 0; t < ty_n; ++t) s += sm[(size_t)t * n + c];
+        partials[(int64_t)blockIdx.x * n + c] = s;
+    }
+}
+
+int launch_bn_act_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo, const float *z, int64_t ldz,
+                      const float *mean, const float *rstd, const float *gamma, float post_scale, float *dz,
+                      int64_t lddz, float *dy_out, int64_t lddy, float *dgamma, float *dbeta, float *dbias,
+                      int64_t m, int32_t n, float *scratch, cudaStream_t stream) {
+    DCNR_REQUIRE(n % 4 == 0 && (ldg & 3) == 0 && (ldo & 3) == 0 && (ldz & 3) == 0 && (lddz & 3) == 0 &&
+                     (dy_out == nullptr || (lddy & 3) == 0),
+                 "bn_act_bwd: n / ld must be multiples of 4");
+    if (m <= 0) return DCNR_OK;
+    const int64_t chunks = ceil_div(m, kChunkRows);
+    const ColMap cm = col_map(n);
+    float *partials = scratch;                          // [chunks][2n]
+    float *sums = scratch + chunks * 2 * (int64_t)n;    // [2][n]
+    size_t smem = (size_t)cm.ty_n * 2 * n * sizeof(float);
+    if (smem > 48 * 1024)
+        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_bn_bwd_reduce, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_bn_bwd_reduce<<<(unsigned)chunks, kT, smem, stream>>>(g, ldg, out, ldo, z, ldz, mean, rstd, post_scale, m, n,
+                                                          cm.tx_n, cm.ty_n, partials);
+    DCNR_LAUNCHED();
+    SegPtrs seg;
+    memset(&seg, 0, sizeof(seg));
+    seg.n = 4;
+    seg.out[0] = sums;       seg.offset[0] = 0; seg.len[0] = n;
+    seg.out[1] = sums + n;   seg.offset[1] = n; seg.len[1] = n;
+    seg.out[2] = dbeta;      seg.offset[2] = 0; seg.len[2] = n;
+    seg.out[3] = dgamma;     seg.offset[3] = n; seg.len[3] = n;
+    DCNR_TRY(launch_sum_partials(partials, chunks, 2 * (int64_t)n, seg, stream));
+    smem = (size_t)cm.ty_n * n * sizeof(float);
+    if (smem > 48 * 1024)
+        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_bn_bwd_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    float *p2 = dbias != nullptr ? partials : nullptr;   // pass-1 partials are dead once sums exist
+    k_bn_bwd_apply<<<(unsigned)chunks, kT, smem, stream>>>(g, ldg, out, ldo, z, ldz, mean, rstd, gamma, sums, post_scale,
+                                                         dz, lddz, dy_out, lddy, m, n, cm.tx_n, cm.ty_n, p2);
+    DCNR_LAUNCHED();
+    if (dbias != nullptr) {
+        memset(&seg, 0, sizeof(seg));
+        seg.n = 1;
+        seg.out[0] = dbias; seg.offset[0] = 0; seg.len[0] = n;
+        DCNR_TRY(launch_sum_partials(partials, chunks, n, seg, stream));
+    }
+    return DCNR_OK;
+}
+
+// ------------------------------------------------------------------------------------ column sums
+__global__ void __launch_bounds__(kT)
+k_colsum_partial(const float *__restrict__ a, int64_t lda, int64_t m, int n, int tx_n, int ty_n,
+                 float *__restrict__ partials) {
+    extern __shared__ __align__(16) float sm[];   // [ty_n][n]
+    const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
+    const int64_t r0 = (int64_t)blockIdx.x * kChunkRows;
+    const int64_t r1 = min(r0 + kChunkRows, m);
+    const int cq = n >> 2;
+    for (int q = tx; q < cq; q += tx_n) {
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int64_t r = r0 + ty; r < r1; r += ty_n) {
+            const float4 v = ldg4(a + r * lda + 4 * q);
+            acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        }
+        st4(sm + (size_t)ty * n + 4 * q, acc);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < n; c += kT) {
+        float s = 0.f;
+        for (int t = 0; t < ty_n; ++t) s += sm[(size_t)t * n + c];
+        partials[(int64_t)blockIdx.x * n + c] = s;
+    }
+}
+
+int launch_colsum(const float *a, int64_t lda, int64_t m, int32_t n, float *out, float *scratch, cudaStream_t stream) {
+    DCNR_REQUIRE(n % 4 == 0 && (lda & 3) == 0, "colsum: n / ld must be multiples of 4");
+    if (m <= 0) return DCNR_OK;
+    const int64_t chunks = ceil_div(m, kChunkRows);
+    const ColMap cm = col_map(n);
+    const size_t smem = (size_t)cm.ty_n * n * sizeof(float);
+    if (smem > 48 * 1024)
+        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_colsum_partial, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_colsum_partial<<<(unsigned)chunks, kT, smem, stream>>>(a, lda, m, n, cm.tx_n, cm.ty_n, scratch);
+    DCNR_LAUNCHED();
+    SegPtrs seg;
+    memset(&seg, 0, sizeof(seg));
+    seg.n = 1;
+    seg.out[0] = out; seg.offset[0] = 0; seg.len[0] = n;
+    return launch_sum_partials(scratch, chunks, n, seg, stream);
+}
+
+// ------------------------------------------------------------------------------------ eval fold, padding
+__global__ void k_bn_fold(const float *__restrict__ gamma, const float *__restrict__ beta,
+                          const float *__restrict__ rm, const float *__restrict__ rv,
+                          const float *__restrict__ lin_bias, float eps, float *__restrict__ scale,
+                          float *__restrict__ shift, int n) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    const double s = (double)gamma[c] / sqrt((double)rv[c] + (double)eps);
+    const double b = lin_bias != nullptr ? (double)lin_bias[c] : 0.0;
+    scale[c] = (float)s;
+    shift[c] = (float)((double)beta[c] + (b - (double)rm[c]) * s);
+}
+
+int launch_bn_fold(const float *gamma, const float *beta, const float *rm, const float *rv, const float *lin_bias,
+                   float eps, float *scale, float *shift, int32_t n, cudaStream_t stream) {
+    k_bn_fold<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(gamma, beta, rm, rv, lin_bias, eps, scale, shift, n);
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}
+
+__global__ void k_pad_rows(const float *__restrict__ src, int64_t lds, float *__restrict__ dst, int64_t ldd, int rows,
+                           int cols, int cols_pad) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= (int64_t)rows * cols_pad) return;
+    const int r = (int)(e / cols_pad), c = (int)(e % cols_pad);
+    dst[(int64_t)r * ldd + c] = c < cols ? src[(int64_t)r * lds + c] : 0.f;
+}
+
+int launch_pad_rows(const float *src, int64_t lds, float *dst, int64_t ldd, int32_t rows, int32_t cols,
+                    int32_t cols_pad, cudaStream_t stream) {
+    const int64_t total = (int64_t)rows * cols_pad;
+    if (total <= 0) return DCNR_OK;
+    k_pad_rows<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(src, lds, dst, ldd, rows, cols, cols_pad);
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}
+
+}  // namespace dcnr
+
+// ------------------------------------------------------------------------------------------------
+using namespace dcnr;
+
+extern "C" int64_t dcnr_bn_scratch_bytes(int64_t m, int32_t n) { return round_up(bn_scratch_floats(m, n) * 4, 256); }
+
+extern "C" int dcnr_bn_stats(const float *z, int64_t ldz, int64_t m, int32_t n, float eps, float momentum, float *mean,
+                             float *rstd, float *running_mean, float *running_var, int64_t *num_batches_tracked,
+                             void *scratch, int64_t scratch_bytes, dcnr_stream_t stream) {
+    DCNR_REQUIRE(z && mean && rstd && scratch, "null argument");
+    if (scratch_bytes < dcnr_bn_scratch_bytes(m, n)) {
+        set_error("bn scratch too small");
+        return DCNR_ERR_WORKSPACE;
+    }
+    return launch_bn_stats(z, ldz, m, n, eps, momentum, mean, rstd, running_mean, running_var, num_batches_tracked,
+                           reinterpret_cast<float *>(scratch), as_stream(stream));
+}
+
+extern "C" int dcnr_bn_act_fwd(const float *z, int64_t ldz, const float *mean, const float *rstd, const float *gamma,
+                               const float *beta, const float *residual, int64_t ldr, const uint8_t *keep, float drop_p,
+                               uint64_t seed, uint32_t layer_tag, float *out, int64_t ldo, int64_t m, int32_t n,
+                               dcnr_stream_t stream) {
+    DCNR_REQUIRE(z && mean && rstd && gamma && beta && out, "null argument");
+    return launch_bn_act_fwd(z, ldz, mean, rstd, gamma, beta, residual, ldr, keep, drop_p, seed, layer_tag, out, ldo, m,
+                             n, as_stream(stream));
+}
+
+extern "C" int dcnr_bn_act_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo, const float *z, int64_t ldz,
+                               const float *mean, const float *rstd, const float *gamma, float post_scale, float *dz,
+                               int64_t lddz, float *dy_out, int64_t lddy, float *dgamma, float *dbeta, float *dbias,
+                               int64_t m, int32_t n, void *scratch, int64_t scratch_bytes, dcnr_stream_t stream) {
+    DCNR_REQUIRE(g && out && z && mean && rstd && gamma && dz && scratch, "null argument");
+    if (scratch_bytes < dcnr_bn_scratch_bytes(m, n)) {
+        set_error("bn scratch too small");
+        return DCNR_ERR_WORKSPACE;
+    }
+    return launch_bn_act_bwd(g, ldg, out, ldo, z, ldz, mean, rstd, gamma, post_scale, dz, lddz, dy_out, lddy, dgamma,
+                             dbeta, dbias, m, n, reinterpret_cast<float *>(scratch), as_stream(stream));
+}

@@ -1,0 +1,184 @@
+// K7: deterministic sorted-segment scatter-add of embedding gradients.
+//
+// Replaces the implicit embedding_dense_backward of loss.backward() (train.py:225) for the tables
+// of train.py:136-139.  The gradient of table row r is the sum of dx0[b, col0:col0+width] over the
+// batch rows b with id_b == r, added in ascending b (the order the reference's CPU kernel uses):
+//   1. (id, b) pairs are radix-sorted by id (stable, so b stays ascending inside a segment);
+//   2. fixed windows of 32 sorted positions are summed sequentially, one thread per
+//      (window, column); segments that live inside one window are written straight to the dense
+//      gradient, window-crossing segments leave a head/tail partial;
+//   3. a fix-up pass walks each window-crossing chain in window order.
+// No atomics, so the result is bit-reproducible.  The radix sort itself is CUB (library plumbing,
+// see DESIGN.md); steps 2-3 are the kernels below.
+#include <cub/device/device_radix_sort.cuh>
+
+#include "kernels.cuh"
+
+namespace dcnr {
+
+constexpr int kWin = 32;
+
+__global__ void k_scatter_prep(const int64_t *__restrict__ ids, int64_t id_stride, int64_t B, int64_t n_rows,
+                               uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B) return;
+    int64_t id = ids[i * id_stride];
+    if (id < 0) id = 0;
+    if (id >= n_rows) id = n_rows - 1;     // out-of-range ids are reported by dcnr_check_ids; stay memory-safe here
+    keys[i] = (uint32_t)id;
+    vals[i] = (uint32_t)i;
+}
+
+// flags[w]: bit0 = first segment continues from window w-1 (head partial in carry[w][0])
+//           bit1 = that head segment also continues into window w+1
+//           bit2 = last segment starts here and continues into window w+1 (tail partial in carry[w][1])
+__global__ void __launch_bounds__(128)
+k_scatter_window(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int64_t B, int width,
+                 const float *__restrict__ dx0, int64_t lddx, int col0, float *__restrict__ grad,
+                 float *__restrict__ carry, uint8_t *__restrict__ flags, int64_t n_windows) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_windows * width) return;
+    const int64_t w = e / width;
+    const int col = (int)(e % width);
+    const int64_t p0 = w * kWin, p1 = min(B, p0 + kWin);
+    const bool has_left = p0 > 0, has_right = p1 < B;
+    const uint32_t left_id = has_left ? keys[p0 - 1] : 0u, right_id = has_right ? keys[p1] : 0u;
+    uint32_t cur = keys[p0];
+    float acc = 0.f;
+    bool first = true;
+    uint8_t fl = 0;
+    for (int64_t p = p0; p < p1; ++p) {
+        const uint32_t id = keys[p];
+        if (id != cur) {
+            if (first && has_left && cur == left_id) {
+                carry[(w * 2 + 0) * width + col] = acc;
+                fl |= 1;
+            } else {
+                grad[(int64_t)cur * width + col] = acc;
+            }
+            cur = id;
+            acc = 0.f;
+            first = false;
+        }
+        acc += __ldg(dx0 + (int64_t)vals[p] * lddx + col0 + col);
+    }
+    const bool left_open = first && has_left && cur == left_id;
+    const bool right_open = has_right && cur == right_id;
+    if (left_open) {
+        carry[(w * 2 + 0) * width + col] = acc;
+        fl |= 1;
+        if (right_open) fl |= 2;
+    } else if (right_open) {
+        carry[(w * 2 + 1) * width + col] = acc;
+        fl |= 4;
+    } else {
+        grad[(int64_t)cur * width + col] = acc;
+    }
+    if (col == 0) flags[w] = fl;
+}
+
+__global__ void __launch_bounds__(128)
+k_scatter_fixup(const uint32_t *__restrict__ keys, int64_t B, int width, float *__restrict__ grad,
+                const float *__restrict__ carry, const uint8_t *__restrict__ flags, int64_t n_windows) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n_windows * width) return;
+    const int64_t w = e / width;
+    const int col = (int)(e % width);
+    if (!(flags[w] & 4)) return;                       // only chain starts do work
+    const int64_t p1 = min(B, (w + 1) * kWin);
+    const uint32_t id = keys[p1 - 1];
+    float acc = carry[(w * 2 + 1) * width + col];
+    for (int64_t w2 = w + 1; w2 < n_windows; ++w2) {
+        acc += carry[(w2 * 2 + 0) * width + col];
+        if (!(flags[w2] & 2)) break;
+    }
+    grad[(int64_t)id * width + col] = acc;
+}
+
+static int sort_bits(int64_t n_rows) {
+    int b = 1;
+    while (((int64_t)1 << b) < n_rows && b < 32) ++b;
+    return b;
+}
+
+static int64_t cub_temp_bytes(int64_t B) {
+    size_t bytes = 0;
+    cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
+    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (int)B, 0, 32, (cudaStream_t)0);
+    return (int64_t)round_up((int64_t)bytes + 256, 256);
+}
+
+int64_t scatter_scratch_bytes(int64_t B) {
+    if (B <= 0) return 256;
+    const int64_t n_windows = ceil_div(B, kWin);
+    int64_t bytes = 4 * round_up(B * 4, 256);                       // keys/vals double buffers
+    bytes += round_up(n_windows * 2 * 256 * 4, 256);                // carry, width <= 256
+    bytes += round_up(n_windows, 256);                              // flags
+    bytes += cub_temp_bytes(B);
+    return bytes;
+}
+
+int launch_embed_scatter(const int64_t *ids, int64_t id_stride, int64_t B, int64_t n_rows, int32_t width,
+                         const float *dx0, int64_t lddx, int32_t col0, float *grad_table, void *scratch,
+                         int64_t scratch_bytes, cudaStream_t stream) {
+    DCNR_REQUIRE(width >= 1 && width <= 256, "embedding width %d unsupported", width);
+    DCNR_REQUIRE(n_rows >= 1 && n_rows <= 0xffffffffLL, "table rows out of range");
+    DCNR_CUDA_CHECK(cudaMemsetAsync(grad_table, 0, (size_t)n_rows * width * sizeof(float), stream));
+    if (B <= 0) return DCNR_OK;
+    DCNR_REQUIRE(B < 0x7fffffffLL, "batch too large for one scatter");
+    if (scratch_bytes < scatter_scratch_bytes(B)) {
+        set_error("scatter scratch too small (%lld < %lld)", (long long)scratch_bytes, (long long)scatter_scratch_bytes(B));
+        return DCNR_ERR_WORKSPACE;
+    }
+    Arena ar(scratch, scratch_bytes);
+    const int64_t n_windows = ceil_div(B, kWin);
+    uint32_t *k0 = ar.take<uint32_t>(B), *k1 = ar.take<uint32_t>(B);
+    uint32_t *v0 = ar.take<uint32_t>(B), *v1 = ar.take<uint32_t>(B);
+    float *carry = ar.take<float>(n_windows * 2 * 256);
+    uint8_t *flags = ar.take<uint8_t>(n_windows);
+    const int64_t temp_bytes = cub_temp_bytes(B);
+    void *temp = ar.take<char>(temp_bytes);
+
+    k_scatter_prep<<<(unsigned)ceil_div(B, 256), 256, 0, stream>>>(ids, id_stride, B, n_rows, k0, v0);
+    DCNR_LAUNCHED();
+    cub::DoubleBuffer<uint32_t> kb(k0, k1), vb(v0, v1);
+    size_t tb = (size_t)temp_bytes;
+    DCNR_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(temp, tb, kb, vb, (int)B, 0, sort_bits(n_rows), stream));
+    count_launch(3);
+    const int64_t threads = n_windows * width;
+    k_scatter_window<<<(unsigned)ceil_div(threads, 128), 128, 0, stream>>>(kb.Current(), vb.Current(), B, width, dx0, lddx,
+                                                                         col0, grad_table, carry, flags, n_windows);
+    DCNR_LAUNCHED();
+    k_scatter_fixup<<<(unsigned)ceil_div(threads, 128), 128, 0, stream>>>(kb.Current(), B, width, grad_table, carry, flags,
+                                                                        n_windows);
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}
+
+}  // namespace dcnr
+
+using namespace dcnr;
+
+extern "C" int dcnr_embed_scatter_bwd(const dcnr_dims *dims, const dcnr_batch *batch, const float *dx0, int64_t lddx,
+                                      const dcnr_grads *grads, void *scratch, int64_t scratch_bytes,
+                                      dcnr_stream_t stream) {
+    DCNR_REQUIRE(dims && batch && dx0 && grads && scratch, "null argument");
+    DCNR_REQUIRE(lddx >= dims->in_dim, "lddx too small");
+    cudaStream_t st = as_stream(stream);
+    const int E = dims->emb_dim;
+    if (grads->user_table)
+        DCNR_TRY(launch_embed_scatter(batch->user_ids, 1, batch->batch, dims->n_users, E, dx0, lddx, 0, grads->user_table,
+                                      scratch, scratch_bytes, st));
+    if (grads->item_table)
+        DCNR_TRY(launch_embed_scatter(batch->item_ids, 1, batch->batch, dims->n_items, E, dx0, lddx, E, grads->item_table,
+                                      scratch, scratch_bytes, st));
+    int col = 2 * E;
+    for (int i = 0; i < dims->n_cat; ++i) {
+        if (grads->cat_table[i])
+            DCNR_TRY(launch_embed_scatter(batch->cat_features + i, dims->n_cat, batch->batch, dims->cat_rows[i],
+                                          dims->cat_width[i], dx0, lddx, col, grads->cat_table[i], scratch,
+                                          scratch_bytes, st));
+        col += dims->cat_width[i];
+    }
+    return DCNR_OK;
+}

@@ -1,0 +1,112 @@
+// Internal kernel-launcher interfaces shared by the translation units of libdcnr_sm100a.so.
+#pragma once
+
+#include <algorithm>
+#include <cstring>
+
+#include "common.cuh"
+
+namespace dcnr {
+
+// ---- gather + cross (embed_cross.cu) ---------------------------------------------------------
+struct GatherSeg {
+    const float *table;
+    const int64_t *ids;      // id of row b is ids[b * id_stride]
+    int64_t rows;
+    int32_t id_stride, width, col0, pad_;
+};
+struct GatherArgs {
+    GatherSeg seg[2 + DCNR_MAX_CAT];
+    const float *num;        // [B, n_num]
+    int32_t n_seg, n_num, num_col0, D;
+};
+struct CrossArgs {
+    const float *w[DCNR_MAX_CROSS];
+    const float *b[DCNR_MAX_CROSS];
+    int32_t L, D;
+};
+
+int make_gather_args(const dcnr_dims *dims, const dcnr_params *params, const dcnr_batch *batch, GatherArgs *out);
+
+// x0 = gather(ga) (or x_in), cross layers applied in registers.  Any of x0_out / y_out /
+// logit_part may be NULL.  logit_part[b] = wf_cross . cross_out[b].
+int launch_embed_cross_fwd(const GatherArgs *ga, const float *x_in, int64_t ldx_in, int64_t B,
+                           const CrossArgs &ca, int32_t dim_pad, float *x0_out, int64_t ldx0, float *y_out,
+                           int64_t ldy, const float *wf_cross, float *logit_part, int32_t *err_flag,
+                           cudaStream_t stream);
+
+int64_t cross_bwd_partial_floats(int64_t B, int32_t dim_pad, int32_t L);
+// upstream gradient either gy [B, ldg] or dlogit[b] * wf_cross (then gwf = d wf_cross is produced)
+int launch_cross_bwd(const float *x, int64_t ldx, int64_t B, const CrossArgs &ca, int32_t dim_pad, const float *gy,
+                     int64_t ldg, const float *dlogit, const float *wf_cross, float *gx, int64_t ldgx,
+                     int accumulate, float *const *gw, float *const *gb, float *gwf, float *partials,
+                     cudaStream_t stream);
+
+// ---- dense layers (gemm_simt.cu / gemm_tc.cu) -------------------------------------------------
+struct GemmEpilogue {
+    const float *col_scale;   // [n] or NULL
+    const float *bias;        // [n] or NULL
+    const float *residual;    // [m, ldr] or NULL
+    int64_t ldr;
+    int relu;
+};
+// C[m,n] = sum_k A(m,k) * B(k,n) with
+//   a_kmajor: A(m,k) = A[m*lda + k]   else A(m,k) = A[k*lda + m]
+//   b_kmajor: B(k,n) = B[n*ldb + k]   else B(k,n) = B[k*ldb + n]
+// split_k > 1: blockIdx.z handles a contiguous k-range and writes its own [m,n] slab at
+// C + z * m * ldc (no epilogue); the caller reduces the slabs in order.
+int launch_gemm_simt(const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,
+                     float *C, int64_t ldc, int64_t m, int64_t n, int64_t k, int split_k,
+                     const GemmEpilogue &epi, cudaStream_t stream);
+
+bool gemm_tc_supported(int precision, bool a_kmajor, bool b_kmajor, int64_t lda, int64_t ldb, int64_t ldc, int64_t m,
+                       int64_t n, int64_t k, int split_k);
+int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,
+                   float *C, int64_t ldc, int64_t m, int64_t n, int64_t k, int split_k, const GemmEpilogue &epi,
+                   cudaStream_t stream);
+// precision dispatch (linear.cu)
+int gemm_any(int precision, const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,
+             float *C, int64_t ldc, int64_t m, int64_t n, int64_t k, int split_k, const GemmEpilogue &epi,
+             cudaStream_t stream);
+int64_t wgrad_scratch_floats(int64_t m, int32_t n, int32_t k);
+// dW[n, 0:k_valid] (ld lddw) = dy^T x over k (padded) columns; db = column sums of dy (may be NULL)
+int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const float *x, int64_t ldx, float *dw,
+                        int64_t lddw, float *db, int64_t m, int32_t n, int32_t k, int32_t k_valid, float *scratch,
+                        cudaStream_t stream);
+
+// ---- batch norm / elementwise (bn.cu) -------------------------------------------------------
+int64_t bn_scratch_floats(int64_t m, int32_t n);
+int launch_bn_stats(const float *z, int64_t ldz, int64_t m, int32_t n, float eps, float momentum, float *mean,
+                    float *rstd, float *running_mean, float *running_var, int64_t *nbt, float *scratch,
+                    cudaStream_t stream);
+int launch_bn_act_fwd(const float *z, int64_t ldz, const float *mean, const float *rstd, const float *gamma,
+                      const float *beta, const float *residual, int64_t ldr, const uint8_t *keep, float drop_p,
+                      uint64_t seed, uint32_t layer_tag, float *out, int64_t ldo, int64_t m, int32_t n,
+                      cudaStream_t stream);
+int launch_bn_act_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo, const float *z, int64_t ldz,
+                      const float *mean, const float *rstd, const float *gamma, float post_scale, float *dz,
+                      int64_t lddz, float *dy_out, int64_t lddy, float *dgamma, float *dbeta, float *dbias,
+                      int64_t m, int32_t n, float *scratch, cudaStream_t stream);
+// eval: scale[c] = gamma*rsqrt(rv+eps), shift[c] = beta + (b_lin - rm)*scale   (folded in double)
+int launch_bn_fold(const float *gamma, const float *beta, const float *rm, const float *rv, const float *lin_bias,
+                   float eps, float *scale, float *shift, int32_t n, cudaStream_t stream);
+// dst[r, 0:cols_pad] = src[r, 0:cols] zero padded
+int launch_pad_rows(const float *src, int64_t lds, float *dst, int64_t ldd, int32_t rows, int32_t cols,
+                    int32_t cols_pad, cudaStream_t stream);
+// column sums of a [m,n] matrix (deterministic); scratch: bn_scratch_floats
+int launch_colsum(const float *a, int64_t lda, int64_t m, int32_t n, float *out, float *scratch, cudaStream_t stream);
+
+// ---- head (head.cu) ---------------------------------------------------------------------------
+int launch_rowdot_fwd(const float *a, int64_t lda, const float *w, const float *extra, const float *bf,
+                      float *out, int64_t m, int32_t n, cudaStream_t stream);
+// dh[b,:] = dlogit[b]*w ; dw[c] = sum_b dlogit[b]*a[b,c] ; dbf = sum_b dlogit[b]
+int launch_rowdot_bwd(const float *dlogit, const float *a, int64_t lda, const float *w, float *dh, int64_t lddh,
+                      float *dw, float *dbf, int64_t m, int32_t n, float *scratch, cudaStream_t stream);
+
+// ---- embedding backward (embed_bwd.cu) ----------------------------------------------------------
+int64_t scatter_scratch_bytes(int64_t B);
+int launch_embed_scatter(const int64_t *ids, int64_t id_stride, int64_t B, int64_t n_rows, int32_t width,
+                         const float *dx0, int64_t lddx, int32_t col0, float *grad_table, void *scratch,
+                         int64_t scratch_bytes, cudaStream_t stream);
+
+}  // namespace dcnr

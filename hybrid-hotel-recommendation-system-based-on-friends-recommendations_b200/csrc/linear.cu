@@ -1,0 +1,85 @@
+// nn.Linear forward / dgrad / wgrad entry points: precision dispatch between the CUDA-core fp32
+// GEMM (gemm_simt.cu) and the tcgen05 tensor-core GEMM (gemm_tc.cu), plus the deterministic
+// split-over-batch reduction of wgrad.
+#include "kernels.cuh"
+
+namespace dcnr {
+
+int gemm_any(int precision, const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,
+             float *C, int64_t ldc, int64_t m, int64_t n, int64_t k, int split_k, const GemmEpilogue &epi,
+             cudaStream_t stream) {
+    if (precision != DCNR_PREC_FP32 && gemm_tc_supported(precision, a_kmajor, b_kmajor, lda, ldb, ldc, m, n, k, split_k))
+        return launch_gemm_tc(precision, A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, m, n, k, split_k, epi, stream);
+    return launch_gemm_simt(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, m, n, k, split_k, epi, stream);
+}
+
+int wgrad_splits(int64_t m, int32_t n, int32_t k) {
+    const int64_t tiles = ceil_div(n, 128) * ceil_div(k, 128);
+    int64_t s = std::min<int64_t>(ceil_div(m, 1024), ceil_div(2 * (int64_t)sm_count(), tiles));
+    return (int)std::max<int64_t>(1, std::min<int64_t>(s, 1024));
+}
+
+int64_t wgrad_scratch_floats(int64_t m, int32_t n, int32_t k) {
+    return (int64_t)wgrad_splits(m, n, k) * n * (int64_t)round_up(k, 4) + bn_scratch_floats(m, n);
+}
+
+int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const float *x, int64_t ldx, float *dw,
+                        int64_t lddw, float *db, int64_t m, int32_t n, int32_t k, int32_t k_valid, float *scratch,
+                        cudaStream_t stream) {
+    // dW[n_out, k_in] = sum_b dy[b, n_out] * x[b, k_in] : both operands have the reduction index as the row
+    const int splits = wgrad_splits(m, n, k);
+    float *slabs = scratch;                                           // [splits][n][k]
+    float *colsum_scratch = scratch + (int64_t)splits * n * (int64_t)round_up(k, 4);
+    if (dw != nullptr) {
+        GemmEpilogue none{nullptr, nullptr, nullptr, 0, 0};
+        if (splits == 1 && k_valid == k) {
+            DCNR_TRY(gemm_any(precision, dy, lddy, false, x, ldx, false, dw, lddw, n, k, m, 1, none, stream));
+        } else {
+            DCNR_TRY(gemm_any(precision, dy, lddy, false, x, ldx, false, slabs, k, n, k, m, splits, none, stream));
+            DCNR_TRY(launch_sum_partials_2d(slabs, splits, n, k, k_valid, dw, lddw, stream));
+        }
+    }
+    if (db != nullptr) DCNR_TRY(launch_colsum(dy, lddy, m, n, db, colsum_scratch, stream));
+    return DCNR_OK;
+}
+
+}  // namespace dcnr
+
+using namespace dcnr;
+
+extern "C" int dcnr_linear_fwd(const float *x, int64_t ldx, const float *w, int64_t ldw, const float *bias,
+                               const float *col_scale, const float *residual, int64_t ldr, int relu, float *y,
+                               int64_t ldy, int64_t m, int32_t n, int32_t k, int32_t precision, dcnr_stream_t stream) {
+    DCNR_REQUIRE(x && w && y, "null argument");
+    DCNR_REQUIRE(ldx >= k && ldw >= k && ldy >= n && (residual == nullptr || ldr >= n), "leading dimension too small");
+    GemmEpilogue epi{col_scale, bias, residual, ldr, relu};
+    return gemm_any(precision, x, ldx, true, w, ldw, true, y, ldy, m, n, k, 1, epi, as_stream(stream));
+}
+
+extern "C" int dcnr_linear_dgrad(const float *dy, int64_t lddy, const float *w, int64_t ldw, const float *residual,
+                                 int64_t ldr, float *dx, int64_t lddx, int64_t m, int32_t n, int32_t k,
+                                 int32_t precision, dcnr_stream_t stream) {
+    DCNR_REQUIRE(dy && w && dx, "null argument");
+    DCNR_REQUIRE(lddy >= n && ldw >= k && lddx >= k && (residual == nullptr || ldr >= k), "leading dimension too small");
+    GemmEpilogue epi{nullptr, nullptr, residual, ldr, 0};
+    // dx[m, k] = sum_n dy[m, n] * W[n, k] : A = dy (reduction index contiguous), B = W (output index contiguous)
+    return gemm_any(precision, dy, lddy, true, w, ldw, false, dx, lddx, m, k, n, 1, epi, as_stream(stream));
+}
+
+extern "C" int64_t dcnr_linear_wgrad_scratch_bytes(int64_t m, int32_t n, int32_t k) {
+    return round_up(wgrad_scratch_floats(m, n, k) * 4, 256);
+}
+
+extern "C" int dcnr_linear_wgrad(const float *dy, int64_t lddy, const float *x, int64_t ldx, float *dw, int64_t lddw,
+                                 float *db, int64_t m, int32_t n, int32_t k, int32_t precision, void *scratch,
+                                 int64_t scratch_bytes, dcnr_stream_t stream) {
+    DCNR_REQUIRE(dy && x && scratch, "null argument");
+    DCNR_REQUIRE(lddy >= n && ldx >= k && (dw == nullptr || lddw >= k), "leading dimension too small");
+    DCNR_REQUIRE(n % 4 == 0 || db == nullptr, "bias gradient needs n %% 4 == 0");
+    if (scratch_bytes < dcnr_linear_wgrad_scratch_bytes(m, n, k)) {
+        set_error("wgrad scratch too small");
+        return DCNR_ERR_WORKSPACE;
+    }
+    return launch_linear_wgrad(precision, dy, lddy, x, ldx, dw, lddw, db, m, n, k, k, reinterpret_cast<float *>(scratch),
+                               as_stream(stream));
+}

@@ -1,0 +1,268 @@
+// Whole-model orchestration: DCN_RecSys.forward in eval and train mode and its backward,
+// chained from the operator launchers on one stream with no host synchronisation.
+//
+// Reference lines: DCN_RecSys.forward train.py:155-170 (main.py:114-127); training step
+// train.py:223-225; ranking call main.py:320-322.
+#include "kernels.cuh"
+
+namespace dcnr {
+
+constexpr int64_t kEvalChunkRows = 1 << 20;   // rows per pass of the eval forward (bounds the workspace)
+
+static int check_dims(const dcnr_dims *d) {
+    DCNR_REQUIRE(d != nullptr, "null dims");
+    DCNR_REQUIRE(d->hidden >= 4 && d->hidden % 4 == 0, "hidden_dim %d must be a multiple of 4", d->hidden);
+    DCNR_REQUIRE(d->n_res >= 0 && d->n_res <= DCNR_MAX_RES, "n_res_blocks %d > %d", d->n_res, DCNR_MAX_RES);
+    DCNR_REQUIRE(d->n_cross >= 0 && d->n_cross <= DCNR_MAX_CROSS, "n_cross_layers %d > %d", d->n_cross, DCNR_MAX_CROSS);
+    DCNR_REQUIRE(d->n_cat >= 0 && d->n_cat <= DCNR_MAX_CAT, "n_cat %d > %d", d->n_cat, DCNR_MAX_CAT);
+    DCNR_REQUIRE(d->in_dim >= 1 && d->in_dim <= 256, "input_dim %d unsupported (max 256)", d->in_dim);
+    DCNR_REQUIRE(d->in_dim_pad == (int32_t)round_up(d->in_dim, DCNR_PAD), "in_dim_pad must be round_up(in_dim, 32)");
+    DCNR_REQUIRE(d->dropout_p >= 0.f && d->dropout_p < 1.f, "dropout must be in [0,1)");
+    return DCNR_OK;
+}
+
+struct TrainSaved {
+    float *x0p, *w0p, *logit_cross;
+    float *h[DCNR_MAX_RES + 1];
+    float *z1[DCNR_MAX_RES], *d1[DCNR_MAX_RES], *z2[DCNR_MAX_RES];
+    float *stats[DCNR_MAX_RES];   // mean1, rstd1, mean2, rstd2 : 4*H each block
+    float *bn_scratch;
+    void layout(const dcnr_dims *d, int64_t B, Arena &a) {
+        const int64_t H = d->hidden, Dp = d->in_dim_pad;
+        x0p = a.take<float>(B * Dp);
+        w0p = a.take<float>(H * Dp);
+        logit_cross = a.take<float>(B);
+        for (int r = 0; r <= d->n_res; ++r) h[r] = a.take<float>(B * H);
+        for (int r = 0; r < d->n_res; ++r) {
+            z1[r] = a.take<float>(B * H);
+            d1[r] = a.take<float>(B * H);
+            z2[r] = a.take<float>(B * H);
+            stats[r] = a.take<float>(4 * H);
+        }
+        bn_scratch = a.take<float>(bn_scratch_floats(B, (int32_t)H));
+    }
+};
+
+struct BwdScratch {
+    float *ga, *gb, *gc, *dx0, *cross_partials, *wgrad, *bn;
+    void *scatter;
+    int64_t scatter_bytes;
+    void layout(const dcnr_dims *d, int64_t B, Arena &a, bool with_scatter) {
+        const int64_t H = d->hidden, Dp = d->in_dim_pad;
+        ga = a.take<float>(B * H);
+        gb = a.take<float>(B * H);
+        gc = a.take<float>(B * H);
+        dx0 = a.take<float>(B * Dp);
+        cross_partials = a.take<float>(cross_bwd_partial_floats(B, (int32_t)Dp, d->n_cross));
+        wgrad = a.take<float>(std::max(wgrad_scratch_floats(B, (int32_t)H, (int32_t)H),
+                                       wgrad_scratch_floats(B, (int32_t)H, (int32_t)Dp)));
+        bn = a.take<float>(bn_scratch_floats(B, (int32_t)H));
+        scatter_bytes = with_scatter ? scatter_scratch_bytes(B) : 0;
+        scatter = a.take<char>(scatter_bytes);
+    }
+};
+
+struct EvalWs {
+    float *x0p, *w0p, *logit_cross, *ha, *hb, *ht, *fold;   // fold: per block scale1, shift1, scale2, shift2
+    void layout(const dcnr_dims *d, int64_t rows, Arena &a) {
+        const int64_t H = d->hidden, Dp = d->in_dim_pad;
+        x0p = a.take<float>(rows * Dp);
+        w0p = a.take<float>(H * Dp);
+        logit_cross = a.take<float>(rows);
+        ha = a.take<float>(rows * H);
+        hb = a.take<float>(rows * H);
+        ht = a.take<float>(rows * H);
+        fold = a.take<float>((int64_t)std::max(d->n_res, 1) * 4 * H);
+    }
+};
+
+static CrossArgs cross_args(const dcnr_dims *d, const dcnr_params *p) {
+    CrossArgs ca;
+    memset(&ca, 0, sizeof(ca));
+    ca.L = d->n_cross;
+    ca.D = d->in_dim;
+    for (int l = 0; l < d->n_cross; ++l) { ca.w[l] = p->cross_w[l]; ca.b[l] = p->cross_b[l]; }
+    return ca;
+}
+
+static dcnr_batch slice_batch(const dcnr_dims *d, const dcnr_batch *b, int64_t r0, int64_t rows) {
+    dcnr_batch s = *b;
+    s.user_ids = b->user_ids + r0;
+    s.item_ids = b->item_ids + r0;
+    s.cat_features = b->cat_features ? b->cat_features + r0 * d->n_cat : nullptr;
+    s.num_features = b->num_features ? b->num_features + r0 * d->n_num : nullptr;
+    s.batch = rows;
+    return s;
+}
+
+}  // namespace dcnr
+
+using namespace dcnr;
+
+extern "C" int64_t dcnr_workspace_bytes(const dcnr_dims *dims, int64_t batch, int kind) {
+    if (check_dims(dims) != DCNR_OK || batch < 0) return -1;
+    Arena a(nullptr, 0);
+    if (kind == 0) {
+        EvalWs w;
+        w.layout(dims, std::min<int64_t>(std::max<int64_t>(batch, 1), kEvalChunkRows), a);
+    } else if (kind == 1) {
+        TrainSaved s;
+        s.layout(dims, std::max<int64_t>(batch, 1), a);
+    } else if (kind == 2) {
+        BwdScratch s;
+        s.layout(dims, std::max<int64_t>(batch, 1), a, true);
+    } else {
+        set_error("workspace kind %d unknown", kind);
+        return -1;
+    }
+    return a.used + 256;
+}
+
+extern "C" int dcnr_forward_eval(const dcnr_dims *dims, const dcnr_params *params, const dcnr_batch *batch,
+                                 float *logits, void *workspace, int64_t workspace_bytes, dcnr_stream_t stream) {
+    DCNR_TRY(check_dims(dims));
+    DCNR_REQUIRE(params && batch && logits && workspace, "null argument");
+    const int64_t B = batch->batch;
+    if (B <= 0) return DCNR_OK;
+    const int64_t chunk = std::min<int64_t>(B, kEvalChunkRows);
+    Arena a(workspace, workspace_bytes);
+    EvalWs w;
+    w.layout(dims, chunk, a);
+    if (!a.ok()) {
+        set_error("eval workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)a.used);
+        return DCNR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    const int H = dims->hidden, D = dims->in_dim, Dp = dims->in_dim_pad, prec = dims->precision;
+    DCNR_TRY(launch_pad_rows(params->w0, D, w.w0p, Dp, H, D, Dp, st));
+    for (int r = 0; r < dims->n_res; ++r) {
+        float *f = w.fold + (int64_t)r * 4 * H;
+        DCNR_TRY(launch_bn_fold(params->res_g1[r], params->res_be1[r], params->res_rm1[r], params->res_rv1[r],
+                                params->res_b1[r], dims->bn_eps, f, f + H, H, st));
+        DCNR_TRY(launch_bn_fold(params->res_g2[r], params->res_be2[r], params->res_rm2[r], params->res_rv2[r],
+                                params->res_b2[r], dims->bn_eps, f + 2 * H, f + 3 * H, H, st));
+    }
+    const CrossArgs ca = cross_args(dims, params);
+    for (int64_t r0 = 0; r0 < B; r0 += chunk) {
+        const int64_t rows = std::min(chunk, B - r0);
+        const dcnr_batch sb = slice_batch(dims, batch, r0, rows);
+        GatherArgs ga;
+        DCNR_TRY(make_gather_args(dims, params, &sb, &ga));
+        DCNR_TRY(launch_embed_cross_fwd(&ga, nullptr, 0, rows, ca, Dp, w.x0p, Dp, nullptr, 0, params->wf + H,
+                                        w.logit_cross, nullptr, st));
+        GemmEpilogue e0{nullptr, params->b0, nullptr, 0, 0};
+        DCNR_TRY(gemm_any(prec, w.x0p, Dp, true, w.w0p, Dp, true, w.ha, H, rows, H, Dp, 1, e0, st));
+        float *h = w.ha, *hn = w.hb;
+        for (int r = 0; r < dims->n_res; ++r) {
+            const float *f = w.fold + (int64_t)r * 4 * H;
+            GemmEpilogue e1{f, f + H, nullptr, 0, 1};
+            DCNR_TRY(gemm_any(prec, h, H, true, params->res_w1[r], H, true, w.ht, H, rows, H, H, 1, e1, st));
+            GemmEpilogue e2{f + 2 * H, f + 3 * H, h, H, 1};
+            DCNR_TRY(gemm_any(prec, w.ht, H, true, params->res_w2[r], H, true, hn, H, rows, H, H, 1, e2, st));
+            std::swap(h, hn);
+        }
+        DCNR_TRY(launch_rowdot_fwd(h, H, params->wf, w.logit_cross, params->bf, logits + r0, rows, H, st));
+    }
+    return DCNR_OK;
+}
+
+extern "C" int dcnr_forward_train(const dcnr_dims *dims, const dcnr_params *params, const dcnr_batch *batch,
+                                  uint64_t dropout_seed, const uint8_t *drop_keep_mask, float *logits, void *saved,
+                                  int64_t saved_bytes, dcnr_stream_t stream) {
+    DCNR_TRY(check_dims(dims));
+    DCNR_REQUIRE(params && batch && logits && saved, "null argument");
+    const int64_t B = batch->batch;
+    DCNR_REQUIRE(B >= 2 || dims->n_res == 0, "Expected more than 1 value per channel when training");
+    Arena a(saved, saved_bytes);
+    TrainSaved s;
+    s.layout(dims, B, a);
+    if (!a.ok()) {
+        set_error("train workspace too small (%lld < %lld)", (long long)saved_bytes, (long long)a.used);
+        return DCNR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    const int H = dims->hidden, D = dims->in_dim, Dp = dims->in_dim_pad, prec = dims->precision;
+    DCNR_TRY(launch_pad_rows(params->w0, D, s.w0p, Dp, H, D, Dp, st));
+    GatherArgs ga;
+    DCNR_TRY(make_gather_args(dims, params, batch, &ga));
+    const CrossArgs ca = cross_args(dims, params);
+    DCNR_TRY(launch_embed_cross_fwd(&ga, nullptr, 0, B, ca, Dp, s.x0p, Dp, nullptr, 0, params->wf + H, s.logit_cross,
+                                    nullptr, st));
+    GemmEpilogue e0{nullptr, params->b0, nullptr, 0, 0};
+    DCNR_TRY(gemm_any(prec, s.x0p, Dp, true, s.w0p, Dp, true, s.h[0], H, B, H, Dp, 1, e0, st));
+    for (int r = 0; r < dims->n_res; ++r) {
+        float *mean1 = s.stats[r], *rstd1 = mean1 + H, *mean2 = mean1 + 2 * H, *rstd2 = mean1 + 3 * H;
+        GemmEpilogue e1{nullptr, params->res_b1[r], nullptr, 0, 0};
+        DCNR_TRY(gemm_any(prec, s.h[r], H, true, params->res_w1[r], H, true, s.z1[r], H, B, H, H, 1, e1, st));
+        DCNR_TRY(launch_bn_stats(s.z1[r], H, B, H, dims->bn_eps, dims->bn_momentum, mean1, rstd1, params->res_rm1[r],
+                                 params->res_rv1[r], params->res_nbt1[r], s.bn_scratch, st));
+        const uint8_t *keep = drop_keep_mask ? drop_keep_mask + (int64_t)r * B * H : nullptr;
+        DCNR_TRY(launch_bn_act_fwd(s.z1[r], H, mean1, rstd1, params->res_g1[r], params->res_be1[r], nullptr, 0, keep,
+                                   dims->dropout_p, dropout_seed, (uint32_t)r, s.d1[r], H, B, H, st));
+        GemmEpilogue e2{nullptr, params->res_b2[r], nullptr, 0, 0};
+        DCNR_TRY(gemm_any(prec, s.d1[r], H, true, params->res_w2[r], H, true, s.z2[r], H, B, H, H, 1, e2, st));
+        DCNR_TRY(launch_bn_stats(s.z2[r], H, B, H, dims->bn_eps, dims->bn_momentum, mean2, rstd2, params->res_rm2[r],
+                                 params->res_rv2[r], params->res_nbt2[r], s.bn_scratch, st));
+        DCNR_TRY(launch_bn_act_fwd(s.z2[r], H, mean2, rstd2, params->res_g2[r], params->res_be2[r], s.h[r], H, nullptr,
+                                   0.f, 0, 0, s.h[r + 1], H, B, H, st));
+    }
+    return launch_rowdot_fwd(s.h[dims->n_res], H, params->wf, s.logit_cross, params->bf, logits, B, H, st);
+}
+
+extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, const dcnr_batch *batch,
+                             const float *grad_logits, const void *saved, int64_t saved_bytes, const dcnr_grads *grads,
+                             void *scratch, int64_t scratch_bytes, dcnr_stream_t stream) {
+    DCNR_TRY(check_dims(dims));
+    DCNR_REQUIRE(params && batch && grad_logits && saved && grads && scratch, "null argument");
+    const int64_t B = batch->batch;
+    Arena a(const_cast<void *>(saved), saved_bytes);
+    TrainSaved s;
+    s.layout(dims, B, a);
+    const bool want_tables = grads->user_table || grads->item_table ||
+                             std::any_of(grads->cat_table, grads->cat_table + dims->n_cat, [](float *p) { return p; });
+    Arena b(scratch, scratch_bytes);
+    BwdScratch w;
+    w.layout(dims, B, b, want_tables);
+    if (!a.ok() || !b.ok()) {
+        set_error("backward workspace too small (saved %lld/%lld, scratch %lld/%lld)", (long long)saved_bytes,
+                  (long long)a.used, (long long)scratch_bytes, (long long)b.used);
+        return DCNR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    const int H = dims->hidden, D = dims->in_dim, Dp = dims->in_dim_pad, R = dims->n_res, prec = dims->precision;
+    const float post = dims->dropout_p > 0.f ? 1.f / (1.f - dims->dropout_p) : 1.f;
+
+    // logit = wf[0:H].h_R + wf[H:].c_L + bf
+    float *g = w.ga, *g2 = w.gb, *g3 = w.gc;
+    DCNR_TRY(launch_rowdot_bwd(grad_logits, s.h[R], H, params->wf, g, H, grads->wf, grads->bf, B, H, w.bn, st));
+    for (int r = R - 1; r >= 0; --r) {
+        const float *mean1 = s.stats[r], *rstd1 = mean1 + H, *mean2 = mean1 + 2 * H, *rstd2 = mean1 + 3 * H;
+        // out = relu(BN2(z2) + h_in): dy2 (kept in g for the identity path), dz2 -> g2
+        DCNR_TRY(launch_bn_act_bwd(g, H, s.h[r + 1], H, s.z2[r], H, mean2, rstd2, params->res_g2[r], 1.f, g2, H, g, H,
+                                   grads->res_g2[r], grads->res_be2[r], grads->res_b2[r], B, H, w.bn, st));
+        if (grads->res_w2[r])
+            DCNR_TRY(launch_linear_wgrad(prec, g2, H, s.d1[r], H, grads->res_w2[r], H, nullptr, B, H, H, H, w.wgrad, st));
+        GemmEpilogue none{nullptr, nullptr, nullptr, 0, 0};
+        DCNR_TRY(gemm_any(prec, g2, H, true, params->res_w2[r], H, false, g3, H, B, H, H, 1, none, st));   // dd1
+        // d1 = dropout(relu(BN1(z1))): dz1 in place in g3
+        DCNR_TRY(launch_bn_act_bwd(g3, H, s.d1[r], H, s.z1[r], H, mean1, rstd1, params->res_g1[r], post, g3, H, nullptr,
+                                   0, grads->res_g1[r], grads->res_be1[r], grads->res_b1[r], B, H, w.bn, st));
+        if (grads->res_w1[r])
+            DCNR_TRY(launch_linear_wgrad(prec, g3, H, s.h[r], H, grads->res_w1[r], H, nullptr, B, H, H, H, w.wgrad, st));
+        GemmEpilogue idn{nullptr, nullptr, g, H, 0};                                                      // + dy2
+        DCNR_TRY(gemm_any(prec, g3, H, true, params->res_w1[r], H, false, g2, H, B, H, H, 1, idn, st));
+        std::swap(g, g2);
+    }
+    // initial_deep_layer: h0 = x0 W0^T + b0
+    if (grads->w0 || grads->b0)
+        DCNR_TRY(launch_linear_wgrad(prec, g, H, s.x0p, Dp, grads->w0, D, grads->b0, B, H, Dp, D, w.wgrad, st));
+    GemmEpilogue none{nullptr, nullptr, nullptr, 0, 0};
+    DCNR_TRY(gemm_any(prec, g, H, true, s.w0p, Dp, false, w.dx0, Dp, B, Dp, H, 1, none, st));
+    // cross network (recomputed from x0), accumulated onto dx0
+    const CrossArgs ca = cross_args(dims, params);
+    DCNR_TRY(launch_cross_bwd(s.x0p, Dp, B, ca, Dp, nullptr, 0, grad_logits, params->wf + H, w.dx0, Dp, 1, grads->cross_w,
+                              grads->cross_b, grads->wf ? grads->wf + H : nullptr, w.cross_partials, st));
+    if (want_tables)
+        DCNR_TRY(dcnr_embed_scatter_bwd(dims, batch, w.dx0, Dp, grads, w.scatter, w.scatter_bytes, stream));
+    return DCNR_OK;
+}

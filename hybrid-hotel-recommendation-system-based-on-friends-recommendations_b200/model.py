@@ -1,0 +1,270 @@
+"""Drop-in ``CrossLayer`` / ``ResBlock`` / ``DCN_RecSys`` for the reference's model classes
+(train.py:90-170, duplicated at main.py:61-127), computing on B200 through libdcnr_sm100a.so.
+
+Same constructor signatures, same ``forward`` signature and output-shape rule, same parameter
+names and shapes (a reference ``final_dcn_model.pth`` loads with ``load_state_dict`` unchanged,
+stock ``torch.optim`` optimizers work on ``.parameters()``), same train()/eval() behaviour
+(batch-statistic BatchNorm that updates running stats and ``num_batches_tracked``, dropout only in
+train()).  The parameter *containers* are ordinary ``nn.Embedding`` / ``nn.Linear`` /
+``nn.BatchNorm1d`` objects so that key names match; their own ``forward`` methods are never called.
+
+There is no CPU path: inputs and parameters must be CUDA tensors.
+"""
+from __future__ import annotations
+
+import os
+from typing import Any, Dict, Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+from torch.autograd import Function
+
+from . import _cabi as C
+from . import functional as F_
+
+
+class CrossLayer(nn.Module):
+    """y = x + x * (x . w) + b   (train.py:90-99 / main.py:61-70: rank-1, uses the layer's own input)."""
+
+    def __init__(self, input_dim: int):
+        super().__init__()
+        self.w = nn.Linear(input_dim, 1, bias=False)
+        self.b = nn.Parameter(torch.zeros(input_dim))
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return F_.cross_network(x, [self.w.weight], [self.b])
+
+
+class ResBlock(nn.Module):
+    """relu(BN2(L2(drop(relu(BN1(L1(x)))))) + x)   (train.py:102-122 / main.py:73-90)."""
+
+    def __init__(self, hidden_dim: int, dropout: float):
+        super().__init__()
+        self.layer1 = nn.Linear(hidden_dim, hidden_dim)
+        self.bn1 = nn.BatchNorm1d(hidden_dim)
+        self.relu = nn.ReLU()
+        self.dropout = nn.Dropout(dropout)
+        self.layer2 = nn.Linear(hidden_dim, hidden_dim)
+        self.bn2 = nn.BatchNorm1d(hidden_dim)
+        self.precision = "fp32"
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        C.require_cuda(x)
+        p = self.precision
+        if self.training:
+            seed = int(torch.empty((), dtype=torch.int64).random_().item()) if self.dropout.p > 0 else 0
+            z1 = F_.linear(x, self.layer1.weight, self.layer1.bias, p)
+            d1 = F_.batchnorm_relu_train(z1, self.bn1.weight, self.bn1.bias, None, self.bn1.running_mean,
+                                         self.bn1.running_var, self.bn1.num_batches_tracked, self.bn1.eps,
+                                         self.bn1.momentum, self.dropout.p, None, seed, 0)
+            z2 = F_.linear(d1, self.layer2.weight, self.layer2.bias, p)
+            return F_.batchnorm_relu_train(z2, self.bn2.weight, self.bn2.bias, x, self.bn2.running_mean,
+                                           self.bn2.running_var, self.bn2.num_batches_tracked, self.bn2.eps,
+                                           self.bn2.momentum, 0.0, None, 0, 0)
+        with torch.no_grad():
+            s1, t1 = F_.fold_batchnorm(self.bn1.weight, self.bn1.bias, self.bn1.running_mean, self.bn1.running_var,
+                                       self.layer1.bias, self.bn1.eps)
+            s2, t2 = F_.fold_batchnorm(self.bn2.weight, self.bn2.bias, self.bn2.running_mean, self.bn2.running_var,
+                                       self.layer2.bias, self.bn2.eps)
+            t = F_.linear_forward_raw(x, self.layer1.weight, t1, s1, None, True, p)
+            return F_.linear_forward_raw(t, self.layer2.weight, t2, s2, x, True, p)
+
+
+class _DCNTrainFn(Function):
+    """DCN_RecSys.forward in train() with autograd: dcnr_forward_train / dcnr_backward."""
+
+    @staticmethod
+    def forward(ctx, model, user_ids, item_ids, cat_features, num_features, *params):
+        dims, pstruct = model._dims(), model._param_struct()
+        B = user_ids.numel()
+        batch = C.Batch(C.ptr(user_ids), C.ptr(item_ids), C.ptr(cat_features), C.ptr(num_features), B)
+        dev = user_ids.device
+        nbytes = C.lib().dcnr_workspace_bytes(dims, B, 1)
+        saved = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        logits = torch.empty(B, dtype=torch.float32, device=dev)
+        seed = int(torch.empty((), dtype=torch.int64).random_().item()) if dims.dropout_p > 0 else 0
+        mask = model._inject_drop_masks
+        C.check(C.lib().dcnr_forward_train(dims, pstruct, batch, seed, C.ptr(mask), C.ptr(logits), C.ptr(saved),
+                                           saved.numel(), C.stream()))
+        ctx.model, ctx.saved_ws, ctx.dims, ctx.pstruct = model, saved, dims, pstruct
+        ctx.inputs = (user_ids, item_ids, cat_features, num_features)
+        ctx.params = params
+        return logits
+
+    @staticmethod
+    def backward(ctx, grad_logits):
+        model, dims = ctx.model, ctx.dims
+        user_ids, item_ids, cat_features, num_features = ctx.inputs
+        B = user_ids.numel()
+        batch = C.Batch(C.ptr(user_ids), C.ptr(item_ids), C.ptr(cat_features), C.ptr(num_features), B)
+        grad_logits = grad_logits.contiguous().float()
+        grads = [torch.empty_like(p) if need else None for p, need in zip(ctx.params, ctx.needs_input_grad[5:])]
+        gstruct = model._grad_struct(grads)
+        dev = user_ids.device
+        scratch = torch.empty(C.lib().dcnr_workspace_bytes(dims, B, 2), dtype=torch.uint8, device=dev)
+        C.check(C.lib().dcnr_backward(dims, ctx.pstruct, batch, C.ptr(grad_logits), C.ptr(ctx.saved_ws),
+                                      ctx.saved_ws.numel(), gstruct, C.ptr(scratch), scratch.numel(), C.stream()))
+        ctx.saved_ws = None
+        return (None, None, None, None, None) + tuple(grads)
+
+
+class DCN_RecSys(nn.Module):
+    """Drop-in for the reference's ``DCN_RecSys`` (train.py:125-170 / main.py:93-127).
+
+    ``params`` needs ``emb_dim``, ``hidden_dim``, ``n_cross_layers``, ``dropout`` and optionally
+    ``n_res_blocks`` (default 2, train.py:134); other keys (lr, batch_size, ...) are ignored like in
+    the reference.  ``precision`` selects the dense-layer arithmetic: "fp32" (CUDA-core IEEE fp32,
+    the parity path), "tf32x3" (tcgen05 3-term split, parity-grade), "tf32" / "bf16" (tensor-core
+    fast paths with stated tolerances).
+    """
+
+    def __init__(self, n_users: int, n_items: int, cat_dims: Dict[str, int], n_num_features: int,
+                 params: Dict[str, Any], precision: Optional[str] = None):
+        super().__init__()
+        emb_dim = params['emb_dim']
+        hidden_dim = params['hidden_dim']
+        n_cross_layers = params['n_cross_layers']
+        dropout = params['dropout']
+        n_res_blocks = params.get('n_res_blocks', 2)
+
+        self.user_embedding = nn.Embedding(n_users, emb_dim)
+        self.item_embedding = nn.Embedding(n_items, emb_dim)
+        widths = [int(np.sqrt(n_cat)) + 1 for n_cat in cat_dims.values()]
+        self.cat_embeddings = nn.ModuleList([nn.Embedding(n, w) for n, w in zip(cat_dims.values(), widths)])
+        input_dim = emb_dim * 2 + sum(widths) + n_num_features
+        self.initial_deep_layer = nn.Linear(input_dim, hidden_dim)
+        self.res_blocks = nn.ModuleList([ResBlock(hidden_dim, dropout) for _ in range(n_res_blocks)])
+        self.cross_network = nn.ModuleList([CrossLayer(input_dim) for _ in range(n_cross_layers)])
+        self.final_linear = nn.Linear(hidden_dim + input_dim, 1)
+
+        if len(widths) > C.MAX_CAT or n_res_blocks > C.MAX_RES or n_cross_layers > C.MAX_CROSS:
+            raise ValueError("model exceeds DCNR_MAX_CAT / DCNR_MAX_RES / DCNR_MAX_CROSS (8 each)")
+        if hidden_dim % 4 != 0:
+            raise ValueError("hidden_dim must be a multiple of 4 (the reference's search space uses multiples of 32)")
+        self._shape = dict(emb_dim=emb_dim, n_num=n_num_features, hidden=hidden_dim, n_cross=n_cross_layers,
+                           n_res=n_res_blocks, in_dim=input_dim, n_users=n_users, n_items=n_items,
+                           cat_rows=list(cat_dims.values()), cat_width=widths, dropout=float(dropout))
+        self.precision = precision or os.environ.get("DCNR_PRECISION", "fp32")
+        self.check_ids = os.environ.get("DCNR_CHECK_IDS", "0") == "1"
+        self._inject_drop_masks = None      # uint8 [n_res, B, H] keep-mask for parity tests
+
+    # ---- C-ABI marshalling -----------------------------------------------------------------
+    def _dims(self) -> C.Dims:
+        s = self._shape
+        d = C.Dims()
+        d.emb_dim, d.n_cat, d.n_num, d.hidden = s["emb_dim"], len(s["cat_rows"]), s["n_num"], s["hidden"]
+        d.n_cross, d.n_res, d.in_dim, d.in_dim_pad = s["n_cross"], s["n_res"], s["in_dim"], C.pad_dim(s["in_dim"])
+        d.n_users, d.n_items = s["n_users"], s["n_items"]
+        for i, (r, w) in enumerate(zip(s["cat_rows"], s["cat_width"])):
+            d.cat_rows[i], d.cat_width[i] = r, w
+        d.dropout_p = s["dropout"] if self.training else 0.0
+        blk = self.res_blocks[0] if len(self.res_blocks) else None
+        d.bn_eps = blk.bn1.eps if blk is not None else 1e-5
+        d.bn_momentum = blk.bn1.momentum if blk is not None else 0.1
+        d.precision = C.PRECISIONS[self.precision]
+        return d
+
+    def _ordered_params(self):
+        """Parameters in the fixed order used by the autograd Function and dcnr_grads."""
+        ps = [self.user_embedding.weight, self.item_embedding.weight] + [e.weight for e in self.cat_embeddings]
+        ps += [self.initial_deep_layer.weight, self.initial_deep_layer.bias]
+        for blk in self.res_blocks:
+            ps += [blk.layer1.weight, blk.layer1.bias, blk.bn1.weight, blk.bn1.bias,
+                   blk.layer2.weight, blk.layer2.bias, blk.bn2.weight, blk.bn2.bias]
+        for cl in self.cross_network:
+            ps += [cl.w.weight, cl.b]
+        ps += [self.final_linear.weight, self.final_linear.bias]
+        return ps
+
+    def _param_struct(self) -> C.Params:
+        p = C.Params()
+        ps = self._ordered_params()
+        for t in ps:
+            if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("DCN_RecSys parameters must be contiguous float32 CUDA tensors "
+                                   "(call model.cuda(); there is no CPU path)")
+        p.user_table, p.item_table = C.ptr(self.user_embedding.weight), C.ptr(self.item_embedding.weight)
+        for i, e in enumerate(self.cat_embeddings):
+            p.cat_table[i] = C.ptr(e.weight)
+        p.w0, p.b0 = C.ptr(self.initial_deep_layer.weight), C.ptr(self.initial_deep_layer.bias)
+        for r, blk in enumerate(self.res_blocks):
+            p.res_w1[r], p.res_b1[r] = C.ptr(blk.layer1.weight), C.ptr(blk.layer1.bias)
+            p.res_g1[r], p.res_be1[r] = C.ptr(blk.bn1.weight), C.ptr(blk.bn1.bias)
+            p.res_rm1[r], p.res_rv1[r] = C.ptr(blk.bn1.running_mean), C.ptr(blk.bn1.running_var)
+            p.res_nbt1[r] = C.ptr(blk.bn1.num_batches_tracked)
+            p.res_w2[r], p.res_b2[r] = C.ptr(blk.layer2.weight), C.ptr(blk.layer2.bias)
+            p.res_g2[r], p.res_be2[r] = C.ptr(blk.bn2.weight), C.ptr(blk.bn2.bias)
+            p.res_rm2[r], p.res_rv2[r] = C.ptr(blk.bn2.running_mean), C.ptr(blk.bn2.running_var)
+            p.res_nbt2[r] = C.ptr(blk.bn2.num_batches_tracked)
+        for l, cl in enumerate(self.cross_network):
+            p.cross_w[l], p.cross_b[l] = C.ptr(cl.w.weight), C.ptr(cl.b)
+        p.wf, p.bf = C.ptr(self.final_linear.weight), C.ptr(self.final_linear.bias)
+        return p
+
+    def _grad_struct(self, grads) -> C.Grads:
+        g = C.Grads()
+        it = iter(grads)
+        g.user_table, g.item_table = C.ptr(next(it)), C.ptr(next(it))
+        for i in range(len(self.cat_embeddings)):
+            g.cat_table[i] = C.ptr(next(it))
+        g.w0, g.b0 = C.ptr(next(it)), C.ptr(next(it))
+        for r in range(len(self.res_blocks)):
+            g.res_w1[r], g.res_b1[r], g.res_g1[r], g.res_be1[r] = (C.ptr(next(it)) for _ in range(4))
+            g.res_w2[r], g.res_b2[r], g.res_g2[r], g.res_be2[r] = (C.ptr(next(it)) for _ in range(4))
+        for l in range(len(self.cross_network)):
+            g.cross_w[l], g.cross_b[l] = C.ptr(next(it)), C.ptr(next(it))
+        g.wf, g.bf = C.ptr(next(it)), C.ptr(next(it))
+        return g
+
+    def _prep_inputs(self, user_ids, item_ids, cat_features, num_features):
+        C.require_cuda(user_ids, item_ids, cat_features, num_features)
+        n_cat = len(self.cat_embeddings)
+        B = user_ids.numel()
+        if item_ids.numel() != B or cat_features.shape[0] != B or num_features.shape[0] != B:
+            raise RuntimeError("Sizes of tensors must match except in dimension 1")     # torch.cat's error
+        if cat_features.dim() != 2 or cat_features.shape[1] < n_cat:
+            raise IndexError("index out of range: cat_features has too few columns")
+        if num_features.shape[1] != self._shape["n_num"]:
+            raise RuntimeError("mat1 and mat2 shapes cannot be multiplied")
+        user_ids = user_ids.reshape(-1).to(torch.int64).contiguous()
+        item_ids = item_ids.reshape(-1).to(torch.int64).contiguous()
+        cat_features = cat_features[:, :n_cat].to(torch.int64).contiguous()
+        num_features = num_features.to(torch.float32).contiguous()
+        return user_ids, item_ids, cat_features, num_features
+
+    # ---- forward ---------------------------------------------------------------------------
+    def forward(self, user_ids: torch.Tensor, item_ids: torch.Tensor, cat_features: torch.Tensor,
+                num_features: torch.Tensor) -> torch.Tensor:
+        user_ids, item_ids, cat_features, num_features = self._prep_inputs(user_ids, item_ids, cat_features,
+                                                                           num_features)
+        B = user_ids.numel()
+        dims = self._dims()
+        batch = C.Batch(C.ptr(user_ids), C.ptr(item_ids), C.ptr(cat_features), C.ptr(num_features), B)
+        if self.check_ids:
+            flag = torch.zeros(1, dtype=torch.int32, device=user_ids.device)
+            C.check(C.lib().dcnr_check_ids(dims, batch, C.ptr(flag), C.stream()))
+        if self.training:
+            if B == 1 and len(self.res_blocks) > 0:
+                raise ValueError(f"Expected more than 1 value per channel when training, got input size "
+                                 f"torch.Size([1, {self._shape['hidden']}])")
+            params = self._ordered_params()
+            if torch.is_grad_enabled() and any(p.requires_grad for p in params):
+                logits = _DCNTrainFn.apply(self, user_ids, item_ids, cat_features, num_features, *params)
+            else:
+                with torch.no_grad():
+                    logits = _DCNTrainFn.forward(_NullCtx(), self, user_ids, item_ids, cat_features, num_features,
+                                                 *params)
+        else:
+            # eval(): folded BatchNorm, no dropout, nothing saved.  The result carries no autograd
+            # graph (the reference only calls eval() forwards under torch.no_grad()).
+            pstruct = self._param_struct()
+            ws = torch.empty(C.lib().dcnr_workspace_bytes(dims, B, 0), dtype=torch.uint8, device=user_ids.device)
+            logits = torch.empty(B, dtype=torch.float32, device=user_ids.device)
+            C.check(C.lib().dcnr_forward_eval(dims, pstruct, batch, C.ptr(logits), C.ptr(ws), ws.numel(), C.stream()))
+        return logits.squeeze()       # [B]; 0-d when B == 1, like train.py:170
+
+
+class _NullCtx:
+    """Stand-in autograd context for the no-grad train() forward."""
+    needs_input_grad = ()

@@ -1,0 +1,78 @@
+"""world_size-2 gloo tests (CPU) of the multi-GPU host logic: request sharding, gradient
+all-reduce, and all-gather + merge of sharded top-k lists.  Compute on the CPU side is the oracle
+(as the checker); the communication helpers under test are the product's."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from dcnr_b200 import distributed as D
+
+
+def _free_port():
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); p = s.getsockname()[1]; s.close(); return p
+
+
+def _worker(rank, world, port, fn, ret):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"; os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ret[rank] = fn(rank, world)
+    finally:
+        dist.destroy_process_group()
+
+
+def _run(fn, world=2):
+    mgr = mp.Manager(); ret = mgr.dict()
+    mp.spawn(_worker, args=(world, _free_port(), fn, ret), nprocs=world, join=True)
+    return [ret[r] for r in range(world)]
+
+
+def test_shard_range_covers_everything():
+    for n in (0, 1, 7, 64, 65537):
+        for w in (1, 2, 3, 8):
+            spans = [D.shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(a[1] == b[0] for a, b in zip(spans[:-1], spans[1:]))
+            assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+def _grad_job(rank, world):
+    torch.manual_seed(0)
+    ps = [torch.nn.Parameter(torch.zeros(5, 3)), torch.nn.Parameter(torch.zeros(7)), torch.nn.Parameter(torch.zeros(64, 4))]
+    for i, p in enumerate(ps):
+        p.grad = torch.full_like(p, float(rank + 1) * (i + 1))
+    n = D.allreduce_gradients(ps, dense_bucket_numel=100)       # third tensor (256 elems) goes alone
+    return n, [float(p.grad.mean()) for p in ps]
+
+
+def test_allreduce_gradients_averages_over_ranks():
+    out = _run(_grad_job)
+    for n, means in out:
+        assert n == 2
+        assert means == pytest.approx([1.5, 3.0, 4.5])
+
+
+def _topk_job(rank, world):
+    from oracle import knn_oracle
+    rng = np.random.default_rng(0)
+    E = rng.standard_normal((4000, 16)).astype(np.float32); E[3000] = E[17]
+    Q = E[[17, 5]]
+    ehat, qhat = knn_oracle.normalize_rows(E), knn_oracle.normalize_rows(Q)
+    b, e = D.shard_range(E.shape[0], rank, world)
+    d, i = knn_oracle.cosine_topk(ehat[b:e], qhat, 50, idx_base=b)          # per-shard result (oracle as stand-in)
+
+    def merge_fn(dp, ip):
+        md, mi = knn_oracle.merge_topk(dp.numpy(), ip.numpy())
+        return torch.from_numpy(md), torch.from_numpy(mi)
+    md, mi = D.gather_topk_and_merge(torch.from_numpy(d), torch.from_numpy(i), merge_fn)
+    fd, fi = knn_oracle.cosine_topk(ehat, qhat, 50)
+    return bool((mi.numpy() == fi).all() and (md.numpy() == fd).all())
+
+
+def test_sharded_topk_gather_and_merge_equals_unsharded():
+    assert all(_run(_topk_job))

@@ -1,0 +1,277 @@
+"""GPU parity tests of the DCN-R path (run on the B200 box: pytest -m gpu).
+
+Every call goes through the C ABI (libdcnr_sm100a.so).  Checkers: the committed golden vectors
+produced by the unmodified reference (tests/golden) and the CPU oracle (oracle/) on seeded inputs.
+Tolerances are the contract's: gathers bit-exact; fp32 logits / gradients <= 1e-5 in the
+max-abs-normalised metric of SURVEY.md 8d, with analytically-zero gradients (pre-BN biases)
+compared absolutely against the global gradient scale and kink rows masked.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import dcnr_oracle as orc
+from tests.helpers import load_model_case, synth_inputs
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-5
+CASES = ["p0", "p0_trained", "odd", "min"]
+
+
+def _build(case, precision="fp32", dropout=0.0):
+    import dcnr_b200
+    params = dict(case["params"]); params["dropout"] = dropout
+    m = dcnr_b200.DCN_RecSys(case["n_users"], case["n_items"], case["cat_dims"], case["n_num"], params,
+                             precision=precision)
+    missing = m.load_state_dict(case["state"], strict=True)      # reference checkpoint loads unchanged
+    assert not missing.missing_keys and not missing.unexpected_keys
+    return m.cuda()
+
+
+def _inputs(case, dev="cuda"):
+    return [case[k].to(dev) for k in ("user_ids", "item_ids", "cat", "num")]
+
+
+def _check_grads(got: dict, ref: dict, tol=TOL):
+    scale = max(float(g.abs().max()) for g in ref.values())
+    worst = 0.0
+    for k, r in ref.items():
+        g = got[k].detach().cpu().double().reshape(r.shape)
+        r = r.double()
+        if float(r.abs().max()) < 1e-6 * scale:
+            err = float((g - r).abs().max()) / scale
+        else:
+            err = orc.max_abs_normalised(g, r)
+        worst = max(worst, err)
+        assert err < tol, f"{k}: {err:.3e}"
+    return worst
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_eval_forward_matches_reference_golden(name):
+    case = load_model_case(name)
+    m = _build(case).eval()
+    with torch.no_grad():
+        out = m(*_inputs(case))
+    assert out.shape == case["logits_eval"].shape
+    assert orc.max_abs_normalised(out.cpu(), case["logits_eval"]) < TOL
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_train_forward_backward_matches_reference_golden(name):
+    case = load_model_case(name)
+    m = _build(case).train()
+    out = m(*_inputs(case))
+    assert orc.max_abs_normalised(out.detach().cpu(), case["logits_train_f64"]) < TOL
+    out.backward(gradient=case["grad_logits"].cuda())
+    got = {k: p.grad for k, p in m.named_parameters()}
+    # fp64 oracle as the arbiter (the reference's own fp32 gradients carry ~1e-6 noise)
+    st64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in case["state"].items()}
+    _, g64, _ = orc.forward_backward(st64, case["user_ids"], case["item_ids"], case["cat"], case["num"].double(),
+                                     grad_logits=case["grad_logits"].double())
+    _check_grads(got, g64)
+    _check_grads(got, case["grads"], tol=2e-4)      # and the reference's fp32 run, at its own noise level
+    # running statistics and num_batches_tracked updated like nn.BatchNorm1d
+    sd = m.state_dict()
+    for k, ref in case["after"].items():
+        if ref.dtype.is_floating_point:
+            assert orc.max_abs_normalised(sd[k].cpu(), ref) < TOL, k
+        else:
+            assert int(sd[k]) == int(ref), k
+
+
+@pytest.mark.parametrize("name", ["odd", "min"])
+def test_loss_backward_matches_reference_golden(name):
+    import dcnr_b200
+    case = load_model_case(name)
+    m = _build(case).train()
+    out = m(*_inputs(case))
+    loss = torch.nn.BCEWithLogitsLoss()(out, case["labels"].cuda())       # the reference's loss object (train.py:206)
+    loss.backward()
+    assert abs(float(loss) - case["loss"]) < 1e-5
+    _check_grads({k: p.grad for k, p in m.named_parameters()}, case["lossgrads"], tol=2e-4)
+    # fused loss kernel agrees with torch's
+    l2, g2 = dcnr_b200.functional.bce_with_logits(out.detach(), case["labels"].cuda())
+    assert abs(float(l2) - float(loss)) < 1e-6
+    ref_g = (torch.sigmoid(out.detach()) - case["labels"].cuda()) / out.numel()
+    assert float((g2 - ref_g).abs().max()) < 1e-7
+
+
+def test_gather_concat_is_bit_exact():
+    import dcnr_b200
+    from dcnr_b200 import _cabi as C
+    case = load_model_case("odd")
+    m = _build(case)
+    u, i, c, x = _inputs(case)
+    dims, ps = m._dims(), m._param_struct()
+    for ld in (dims.in_dim_pad, dims.in_dim):
+        x0 = torch.full((u.numel(), ld), float("nan"), device="cuda")
+        batch = C.Batch(C.ptr(u), C.ptr(i), C.ptr(c), C.ptr(x), u.numel())
+        C.check(C.lib().dcnr_embed_concat_fwd(dims, ps, batch, C.ptr(x0), ld, C.stream()))
+        ref = orc.gather_concat(case["state"], case["user_ids"], case["item_ids"], case["cat"], case["num"])
+        assert torch.equal(x0[:, :dims.in_dim].cpu(), ref)
+        if ld > dims.in_dim:
+            assert float(x0[:, dims.in_dim:].abs().max()) == 0.0
+
+
+@pytest.mark.parametrize("zipf", [False, True])
+def test_large_batch_against_fp64_oracle(zipf):
+    """B = 4096 (configs[0] size), P0, kink-masked gradient parity against the float64 oracle."""
+    import dcnr_b200
+    n_users, n_items, cat_dims, n_num = 20000, 5000, {"city": 100, "hotel_type": 6}, 11
+    params = dict(emb_dim=16, hidden_dim=256, n_cross_layers=3, n_res_blocks=2, dropout=0.0)
+    state = orc.make_state(n_users, n_items, cat_dims, n_num, params, seed=7, emb_scale=0.1, randomize_bn=True)
+    u, i, c, x, y = synth_inputs(n_users, n_items, cat_dims, n_num, 4096, seed=1234, zipf=zipf)
+    m = dcnr_b200.DCN_RecSys(n_users, n_items, cat_dims, n_num, params)
+    m.load_state_dict(state)
+    m = m.cuda().train()
+    bad = orc.kink_mask(state, u, i, c, x)
+    g = torch.randn(4096, generator=torch.Generator().manual_seed(5)) / 4096
+    g[bad] = 0.0
+    st64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in state.items()}
+    ref_logits, ref_grads, _ = orc.forward_backward(st64, u, i, c, x.double(), grad_logits=g.double())
+    out = m(u.cuda(), i.cuda(), c.cuda(), x.cuda())
+    assert orc.max_abs_normalised(out.detach().cpu(), ref_logits) < TOL
+    out.backward(gradient=g.cuda())
+    _check_grads({k: p.grad for k, p in m.named_parameters()}, ref_grads)
+    m.eval()
+    with torch.no_grad():
+        ev = m(u.cuda(), i.cuda(), c.cuda(), x.cuda())
+    ref_ev = orc.forward(st64, u, i, c, x.double(), training=False)
+    assert orc.max_abs_normalised(ev.cpu(), ref_ev) < TOL
+
+
+def test_backward_is_deterministic():
+    case = load_model_case("p0_trained")
+    runs = []
+    for _ in range(2):
+        m = _build(case).train()
+        out = m(*_inputs(case))
+        out.backward(gradient=case["grad_logits"].cuda())
+        runs.append({k: p.grad.clone() for k, p in m.named_parameters()})
+    for k in runs[0]:
+        assert torch.equal(runs[0][k], runs[1][k]), k
+
+
+def test_injected_dropout_mask_matches_oracle():
+    case = load_model_case("odd")
+    p = 0.4
+    m = _build(case, dropout=p).train()
+    B, H, R = case["B"], case["params"]["hidden_dim"], case["params"]["n_res_blocks"]
+    gen = torch.Generator().manual_seed(9)
+    masks = (torch.rand(R, B, H, generator=gen) >= p)
+    m._inject_drop_masks = masks.to(torch.uint8).cuda().contiguous()
+    out = m(*_inputs(case))
+    out.backward(gradient=case["grad_logits"].cuda())
+    st64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in case["state"].items()}
+    ref_logits, ref_grads, _ = orc.forward_backward(st64, case["user_ids"], case["item_ids"], case["cat"],
+                                                    case["num"].double(), grad_logits=case["grad_logits"].double(),
+                                                    drop_masks=[masks[r] for r in range(R)], dropout_p=p)
+    assert orc.max_abs_normalised(out.detach().cpu(), ref_logits) < TOL
+    _check_grads({k: q.grad for k, q in m.named_parameters()}, ref_grads)
+
+
+def test_philox_dropout_rate_and_reproducibility():
+    import dcnr_b200
+    z = torch.randn(4096, 256, device="cuda").abs() + 1.0
+    gamma, beta = torch.ones(256, device="cuda"), torch.full((256,), 3.0, device="cuda")   # everything positive after BN
+    a = dcnr_b200.functional.batchnorm_relu_train(z, gamma, beta, drop_p=0.6, seed=123, layer_tag=1)
+    b = dcnr_b200.functional.batchnorm_relu_train(z, gamma, beta, drop_p=0.6, seed=123, layer_tag=1)
+    c = dcnr_b200.functional.batchnorm_relu_train(z, gamma, beta, drop_p=0.6, seed=124, layer_tag=1)
+    assert torch.equal(a, b) and not torch.equal(a, c)
+    kept = float((a > 0).float().mean())
+    assert abs(kept - 0.4) < 0.01
+    full = dcnr_b200.functional.batchnorm_relu_train(z, gamma, beta)
+    assert torch.allclose(a[a > 0], (full / 0.4)[a > 0], rtol=1e-6)
+
+
+def test_b1_shape_rule_and_errors():
+    case = load_model_case("min")
+    m = _build(case).eval()
+    u, i, c, x = _inputs(case)
+    with torch.no_grad():
+        out = m(u[:1], i[:1], c[:1], x[:1])
+    assert out.dim() == 0                                     # .squeeze() at train.py:170
+    m.train()
+    with pytest.raises(ValueError):
+        m(u[:1], i[:1], c[:1], x[:1])
+    m.check_ids = True
+    bad = u.clone(); bad[0] = case["n_users"]
+    with pytest.raises(IndexError):
+        m(bad, i, c, x)
+    with pytest.raises(RuntimeError):
+        m(u.cpu(), i.cpu(), c.cpu(), x.cpu())                  # no CPU fallback
+
+
+def test_cross_layer_module_matches_reference_golden():
+    import os
+    import dcnr_b200
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "cross_layer.npz"))
+    layer = dcnr_b200.CrossLayer(57).cuda()
+    with torch.no_grad():
+        layer.w.weight.copy_(torch.from_numpy(z["w"])); layer.b.copy_(torch.from_numpy(z["b"]))
+    x = torch.from_numpy(z["x"]).cuda().requires_grad_(True)
+    y = layer(x)
+    y.backward(torch.from_numpy(z["g"]).cuda())
+    assert orc.max_abs_normalised(y.detach().cpu(), z["y"]) < TOL
+    assert orc.max_abs_normalised(x.grad.cpu(), z["gx"]) < TOL
+    assert orc.max_abs_normalised(layer.w.weight.grad.cpu(), z["gw"]) < TOL
+    assert orc.max_abs_normalised(layer.b.grad.cpu(), z["gb"]) < TOL
+
+
+def test_res_block_module_matches_reference_golden():
+    import os
+    import dcnr_b200
+    from tests.helpers import GOLDEN
+    z = np.load(os.path.join(GOLDEN, "res_block.npz"))
+    blk = dcnr_b200.ResBlock(64, 0.0)
+    blk.load_state_dict({k[4:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd::")})
+    blk = blk.cuda().train()
+    x = torch.from_numpy(z["x"]).cuda().requires_grad_(True)
+    y = blk(x)
+    y.backward(torch.from_numpy(z["g"]).cuda())
+    assert orc.max_abs_normalised(y.detach().cpu(), z["y"]) < TOL
+    assert orc.max_abs_normalised(x.grad.cpu(), z["gx"]) < 5e-5
+    scale = max(float(np.abs(z[k]).max()) for k in z.files if k.startswith("grad::"))
+    for k in z.files:
+        if k.startswith("grad::"):
+            g = dict(blk.named_parameters())[k[6:]].grad.cpu().numpy()
+            assert np.abs(g - z[k]).max() < 5e-5 * scale, k
+    blk.eval()
+    with torch.no_grad():
+        ye = blk(torch.from_numpy(z["x"]).cuda())
+    assert orc.max_abs_normalised(ye.cpu(), z["y_eval"]) < TOL
+
+
+def test_scatter_heavy_duplicates_and_order():
+    """Sorted-segment scatter: duplicate-heavy ids (tiny tables, Zipf head) against float64 index_add."""
+    from dcnr_b200 import _cabi as C
+    case = load_model_case("p0")
+    m = _build(case)
+    dims = m._dims()
+    B = 70001
+    g = torch.Generator().manual_seed(3)
+    u = (torch.rand(B, generator=g) ** 6 * case["n_users"]).long().clamp_(0, case["n_users"] - 1)
+    i = torch.randint(0, case["n_items"], (B,), generator=g)
+    c = torch.stack([torch.randint(0, n, (B,), generator=g) for n in case["cat_dims"].values()], 1)
+    dx0 = torch.randn(B, dims.in_dim_pad, generator=g)
+    grads_t = [torch.full_like(p, float("nan")) for p in m._ordered_params()]
+    gs = m._grad_struct([t if n < 2 + dims.n_cat else None for n, t in enumerate(grads_t)])
+    batch = C.Batch(C.ptr(u.cuda()), C.ptr(i.cuda()), C.ptr(c.cuda()), None, B)
+    ub, ib, cb = u.cuda(), i.cuda(), c.cuda()
+    batch = C.Batch(C.ptr(ub), C.ptr(ib), C.ptr(cb), None, B)
+    ws = torch.empty(C.lib().dcnr_workspace_bytes(dims, B, 2), dtype=torch.uint8, device="cuda")
+    dx = dx0.cuda()
+    C.check(C.lib().dcnr_embed_scatter_bwd(dims, batch, C.ptr(dx), dims.in_dim_pad, gs, C.ptr(ws), ws.numel(), C.stream()))
+    E = dims.emb_dim
+    cols = [(u, 0, E), (i, E, E)]
+    off = 2 * E
+    for j, w in enumerate(case["cat_dims"].values()):
+        width = int(np.sqrt(w)) + 1
+        cols.append((c[:, j], off, width)); off += width
+    for (ids, c0, width), got in zip(cols, grads_t):
+        ref = torch.zeros(got.shape, dtype=torch.float64)
+        ref.index_add_(0, ids, dx0[:, c0:c0 + width].double())
+        assert orc.max_abs_normalised(got.cpu(), ref) < 2e-6
