@@ -1,0 +1,366 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the DCN-R hot path on B200.
+
+Workload (BASELINE.json configs[1]): DCN-R ranking inference, 1 user x 500 candidates per request,
+65 536 synthetic requests batched = 32 768 000 candidate rows per step, model P0 (emb 16, hidden
+256, 3 cross layers, 2 ResBlocks), tables 1 M users x 100 K hotels, eval mode.
+A "step" is one pass of the ranking forward over all rows.
+
+  value     candidates/s with the inputs already resident in HBM (CUDA events, max over ranks)
+  e2e       the same through serving.RankingEngine with HOST (pinned) buffers: H2D of the inputs
+            and D2H of the scores inside the timed region
+  roofline  the dominant kernel (the H x H dense layer of the ResBlocks) timed live
+  cpu_baseline / --impl reference: the oracle port of the reference's CPU PyTorch path
+            (oracle/dcnr_oracle.py, same ATen ops) on the box's host cores, bounded sample
+Extra (not part of the contract line's headline): "train" = configs[2] training step, "similarity"
+= configs[3] cosine top-k, both single-GPU-per-rank measurements with their own units.
+
+N > 1 (torchrun): requests are sharded, every rank scores its own 32 768 000 rows (weak scaling),
+no collective on the data path; value = all ranks' rows / max-over-ranks time.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+P0 = dict(emb_dim=16, hidden_dim=256, n_cross_layers=3, n_res_blocks=2, dropout=0.6)
+N_USERS, N_ITEMS = 1_000_000, 100_000
+CAT_DIMS = {"city": 100, "hotel_type": 6}
+N_NUM = 11
+REQUESTS, CANDIDATES = 65_536, 500
+FLOP_PER_ROW = 2 * 57 * 256 + 2 * 2 * 2 * 256 * 256 + 2 * 313          # 554 098
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        p = json.load(open(path))
+        return dict(hbm=p["hbm_gbs"], tensor=p["bf16_tflops_sustained"], tensor_burst=p["bf16_tflops"], src="measured")
+    return dict(hbm=6650.0, tensor=1400.0, tensor_burst=1590.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                       "-lms", "200", "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = dict(sm_mhz=None, sm_max_mhz=None, reasons=[], samples=0)
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        rows = [l.strip().split(", ") for l in open(self.f.name) if l.strip()]
+        os.unlink(self.f.name)
+        sm, reasons = [], set()
+        for r in rows:
+            try:
+                sm.append(float(r[0])); out["sm_max_mhz"] = float(r[1])
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.strip().lower().startswith("active"):
+                    reasons.add(name)
+        if sm:
+            busy = sorted(sm)[len(sm) // 2:]            # upper half = samples under load
+            out["sm_mhz"] = statistics.median(busy)
+        out["reasons"], out["samples"] = sorted(reasons), len(sm)
+        return out
+
+
+def make_state(seed=42):
+    """P0 parameters, 'trained-like' (SURVEY.md 8d): embeddings x0.1, randomised BN statistics."""
+    from oracle import dcnr_oracle as orc          # only used as an initialiser of synthetic weights
+    return orc.make_state(N_USERS, N_ITEMS, CAT_DIMS, N_NUM, P0, seed=seed, emb_scale=0.1, randomize_bn=True)
+
+
+def synth_state_device(dev, seed=42):
+    """Same shapes as make_state but generated on the device (1 M x 16 tables)."""
+    import dcnr_b200
+    torch.manual_seed(seed)
+    m = dcnr_b200.DCN_RecSys(N_USERS, N_ITEMS, CAT_DIMS, N_NUM, P0)
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for e in [m.user_embedding, m.item_embedding, *m.cat_embeddings]:
+            e.weight.mul_(0.1)
+        for blk in m.res_blocks:
+            for bn in (blk.bn1, blk.bn2):
+                bn.weight.copy_(0.5 + torch.rand(bn.weight.shape, generator=g))
+                bn.bias.copy_(torch.randn(bn.bias.shape, generator=g) * 0.2)
+                bn.running_mean.copy_(torch.randn(bn.bias.shape, generator=g) * 0.3)
+                bn.running_var.copy_(0.5 + torch.rand(bn.bias.shape, generator=g))
+    return m.to(dev)
+
+
+def synth_requests(n_req, n_cand, seed, device):
+    """Ranking inputs in the hackathon_augmented_data.csv tensor schema (main.py:215-230): one user
+    index repeated per request, item ids, (city, hotel_type) as functions of the hotel, 11 scaled numerics."""
+    g = torch.Generator(device=device).manual_seed(seed)
+    users = torch.randint(0, N_USERS, (n_req,), generator=g, device=device)
+    user_ids = users.repeat_interleave(n_cand)
+    item_ids = torch.randint(0, N_ITEMS, (n_req * n_cand,), generator=g, device=device)
+    city_of = torch.randint(0, CAT_DIMS["city"], (N_ITEMS,), generator=g, device=device)
+    type_of = torch.randint(0, CAT_DIMS["hotel_type"], (N_ITEMS,), generator=g, device=device)
+    cat = torch.stack([city_of[item_ids], type_of[item_ids]], dim=1).contiguous()
+    num = torch.rand((n_req * n_cand, N_NUM), generator=g, device=device)
+    return user_ids, item_ids, cat, num
+
+
+def time_steps(fn, steps, warmup, barrier):
+    for _ in range(warmup):
+        fn()
+    barrier()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record()
+    for s in range(steps):
+        fn()
+        ev[s + 1].record()
+    torch.cuda.synchronize()
+    barrier()
+    return ev[0].elapsed_time(ev[-1]) / 1e3       # seconds for exactly `steps` steps
+
+
+def reference_arm(args):
+    """The reference's CPU PyTorch path (oracle port: same ATen ops as main.DCN_RecSys) on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import dcnr_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    state = make_state()
+    n_req = 128                                                     # bounded sample per step: 64 000 rows
+    u, i, c, x = synth_requests(n_req, CANDIDATES, 1234, "cpu")
+    rows = u.numel()
+
+    def step():
+        with torch.no_grad():
+            orc.forward(state, u, i, c, x, training=False)
+    for _ in range(args.warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step()
+    dt = time.perf_counter() - t0
+    value = rows * args.steps / dt
+    sample = f"{n_req} requests x {CANDIDATES} candidates = {rows} rows per step (of {REQUESTS * CANDIDATES})"
+    print(json.dumps({
+        "impl": "reference", "metric": "ranking_candidates_per_s", "value": value, "unit": "candidates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "DCN-R P0 ranking inference, 1 user x 500 candidates/request (BASELINE configs[1])",
+                   "tables": f"{N_USERS} users x {N_ITEMS} hotels", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": torch.get_num_threads(), "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="dcnr_b200", choices=["dcnr_b200", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("DCNR_PRECISION", "fp32"))
+    ap.add_argument("--requests", type=int, default=REQUESTS)
+    ap.add_argument("--skip-extras", action="store_true", help="skip the train / similarity side measurements")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+        return
+
+    import dcnr_b200
+    from dcnr_b200 import _cabi as C
+    rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a B200 (the product has no CPU path)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    pk = peaks()
+    model = synth_state_device(dev).eval()
+    model.precision = args.precision
+    rows = args.requests * CANDIDATES
+    u, i, c, x = synth_requests(args.requests, CANDIDATES, 1234 + rank, dev)
+    out_dev = {}
+
+    def step_resident():
+        with torch.no_grad():
+            out_dev["logits"] = model(u, i, c, x)
+
+    # ---- value: inputs resident in HBM ----------------------------------------------------------
+    C.launch_count(reset=True)
+    sampler = ClockSampler(local)
+    for _ in range(args.warmup):
+        step_resident()
+    torch.cuda.synchronize()
+    C.launch_count(reset=True)
+    secs = time_steps(step_resident, args.steps, 0, barrier)
+    launches = C.launch_count()
+    clocks = sampler.stop()
+    secs = max_over_ranks(secs)
+    value = world * rows * args.steps / secs
+    checksum = float(out_dev["logits"].double().sum())
+
+    # ---- e2e: host buffers through the public serving call ----------------------------------------
+    hu, hi, hc, hx = (t.cpu().pin_memory() for t in (u, i, c, x))
+    engine = dcnr_b200.serving.RankingEngine(model, chunk_rows=1 << 20)
+    hout = torch.empty(rows, dtype=torch.float32, pin_memory=True)
+    e2e_steps = max(2, min(args.steps, 3))
+    e2e_secs = max_over_ranks(time_steps(lambda: engine.score(hu, hi, hc, hx, out=hout), e2e_steps, 1, barrier))
+    e2e_value = world * rows * e2e_steps / e2e_secs
+    assert abs(float(hout.double().sum()) - checksum) <= 1e-6 * max(1.0, abs(checksum)) * 10, "e2e result differs"
+
+    # ---- roofline of the dominant kernel: the H x H dense layer (4 of the 5 GEMMs, 95 % of the FLOPs) ----
+    M, H = min(rows, 1 << 20), P0["hidden_dim"]
+    a = torch.randn(M, H, device=dev); w = torch.randn(H, H, device=dev) / 16
+    sc = torch.rand(H, device=dev); sh = torch.rand(H, device=dev)
+    prec = C.PRECISIONS[args.precision]
+    k_secs = time_steps(lambda: dcnr_b200.functional.linear_forward_raw(a, w, sh, sc, a, True, prec), 10, 3, lambda: None)
+    k_flops = 2.0 * M * H * H
+    achieved = k_flops * 10 / k_secs / 1e12
+    roofline = {"bound": "tensor", "achieved": achieved, "peak": pk["tensor"], "unit": "TFLOP/s",
+                "frac": achieved / pk["tensor"], "traffic": None,
+                "kernel": "k_sgemm<true,true> (fp32 CUDA-core)" if args.precision == "fp32" else f"tcgen05 gemm ({args.precision})",
+                "how": f"dcnr_linear_fwd {M}x{H}x{H} + scale/shift/residual/relu epilogue, 10 launches, CUDA events; "
+                       f"algorithmic flops 2MNK; peak = bf16 sustained ({pk['src']})",
+                "step_algorithmic_tflops": FLOP_PER_ROW * rows * args.steps / secs / 1e12}
+    del a, w
+
+    result = {
+        "metric": "ranking_candidates_per_s", "value": value, "unit": "candidates/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": {"fp32": "f32", "tf32x3": "tf32x3 (fp32-parity split, fp32 accumulate)", "tf32": "tf32", "bf16": "bf16"}[args.precision],
+        "data": "synthetic",
+        "config": {"workload": "DCN-R P0 ranking inference, 1 user x 500 candidates/request, "
+                               f"{args.requests} requests/step per GPU (BASELINE configs[1])",
+                   "rows_per_step_per_gpu": rows, "tables": f"{N_USERS} users x {N_ITEMS} hotels",
+                   "model": "emb16 hidden256 cross3 res2 (P0)", "l2": "inputs 2.5 GB per step > 126 MB L2, no flush needed",
+                   "parallelism": f"requests sharded x{world}, no data-path collective"},
+        "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": rows * engine.bytes_per_row_h2d,
+                "d2h_bytes_per_step": rows * engine.bytes_per_row_d2h, "steps": e2e_steps,
+                "ms_per_step": e2e_secs / e2e_steps * 1e3},
+        "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "checksum": checksum,
+    }
+
+    if not args.skip_extras:
+        result["train"] = bench_train(model, dev, world, rank, dist, barrier, max_over_ranks)
+        if world == 1:
+            result["similarity"] = bench_similarity(dev, pk)
+    if rank == 0 and world == 1:
+        result["cpu_baseline"] = cpu_baseline()
+    if rank == 0:
+        print(json.dumps(result))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def bench_train(model, dev, world, rank, dist, barrier, max_over_ranks, global_batch=65_536, steps=10):
+    """BASELINE configs[2]: P0 training step (fwd + bwd + gradient all-reduce), global batch 65 536
+    split over the ranks (strong scaling), 1 M x 100 K tables, dropout 0.6, dense embedding grads."""
+    import dcnr_b200
+    from dcnr_b200 import _cabi as C
+    from dcnr_b200.distributed import allreduce_gradients
+    B = global_batch // world
+    g = torch.Generator(device=dev).manual_seed(99 + rank)
+    u = torch.randint(0, N_USERS, (B,), generator=g, device=dev)
+    i = torch.randint(0, N_ITEMS, (B,), generator=g, device=dev)
+    c = torch.stack([torch.randint(0, n, (B,), generator=g, device=dev) for n in CAT_DIMS.values()], 1)
+    x = torch.rand((B, N_NUM), generator=g, device=dev)
+    y = (torch.rand(B, generator=g, device=dev) < 0.3).float()
+    model.train()
+    params = list(model.parameters())
+
+    def step():
+        for p in params:
+            p.grad = None
+        logits = model(u, i, c, x)
+        _, dl = dcnr_b200.functional.bce_with_logits(logits.detach(), y)
+        logits.backward(gradient=dl)
+        allreduce_gradients(params)
+    C.launch_count(reset=True)
+    step(); torch.cuda.synchronize()
+    per_step = C.launch_count()
+    secs = max_over_ranks(time_steps(step, steps, 3, barrier))
+    model.eval()
+    return {"metric": "train_samples_per_s", "value": global_batch * steps / secs, "unit": "samples/s",
+            "global_batch": global_batch, "per_gpu_batch": B, "ms_per_step": secs / steps * 1e3, "scaling": "strong",
+            "includes": "forward + BCE + backward + NCCL gradient all-reduce (optimizer excluded)",
+            "gpu_launches_per_step": per_step}
+
+
+def bench_similarity(dev, pk, n=10_000_000, d=16, k=201):
+    """BASELINE configs[3] on one GPU: cosine top-201 over a 10 M x 16 catalog (640 MB scan per query batch)."""
+    import dcnr_b200
+    g = torch.Generator(device=dev).manual_seed(7)
+    E = torch.randn(n, d, device=dev, generator=g)
+    model = dcnr_b200.NearestNeighbors().fit(E)
+    out = {}
+    for nq in (1, 32):
+        Q = E[torch.randint(0, n, (nq,), device=dev, generator=g)]
+        secs = time_steps(lambda: model.kneighbors_tensor(Q, k), 5, 2, lambda: None) / 5
+        out[f"q{nq}"] = {"ms": secs * 1e3, "pairs_per_s": nq * n / secs,
+                         "hbm_frac": (n * d * 4 * ((nq + 7) // 8)) / secs / 1e9 / pk["hbm"]}
+    return {"metric": "similarity_query_candidate_pairs_per_s", "catalog": f"{n} x {d} f32", "k": k, **out}
+
+
+def cpu_baseline(budget_s=12.0):
+    """Oracle port of the reference's CPU path on this box's host cores, bounded sample."""
+    from oracle import dcnr_oracle as orc
+    torch.set_num_threads(os.cpu_count() or 1)
+    state = make_state()
+    n_req = 128
+    u, i, c, x = synth_requests(n_req, CANDIDATES, 1234, "cpu")
+    with torch.no_grad():
+        orc.forward(state, u, i, c, x, training=False)
+        t0 = time.perf_counter(); n = 0
+        while time.perf_counter() - t0 < budget_s:
+            orc.forward(state, u, i, c, x, training=False); n += 1
+    dt = time.perf_counter() - t0
+    return {"value": n * u.numel() / dt, "unit": "candidates/s", "cores": torch.get_num_threads(), "kind": "port",
+            "sample": f"{n} passes over {n_req} requests x {CANDIDATES} candidates ({u.numel()} rows each), {dt:.1f} s, "
+                      "torch CPU fp32, eval mode"}
+
+
+if __name__ == "__main__":
+    main()

@@ -1,4 +1,5 @@
 // Error reporting, launch accounting and the generic deterministic partial-sum finalizers.
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 
@@ -7,7 +8,7 @@
 namespace dcnr {
 
 static thread_local char g_err[512] = "";
-static thread_local int64_t g_launches = 0;
+static std::atomic<int64_t> g_launches{0};   // process-wide: autograd runs backward on its own thread
 
 void set_error(const char *fmt, ...) {
     va_list ap;
@@ -86,8 +87,6 @@ extern "C" {
 int dcnr_abi_version(void) { return DCNR_ABI_VERSION; }
 const char *dcnr_last_error_string(void) { return dcnr::g_err; }
 int64_t dcnr_launch_count(int reset) {
-    int64_t v = dcnr::g_launches;
-    if (reset) dcnr::g_launches = 0;
-    return v;
+    return reset ? dcnr::g_launches.exchange(0) : dcnr::g_launches.load();
 }
 }

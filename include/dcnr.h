@@ -53,7 +53,7 @@ typedef void *dcnr_stream_t;
 
 int dcnr_abi_version(void);
 const char *dcnr_last_error_string(void);
-/* Number of kernels this library has launched on the calling thread since the last reset
+/* Number of kernels this library has launched (process-wide) since the last reset
  * (bench.py's gpu_launches). */
 int64_t dcnr_launch_count(int reset);
 

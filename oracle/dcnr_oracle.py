@@ -366,21 +366,28 @@ def max_abs_normalised(a, b) -> float:
     return float((a - b).abs().max()) / denom
 
 
-def kink_mask(state, user_ids, item_ids, cat_features, num_features, thresh: float = 1e-5) -> torch.Tensor:
-    """Rows whose float64 forward has a ReLU pre-activation within ``thresh`` of zero
-    (their upstream gradient is zeroed in gradient-parity tests, SURVEY.md section 8d-ii)."""
+def relu_preactivations(state, user_ids, item_ids, cat_features, num_features, dtype=torch.float64):
+    """Train-mode inputs of every ReLU, in order [blk0.relu1, blk0.relu2, blk1.relu1, ...], each [B,H]."""
     shp = model_shape(state)
-    st = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in state.items()}
-    x0 = gather_concat(st, user_ids, item_ids, cat_features, num_features.double())
+    st = {k: (v.to(dtype) if v.dtype.is_floating_point else v) for k, v in state.items()}
+    x0 = gather_concat(st, user_ids, item_ids, cat_features, num_features.to(dtype))
     h = F.linear(x0, st["initial_deep_layer.weight"], st["initial_deep_layer.bias"])
-    bad = torch.zeros(x0.shape[0], dtype=torch.bool)
+    pre = []
     for r in range(shp["R"]):
         p = f"res_blocks.{r}."
         z1 = F.linear(h, st[p + "layer1.weight"], st[p + "layer1.bias"])
         y1, _, _ = batchnorm_train(z1, st[p + "bn1.weight"], st[p + "bn1.bias"])
-        bad |= (y1.abs() < thresh).any(dim=1)
         z2 = F.linear(torch.relu(y1), st[p + "layer2.weight"], st[p + "layer2.bias"])
         y2, _, _ = batchnorm_train(z2, st[p + "bn2.weight"], st[p + "bn2.bias"])
-        bad |= ((y2 + h).abs() < thresh).any(dim=1)
+        pre += [y1, y2 + h]
         h = torch.relu(y2 + h)
+    return pre
+
+
+def kink_mask(state, user_ids, item_ids, cat_features, num_features, thresh: float = 1e-5) -> torch.Tensor:
+    """Rows whose float64 forward has a ReLU pre-activation within ``thresh`` of zero
+    (their upstream gradient is zeroed in gradient-parity tests, SURVEY.md section 8d-ii)."""
+    bad = torch.zeros(user_ids.shape[0], dtype=torch.bool)
+    for y in relu_preactivations(state, user_ids, item_ids, cat_features, num_features):
+        bad |= (y.abs() < thresh).any(dim=1)
     return bad

@@ -1,0 +1,56 @@
+"""Per-tensor parity report on the GPU box: ours vs the float64 oracle, next to the reference
+arithmetic's own fp32 noise (oracle in fp32 on torch CPU).  Writes gpurun_out/parity_report.md."""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import dcnr_b200  # noqa: E402
+from oracle import dcnr_oracle as orc  # noqa: E402
+from tests.helpers import synth_inputs  # noqa: E402
+
+
+def run(zipf, B, precision, lines, thresh=1e-4):
+    n_users, n_items, cat_dims, n_num = 20000, 5000, {"city": 100, "hotel_type": 6}, 11
+    params = dict(emb_dim=16, hidden_dim=256, n_cross_layers=3, n_res_blocks=2, dropout=0.0)
+    state = orc.make_state(n_users, n_items, cat_dims, n_num, params, seed=7, emb_scale=0.1, randomize_bn=True)
+    u, i, c, x, y = synth_inputs(n_users, n_items, cat_dims, n_num, B, seed=1234, zipf=zipf)
+    m = dcnr_b200.DCN_RecSys(n_users, n_items, cat_dims, n_num, params, precision=precision)
+    m.load_state_dict(state)
+    m = m.cuda().train()
+    st64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in state.items()}
+    bad = orc.kink_mask(state, u, i, c, x, thresh=thresh)
+    g = torch.randn(B, generator=torch.Generator().manual_seed(5)) / B
+    g[bad] = 0.0
+    ref_logits, ref_grads, _ = orc.forward_backward(st64, u, i, c, x.double(), grad_logits=g.double())
+    n32_logits, n32_grads, _ = orc.forward_backward(state, u, i, c, x, grad_logits=g)
+    out = m(u.cuda(), i.cuda(), c.cuda(), x.cuda())
+    out.backward(gradient=g.cuda())
+    lines.append(f"\n### ids {'zipf' if zipf else 'uniform'}, B={B}, precision={precision}, kink rows masked {int(bad.sum())}\n")
+    lines.append("| tensor | ours vs fp64 | reference-fp32 vs fp64 | max abs ref |")
+    lines.append("|---|---|---|---|")
+    lines.append(f"| logits | {orc.max_abs_normalised(out.detach().cpu(), ref_logits):.2e} | "
+                 f"{orc.max_abs_normalised(n32_logits, ref_logits):.2e} | {float(ref_logits.abs().max()):.2e} |")
+    for k, p in m.named_parameters():
+        r = ref_grads[k]
+        lines.append(f"| {k} | {orc.max_abs_normalised(p.grad.cpu(), r):.2e} | {orc.max_abs_normalised(n32_grads[k], r):.2e} | "
+                     f"{float(r.abs().max()):.2e} |")
+    # where does the user-table error sit?
+    d = (m.user_embedding.weight.grad.cpu().double() - ref_grads["user_embedding.weight"]).abs().max(dim=1).values
+    top = torch.topk(d, 5)
+    cnt = torch.bincount(u, minlength=n_users)
+    lines.append("\nworst user rows (row, abs err, duplicates in batch): " +
+                 ", ".join(f"({int(r)}, {float(e):.2e}, {int(cnt[r])})" for e, r in zip(top.values, top.indices)))
+
+
+if __name__ == "__main__":
+    lines = ["# Parity report (GPU)"]
+    for prec in sys.argv[1:] or ["fp32"]:
+        for zipf in (False, True):
+            run(zipf, 4096, prec, lines)
+        run(True, 65536, prec, lines)
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    open(os.path.join(ROOT, "gpurun_out", "parity_report.md"), "w").write("\n".join(lines) + "\n")
+    print("\n".join(lines))

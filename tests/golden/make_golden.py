@@ -121,12 +121,13 @@ def resblock_case():
         for bn in (blk.bn1, blk.bn2):
             bn.weight.copy_(0.5 + torch.rand(64)); bn.bias.copy_(torch.randn(64) * 0.2)
     x = torch.randn(48, 64, requires_grad=True)
+    sd0 = {k: v.clone() for k, v in blk.state_dict().items()}      # BEFORE the train step updates running stats
     blk.train()
     y = blk(x)
     g = torch.randn(48, 64)
     y.backward(g)
     d = dict(x=x.detach().numpy(), y=y.detach().numpy(), g=g.numpy(), gx=x.grad.numpy())
-    d.update({"sd::" + k: v.numpy() for k, v in blk.state_dict().items()})
+    d.update({"sd::" + k: v.numpy() for k, v in sd0.items()})
     d.update({"grad::" + k: p.grad.numpy() for k, p in blk.named_parameters()})
     blk.eval()
     with torch.no_grad():

@@ -115,9 +115,41 @@ def test_gather_concat_is_bit_exact():
             assert float(x0[:, dims.in_dim:].abs().max()) == 0.0
 
 
+def _relu_patterns_gpu(m, u, i, c, x):
+    """ReLU activity pattern of OUR kernels, obtained by chaining the operator-level entry points
+    (same kernels and summation order as the whole-model call)."""
+    import dcnr_b200
+    from dcnr_b200 import _cabi as C
+    F_ = dcnr_b200.functional
+    dims, ps = m._dims(), m._param_struct()
+    B = u.numel()
+    x0 = torch.empty(B, dims.in_dim_pad, device="cuda")
+    batch = C.Batch(C.ptr(u), C.ptr(i), C.ptr(c), C.ptr(x), B)
+    C.check(C.lib().dcnr_embed_concat_fwd(dims, ps, batch, C.ptr(x0), dims.in_dim_pad, C.stream()))
+    with torch.no_grad():
+        h = F_.linear(x0[:, :dims.in_dim].contiguous(), m.initial_deep_layer.weight, m.initial_deep_layer.bias)
+        pats = []
+        for blk in m.res_blocks:
+            z1 = F_.linear(h, blk.layer1.weight, blk.layer1.bias)
+            d1 = F_.batchnorm_relu_train(z1, blk.bn1.weight, blk.bn1.bias)
+            z2 = F_.linear(d1, blk.layer2.weight, blk.layer2.bias)
+            out = F_.batchnorm_relu_train(z2, blk.bn2.weight, blk.bn2.bias, h)
+            pats += [d1 > 0, out > 0]
+            h = out
+    return [p.cpu() for p in pats]
+
+
 @pytest.mark.parametrize("zipf", [False, True])
 def test_large_batch_against_fp64_oracle(zipf):
-    """B = 4096 (configs[0] size), P0, kink-masked gradient parity against the float64 oracle."""
+    """B = 4096 (configs[0] size), P0: logits and every gradient against the float64 oracle.
+
+    Kink masking: a row gets zero upstream gradient when any ReLU input is within
+    1e-5 of zero in float64 OR when its ReLU on/off pattern differs between float64 and an fp32
+    evaluation (ours, or the reference arithmetic's) -- a flipped ReLU is a discontinuity, not an
+    arithmetic error; flipped inputs are asserted to be tiny (|y| < 1e-3) and rare (< 1 % of rows).
+    Criterion per tensor: err(ours vs fp64) <= max(1e-5, 2 x err(reference fp32 arithmetic vs fp64)),
+    the second term being the reference's own fp32 noise on the same inputs (it reaches ~2e-5 on
+    duplicate-heavy ids, so a flat 1e-5 would fail the reference against itself)."""
     import dcnr_b200
     n_users, n_items, cat_dims, n_num = 20000, 5000, {"city": 100, "hotel_type": 6}, 11
     params = dict(emb_dim=16, hidden_dim=256, n_cross_layers=3, n_res_blocks=2, dropout=0.0)
@@ -125,21 +157,39 @@ def test_large_batch_against_fp64_oracle(zipf):
     u, i, c, x, y = synth_inputs(n_users, n_items, cat_dims, n_num, 4096, seed=1234, zipf=zipf)
     m = dcnr_b200.DCN_RecSys(n_users, n_items, cat_dims, n_num, params)
     m.load_state_dict(state)
-    m = m.cuda().train()
-    bad = orc.kink_mask(state, u, i, c, x)
-    g = torch.randn(4096, generator=torch.Generator().manual_seed(5)) / 4096
-    g[bad] = 0.0
+    m = m.cuda()
     st64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in state.items()}
-    ref_logits, ref_grads, _ = orc.forward_backward(st64, u, i, c, x.double(), grad_logits=g.double())
-    out = m(u.cuda(), i.cuda(), c.cuda(), x.cuda())
-    assert orc.max_abs_normalised(out.detach().cpu(), ref_logits) < TOL
-    out.backward(gradient=g.cuda())
-    _check_grads({k: p.grad for k, p in m.named_parameters()}, ref_grads)
     m.eval()
     with torch.no_grad():
         ev = m(u.cuda(), i.cuda(), c.cuda(), x.cuda())
     ref_ev = orc.forward(st64, u, i, c, x.double(), training=False)
     assert orc.max_abs_normalised(ev.cpu(), ref_ev) < TOL
+    m.train()
+    pre64 = orc.relu_preactivations(state, u, i, c, x)
+    pre32 = orc.relu_preactivations(state, u, i, c, x, dtype=torch.float32)
+    ours = _relu_patterns_gpu(m, u.cuda(), i.cuda(), c.cuda(), x.cuda())
+    bad = torch.zeros(4096, dtype=torch.bool)
+    for y64, y32, pat in zip(pre64, pre32, ours):
+        flipped = (pat != (y64 > 0)) | ((y32 > 0) != (y64 > 0))
+        assert float(y64[flipped].abs().max() if flipped.any() else 0.0) < 1e-3       # only true kinks flip
+        bad |= flipped.any(dim=1) | (y64.abs() < 1e-5).any(dim=1)
+    assert int(bad.sum()) < 0.01 * 4096 + 64
+    g = torch.randn(4096, generator=torch.Generator().manual_seed(5)) / 4096
+    g[bad] = 0.0
+    ref_logits, ref_grads, _ = orc.forward_backward(st64, u, i, c, x.double(), grad_logits=g.double())
+    _, noise_grads, _ = orc.forward_backward(state, u, i, c, x, grad_logits=g)       # reference arithmetic, fp32
+    out = m(u.cuda(), i.cuda(), c.cuda(), x.cuda())
+    assert orc.max_abs_normalised(out.detach().cpu(), ref_logits) < TOL
+    out.backward(gradient=g.cuda())
+    scale = max(float(v.abs().max()) for v in ref_grads.values())
+    for k, p in m.named_parameters():
+        r = ref_grads[k]
+        if float(r.abs().max()) < 1e-6 * scale:
+            assert float((p.grad.cpu().double() - r).abs().max()) < TOL * scale, k
+            continue
+        err = orc.max_abs_normalised(p.grad.cpu(), r)
+        noise = orc.max_abs_normalised(noise_grads[k], r)
+        assert err <= max(TOL, 2.0 * noise), f"{k}: ours {err:.2e} vs reference-fp32 noise {noise:.2e}"
 
 
 def test_backward_is_deterministic():
@@ -259,7 +309,6 @@ def test_scatter_heavy_duplicates_and_order():
     dx0 = torch.randn(B, dims.in_dim_pad, generator=g)
     grads_t = [torch.full_like(p, float("nan")) for p in m._ordered_params()]
     gs = m._grad_struct([t if n < 2 + dims.n_cat else None for n, t in enumerate(grads_t)])
-    batch = C.Batch(C.ptr(u.cuda()), C.ptr(i.cuda()), C.ptr(c.cuda()), None, B)
     ub, ib, cb = u.cuda(), i.cuda(), c.cuda()
     batch = C.Batch(C.ptr(ub), C.ptr(ib), C.ptr(cb), None, B)
     ws = torch.empty(C.lib().dcnr_workspace_bytes(dims, B, 2), dtype=torch.uint8, device="cuda")
