@@ -61,13 +61,23 @@ int launch_gemm_simt(const float *A, int64_t lda, bool a_kmajor, const float *B,
 
 bool gemm_tc_supported(int precision, bool a_kmajor, bool b_kmajor, int64_t lda, int64_t ldb, int64_t ldc, int64_t m,
                        int64_t n, int64_t k, int split_k);
+// TF32X3: B is the tf32-rounded (hi) half of the weight and B_lo its exact remainder (launch_split_tf32)
 int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,
                    float *C, int64_t ldc, int64_t m, int64_t n, int64_t k, int split_k, const GemmEpilogue &epi,
-                   cudaStream_t stream);
-// precision dispatch (linear.cu)
+                   cudaStream_t stream, const float *B_lo);
+// hi = rn_tf32(src), lo = src - hi, dense [rows, cols] (or transposed: [cols, rows]); lo may be NULL when transposing
+int launch_split_tf32(const float *src, int64_t lds, float *hi, float *lo, int32_t rows, int32_t cols, bool transpose,
+                      cudaStream_t stream);
+// A pre-processed weight operand for the tensor-core path: `w` [n, k] row-major dense (ld = k).
+struct WeightOp {
+    const float *hi;   // tf32-rounded weight (TF32X3) or the raw weight (other precisions)
+    const float *lo;   // remainder (TF32X3 only), else NULL
+    int64_t ld;
+};
+// precision dispatch (linear.cu).  wop == NULL -> B is used as is (CUDA-core path unless precision == TF32).
 int gemm_any(int precision, const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,
              float *C, int64_t ldc, int64_t m, int64_t n, int64_t k, int split_k, const GemmEpilogue &epi,
-             cudaStream_t stream);
+             cudaStream_t stream, const WeightOp *wop = nullptr);
 int64_t wgrad_scratch_floats(int64_t m, int32_t n, int32_t k);
 // dW[n, 0:k_valid] (ld lddw) = dy^T x over k (padded) columns; db = column sums of dy (may be NULL)
 int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const float *x, int64_t ldx, float *dw,

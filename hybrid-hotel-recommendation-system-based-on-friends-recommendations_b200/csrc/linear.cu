@@ -7,11 +7,44 @@ namespace dcnr {
 
 int gemm_any(int precision, const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,
              float *C, int64_t ldc, int64_t m, int64_t n, int64_t k, int split_k, const GemmEpilogue &epi,
-             cudaStream_t stream) {
-    if (precision != DCNR_PREC_FP32 && gemm_tc_supported(precision, a_kmajor, b_kmajor, lda, ldb, ldc, m, n, k, split_k))
-        return launch_gemm_tc(precision, A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, m, n, k, split_k, epi, stream);
+             cudaStream_t stream, const WeightOp *wop) {
+    if (precision == DCNR_PREC_BF16) precision = DCNR_PREC_TF32;     // no bf16 kernel yet: nearest tensor-core mode
+    if (precision == DCNR_PREC_TF32X3 && wop != nullptr && wop->lo != nullptr &&
+        gemm_tc_supported(precision, a_kmajor, true, lda, wop->ld, ldc, m, n, k, split_k))
+        return launch_gemm_tc(precision, A, lda, a_kmajor, wop->hi, wop->ld, true, C, ldc, m, n, k, split_k, epi, stream,
+                              wop->lo);
+    if (precision == DCNR_PREC_TF32) {
+        const float *Bt = wop != nullptr ? wop->hi : B;
+        const int64_t ldt = wop != nullptr ? wop->ld : ldb;
+        const bool bk = wop != nullptr ? true : b_kmajor;
+        if (gemm_tc_supported(precision, a_kmajor, bk, lda, ldt, ldc, m, n, k, split_k))
+            return launch_gemm_tc(precision, A, lda, a_kmajor, Bt, ldt, true, C, ldc, m, n, k, split_k, epi, stream, nullptr);
+    }
     return launch_gemm_simt(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, m, n, k, split_k, epi, stream);
 }
+
+// Stream-ordered temporary for the operator-level entry points (the whole-model calls carve the
+// split weights out of their workspaces instead).
+struct TempSplit {
+    float *buf = nullptr;
+    cudaStream_t st;
+    WeightOp op{nullptr, nullptr, 0};
+    int make(int precision, const float *w, int64_t ldw, int32_t rows, int32_t cols, bool transpose, cudaStream_t s) {
+        st = s;
+        if (precision != DCNR_PREC_TF32X3 && !(transpose && precision != DCNR_PREC_FP32)) return DCNR_OK;
+        const int64_t n = (int64_t)rows * cols;
+        DCNR_CUDA_CHECK(cudaMallocAsync(&buf, (size_t)n * 2 * sizeof(float), s));
+        DCNR_TRY(launch_split_tf32(w, ldw, buf, buf + n, rows, cols, transpose, s));
+        op.hi = buf;
+        op.lo = precision == DCNR_PREC_TF32X3 ? buf + n : nullptr;
+        op.ld = transpose ? rows : cols;
+        return DCNR_OK;
+    }
+    const WeightOp *get() const { return buf != nullptr ? &op : nullptr; }
+    ~TempSplit() {
+        if (buf != nullptr) cudaFreeAsync(buf, st);
+    }
+};
 
 int wgrad_splits(int64_t m, int32_t n, int32_t k) {
     const int64_t tiles = ceil_div(n, 128) * ceil_div(k, 128);
@@ -53,7 +86,10 @@ extern "C" int dcnr_linear_fwd(const float *x, int64_t ldx, const float *w, int6
     DCNR_REQUIRE(x && w && y, "null argument");
     DCNR_REQUIRE(ldx >= k && ldw >= k && ldy >= n && (residual == nullptr || ldr >= n), "leading dimension too small");
     GemmEpilogue epi{col_scale, bias, residual, ldr, relu};
-    return gemm_any(precision, x, ldx, true, w, ldw, true, y, ldy, m, n, k, 1, epi, as_stream(stream));
+    TempSplit ts;
+    if (precision != DCNR_PREC_FP32 && gemm_tc_supported(DCNR_PREC_TF32, true, true, ldx, k, ldy, m, n, k, 1))
+        DCNR_TRY(ts.make(precision, w, ldw, n, k, false, as_stream(stream)));
+    return gemm_any(precision, x, ldx, true, w, ldw, true, y, ldy, m, n, k, 1, epi, as_stream(stream), ts.get());
 }
 
 extern "C" int dcnr_linear_dgrad(const float *dy, int64_t lddy, const float *w, int64_t ldw, const float *residual,
@@ -62,8 +98,12 @@ extern "C" int dcnr_linear_dgrad(const float *dy, int64_t lddy, const float *w, 
     DCNR_REQUIRE(dy && w && dx, "null argument");
     DCNR_REQUIRE(lddy >= n && ldw >= k && lddx >= k && (residual == nullptr || ldr >= k), "leading dimension too small");
     GemmEpilogue epi{nullptr, nullptr, residual, ldr, 0};
-    // dx[m, k] = sum_n dy[m, n] * W[n, k] : A = dy (reduction index contiguous), B = W (output index contiguous)
-    return gemm_any(precision, dy, lddy, true, w, ldw, false, dx, lddx, m, k, n, 1, epi, as_stream(stream));
+    // dx[m, k] = sum_n dy[m, n] * W[n, k] : A = dy (reduction index contiguous), B = W (output index contiguous).
+    // The tensor-core kernel takes K-major operands only, so it is fed W^T (one small transpose per call).
+    TempSplit ts;
+    if (precision != DCNR_PREC_FP32 && gemm_tc_supported(DCNR_PREC_TF32, true, true, lddy, n, lddx, m, k, n, 1))
+        DCNR_TRY(ts.make(precision, w, ldw, n, k, true, as_stream(stream)));
+    return gemm_any(precision, dy, lddy, true, w, ldw, false, dx, lddx, m, k, n, 1, epi, as_stream(stream), ts.get());
 }
 
 extern "C" int64_t dcnr_linear_wgrad_scratch_bytes(int64_t m, int32_t n, int32_t k) {

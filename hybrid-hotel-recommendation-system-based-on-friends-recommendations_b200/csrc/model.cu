@@ -21,12 +21,46 @@ static int check_dims(const dcnr_dims *d) {
     return DCNR_OK;
 }
 
+// Tensor-core operand forms of the dense-layer weights, carved from a workspace.
+//   forward : [n, k] hi/lo split (TF32X3 only; TF32 reads the raw weight)
+//   dgrad   : W^T [k, n] (hi, and lo for TF32X3) because the tcgen05 kernel takes K-major operands
+struct WeightOps {
+    WeightOp w0, w1[DCNR_MAX_RES], w2[DCNR_MAX_RES];
+    bool on = false;
+    static int64_t floats(const dcnr_dims *d) {
+        return 2 * ((int64_t)d->hidden * d->in_dim_pad + 2 * (int64_t)d->n_res * d->hidden * d->hidden) + 64;
+    }
+    const WeightOp *get(const WeightOp &w) const { return on ? &w : nullptr; }
+    int prepare(const dcnr_dims *d, const dcnr_params *p, const float *w0p, float *buf, bool transpose, cudaStream_t st) {
+        const int prec = d->precision == DCNR_PREC_BF16 ? DCNR_PREC_TF32 : d->precision;
+        on = prec == DCNR_PREC_TF32X3 || (transpose && prec == DCNR_PREC_TF32);
+        if (!on) return DCNR_OK;
+        const bool lo = prec == DCNR_PREC_TF32X3;
+        const int H = d->hidden, Dp = d->in_dim_pad;
+        auto one = [&](WeightOp &op, const float *w, int64_t ldw, int rows, int cols) -> int {
+            const int64_t n = (int64_t)rows * cols;
+            op.hi = buf;
+            op.lo = lo ? buf + n : nullptr;
+            op.ld = transpose ? rows : cols;
+            DCNR_TRY(launch_split_tf32(w, ldw, buf, lo ? buf + n : nullptr, rows, cols, transpose, st));
+            buf += 2 * n;
+            return DCNR_OK;
+        };
+        DCNR_TRY(one(w0, w0p, Dp, H, Dp));
+        for (int r = 0; r < d->n_res; ++r) {
+            DCNR_TRY(one(w1[r], p->res_w1[r], H, H, H));
+            DCNR_TRY(one(w2[r], p->res_w2[r], H, H, H));
+        }
+        return DCNR_OK;
+    }
+};
+
 struct TrainSaved {
     float *x0p, *w0p, *logit_cross;
     float *h[DCNR_MAX_RES + 1];
     float *z1[DCNR_MAX_RES], *d1[DCNR_MAX_RES], *z2[DCNR_MAX_RES];
     float *stats[DCNR_MAX_RES];   // mean1, rstd1, mean2, rstd2 : 4*H each block
-    float *bn_scratch;
+    float *bn_scratch, *wsplit;
     void layout(const dcnr_dims *d, int64_t B, Arena &a) {
         const int64_t H = d->hidden, Dp = d->in_dim_pad;
         x0p = a.take<float>(B * Dp);
@@ -40,11 +74,12 @@ struct TrainSaved {
             stats[r] = a.take<float>(4 * H);
         }
         bn_scratch = a.take<float>(bn_scratch_floats(B, (int32_t)H));
+        wsplit = a.take<float>(WeightOps::floats(d));
     }
 };
 
 struct BwdScratch {
-    float *ga, *gb, *gc, *dx0, *cross_partials, *wgrad, *bn;
+    float *ga, *gb, *gc, *dx0, *cross_partials, *wgrad, *bn, *wsplit;
     void *scatter;
     int64_t scatter_bytes;
     void layout(const dcnr_dims *d, int64_t B, Arena &a, bool with_scatter) {
@@ -57,13 +92,14 @@ struct BwdScratch {
         wgrad = a.take<float>(std::max(wgrad_scratch_floats(B, (int32_t)H, (int32_t)H),
                                        wgrad_scratch_floats(B, (int32_t)H, (int32_t)Dp)));
         bn = a.take<float>(bn_scratch_floats(B, (int32_t)H));
+        wsplit = a.take<float>(WeightOps::floats(d));
         scatter_bytes = with_scatter ? scatter_scratch_bytes(B) : 0;
         scatter = a.take<char>(scatter_bytes);
     }
 };
 
 struct EvalWs {
-    float *x0p, *w0p, *logit_cross, *ha, *hb, *ht, *fold;   // fold: per block scale1, shift1, scale2, shift2
+    float *x0p, *w0p, *logit_cross, *ha, *hb, *ht, *fold, *wsplit;   // fold: per block scale1, shift1, scale2, shift2
     void layout(const dcnr_dims *d, int64_t rows, Arena &a) {
         const int64_t H = d->hidden, Dp = d->in_dim_pad;
         x0p = a.take<float>(rows * Dp);
@@ -73,6 +109,7 @@ struct EvalWs {
         hb = a.take<float>(rows * H);
         ht = a.take<float>(rows * H);
         fold = a.take<float>((int64_t)std::max(d->n_res, 1) * 4 * H);
+        wsplit = a.take<float>(WeightOps::floats(d));
     }
 };
 
@@ -142,6 +179,8 @@ extern "C" int dcnr_forward_eval(const dcnr_dims *dims, const dcnr_params *param
         DCNR_TRY(launch_bn_fold(params->res_g2[r], params->res_be2[r], params->res_rm2[r], params->res_rv2[r],
                                 params->res_b2[r], dims->bn_eps, f + 2 * H, f + 3 * H, H, st));
     }
+    WeightOps wo;
+    DCNR_TRY(wo.prepare(dims, params, w.w0p, w.wsplit, false, st));
     const CrossArgs ca = cross_args(dims, params);
     for (int64_t r0 = 0; r0 < B; r0 += chunk) {
         const int64_t rows = std::min(chunk, B - r0);
@@ -151,14 +190,14 @@ extern "C" int dcnr_forward_eval(const dcnr_dims *dims, const dcnr_params *param
         DCNR_TRY(launch_embed_cross_fwd(&ga, nullptr, 0, rows, ca, Dp, w.x0p, Dp, nullptr, 0, params->wf + H,
                                         w.logit_cross, nullptr, st));
         GemmEpilogue e0{nullptr, params->b0, nullptr, 0, 0};
-        DCNR_TRY(gemm_any(prec, w.x0p, Dp, true, w.w0p, Dp, true, w.ha, H, rows, H, Dp, 1, e0, st));
+        DCNR_TRY(gemm_any(prec, w.x0p, Dp, true, w.w0p, Dp, true, w.ha, H, rows, H, Dp, 1, e0, st, wo.get(wo.w0)));
         float *h = w.ha, *hn = w.hb;
         for (int r = 0; r < dims->n_res; ++r) {
             const float *f = w.fold + (int64_t)r * 4 * H;
             GemmEpilogue e1{f, f + H, nullptr, 0, 1};
-            DCNR_TRY(gemm_any(prec, h, H, true, params->res_w1[r], H, true, w.ht, H, rows, H, H, 1, e1, st));
+            DCNR_TRY(gemm_any(prec, h, H, true, params->res_w1[r], H, true, w.ht, H, rows, H, H, 1, e1, st, wo.get(wo.w1[r])));
             GemmEpilogue e2{f + 2 * H, f + 3 * H, h, H, 1};
-            DCNR_TRY(gemm_any(prec, w.ht, H, true, params->res_w2[r], H, true, hn, H, rows, H, H, 1, e2, st));
+            DCNR_TRY(gemm_any(prec, w.ht, H, true, params->res_w2[r], H, true, hn, H, rows, H, H, 1, e2, st, wo.get(wo.w2[r])));
             std::swap(h, hn);
         }
         DCNR_TRY(launch_rowdot_fwd(h, H, params->wf, w.logit_cross, params->bf, logits + r0, rows, H, st));
@@ -183,24 +222,26 @@ extern "C" int dcnr_forward_train(const dcnr_dims *dims, const dcnr_params *para
     cudaStream_t st = as_stream(stream);
     const int H = dims->hidden, D = dims->in_dim, Dp = dims->in_dim_pad, prec = dims->precision;
     DCNR_TRY(launch_pad_rows(params->w0, D, s.w0p, Dp, H, D, Dp, st));
+    WeightOps wo;
+    DCNR_TRY(wo.prepare(dims, params, s.w0p, s.wsplit, false, st));
     GatherArgs ga;
     DCNR_TRY(make_gather_args(dims, params, batch, &ga));
     const CrossArgs ca = cross_args(dims, params);
     DCNR_TRY(launch_embed_cross_fwd(&ga, nullptr, 0, B, ca, Dp, s.x0p, Dp, nullptr, 0, params->wf + H, s.logit_cross,
                                     nullptr, st));
     GemmEpilogue e0{nullptr, params->b0, nullptr, 0, 0};
-    DCNR_TRY(gemm_any(prec, s.x0p, Dp, true, s.w0p, Dp, true, s.h[0], H, B, H, Dp, 1, e0, st));
+    DCNR_TRY(gemm_any(prec, s.x0p, Dp, true, s.w0p, Dp, true, s.h[0], H, B, H, Dp, 1, e0, st, wo.get(wo.w0)));
     for (int r = 0; r < dims->n_res; ++r) {
         float *mean1 = s.stats[r], *rstd1 = mean1 + H, *mean2 = mean1 + 2 * H, *rstd2 = mean1 + 3 * H;
         GemmEpilogue e1{nullptr, params->res_b1[r], nullptr, 0, 0};
-        DCNR_TRY(gemm_any(prec, s.h[r], H, true, params->res_w1[r], H, true, s.z1[r], H, B, H, H, 1, e1, st));
+        DCNR_TRY(gemm_any(prec, s.h[r], H, true, params->res_w1[r], H, true, s.z1[r], H, B, H, H, 1, e1, st, wo.get(wo.w1[r])));
         DCNR_TRY(launch_bn_stats(s.z1[r], H, B, H, dims->bn_eps, dims->bn_momentum, mean1, rstd1, params->res_rm1[r],
                                  params->res_rv1[r], params->res_nbt1[r], s.bn_scratch, st));
         const uint8_t *keep = drop_keep_mask ? drop_keep_mask + (int64_t)r * B * H : nullptr;
         DCNR_TRY(launch_bn_act_fwd(s.z1[r], H, mean1, rstd1, params->res_g1[r], params->res_be1[r], nullptr, 0, keep,
                                    dims->dropout_p, dropout_seed, (uint32_t)r, s.d1[r], H, B, H, st));
         GemmEpilogue e2{nullptr, params->res_b2[r], nullptr, 0, 0};
-        DCNR_TRY(gemm_any(prec, s.d1[r], H, true, params->res_w2[r], H, true, s.z2[r], H, B, H, H, 1, e2, st));
+        DCNR_TRY(gemm_any(prec, s.d1[r], H, true, params->res_w2[r], H, true, s.z2[r], H, B, H, H, 1, e2, st, wo.get(wo.w2[r])));
         DCNR_TRY(launch_bn_stats(s.z2[r], H, B, H, dims->bn_eps, dims->bn_momentum, mean2, rstd2, params->res_rm2[r],
                                  params->res_rv2[r], params->res_nbt2[r], s.bn_scratch, st));
         DCNR_TRY(launch_bn_act_fwd(s.z2[r], H, mean2, rstd2, params->res_g2[r], params->res_be2[r], s.h[r], H, nullptr,
@@ -232,6 +273,8 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
     const int H = dims->hidden, D = dims->in_dim, Dp = dims->in_dim_pad, R = dims->n_res, prec = dims->precision;
     const float post = dims->dropout_p > 0.f ? 1.f / (1.f - dims->dropout_p) : 1.f;
 
+    WeightOps wt;      // transposed weights for the tensor-core dgrads
+    DCNR_TRY(wt.prepare(dims, params, s.w0p, w.wsplit, true, st));
     // logit = wf[0:H].h_R + wf[H:].c_L + bf
     float *g = w.ga, *g2 = w.gb, *g3 = w.gc;
     DCNR_TRY(launch_rowdot_bwd(grad_logits, s.h[R], H, params->wf, g, H, grads->wf, grads->bf, B, H, w.bn, st));
@@ -243,21 +286,21 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
         if (grads->res_w2[r])
             DCNR_TRY(launch_linear_wgrad(prec, g2, H, s.d1[r], H, grads->res_w2[r], H, nullptr, B, H, H, H, w.wgrad, st));
         GemmEpilogue none{nullptr, nullptr, nullptr, 0, 0};
-        DCNR_TRY(gemm_any(prec, g2, H, true, params->res_w2[r], H, false, g3, H, B, H, H, 1, none, st));   // dd1
+        DCNR_TRY(gemm_any(prec, g2, H, true, params->res_w2[r], H, false, g3, H, B, H, H, 1, none, st, wt.get(wt.w2[r])));   // dd1
         // d1 = dropout(relu(BN1(z1))): dz1 in place in g3
         DCNR_TRY(launch_bn_act_bwd(g3, H, s.d1[r], H, s.z1[r], H, mean1, rstd1, params->res_g1[r], post, g3, H, nullptr,
                                    0, grads->res_g1[r], grads->res_be1[r], grads->res_b1[r], B, H, w.bn, st));
         if (grads->res_w1[r])
             DCNR_TRY(launch_linear_wgrad(prec, g3, H, s.h[r], H, grads->res_w1[r], H, nullptr, B, H, H, H, w.wgrad, st));
         GemmEpilogue idn{nullptr, nullptr, g, H, 0};                                                      // + dy2
-        DCNR_TRY(gemm_any(prec, g3, H, true, params->res_w1[r], H, false, g2, H, B, H, H, 1, idn, st));
+        DCNR_TRY(gemm_any(prec, g3, H, true, params->res_w1[r], H, false, g2, H, B, H, H, 1, idn, st, wt.get(wt.w1[r])));
         std::swap(g, g2);
     }
     // initial_deep_layer: h0 = x0 W0^T + b0
     if (grads->w0 || grads->b0)
         DCNR_TRY(launch_linear_wgrad(prec, g, H, s.x0p, Dp, grads->w0, D, grads->b0, B, H, Dp, D, w.wgrad, st));
     GemmEpilogue none{nullptr, nullptr, nullptr, 0, 0};
-    DCNR_TRY(gemm_any(prec, g, H, true, s.w0p, Dp, false, w.dx0, Dp, B, Dp, H, 1, none, st));
+    DCNR_TRY(gemm_any(prec, g, H, true, s.w0p, Dp, false, w.dx0, Dp, B, Dp, H, 1, none, st, wt.get(wt.w0)));
     // cross network (recomputed from x0), accumulated onto dx0
     const CrossArgs ca = cross_args(dims, params);
     DCNR_TRY(launch_cross_bwd(s.x0p, Dp, B, ca, Dp, nullptr, 0, grad_logits, params->wf + H, w.dx0, Dp, 1, grads->cross_w,

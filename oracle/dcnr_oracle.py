@@ -384,6 +384,37 @@ def relu_preactivations(state, user_ids, item_ids, cat_features, num_features, d
     return pre
 
 
+def desensitize_relus(state, user_ids, item_ids, cat_features, num_features, search: float = 0.05):
+    """Returns (new_state, margin): a copy of ``state`` whose BatchNorm biases are nudged (by at most
+    ``search`` per channel) so that, for THIS batch, no train-mode ReLU input lies within ``margin``
+    of zero.  Gradient-parity tests use it to compare arithmetic instead of ReLU discontinuities:
+    zeroing a near-kink row's upstream gradient is not enough in train mode because BatchNorm
+    couples the rows (a flipped ReLU in a masked row still leaks through the batch statistics), and
+    dropping rows only moves the problem (the statistics change and new near-kinks appear).
+    For each ReLU layer in forward order and each channel, the bias shift puts zero in the middle of
+    the widest gap between consecutive sorted pre-activations near zero."""
+    st = OrderedDict((k, v.clone()) for k, v in state.items())
+    shp = model_shape(st)
+    names = []
+    for r in range(shp["R"]):
+        names += [f"res_blocks.{r}.bn1.bias", f"res_blocks.{r}.bn2.bias"]
+    margin = float("inf")
+    for j, name in enumerate(names):
+        y = relu_preactivations(st, user_ids, item_ids, cat_features, num_features)[j]      # [B,H] float64
+        v, _ = torch.sort(y, dim=0)
+        mid = 0.5 * (v[1:] + v[:-1])
+        gap = v[1:] - v[:-1]
+        gap = torch.where(mid.abs() <= search, gap, torch.zeros_like(gap))
+        best = gap.argmax(dim=0)                                                            # per channel
+        cols = torch.arange(y.shape[1])
+        shift = -mid[best, cols]
+        shift = torch.where(gap[best, cols] > 0, shift, torch.zeros_like(shift))
+        st[name] = (st[name].double() + shift).to(st[name].dtype)
+    for y in relu_preactivations(st, user_ids, item_ids, cat_features, num_features):
+        margin = min(margin, float(y.abs().min()))
+    return st, margin
+
+
 def kink_mask(state, user_ids, item_ids, cat_features, num_features, thresh: float = 1e-5) -> torch.Tensor:
     """Rows whose float64 forward has a ReLU pre-activation within ``thresh`` of zero
     (their upstream gradient is zeroed in gradient-parity tests)."""

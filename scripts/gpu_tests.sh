@@ -1,4 +1,4 @@
 mkdir -p gpurun_out
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/smoke.log 2>&1; echo "smoke exit $?" >> gpurun_out/smoke.log
 timeout 1500 python -m pytest tests -m gpu -q --maxfail=60 -p no:cacheprovider > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" >> gpurun_out/pytest_gpu.log
-tail -3 gpurun_out/smoke.log; tail -30 gpurun_out/pytest_gpu.log
+tail -3 gpurun_out/smoke.log; grep -E "^(FAILED|ERROR)|passed|failed|AssertionError:" gpurun_out/pytest_gpu.log | head -60
