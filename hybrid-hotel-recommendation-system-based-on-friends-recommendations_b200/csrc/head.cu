@@ -38,6 +38,24 @@ int launch_rowdot_fwd(const float *a, int64_t lda, const float *w, const float *
     return DCNR_OK;
 }
 
+// out[m] = sum_t parts[t][m] + extra[m] + bf   (the partial row dots of the fused GEMM epilogue)
+__global__ void k_combine_logits(const float *__restrict__ parts, int n_parts, int64_t m, const float *__restrict__ extra,
+                                 const float *__restrict__ bf, float *__restrict__ out) {
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= m) return;
+    float acc = 0.f;
+    for (int t = 0; t < n_parts; ++t) acc += parts[(int64_t)t * m + i];
+    out[i] = acc + (extra != nullptr ? extra[i] : 0.f) + (bf != nullptr ? __ldg(bf) : 0.f);
+}
+
+int launch_combine_logits(const float *parts, int n_parts, int64_t m, const float *extra, const float *bf, float *out,
+                          cudaStream_t stream) {
+    if (m <= 0) return DCNR_OK;
+    k_combine_logits<<<(unsigned)ceil_div(m, 256), 256, 0, stream>>>(parts, n_parts, m, extra, bf, out);
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}
+
 // dh[b,:] = dlogit[b] * w ;  partial[chunk][c] = sum_b dlogit[b]*a[b,c] ;  partial[chunk][n] = sum_b dlogit[b]
 __global__ void __launch_bounds__(kT)
 k_rowdot_bwd(const float *__restrict__ dlogit, const float *__restrict__ a, int64_t lda, const float *__restrict__ w,

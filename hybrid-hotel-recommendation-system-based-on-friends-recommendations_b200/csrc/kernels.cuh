@@ -64,7 +64,8 @@ bool gemm_tc_supported(int precision, bool a_kmajor, bool b_kmajor, int64_t lda,
 // TF32X3: B is the tf32-rounded (hi) half of the weight and B_lo its exact remainder (launch_split_tf32)
 int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,
                    float *C, int64_t ldc, int64_t m, int64_t n, int64_t k, int split_k, const GemmEpilogue &epi,
-                   cudaStream_t stream, const float *B_lo);
+                   cudaStream_t stream, const float *B_lo, const float *dot_w = nullptr, float *dot_out = nullptr);
+int gemm_tc_n_tiles(int64_t n);   // column tiles the tensor-core kernel uses for an output width n
 // hi = rn_tf32(src), lo = src - hi, dense [rows, cols] (or transposed: [cols, rows]); lo may be NULL when transposing
 int launch_split_tf32(const float *src, int64_t lds, float *hi, float *lo, int32_t rows, int32_t cols, bool transpose,
                       cudaStream_t stream);
@@ -74,10 +75,19 @@ struct WeightOp {
     const float *lo;   // remainder (TF32X3 only), else NULL
     int64_t ld;
 };
+// Optional fusion of the final row dot into the GEMM epilogue (tensor-core path only):
+// dot_out[tile][m] = sum over the tile's columns of epilogue(C)[m,n] * dot_w[n]; C itself is not stored.
+struct FusedDot {
+    const float *w;
+    float *out;       // [gemm_tc_n_tiles(n)][m]
+};
 // precision dispatch (linear.cu).  wop == NULL -> B is used as is (CUDA-core path unless precision == TF32).
 int gemm_any(int precision, const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,
              float *C, int64_t ldc, int64_t m, int64_t n, int64_t k, int split_k, const GemmEpilogue &epi,
-             cudaStream_t stream, const WeightOp *wop = nullptr);
+             cudaStream_t stream, const WeightOp *wop = nullptr, const FusedDot *dot = nullptr);
+// true when gemm_any would run this forward GEMM on the tensor-core kernel (so a FusedDot may be passed)
+bool gemm_any_uses_tc(int precision, int64_t lda, int64_t ldc, int64_t m, int64_t n, int64_t k, const WeightOp *wop,
+                      int64_t ldb);
 int64_t wgrad_scratch_floats(int64_t m, int32_t n, int32_t k);
 // dW[n, 0:k_valid] (ld lddw) = dy^T x over k (padded) columns; db = column sums of dy (may be NULL)
 int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const float *x, int64_t ldx, float *dw,
@@ -109,6 +119,8 @@ int launch_colsum(const float *a, int64_t lda, int64_t m, int32_t n, float *out,
 // ---- head (head.cu) ---------------------------------------------------------------------------
 int launch_rowdot_fwd(const float *a, int64_t lda, const float *w, const float *extra, const float *bf,
                       float *out, int64_t m, int32_t n, cudaStream_t stream);
+int launch_combine_logits(const float *parts, int n_parts, int64_t m, const float *extra, const float *bf, float *out,
+                          cudaStream_t stream);
 // dh[b,:] = dlogit[b]*w ; dw[c] = sum_b dlogit[b]*a[b,c] ; dbf = sum_b dlogit[b]
 int launch_rowdot_bwd(const float *dlogit, const float *a, int64_t lda, const float *w, float *dh, int64_t lddh,
                       float *dw, float *dbf, int64_t m, int32_t n, float *scratch, cudaStream_t stream);

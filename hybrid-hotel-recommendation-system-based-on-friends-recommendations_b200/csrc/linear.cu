@@ -5,21 +5,35 @@
 
 namespace dcnr {
 
+bool gemm_any_uses_tc(int precision, int64_t lda, int64_t ldc, int64_t m, int64_t n, int64_t k, const WeightOp *wop,
+                      int64_t ldb) {
+    if (precision == DCNR_PREC_BF16) precision = DCNR_PREC_TF32;
+    if (precision == DCNR_PREC_TF32X3)
+        return wop != nullptr && wop->lo != nullptr && gemm_tc_supported(precision, true, true, lda, wop->ld, ldc, m, n, k, 1);
+    if (precision == DCNR_PREC_TF32)
+        return gemm_tc_supported(precision, true, true, lda, wop != nullptr ? wop->ld : ldb, ldc, m, n, k, 1);
+    return false;
+}
+
 int gemm_any(int precision, const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,
              float *C, int64_t ldc, int64_t m, int64_t n, int64_t k, int split_k, const GemmEpilogue &epi,
-             cudaStream_t stream, const WeightOp *wop) {
+             cudaStream_t stream, const WeightOp *wop, const FusedDot *dot) {
     if (precision == DCNR_PREC_BF16) precision = DCNR_PREC_TF32;     // no bf16 kernel yet: nearest tensor-core mode
+    const float *dw = dot != nullptr ? dot->w : nullptr;
+    float *dout = dot != nullptr ? dot->out : nullptr;
     if (precision == DCNR_PREC_TF32X3 && wop != nullptr && wop->lo != nullptr &&
         gemm_tc_supported(precision, a_kmajor, true, lda, wop->ld, ldc, m, n, k, split_k))
         return launch_gemm_tc(precision, A, lda, a_kmajor, wop->hi, wop->ld, true, C, ldc, m, n, k, split_k, epi, stream,
-                              wop->lo);
+                              wop->lo, dw, dout);
     if (precision == DCNR_PREC_TF32) {
         const float *Bt = wop != nullptr ? wop->hi : B;
         const int64_t ldt = wop != nullptr ? wop->ld : ldb;
         const bool bk = wop != nullptr ? true : b_kmajor;
         if (gemm_tc_supported(precision, a_kmajor, bk, lda, ldt, ldc, m, n, k, split_k))
-            return launch_gemm_tc(precision, A, lda, a_kmajor, Bt, ldt, true, C, ldc, m, n, k, split_k, epi, stream, nullptr);
+            return launch_gemm_tc(precision, A, lda, a_kmajor, Bt, ldt, true, C, ldc, m, n, k, split_k, epi, stream, nullptr,
+                                  dw, dout);
     }
+    DCNR_REQUIRE(dot == nullptr, "fused row dot needs the tensor-core path");
     return launch_gemm_simt(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, m, n, k, split_k, epi, stream);
 }
 
@@ -33,6 +47,16 @@ struct TempSplit {
         st = s;
         if (precision != DCNR_PREC_TF32X3 && !(transpose && precision != DCNR_PREC_FP32)) return DCNR_OK;
         const int64_t n = (int64_t)rows * cols;
+        static thread_local bool pool_ready = false;
+        if (!pool_ready) {       // keep freed blocks cached in the stream-ordered pool instead of returning them at every sync
+            int dev = 0;
+            cudaMemPool_t pool;
+            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
+                uint64_t keep = 1ull << 28;
+                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            }
+            pool_ready = true;
+        }
         DCNR_CUDA_CHECK(cudaMallocAsync(&buf, (size_t)n * 2 * sizeof(float), s));
         DCNR_TRY(launch_split_tf32(w, ldw, buf, buf + n, rows, cols, transpose, s));
         op.hi = buf;

@@ -99,7 +99,7 @@ struct BwdScratch {
 };
 
 struct EvalWs {
-    float *x0p, *w0p, *logit_cross, *ha, *hb, *ht, *fold, *wsplit;   // fold: per block scale1, shift1, scale2, shift2
+    float *x0p, *w0p, *logit_cross, *ha, *hb, *ht, *fold, *wsplit, *dot_parts;   // fold: per block scale1, shift1, scale2, shift2
     void layout(const dcnr_dims *d, int64_t rows, Arena &a) {
         const int64_t H = d->hidden, Dp = d->in_dim_pad;
         x0p = a.take<float>(rows * Dp);
@@ -110,6 +110,7 @@ struct EvalWs {
         ht = a.take<float>(rows * H);
         fold = a.take<float>((int64_t)std::max(d->n_res, 1) * 4 * H);
         wsplit = a.take<float>(WeightOps::floats(d));
+        dot_parts = a.take<float>(rows * 4);
     }
 };
 
@@ -189,18 +190,35 @@ extern "C" int dcnr_forward_eval(const dcnr_dims *dims, const dcnr_params *param
         DCNR_TRY(make_gather_args(dims, params, &sb, &ga));
         DCNR_TRY(launch_embed_cross_fwd(&ga, nullptr, 0, rows, ca, Dp, w.x0p, Dp, nullptr, 0, params->wf + H,
                                         w.logit_cross, nullptr, st));
+        // The last GEMM of the tower never writes its output: the deep half of the final dot
+        // (train.py:169-170) is taken in its epilogue when that GEMM runs on the tensor-core kernel.
+        const int last = 2 * dims->n_res;                  // GEMM index: 0 = initial layer, 2r+1 / 2r+2 = block r
+        auto run = [&](int idx, const float *A, int64_t lda, const float *W, int64_t ldw, const WeightOp &wop,
+                       const GemmEpilogue &epi, float *out, int32_t K, bool *fused) -> int {
+            *fused = false;
+            if (idx == last && gemm_tc_n_tiles(H) <= 4 && gemm_any_uses_tc(prec, lda, H, rows, H, K, wo.get(wop), ldw)) {
+                FusedDot fd{params->wf, w.dot_parts};
+                *fused = true;
+                return gemm_any(prec, A, lda, true, W, ldw, true, nullptr, H, rows, H, K, 1, epi, st, wo.get(wop), &fd);
+            }
+            return gemm_any(prec, A, lda, true, W, ldw, true, out, H, rows, H, K, 1, epi, st, wo.get(wop));
+        };
+        bool fused = false;
         GemmEpilogue e0{nullptr, params->b0, nullptr, 0, 0};
-        DCNR_TRY(gemm_any(prec, w.x0p, Dp, true, w.w0p, Dp, true, w.ha, H, rows, H, Dp, 1, e0, st, wo.get(wo.w0)));
+        DCNR_TRY(run(0, w.x0p, Dp, w.w0p, Dp, wo.w0, e0, w.ha, Dp, &fused));
         float *h = w.ha, *hn = w.hb;
         for (int r = 0; r < dims->n_res; ++r) {
             const float *f = w.fold + (int64_t)r * 4 * H;
             GemmEpilogue e1{f, f + H, nullptr, 0, 1};
-            DCNR_TRY(gemm_any(prec, h, H, true, params->res_w1[r], H, true, w.ht, H, rows, H, H, 1, e1, st, wo.get(wo.w1[r])));
+            DCNR_TRY(run(2 * r + 1, h, H, params->res_w1[r], H, wo.w1[r], e1, w.ht, H, &fused));
             GemmEpilogue e2{f + 2 * H, f + 3 * H, h, H, 1};
-            DCNR_TRY(gemm_any(prec, w.ht, H, true, params->res_w2[r], H, true, hn, H, rows, H, H, 1, e2, st, wo.get(wo.w2[r])));
+            DCNR_TRY(run(2 * r + 2, w.ht, H, params->res_w2[r], H, wo.w2[r], e2, hn, H, &fused));
             std::swap(h, hn);
         }
-        DCNR_TRY(launch_rowdot_fwd(h, H, params->wf, w.logit_cross, params->bf, logits + r0, rows, H, st));
+        if (fused)
+            DCNR_TRY(launch_combine_logits(w.dot_parts, gemm_tc_n_tiles(H), rows, w.logit_cross, params->bf, logits + r0, st));
+        else
+            DCNR_TRY(launch_rowdot_fwd(h, H, params->wf, w.logit_cross, params->bf, logits + r0, rows, H, st));
     }
     return DCNR_OK;
 }

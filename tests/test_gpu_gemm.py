@@ -7,7 +7,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 2e-6, "tf32x3": 3e-6, "tf32": 2e-3}
+TOL = {"fp32": 2e-6, "tf32x3": 6e-6, "tf32": 2e-3}
 SHAPES = [(1000, 256, 256), (128, 256, 64), (4133, 512, 256), (300, 96, 96), (5000, 32, 32), (77, 256, 64),
           (2048, 160, 224)]
 
