@@ -20,6 +20,8 @@
 // by k_split_tf32 and both halves are streamed by TMA (they stay L2 resident).
 #include <cuda.h>
 
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace dcnr {
@@ -56,12 +58,62 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (!ok && spins > (1u << 24)) __trap();
     }
 }
+// mbarrier wait that synchronises with arrivals from the other CTA of a pair (remote arrive / multicast commit)
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spins = 0; !ok; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok && spins > (1u << 24)) __trap();
+    }
+}
+// arrive on a barrier given by its shared::cluster address (possibly in the peer CTA)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar) : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of `addr` (a shared::cta address of this CTA) in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// pair form: the completion bytes are counted on `cluster_bar`, a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t cluster_bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(cluster_bar)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {      // at most N most recent bulk groups still READING shared memory
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
                                           uint32_t accumulate) {
     asm volatile(
@@ -73,6 +125,24 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+// 2-CTA MMA (M = 256 over the pair, each CTA feeds its 128 rows of A and half of B's rows); leader thread only
+__device__ __forceinline__ void umma_tf32_pair(uint32_t tmem_d, uint64_t a_desc, uint64_t b_desc, uint32_t idesc,
+                                               uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// arrives on the barrier at this shared-memory offset in BOTH CTAs of the pair once the MMAs issued so far are done
+__device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
+    asm volatile(
+        "{\n\t.reg .b16 m;\n\tmov.b16 m, 3;\n\t"
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], m;\n\t}"
+        ::"r"(bar)
+        : "memory");
 }
 // K-major, SWIZZLE_128B canonical layout: 8-row groups 1024 B apart (SBO), LBO unused (1), version 1.
 __device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
@@ -101,6 +171,7 @@ struct Params {
     int64_t M;
     int32_t N_total, K, block_n, terms, stages, acc_cols, acc_stages, corr_sep, tmem_cols;
     int32_t num_m_tiles, num_n_tiles;
+    int32_t debug;            // timing experiments only (DCNR_GEMM_DEBUG): bit0 skip the split arithmetic, bit1 hi.hi MMA only
     float *C;                 // may be NULL when only the fused row dot is wanted
     int64_t ldc;
     GemmEpilogue epi;
@@ -108,94 +179,153 @@ struct Params {
     float *dot_out;           // [num_n_tiles][M] partial dots (summed by the caller)
 };
 
-constexpr int kThreadsP = 320;
-constexpr int kEpiStageBytes = 4 * 32 * 36 * 4;   // per-warp 32x36 fp32 transpose tiles of the epilogue   // warp 0 TMA, warp 1 MMA, warps 2-5 operand split, warps 6-9 epilogue
+constexpr int kThreadsP = 320;                      // warp 0 TMA, warp 1 MMA, warps 2-5 operand split, warps 6-9 epilogue
+constexpr int kEpiSlotBytes = 32 * 32 * 4;          // one epilogue slot: 32 rows x 32 fp32 columns, 128B-swizzled
+constexpr int kEpiSlots = 4;                        // slots per epilogue warp (residual prefetch depth 3)
+constexpr int kEpiBytes = 4 * kEpiSlots * kEpiSlotBytes;
+constexpr int kEpiVecBytes = 4 * 3 * 256 * 4;       // per-warp copies of col_scale / bias / dot_w for the tile's columns
+constexpr int kBarBytes = 512;                      // mbarriers + the TMEM base slot
 
-// Persistent, warp-specialised: every CTA (one per SM) walks tiles t = blockIdx.x, +gridDim.x, ...
-// Three rings run concurrently: shared-memory stages (TMA -> split -> MMA), TMEM accumulator stages
-// (MMA -> epilogue) and the tile sequence itself, so the epilogue of tile i overlaps the loads and
-// MMAs of tile i+1.
+// Persistent, warp-specialised: every CTA (CTAS = 1) or CTA pair (CTAS = 2, a 2-CTA cluster) walks
+// output tiles t = id, id + n, ...  Three rings run concurrently: shared-memory stages (TMA -> split
+// -> MMA), TMEM accumulator stages (MMA -> epilogue) and the tile sequence itself, so the epilogue of
+// tile i overlaps the loads and MMAs of tile i+1.
+//
+// CTAS = 2: one tcgen05.mma.cta_group::2 covers 256 rows -- each CTA stages its own 128 rows of A and
+// HALF of the weight tile's rows, so the weight stream from L2 (the measured bottleneck of the 1-CTA
+// kernel: 64 KB per k-block per SM against a ~42 B/clk/SM L2 share) and the shared-memory operand
+// reads per CTA are halved.  The MMAs are issued by the leader CTA (cluster rank 0) only; barriers
+// that gate them (fullB, ready, tempty) live in the leader and are arrived on remotely by the peer;
+// barriers the leader releases (empty, tfull) are signalled in both CTAs by a multicast commit.
+template <int CTAS>
 __global__ void __launch_bounds__(kThreadsP, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
-          const __grid_constant__ CUtensorMap tmBlo, Params p) {
+          const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmR,
+          const __grid_constant__ CUtensorMap tmC, Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
-    const int b_tile_bytes = p.block_n * BLOCK_K * 4;
+    const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int bn_cta = p.block_n / CTAS;                 // weight rows staged by this CTA
+    const int b_tile_bytes = bn_cta * BLOCK_K * 4;
     const int stage_bytes = (p.terms == 3 ? 2 : 1) * (A_TILE_BYTES + b_tile_bytes);
     const int stages = p.stages, acc_stages = p.acc_stages;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(smem + (size_t)stages * stage_bytes);
-    // bars: full[stages], ready[stages], empty[stages], tfull[acc_stages], tempty[acc_stages]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 3 * stages + 2 * acc_stages);
+    uint8_t *epi_slots = smem + (size_t)stages * stage_bytes;            // 1024-aligned (stage sizes are multiples of 1 KB)
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_slots + kEpiBytes);
+    // bars: fullA[stages], fullB[stages], ready[stages], empty[stages], tfull[acc_stages], tempty[acc_stages], rfull[4][kEpiSlots]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * stages + 2 * acc_stages + 4 * kEpiSlots);
+    float *epi_vecs = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(bars) + kBarBytes);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t full0 = smem_u32(bars), ready0 = smem_u32(bars + stages), empty0 = smem_u32(bars + 2 * stages),
-                   tfull0 = smem_u32(bars + 3 * stages), tempty0 = smem_u32(bars + 3 * stages + acc_stages);
+    const uint32_t fullA0 = smem_u32(bars), fullB0 = smem_u32(bars + stages), ready0 = smem_u32(bars + 2 * stages),
+                   empty0 = smem_u32(bars + 3 * stages), tfull0 = smem_u32(bars + 4 * stages),
+                   tempty0 = smem_u32(bars + 4 * stages + acc_stages),
+                   rfull0 = smem_u32(bars + 4 * stages + 2 * acc_stages);
+    // the same barriers in the leader CTA, as shared::cluster addresses (identity for CTAS == 1)
+    const uint32_t L_fullB0 = CTAS == 2 ? mapa(fullB0, 0) : fullB0, L_ready0 = CTAS == 2 ? mapa(ready0, 0) : ready0,
+                   L_tempty0 = CTAS == 2 ? mapa(tempty0, 0) : tempty0;
     const int num_kb = p.K / BLOCK_K;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
+    const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
-            mbar_init(full0 + 8 * s, 1);
-            mbar_init(ready0 + 8 * s, 128);
+            mbar_init(fullA0 + 8 * s, 1);
+            mbar_init(fullB0 + 8 * s, 1);
+            mbar_init(ready0 + 8 * s, 128 * CTAS);
             mbar_init(empty0 + 8 * s, 1);
         }
         for (int a = 0; a < acc_stages; ++a) {
             mbar_init(tfull0 + 8 * a, 1);
-            mbar_init(tempty0 + 8 * a, 128);
+            mbar_init(tempty0 + 8 * a, 128 * CTAS);
         }
+        for (int i = 0; i < 4 * kEpiSlots; ++i) mbar_init(rfull0 + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
-                     "r"((uint32_t)p.tmem_cols)
-                     : "memory");
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        if (CTAS == 2) {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)p.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)),
+                         "r"((uint32_t)p.tmem_cols)
+                         : "memory");
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CTAS == 2) cluster_sync();                     // the peer's barriers are initialised before anyone signals them
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t corr_off = p.corr_sep ? (uint32_t)p.acc_cols : 0u;       // TF32X3 lo-term accumulator
     const uint32_t acc_stride = (uint32_t)(p.corr_sep ? 2 * p.acc_cols : p.acc_cols);
 
+    auto wait_x = [](uint32_t bar, uint32_t parity) {    // barriers signalled from the other CTA / by multicast commits
+        if (CTAS == 2) mbar_wait_cluster(bar, parity);
+        else mbar_wait(bar, parity);
+    };
+
     if (warp == 0) {
-        // ---------------- TMA producer ----------------
+        // ---------------- TMA producer (both CTAs of a pair) ----------------
         if (lane == 0) {
-            const uint32_t tx = (uint32_t)(A_TILE_BYTES + (p.terms == 3 ? 2 : 1) * b_tile_bytes);
             uint32_t it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
-                const int m0 = (t / p.num_n_tiles) * BLOCK_M, n0 = (t % p.num_n_tiles) * p.block_n;
+            for (int t = tile0; t < num_tiles; t += tile_step) {
+                const int m0 = (t / p.num_n_tiles) * (BLOCK_M * CTAS) + (int)rank * BLOCK_M;
+                const int n0 = (t % p.num_n_tiles) * p.block_n + (int)rank * bn_cta;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1;
-                    mbar_wait(empty0 + 8 * s, ph ^ 1);
+                    wait_x(empty0 + 8 * s, ph ^ 1);
                     uint8_t *st = smem + (size_t)s * stage_bytes;
-                    mbar_expect_tx(full0 + 8 * s, tx);
-                    tma_load_2d(smem_u32(st), &tmA, kb * BLOCK_K, m0, full0 + 8 * s);
+                    const uint32_t fb = L_fullB0 + 8 * s;
                     if (p.terms == 3) {
-                        tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES), &tmBhi, kb * BLOCK_K, n0, full0 + 8 * s);
-                        tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + b_tile_bytes), &tmBlo, kb * BLOCK_K, n0, full0 + 8 * s);
+                        // A lands on this CTA's own barrier (its split warps wait for it), the weight halves on the leader's
+                        mbar_expect_tx(fullA0 + 8 * s, (uint32_t)A_TILE_BYTES);
+                        tma_load_2d(smem_u32(st), &tmA, kb * BLOCK_K, m0, fullA0 + 8 * s);
+                        if (leader) mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(CTAS * 2 * b_tile_bytes));
+                        if (CTAS == 2) {
+                            tma_load_2d_pair(smem_u32(st + 2 * A_TILE_BYTES), &tmBhi, kb * BLOCK_K, n0, fb);
+                            tma_load_2d_pair(smem_u32(st + 2 * A_TILE_BYTES + b_tile_bytes), &tmBlo, kb * BLOCK_K, n0, fb);
+                        } else {
+                            tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES), &tmBhi, kb * BLOCK_K, n0, fb);
+                            tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + b_tile_bytes), &tmBlo, kb * BLOCK_K, n0, fb);
+                        }
                     } else {
-                        tma_load_2d(smem_u32(st + A_TILE_BYTES), &tmBhi, kb * BLOCK_K, n0, full0 + 8 * s);
+                        if (leader) mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(CTAS * (A_TILE_BYTES + b_tile_bytes)));
+                        if (CTAS == 2) {
+                            tma_load_2d_pair(smem_u32(st), &tmA, kb * BLOCK_K, m0, fb);
+                            tma_load_2d_pair(smem_u32(st + A_TILE_BYTES), &tmBhi, kb * BLOCK_K, n0, fb);
+                        } else {
+                            tma_load_2d(smem_u32(st), &tmA, kb * BLOCK_K, m0, fb);
+                            tma_load_2d(smem_u32(st + A_TILE_BYTES), &tmBhi, kb * BLOCK_K, n0, fb);
+                        }
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        // ---------------- MMA issuer (leader CTA only) ----------------
+        if (lane == 0 && leader) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
-                                   ((uint32_t)(BLOCK_M >> 4) << 24);
+                                   ((uint32_t)((BLOCK_M * CTAS) >> 4) << 24);
+            auto mma = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t acc) {
+                if (CTAS == 2) umma_tf32_pair(d, make_desc(a), make_desc(b), idesc, acc);
+                else umma_tf32(d, make_desc(a), make_desc(b), idesc, acc);
+            };
             uint32_t it = 0, tl = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tl) {
+            for (int t = tile0; t < num_tiles; t += tile_step, ++tl) {
                 const int as = tl % acc_stages;
-                mbar_wait(tempty0 + 8 * as, ((tl / acc_stages) & 1) ^ 1);     // epilogue drained this accumulator
+                wait_x(tempty0 + 8 * as, ((tl / acc_stages) & 1) ^ 1);        // epilogues drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_main = tmem_base + as * acc_stride, d_corr = d_main + corr_off;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1;
-                    mbar_wait((p.terms == 3 ? ready0 : full0) + 8 * s, ph);
+                    wait_x(fullB0 + 8 * s, ph);
+                    if (p.terms == 3) wait_x(ready0 + 8 * s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     uint8_t *st = smem + (size_t)s * stage_bytes;
                     const uint32_t a_hi = smem_u32(st);
@@ -206,22 +336,27 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             const uint32_t off = k * UMMA_K * 4;
                             // lo terms first; with a separate accumulator (corr_sep) the long-running main sum
                             // sees a third of the additions (the tensor core's fp32 accumulate truncates)
-                            umma_tf32(d_corr, make_desc(a_lo + off), make_desc(b_hi + off), idesc, (kb | k) != 0);
-                            umma_tf32(d_corr, make_desc(a_hi + off), make_desc(b_lo + off), idesc, 1);
-                            umma_tf32(d_main, make_desc(a_hi + off), make_desc(b_hi + off), idesc,
-                                      p.corr_sep ? (uint32_t)((kb | k) != 0) : 1u);
+                            if (p.debug & 2) {
+                                mma(d_main, a_hi + off, b_hi + off, (uint32_t)((kb | k) != 0));
+                                continue;
+                            }
+                            mma(d_corr, a_lo + off, b_hi + off, (kb | k) != 0);
+                            mma(d_corr, a_hi + off, b_lo + off, 1);
+                            mma(d_main, a_hi + off, b_hi + off, p.corr_sep ? (uint32_t)((kb | k) != 0) : 1u);
                         }
                     } else {
                         const uint32_t b_hi = a_hi + A_TILE_BYTES;
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                             const uint32_t off = k * UMMA_K * 4;
-                            umma_tf32(d_main, make_desc(a_hi + off), make_desc(b_hi + off), idesc, (kb | k) != 0);
+                            mma(d_main, a_hi + off, b_hi + off, (kb | k) != 0);
                         }
                     }
-                    umma_commit(empty0 + 8 * s);
+                    if (CTAS == 2) umma_commit_pair(empty0 + 8 * s);
+                    else umma_commit(empty0 + 8 * s);
                 }
-                umma_commit(tfull0 + 8 * as);
+                if (CTAS == 2) umma_commit_pair(tfull0 + 8 * as);
+                else umma_commit(tfull0 + 8 * as);
             }
         }
     } else if (warp < 6) {
@@ -229,15 +364,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         if (p.terms == 3) {
             const int tt = threadIdx.x - 64;               // 0..127
             uint32_t it = 0;
-            for (int t = blockIdx.x; t < num_tiles; t += gridDim.x) {
+            for (int t = tile0; t < num_tiles; t += tile_step) {
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1;
-                    mbar_wait(full0 + 8 * s, ph);
+                    mbar_wait(fullA0 + 8 * s, ph);
                     float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * stage_bytes);
                     float4 *lo = hi + A_TILE_BYTES / 16;
 #pragma unroll
                     for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {
+                        if (p.debug & 1) break;
                         const float4 v = hi[tt + 128 * i];
                         float4 h, l;
                         uint32_t u;
@@ -248,58 +384,71 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         hi[tt + 128 * i] = h;
                         lo[tt + 128 * i] = l;
                     }
-                    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    mbar_arrive(ready0 + 8 * s);
+                    if (CTAS == 2) {
+                        asm volatile("fence.proxy.async;" ::: "memory");
+                        mbar_arrive_cluster(L_ready0 + 8 * s);
+                    } else {
+                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                        mbar_arrive(ready0 + 8 * s);
+                    }
                 }
             }
         }
     } else {
-        // ---------------- warps 6..9: epilogue ----------------
-        // TMEM gives each lane one accumulator ROW (32 columns per tcgen05.ld).  Stored directly that
-        // is 32 different 128-byte lines per instruction (measured: the L1 wavefront replays made the
-        // epilogue 3x longer than the main loop).  Each warp therefore transposes its 32x32 chunk through
-        // a private padded shared-memory tile so that 8 lanes cover one 128-byte row segment and every
-        // global access (residual read, C write) is a fully coalesced float4.
+        // ---------------- warps 6..9: epilogue (each CTA drains its own 128 accumulator rows) ----------------
+        // TMEM gives each lane one accumulator ROW (32 columns per tcgen05.ld), so the arithmetic is done
+        // row-per-thread; all global traffic is TMA.  A warp owns kEpiSlots shared-memory slots of
+        // 32 rows x 32 columns (128B-swizzled, so a lane reads / writes its own 128-byte row without bank
+        // conflicts).  Per 32-column chunk: the residual box was TMA-loaded into the slot up to three chunks
+        // ahead (48 KB in flight per SM -- with register-staged loads the epilogue was latency-bound at
+        // ~2.4 TB/s), the lane combines accumulator, scale, bias, residual, ReLU in place, and one lane
+        // TMA-stores the slot to C (rows past M are clipped by the tensor map).
+        const int ew = warp - 6;
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
-        float *stg = reinterpret_cast<float *>(smem + (size_t)stages * stage_bytes + 512) + (warp - 6) * (32 * 36);
-        const int sub_row = lane >> 3, col4 = lane & 7;    // transposed domain: 4 rows x 8 float4 per pass
-        uint32_t tl = 0;
-        for (int t = blockIdx.x; t < num_tiles; t += gridDim.x, ++tl) {
+        uint8_t *slots = epi_slots + (size_t)ew * kEpiSlots * kEpiSlotBytes;
+        const uint32_t rf0 = rfull0 + 8 * ew * kEpiSlots;
+        float *vscale = epi_vecs + ew * 3 * 256, *vbias = vscale + 256, *vdot = vbias + 256;
+        const bool has_res = p.epi.residual != nullptr, has_c = p.C != nullptr;
+        const int cpt = (p.block_n + 31) / 32;             // chunks per tile
+        const uint32_t swz = (uint32_t)(lane & 7);
+        auto issue_res_load = [&](uint32_t g) {            // lane 0: residual box of global chunk g into slot g % kEpiSlots
+            const int t = tile0 + (int)(g / cpt) * tile_step;
+            if (t >= num_tiles) return;
+            const int m0 = (t / p.num_n_tiles) * (BLOCK_M * CTAS) + (int)rank * BLOCK_M + quad * 32;
+            const int n = (t % p.num_n_tiles) * p.block_n + (int)(g % cpt) * 32;
+            const uint32_t sl = g % kEpiSlots;
+            mbar_expect_tx(rf0 + 8 * sl, (uint32_t)kEpiSlotBytes);
+            tma_load_2d(smem_u32(slots + sl * kEpiSlotBytes), &tmR, n, m0, rf0 + 8 * sl);
+        };
+        if (has_res && lane == 0)
+            for (uint32_t g = 0; g + 1 < (uint32_t)kEpiSlots; ++g) issue_res_load(g);
+        uint32_t tl = 0, g = 0;
+        for (int t = tile0; t < num_tiles; t += tile_step, ++tl) {
             const int as = tl % acc_stages;
-            const int m0 = (t / p.num_n_tiles) * BLOCK_M, n_tile = t % p.num_n_tiles, n0 = n_tile * p.block_n;
-            mbar_wait(tfull0 + 8 * as, (tl / acc_stages) & 1);
-            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int64_t mw = (int64_t)m0 + quad * 32;     // first row of this warp
-            const uint32_t t_main = tmem_base + as * acc_stride + ((uint32_t)(quad * 32) << 16);
-            float dot[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) dot[i] = 0.f;
-            // residual rows are prefetched one chunk ahead: 8 independent 16-byte loads per lane stay in
-            // flight while the previous chunk is fetched from TMEM, transposed and stored (issued one by
-            // one between the stores they were the epilogue's critical path: 2.0 ms -> 0.85 ms per layer)
-            auto load_res = [&](int c0n, float4 (&dst)[8]) {
-                const int ccn = c0n + 4 * col4;
-                const bool okn = p.epi.residual != nullptr && c0n < p.block_n && ccn < p.block_n;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    const int64_t m = mw + 4 * i + sub_row;
-                    dst[i] = (okn && m < p.M) ? ldg4(p.epi.residual + m * p.epi.ldr + n0 + ccn) : make_float4(0.f, 0.f, 0.f, 0.f);
+            const int m0 = (t / p.num_n_tiles) * (BLOCK_M * CTAS) + (int)rank * BLOCK_M;
+            const int n_tile = t % p.num_n_tiles, n0 = n_tile * p.block_n;
+            if (tl == 0 || p.num_n_tiles > 1) {            // this tile's per-column vectors (private copy per warp)
+                __syncwarp();
+                for (int c = lane; c < p.block_n; c += 32) {
+                    vscale[c] = p.epi.col_scale != nullptr ? __ldg(p.epi.col_scale + n0 + c) : 1.f;
+                    vbias[c] = p.epi.bias != nullptr ? __ldg(p.epi.bias + n0 + c) : 0.f;
+                    vdot[c] = p.dot_w != nullptr ? __ldg(p.dot_w + n0 + c) : 0.f;
                 }
-            };
-            float4 res[8], res_next[8];
-            load_res(0, res_next);
-            for (int c0 = 0; c0 < p.block_n; c0 += 32) {
-                const int cc = c0 + 4 * col4;              // column inside the tile of this lane's float4
-                const bool col_ok = cc < p.block_n;        // block_n is a multiple of 16
-                const int n = n0 + cc;
-#pragma unroll
-                for (int i = 0; i < 8; ++i) res[i] = res_next[i];
-                load_res(c0 + 32, res_next);
-                float4 s4 = make_float4(1.f, 1.f, 1.f, 1.f), b4 = make_float4(0.f, 0.f, 0.f, 0.f), w4 = b4;
-                if (col_ok) {
-                    if (p.epi.col_scale != nullptr) s4 = ldg4(p.epi.col_scale + n);
-                    if (p.epi.bias != nullptr) b4 = ldg4(p.epi.bias + n);
-                    if (p.dot_w != nullptr) w4 = ldg4(p.dot_w + n);
+                __syncwarp();
+            }
+            wait_x(tfull0 + 8 * as, (tl / acc_stages) & 1);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const int mw = m0 + quad * 32;                  // first row of this warp
+            const uint32_t t_main = tmem_base + as * acc_stride + ((uint32_t)(quad * 32) << 16);
+            float dot = 0.f;
+            for (int c0 = 0; c0 < p.block_n; c0 += 32, ++g) {
+                const uint32_t sl = g % kEpiSlots;
+                uint8_t *row = slots + sl * kEpiSlotBytes + lane * 128;
+                if (has_res) {
+                    mbar_wait(rf0 + 8 * sl, (g / kEpiSlots) & 1);
+                } else if (has_c) {                         // the store that last used this slot has finished reading it
+                    if (lane == 0) bulk_wait_read<kEpiSlots - 1>();
+                    __syncwarp();
                 }
                 uint32_t r[32];
                 tmem_ld32(t_main + (uint32_t)c0, r);
@@ -310,50 +459,57 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     for (int j = 0; j < 32; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(r2[j]));
                 }
 #pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    *reinterpret_cast<float4 *>(stg + lane * 36 + j) =
-                        make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
-                                    __uint_as_float(r[j + 3]));
+                for (int j = 0; j < 8; ++j) {
+                    float4 *cell = reinterpret_cast<float4 *>(row + (((uint32_t)j ^ swz) << 4));
+                    const float4 s4 = *reinterpret_cast<const float4 *>(vscale + c0 + 4 * j);
+                    const float4 b4 = *reinterpret_cast<const float4 *>(vbias + c0 + 4 * j);
+                    float4 v;
+                    v.x = fmaf(__uint_as_float(r[4 * j]), s4.x, b4.x); v.y = fmaf(__uint_as_float(r[4 * j + 1]), s4.y, b4.y);
+                    v.z = fmaf(__uint_as_float(r[4 * j + 2]), s4.z, b4.z); v.w = fmaf(__uint_as_float(r[4 * j + 3]), s4.w, b4.w);
+                    if (has_res) {
+                        const float4 q = *cell;
+                        v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
+                    }
+                    if (p.epi.relu) {
+                        v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+                    }
+                    if (p.dot_w != nullptr) {
+                        const float4 w4 = *reinterpret_cast<const float4 *>(vdot + c0 + 4 * j);
+                        dot = fmaf(v.x, w4.x, fmaf(v.y, w4.y, fmaf(v.z, w4.z, fmaf(v.w, w4.w, dot))));
+                    }
+                    if (has_c) *cell = v;
+                }
+                if (has_c) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (col_ok) {
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) {
-                        const int row = 4 * i + sub_row;
-                        const int64_t m = mw + row;
-                        float4 v = *reinterpret_cast<const float4 *>(stg + row * 36 + 4 * col4);
-                        v.x = fmaf(v.x, s4.x, b4.x) + res[i].x; v.y = fmaf(v.y, s4.y, b4.y) + res[i].y;
-                        v.z = fmaf(v.z, s4.z, b4.z) + res[i].z; v.w = fmaf(v.w, s4.w, b4.w) + res[i].w;
-                        if (p.epi.relu) {
-                            v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
-                        }
-                        if (m < p.M) {
-                            if (p.C != nullptr) st4(p.C + m * p.ldc + n, v);
-                            dot[i] = fmaf(v.x, w4.x, fmaf(v.y, w4.y, fmaf(v.z, w4.z, fmaf(v.w, w4.w, dot[i]))));
-                        }
+                if (lane == 0) {
+                    if (has_c) {
+                        tma_store_2d(&tmC, smem_u32(slots + sl * kEpiSlotBytes), n0 + c0, mw);
+                        bulk_commit();
+                    }
+                    if (has_res) {                          // refill the slot chunk g-1 used: its store must be done reading
+                        if (has_c) bulk_wait_read<1>();
+                        issue_res_load(g + kEpiSlots - 1);
                     }
                 }
-                __syncwarp();
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            mbar_arrive(tempty0 + 8 * as);                 // 128 arrivals free the accumulator stage
-            if (p.dot_w != nullptr) {                      // fused row dot: out[n_tile][m] = sum_n v[m,n] * w[n]
-#pragma unroll
-                for (int i = 0; i < 8; ++i) {
-                    float d = dot[i];
-                    d += __shfl_xor_sync(0xffffffffu, d, 1);
-                    d += __shfl_xor_sync(0xffffffffu, d, 2);
-                    d += __shfl_xor_sync(0xffffffffu, d, 4);
-                    const int64_t m = mw + 4 * i + sub_row;
-                    if (col4 == 0 && m < p.M) p.dot_out[(int64_t)n_tile * p.M + m] = d;
-                }
-            }
+            if (CTAS == 2) mbar_arrive_cluster(L_tempty0 + 8 * as);     // 128 arrivals per CTA free the accumulator stage
+            else mbar_arrive(tempty0 + 8 * as);
+            if (p.dot_w != nullptr && (int64_t)mw + lane < p.M)        // fused row dot: out[n_tile][m] = sum_n v[m,n] * w[n]
+                p.dot_out[(int64_t)n_tile * p.M + mw + lane] = dot;
         }
+        if (lane == 0) bulk_wait_all();
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CTAS == 2) cluster_sync();                     // no CTA leaves while its pair may still read its memory or barriers
     if (warp == 1) {
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
-                     : "memory");
+        if (CTAS == 2)
+            asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                         : "memory");
+        else
+            asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)p.tmem_cols)
+                         : "memory");
     }
 }
 
@@ -409,7 +565,8 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-static int make_map(CUtensorMap *tm, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+static int make_map(CUtensorMap *tm, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
+                    int box_cols = BLOCK_K) {
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) {
         set_error("cuTensorMapEncodeTiled entry point not available");
@@ -417,7 +574,7 @@ static int make_map(CUtensorMap *tm, const float *base, int64_t rows, int64_t co
     }
     cuuint64_t dims[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
     cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
-    cuuint32_t box[2] = {(cuuint32_t)BLOCK_K, (cuuint32_t)box_rows};
+    cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -431,7 +588,7 @@ static int make_map(CUtensorMap *tm, const float *base, int64_t rows, int64_t co
 }
 
 static int pick_block_n(int64_t n) {
-    for (int bn = 256; bn >= 16; bn -= 16)
+    for (int bn = 256; bn >= 32; bn -= 32)       // the epilogue moves 32-column boxes
         if (n % bn == 0) return bn;
     return 0;
 }
@@ -448,7 +605,7 @@ bool gemm_tc_supported(int precision, bool a_kmajor, bool b_kmajor, int64_t lda,
     if (precision != DCNR_PREC_TF32X3 && precision != DCNR_PREC_TF32) return false;
     if (!a_kmajor || !b_kmajor || split_k != 1) return false;
     if (k < tc::BLOCK_K || k % tc::BLOCK_K != 0 || (lda & 3) || (ldb & 3) || (ldc & 3)) return false;
-    if (n % 16 != 0 || tc::pick_block_n(n) == 0 || m <= 0 || m > 0x7fffff00LL) return false;
+    if (n % 32 != 0 || tc::pick_block_n(n) == 0 || m <= 0 || m > 0x7fffff00LL) return false;
     return true;
 }
 
@@ -490,6 +647,11 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     p.terms = terms;
     p.C = C; p.ldc = ldc; p.epi = epi;
     p.dot_w = dot_w; p.dot_out = dot_out;
+    static const int debug_bits = [] {
+        const char *e = getenv("DCNR_GEMM_DEBUG");
+        return e != nullptr ? atoi(e) : 0;
+    }();
+    p.debug = debug_bits;
     p.acc_cols = 32;
     while (p.acc_cols < p.block_n) p.acc_cols <<= 1;
     p.corr_sep = (terms == 3 && 4 * p.acc_cols <= 512) ? 1 : 0;      // room for main + lo accumulators, double buffered
@@ -497,20 +659,61 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     p.acc_stages = 2 * per_stage_cols <= 512 ? 2 : 1;
     p.tmem_cols = 32;
     while (p.tmem_cols < p.acc_stages * per_stage_cols) p.tmem_cols <<= 1;
-    const int stage_bytes = (terms == 3 ? 2 : 1) * (A_TILE_BYTES + p.block_n * BLOCK_K * 4);
-    int stages = std::max(1, std::min(6, (200 * 1024) / stage_bytes));
-    p.stages = stages;
-    p.num_m_tiles = (int32_t)ceil_div(m, BLOCK_M);
     p.num_n_tiles = (int32_t)(n / p.block_n);
-    const size_t smem = (size_t)stages * stage_bytes + 1024 + 512 + kEpiStageBytes;
-    CUtensorMap tmA, tmBhi, tmBlo;
+
+    // CTA pairs (2-CTA MMA) whenever the tile splits evenly and a pair has work; DCNR_GEMM_CTAS=1 forces single CTAs
+    static const int forced_ctas = [] {
+        const char *e = getenv("DCNR_GEMM_CTAS");
+        return e != nullptr ? atoi(e) : 0;
+    }();
+    int ctas = m > BLOCK_M ? 2 : 1;
+    if (forced_ctas == 1) ctas = 1;
+    int max_pairs = 0;
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute attr[1];
+    auto plan = [&](int c, size_t *smem_out) {
+        const int stage_bytes = (terms == 3 ? 2 : 1) * (A_TILE_BYTES + (p.block_n / c) * BLOCK_K * 4);
+        const int budget = 227 * 1024 - 1024 - kBarBytes - kEpiVecBytes - kEpiBytes;
+        p.stages = std::max(1, std::min(6, budget / stage_bytes));
+        *smem_out = (size_t)p.stages * stage_bytes + 1024 + kBarBytes + kEpiVecBytes + kEpiBytes;
+    };
+    size_t smem = 0;
+    if (ctas == 2) {
+        plan(2, &smem);
+        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        cfg.gridDim = dim3(2 * (unsigned)sm_count(), 1, 1);
+        cfg.blockDim = dim3(kThreadsP, 1, 1);
+        cfg.dynamicSmemBytes = smem;
+        cfg.stream = stream;
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        if (cudaOccupancyMaxActiveClusters(&max_pairs, k_gemm_tc<2>, &cfg) != cudaSuccess || max_pairs < 1) {
+            cudaGetLastError();
+            ctas = 1;
+        }
+    }
+    CUtensorMap tmA, tmBhi, tmBlo, tmR, tmC;
     DCNR_TRY(make_map(&tmA, A, m, k, lda, BLOCK_M));
-    DCNR_TRY(make_map(&tmBhi, B, n, k, ldb, p.block_n));
-    DCNR_TRY(make_map(&tmBlo, terms == 3 ? B_lo : B, n, k, ldb, p.block_n));
-    DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    // epilogue boxes: 32 rows x 32 columns of the residual / output (rows and columns past the matrix are
+    // zero-filled on load and clipped on store)
+    if (C != nullptr) DCNR_TRY(make_map(&tmC, C, m, n, ldc, 32, 32));
+    else tmC = tmA;                                  // never dereferenced
+    if (epi.residual != nullptr) DCNR_TRY(make_map(&tmR, epi.residual, m, n, epi.ldr, 32, 32));
+    else tmR = tmA;
+    DCNR_TRY(make_map(&tmBhi, B, n, k, ldb, p.block_n / ctas));
+    DCNR_TRY(make_map(&tmBlo, terms == 3 ? B_lo : B, n, k, ldb, p.block_n / ctas));
+    p.num_m_tiles = (int32_t)ceil_div(m, BLOCK_M * ctas);
     const int64_t num_tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
-    const unsigned grid = (unsigned)std::min<int64_t>(num_tiles, sm_count());
-    k_gemm_tc<<<grid, kThreadsP, smem, stream>>>(tmA, tmBhi, tmBlo, p);
+    if (ctas == 2) {
+        cfg.gridDim = dim3(2 * (unsigned)std::min<int64_t>(num_tiles, max_pairs), 1, 1);
+        DCNR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tc<2>, tmA, tmBhi, tmBlo, tmR, tmC, p));
+    } else {
+        plan(1, &smem);
+        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const unsigned grid = (unsigned)std::min<int64_t>(num_tiles, sm_count());
+        k_gemm_tc<1><<<grid, kThreadsP, smem, stream>>>(tmA, tmBhi, tmBlo, tmR, tmC, p);
+    }
     DCNR_LAUNCHED();
     return DCNR_OK;
 }
