@@ -123,6 +123,11 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint
         ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *tm, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1)
+                 : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -232,12 +237,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int s = 0; s < stages; ++s) {
             mbar_init(fullA0 + 8 * s, 1);
             mbar_init(fullB0 + 8 * s, 1);
-            mbar_init(ready0 + 8 * s, 128 * CTAS);
+            mbar_init(ready0 + 8 * s, 4 * CTAS);        // one arrival per split warp
             mbar_init(empty0 + 8 * s, 1);
         }
         for (int a = 0; a < acc_stages; ++a) {
             mbar_init(tfull0 + 8 * a, 1);
-            mbar_init(tempty0 + 8 * a, 128 * CTAS);
+            mbar_init(tempty0 + 8 * a, 4 * CTAS);       // one arrival per epilogue warp
         }
         for (int i = 0; i < 4 * kEpiSlots; ++i) mbar_init(rfull0 + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -384,12 +389,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         hi[tt + 128 * i] = h;
                         lo[tt + 128 * i] = l;
                     }
-                    if (CTAS == 2) {
-                        asm volatile("fence.proxy.async;" ::: "memory");
-                        mbar_arrive_cluster(L_ready0 + 8 * s);
-                    } else {
-                        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                        mbar_arrive(ready0 + 8 * s);
+                    // every lane publishes its writes to the async proxy, then one lane per warp arrives
+                    // (128 remote arrivals per k-block from the peer CTA were a measurable part of the hop)
+                    if (CTAS == 2) asm volatile("fence.proxy.async;" ::: "memory");
+                    else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CTAS == 2) mbar_arrive_cluster(L_ready0 + 8 * s);
+                        else mbar_arrive(ready0 + 8 * s);
                     }
                 }
             }
@@ -493,8 +500,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-            if (CTAS == 2) mbar_arrive_cluster(L_tempty0 + 8 * as);     // 128 arrivals per CTA free the accumulator stage
-            else mbar_arrive(tempty0 + 8 * as);
+            __syncwarp();
+            if (lane == 0) {                                // one arrival per epilogue warp frees the accumulator stage
+                if (CTAS == 2) mbar_arrive_cluster(L_tempty0 + 8 * as);
+                else mbar_arrive(tempty0 + 8 * as);
+            }
             if (p.dot_w != nullptr && (int64_t)mw + lane < p.M)        // fused row dot: out[n_tile][m] = sum_n v[m,n] * w[n]
                 p.dot_out[(int64_t)n_tile * p.M + mw + lane] = dot;
         }
