@@ -5,13 +5,18 @@
 // Arithmetic contract (bit-exact with oracle/knn_oracle.c, see its header): sequential-fma norms
 // and dot products, dist = clip(1 - sim, 0, 2), total order (dist ascending, index ascending).
 //
-// Scan kernel: the catalog is cut into contiguous slices, one CTA per (slice, query tile).  Each
-// thread scores one catalog row per round against the tile's queries (queries broadcast from
-// shared memory).  A candidate is kept only if its 64-bit key (dist bits << 32 | row) beats the
-// CTA's current k-th best key for that query; survivors go to a small shared buffer that is
-// bitonic-sorted and truncated to k whenever it could overflow.  Keys are unique, so the selection
-// is deterministic although the append order is not.  Per-slice lists are then merged by sorting
-// groups of lists in shared memory.
+// Scan kernel: the catalog is cut into contiguous slices, one CTA per (slice, query tile of 1 or 8).
+// Every warp streams groups of 32 consecutive rows through its own cp.async ring (16-byte
+// LDGSTS, fully coalesced 512-byte requests, 2-5 groups in flight per warp so ~50-100 KB per SM are
+// outstanding -- the first version's one-row-per-thread __ldg loop had 16 KB and ran at 18 % of HBM);
+// rows are staged with a one-float4 pad so that each lane then reads ITS row with conflict-free
+// LDS.128 and scores it against the tile's queries (broadcast from shared memory) with the
+// sequential-fma order of the oracle.  A candidate is kept only if its 64-bit key
+// (dist bits << 32 | row) beats the CTA's current k-th best key for that query; survivors go to a
+// shared buffer that is bitonic-sorted and truncated to k whenever it could overflow.  Keys are
+// unique, so the selection is deterministic although the append order is not.  Per-slice lists are
+// then merged by sorting groups of lists in shared memory.  (k_knn_scan below is the generic-width
+// fallback for embedding widths outside {16, 24, 32, 48, 64}.)
 #include "kernels.cuh"
 
 namespace dcnr {
@@ -19,7 +24,6 @@ namespace dcnr {
 constexpr int kTT = 256;        // threads per CTA
 constexpr int kQT = 8;          // queries per CTA tile
 constexpr int kMaxD = 128;      // embedding dim limit (floats), multiple of 4
-constexpr int kMergeMaxKeys = 8192;
 constexpr int kCap = 512;       // per-query candidate buffer: >= k + kTT, power of two (k <= 256)
 typedef unsigned long long u64;
 constexpr u64 kMaxKey = ~0ull;
@@ -131,37 +135,259 @@ k_knn_scan(const float *__restrict__ cat, int64_t n, int d, const float *__restr
     }
 }
 
-// Sorts `group` lists of kp keys per query in shared memory and keeps the best kp.
-// in: [n_lists][nq][kp]; out: [ceil(n_lists/group)][nq][kp].  When dist_out != NULL this is the
-// last level and (dist, idx_base + row) are written instead.
+constexpr int kCap2 = 1024;     // candidate buffer of the streaming kernel (flushed when > kCap2 - kTT)
+
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(dst_smem)), "l"(src)
+                 : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int DV, int QT>   // DV float4 per row (d = 4*DV), QT queries per CTA
 __global__ void __launch_bounds__(kTT)
-k_knn_merge_keys(const u64 *__restrict__ in, int n_lists, int nq, int kp, int k, int group, int n_sort,
-                 u64 *__restrict__ out, float *__restrict__ dist_out, int64_t *__restrict__ idx_out, int64_t idx_base) {
+k_knn_stream(const float *__restrict__ cat, int64_t n, const float *__restrict__ queries, int nq, int k, int kp,
+             int64_t groups_per_slice, int64_t gstride, int n_stages, const u64 *__restrict__ tau0,
+             u64 *__restrict__ out_keys) {
+    constexpr int d = 4 * DV;
+    constexpr int ROWQ = DV + ((DV & 1) ? 0 : 1);      // staged row pitch in float4: odd => conflict-free LDS.128
+    constexpr int cap = kCap2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    u64 *a = reinterpret_cast<u64 *>(smem_raw);
-    const int q = blockIdx.x, g = blockIdx.y, tid = threadIdx.x;
-    const int l0 = g * group, l1 = min(n_lists, l0 + group);
-    const int have = (l1 - l0) * kp;
-    for (int i = tid; i < n_sort; i += kTT) {
-        u64 v = kMaxKey;
-        if (i < have) v = in[((int64_t)(l0 + i / kp) * nq + q) * kp + (i % kp)];
-        a[i] = v;
+    u64 *buf = reinterpret_cast<u64 *>(smem_raw);                      // [QT][cap]
+    u64 *tau = buf + (size_t)QT * cap;                                 // [8] (QT used)
+    int *cnt = reinterpret_cast<int *>(tau + 8);                       // [8] (QT used)
+    unsigned *flush_mask = reinterpret_cast<unsigned *>(cnt + 8);      // [1] (+3 pad) -- every section stays 16-byte aligned
+    float *sq = reinterpret_cast<float *>(flush_mask + 4);             // [QT][d]
+    float4 *ring = reinterpret_cast<float4 *>(sq + QT * d);            // [8 warps][n_stages][32][ROWQ]
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int q0 = blockIdx.y * QT;
+    const int nqt = min(QT, nq - q0);
+    for (int i = tid; i < QT * d; i += kTT) sq[i] = (i / d) < nqt ? queries[(int64_t)q0 * d + i] : 0.f;
+    if (tid < QT) {
+        // a sampled pre-pass (same kernel, gstride > 1) may hand in the k-th best key of a row subset: every key
+        // above it is already known not to be in the top k, so the buffers below almost never fill
+        u64 t0 = kMaxKey;
+        if (tau0 != nullptr && tid < nqt && tau0[q0 + tid] != kMaxKey) t0 = tau0[q0 + tid] + 1;
+        tau[tid] = t0;
+        cnt[tid] = 0;
     }
+    if (tid == 0) *flush_mask = 0u;
     __syncthreads();
-    bitonic_sort_u64(a, n_sort, tid, kTT);
-    if (dist_out != nullptr) {
-        for (int i = tid; i < k; i += kTT) {
-            const u64 key = a[i];
-            if (key == kMaxKey) {
-                dist_out[(int64_t)q * k + i] = __int_as_float(0x7f800000);
-                idx_out[(int64_t)q * k + i] = -1;
-            } else {
-                dist_out[(int64_t)q * k + i] = __uint_as_float((uint32_t)(key >> 32));
-                idx_out[(int64_t)q * k + i] = idx_base + (int64_t)(uint32_t)key;
+
+    // the slice is a range of 32-row groups; with gstride > 1 only every gstride-th group of the catalog is visited
+    const int64_t n_groups = (n + 32 * gstride - 1) / (32 * gstride);
+    const int64_t vg0 = (int64_t)blockIdx.x * groups_per_slice;
+    const int64_t vg1 = min(n_groups, vg0 + groups_per_slice);
+    const int iters = vg1 > vg0 ? (int)((vg1 - vg0 + 7) / 8) : 0;        // one group per warp per iteration
+    float4 *wring = ring + (size_t)warp * n_stages * 32 * ROWQ;
+    const float4 *cat4 = reinterpret_cast<const float4 *>(cat);
+
+    auto issue = [&](int it) {                           // this warp's group of iteration `it` into ring slot it % n_stages
+        const int64_t vg = vg0 + (int64_t)it * 8 + warp;
+        if (it < iters && vg < vg1) {
+            const int64_t g0 = vg * gstride * 32;         // first row of the group
+            float4 *st = wring + (size_t)(it % n_stages) * 32 * ROWQ;
+#pragma unroll
+            for (int i = 0; i < DV; ++i) {
+                const int f = lane + 32 * i;              // float4 index inside the group: row f / DV, part f % DV
+                const int r = f / DV, part = f % DV;
+                if (g0 + r < n) cp_async16(st + r * ROWQ + part, cat4 + g0 * DV + f);
             }
         }
-    } else {
-        for (int i = tid; i < kp; i += kTT) out[((int64_t)g * nq + q) * kp + i] = a[i];
+        cp_async_commit();
+    };
+    auto flush = [&](int q) {                            // CTA-wide: keep the best k of buffer q, tighten tau
+        const int c = min(cnt[q], cap);
+        int n_sort = 32;
+        while (n_sort < c) n_sort <<= 1;
+        u64 *b = buf + (size_t)q * cap;
+        for (int i = c + tid; i < n_sort; i += kTT) b[i] = kMaxKey;
+        __syncthreads();
+        bitonic_sort_u64(b, n_sort, tid, kTT);
+        if (tid == 0) {
+            cnt[q] = min(c, k);
+            if (c >= k) tau[q] = min(tau[q], b[k - 1]);
+        }
+        __syncthreads();
+    };
+
+    for (int i = 0; i < n_stages - 1; ++i) issue(i);
+    for (int it = 0; it < iters; ++it) {
+        issue(it + n_stages - 1);
+        // all but the n_stages-1 most recent groups have landed => group `it` is in shared memory
+        switch (n_stages) {
+            case 2: cp_async_wait<1>(); break;
+            case 3: cp_async_wait<2>(); break;
+            case 4: cp_async_wait<3>(); break;
+            case 5: cp_async_wait<4>(); break;
+            default: cp_async_wait<5>(); break;
+        }
+        __syncwarp();
+        const int64_t vg = vg0 + (int64_t)it * 8 + warp;
+        const int64_t row = vg < vg1 ? vg * gstride * 32 + lane : n;
+        const float4 *rp = wring + (size_t)(it % n_stages) * 32 * ROWQ + lane * ROWQ;
+        float sim[QT];
+#pragma unroll
+        for (int q = 0; q < QT; ++q) sim[q] = 0.f;
+#pragma unroll
+        for (int j = 0; j < DV; ++j) {
+            const float4 e = rp[j];
+#pragma unroll
+            for (int q = 0; q < QT; ++q) {
+                const float4 qv = *reinterpret_cast<const float4 *>(sq + q * d + 4 * j);
+                sim[q] = __fmaf_rn(qv.x, e.x, sim[q]);
+                sim[q] = __fmaf_rn(qv.y, e.y, sim[q]);
+                sim[q] = __fmaf_rn(qv.z, e.z, sim[q]);
+                sim[q] = __fmaf_rn(qv.w, e.w, sim[q]);
+            }
+        }
+        if (row < n) {
+#pragma unroll
+            for (int q = 0; q < QT; ++q) {
+                if (q < nqt) {
+                    float dist = __fsub_rn(1.0f, sim[q]);
+                    dist = fminf(fmaxf(dist, 0.f), 2.f);
+                    const u64 key = ((u64)__float_as_uint(dist) << 32) | (u64)(uint32_t)row;
+                    if (key < tau[q]) {
+                        const int pos = atomicAdd(&cnt[q], 1);          // < cap: cnt <= cap - kTT when the round starts
+                        buf[(size_t)q * cap + pos] = key;
+                        if (pos >= cap - kTT) atomicOr(flush_mask, 1u << q);
+                    }
+                }
+            }
+        }
+        __syncthreads();                                  // appends visible; every lane is done with its ring slot
+        const unsigned mask = *reinterpret_cast<volatile unsigned *>(flush_mask);
+        if (mask != 0u) {                                 // CTA-uniform
+            __syncthreads();
+            if (tid == 0) *flush_mask = 0u;
+            for (int q = 0; q < nqt; ++q)
+                if (mask & (1u << q)) flush(q);
+        }
+    }
+    cp_async_wait<0>();
+    // final: sort every query's survivors and emit the slice's best kp keys
+    for (int q = 0; q < nqt; ++q) {
+        flush(q);
+        const u64 *b = buf + (size_t)q * cap;
+        const int c = cnt[q];
+        u64 *o = out_keys + ((int64_t)blockIdx.x * nq + (q0 + q)) * kp;
+        for (int i = tid; i < kp; i += kTT) o[i] = (i < c) ? b[i] : kMaxKey;
+        __syncthreads();
+    }
+}
+
+static int stream_stage_bytes(int dv) { return 32 * (dv + ((dv & 1) ? 0 : 1)) * 16; }
+static bool stream_supported(int d) { return d == 16 || d == 24 || d == 32 || d == 48 || d == 64; }
+static int stream_stages(int d, int qt) {
+    const int budget = (qt == 1 ? 92 : 136) * 1024;
+    return std::max(2, std::min(6, budget / (8 * stream_stage_bytes(d / 4))));
+}
+static size_t stream_smem(int d, int qt) {
+    return (size_t)qt * kCap2 * 8 + 8 * 8 + 8 * 4 + 16 + (size_t)qt * d * 4 +
+           (size_t)8 * stream_stages(d, qt) * stream_stage_bytes(d / 4);
+}
+
+// Merge of the per-slice lists ([n_lists][nq][kp], each sorted ascending, kMaxKey padded) into the final
+// top k of one query per CTA.  A threshold prunes first: with j = the probe depth and r = ceil(k / j), the
+// r-th smallest of the lists' j-th entries T bounds the k-th best key from above (r lists hold j keys <= T
+// each), so only list prefixes <= T can matter -- typically a few hundred keys instead of n_lists * k.  The
+// prefixes are appended to a candidate buffer 16 lists at a time and the buffer is sorted / truncated to
+// k (which tightens T) whenever the next chunk might not fit, so any input is handled; the usual case is
+// one small sort.  tau_out != NULL: only the k-th best key is wanted (the sampled pre-pass).
+constexpr int kCandCap = 8192;
+constexpr int kChunkLists = 16;
+__global__ void __launch_bounds__(kTT)
+k_knn_merge_select(const u64 *__restrict__ lists, int n_lists, int nq, int kp, int k, int n_probe_sort,
+                   float *__restrict__ dist_out, int64_t *__restrict__ idx_out, int64_t idx_base,
+                   u64 *__restrict__ tau_out) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    u64 *cand = reinterpret_cast<u64 *>(smem_raw);                    // [kCandCap]
+    u64 *probe = cand + kCandCap;                                      // [n_probe_sort]
+    __shared__ int s_cnt;
+    __shared__ u64 s_tau;
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int klist = min(k, kp);
+    int j = max(1, (2 * k + n_lists - 1) / n_lists);
+    j = min(j, klist);
+    int r = (k + j - 1) / j;
+    if (r > n_lists) {                                                 // few lists: probe deeper
+        j = min(klist, (k + n_lists - 1) / n_lists);
+        r = min(n_lists, (k + j - 1) / j);
+    }
+    for (int i = tid; i < n_probe_sort; i += kTT)
+        probe[i] = i < n_lists ? lists[((int64_t)i * nq + q) * kp + (j - 1)] : kMaxKey;
+    if (tid == 0) s_cnt = 0;
+    __syncthreads();
+    bitonic_sort_u64(probe, n_probe_sort, tid, kTT);
+    if (tid == 0) s_tau = (int64_t)r * j >= k ? probe[r - 1] : kMaxKey;  // inclusive bound (kMaxKey: no pruning)
+    __syncthreads();
+
+    auto compact = [&]() {                                             // keep the best k candidates, tighten the bound
+        const int c = s_cnt;
+        int n_sort = 32;
+        while (n_sort < c) n_sort <<= 1;
+        for (int i = c + tid; i < n_sort; i += kTT) cand[i] = kMaxKey;
+        __syncthreads();
+        bitonic_sort_u64(cand, n_sort, tid, kTT);
+        if (tid == 0) {
+            s_cnt = min(c, k);
+            if (c >= k) s_tau = min(s_tau, cand[k - 1]);
+        }
+        __syncthreads();
+    };
+    // Lists are sorted, so the keys <= tau of a list are a prefix: 16 lanes read a list 16 keys at a time and stop at
+    // the first block that is not entirely below the bound (with a tight bound that is the first block).  Four
+    // chunks of 16 lists are in flight per pass, so the usual merge is a handful of dependent memory round trips.
+    constexpr int kLanes = kTT / kChunkLists;                          // 16 lanes per list
+    const int sub = tid % kLanes, grp = tid / kLanes;
+    const unsigned gmask = 0xffffu << ((tid & 31) & ~(kLanes - 1));   // this list's lanes inside the warp
+    for (int l0 = 0; l0 < n_lists; l0 += 4 * kChunkLists) {
+        if (s_cnt > kCandCap - 4 * kChunkLists * kLanes) compact();   // uniform: s_cnt is read after a barrier
+        const u64 tau = s_tau;
+        u64 first[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const int li = l0 + u * kChunkLists + grp;
+            first[u] = (li < n_lists && sub < klist) ? lists[((int64_t)li * nq + q) * kp + sub] : kMaxKey;
+        }
+        bool more = false;
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const bool take = first[u] <= tau && first[u] != kMaxKey;
+            if (take) cand[atomicAdd(&s_cnt, 1)] = first[u];
+            more |= __all_sync(gmask, take) && kLanes < klist;         // whole block below the bound: the list goes on
+        }
+        __syncthreads();
+        if (__syncthreads_or(more)) {                                  // rare: loose bound or long runs in one list
+            for (int u = 0; u < 4; ++u) {
+                const int li = l0 + u * kChunkLists + grp;
+                for (int b0 = kLanes; b0 < klist; b0 += kLanes) {      // uniform trip count; appends <= 16 lists x 16 per pass
+                    if (s_cnt > kCandCap - kChunkLists * kLanes) compact();
+                    const u64 t2 = s_tau;
+                    const u64 key = (li < n_lists && b0 + sub < klist) ? lists[((int64_t)li * nq + q) * kp + b0 + sub] : kMaxKey;
+                    if (key <= t2 && key != kMaxKey) cand[atomicAdd(&s_cnt, 1)] = key;
+                    __syncthreads();
+                }
+            }
+        }
+    }
+    compact();
+    const int c = s_cnt;
+    if (tau_out != nullptr) {
+        if (tid == 0) tau_out[q] = c >= k ? cand[k - 1] : kMaxKey;
+        return;
+    }
+    for (int i = tid; i < k; i += kTT) {
+        const u64 key = i < c ? cand[i] : kMaxKey;
+        if (key == kMaxKey) {
+            dist_out[(int64_t)q * k + i] = __int_as_float(0x7f800000);
+            idx_out[(int64_t)q * k + i] = -1;
+        } else {
+            dist_out[(int64_t)q * k + i] = __uint_as_float((uint32_t)(key >> 32));
+            idx_out[(int64_t)q * k + i] = idx_base + (int64_t)(uint32_t)key;
+        }
     }
 }
 
@@ -217,26 +443,38 @@ static int next_pow2(int x) {
 }
 
 struct KnnPlan {
-    int kp, tiles, slices, group;
-    int64_t rows_per_slice;
-    int levels;
-    int64_t lists[8];   // list count entering each merge level
+    int kp, qt, tiles, slices;
+    int64_t groups_per_slice;      // 32-row groups per CTA of the main scan
+    bool stream;                   // streaming kernel (supported width) or the generic fallback
+    // sampled pre-pass (streaming kernel only, large catalogs): every pre_gstride-th group, pre_slices CTAs per tile
+    int pre_slices;
+    int64_t pre_gstride, pre_groups_per_slice;
 };
 
-static int make_plan(int64_t n, int nq, int k, KnnPlan *p) {
+constexpr int64_t kPrepassMinRows = 1 << 18;      // below this the local filters are good enough
+constexpr int64_t kPrepassSampleRows = 1 << 16;
+
+static int make_plan(int64_t n, int32_t d, int nq, int k, KnnPlan *p) {
     p->kp = std::max(next_pow2(k), 32);
-    p->tiles = (int)ceil_div(nq, kQT);
-    int64_t want = std::max<int64_t>(1, ceil_div(2 * (int64_t)sm_count(), p->tiles));
-    int64_t rows = round_up(ceil_div(std::max<int64_t>(n, 1), want), kTT);
-    p->rows_per_slice = rows;
-    p->slices = (int)std::max<int64_t>(1, ceil_div(n, rows));
-    p->group = std::max(2, kMergeMaxKeys / p->kp);
-    p->levels = 0;
-    int64_t cur = p->slices;
-    do {
-        p->lists[p->levels++] = cur;
-        cur = ceil_div(cur, p->group);
-    } while (cur > 1 && p->levels < 8);
+    p->stream = stream_supported(d);
+    p->qt = (p->stream && nq == 1) ? 1 : kQT;
+    p->tiles = (int)ceil_div(nq, p->qt);
+    // CTAs resident at once: the single-query streaming kernel fits 2 per SM, everything else 1 per SM
+    const int64_t resident = (p->stream && p->qt == kQT ? 1 : 2) * (int64_t)sm_count();
+    const int64_t want = std::max<int64_t>(1, ceil_div(resident, p->tiles));
+    const int64_t groups = ceil_div(std::max<int64_t>(n, 1), 32);
+    p->groups_per_slice = round_up(ceil_div(groups, want), 8);          // whole CTA rounds (8 warps x 1 group)
+    p->slices = (int)std::max<int64_t>(1, ceil_div(groups, p->groups_per_slice));
+    p->pre_slices = 0;
+    p->pre_gstride = 1;
+    p->pre_groups_per_slice = 0;
+    if (p->stream && n >= kPrepassMinRows && k <= kPrepassSampleRows / 64) {
+        p->pre_gstride = std::max<int64_t>(2, n / kPrepassSampleRows);
+        const int64_t pre_groups = ceil_div(n, 32 * p->pre_gstride);
+        // 512-row slices (two CTA rounds, one 512-key sort each; >= 2k rows so every list is full)
+        p->pre_groups_per_slice = std::max<int64_t>(16, round_up(ceil_div(2 * (int64_t)k, 32), 8));
+        p->pre_slices = (int)ceil_div(pre_groups, p->pre_groups_per_slice);
+    }
     return DCNR_OK;
 }
 
@@ -253,13 +491,56 @@ extern "C" int dcnr_knn_normalize(const float *in, float *out, int64_t n, int32_
 }
 
 extern "C" int64_t dcnr_knn_scratch_bytes(int64_t n, int32_t d, int32_t n_queries, int32_t k) {
-    (void)d;
     if (n_queries <= 0 || k <= 0) return 256;
     KnnPlan p;
-    make_plan(n, n_queries, k, &p);
-    int64_t bytes = 0;
-    for (int l = 0; l < p.levels; ++l) bytes += round_up(p.lists[l] * n_queries * (int64_t)p.kp * 8, 256);
+    make_plan(n, d, n_queries, k, &p);
+    int64_t bytes = round_up((int64_t)p.slices * n_queries * (int64_t)p.kp * 8, 256);
+    bytes += round_up((int64_t)std::max(p.pre_slices, 1) * n_queries * (int64_t)p.kp * 8, 256);
+    bytes += round_up((int64_t)n_queries * 8, 256);
     return bytes + 256;
+}
+
+static int launch_merge_select(const u64 *lists, int n_lists, int nq, int kp, int k, float *dist_out, int64_t *idx_out,
+                               int64_t idx_base, u64 *tau_out, cudaStream_t st) {
+    const int n_probe_sort = std::max(32, next_pow2(n_lists));
+    DCNR_REQUIRE(n_probe_sort <= 16384, "top-k merge fan-in too large (%d lists)", n_lists);
+    const size_t smem = (size_t)(kCandCap + n_probe_sort) * 8;
+    DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_knn_merge_select, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_knn_merge_select<<<(unsigned)nq, kTT, smem, st>>>(lists, n_lists, nq, kp, k, n_probe_sort, dist_out, idx_out, idx_base,
+                                                       tau_out);
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}
+
+template <int DV, int QT>
+static int launch_stream(const float *cat, int64_t n, const float *q, int nq, int k, const KnnPlan &p, int slices,
+                         int64_t groups_per_slice, int64_t gstride, const u64 *tau0, u64 *out, cudaStream_t st) {
+    constexpr int d = 4 * DV;
+    const size_t smem = stream_smem(d, QT);
+    DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_knn_stream<DV, QT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    dim3 grid((unsigned)slices, (unsigned)p.tiles);
+    k_knn_stream<DV, QT><<<grid, kTT, smem, st>>>(cat, n, q, nq, k, p.kp, groups_per_slice, gstride, stream_stages(d, QT), tau0,
+                                                  out);
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}
+
+template <int DV>
+static int launch_stream_q(const float *cat, int64_t n, const float *q, int nq, int k, const KnnPlan &p, int slices,
+                           int64_t groups_per_slice, int64_t gstride, const u64 *tau0, u64 *out, cudaStream_t st) {
+    if (p.qt == 1) return launch_stream<DV, 1>(cat, n, q, nq, k, p, slices, groups_per_slice, gstride, tau0, out, st);
+    return launch_stream<DV, kQT>(cat, n, q, nq, k, p, slices, groups_per_slice, gstride, tau0, out, st);
+}
+
+static int launch_stream_any(int d, const float *cat, int64_t n, const float *q, int nq, int k, const KnnPlan &p, int slices,
+                             int64_t groups_per_slice, int64_t gstride, const u64 *tau0, u64 *out, cudaStream_t st) {
+    switch (d) {
+        case 16: return launch_stream_q<4>(cat, n, q, nq, k, p, slices, groups_per_slice, gstride, tau0, out, st);
+        case 24: return launch_stream_q<6>(cat, n, q, nq, k, p, slices, groups_per_slice, gstride, tau0, out, st);
+        case 32: return launch_stream_q<8>(cat, n, q, nq, k, p, slices, groups_per_slice, gstride, tau0, out, st);
+        case 48: return launch_stream_q<12>(cat, n, q, nq, k, p, slices, groups_per_slice, gstride, tau0, out, st);
+        default: return launch_stream_q<16>(cat, n, q, nq, k, p, slices, groups_per_slice, gstride, tau0, out, st);
+    }
 }
 
 extern "C" int dcnr_knn_topk(const float *catalog_hat, int64_t n, int32_t d, const float *queries_hat, int32_t n_queries,
@@ -277,42 +558,32 @@ extern "C" int dcnr_knn_topk(const float *catalog_hat, int64_t n, int32_t d, con
     }
     cudaStream_t st = as_stream(stream);
     KnnPlan p;
-    make_plan(n, n_queries, k, &p);
+    make_plan(n, d, n_queries, k, &p);
     Arena ar(scratch, scratch_bytes);
-    u64 *level_buf[8];
-    for (int l = 0; l < p.levels; ++l) level_buf[l] = ar.take<u64>(p.lists[l] * n_queries * (int64_t)p.kp);
+    u64 *lists = ar.take<u64>((int64_t)p.slices * n_queries * p.kp);
+    u64 *pre_lists = ar.take<u64>((int64_t)std::max(p.pre_slices, 1) * n_queries * p.kp);
+    u64 *tau0 = ar.take<u64>(n_queries);
 
-    const size_t smem = (size_t)kQT * kCap * 8 + kQT * 8 + kQT * 4 + (size_t)kQT * d * 4;
-    dim3 grid((unsigned)p.slices, (unsigned)p.tiles);
-#define DCNR_SCAN(DVV)                                                                                              \
-    do {                                                                                                            \
-        if (smem > 48 * 1024)                                                                                       \
-            DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_knn_scan<DVV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
-        k_knn_scan<DVV><<<grid, kTT, smem, st>>>(catalog_hat, n, d, queries_hat, n_queries, k, p.kp, p.rows_per_slice, \
-                                                 level_buf[0]);                                                     \
-    } while (0)
-    if (d == 16) DCNR_SCAN(4);
-    else if (d == 32) DCNR_SCAN(8);
-    else if (d == 64) DCNR_SCAN(16);
-    else DCNR_SCAN(0);
-#undef DCNR_SCAN
-    DCNR_LAUNCHED();
-    for (int l = 0; l < p.levels; ++l) {
-        const int n_lists = (int)p.lists[l];
-        const bool last = l == p.levels - 1;
-        const int group = last ? n_lists : p.group;
-        const int n_sort = next_pow2(std::min(group, n_lists) * p.kp);
-        DCNR_REQUIRE(n_sort <= 2 * kMergeMaxKeys, "top-k merge fan-in too large");
-        const size_t msmem = (size_t)n_sort * 8;
-        if (msmem > 48 * 1024)
-            DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_knn_merge_keys, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)msmem));
-        dim3 mg((unsigned)n_queries, (unsigned)ceil_div(n_lists, group));
-        k_knn_merge_keys<<<mg, kTT, msmem, st>>>(level_buf[l], n_lists, n_queries, p.kp, k, group, n_sort,
-                                                 last ? nullptr : level_buf[l + 1], last ? dist_out : nullptr,
-                                                 last ? idx_out : nullptr, idx_base);
+    if (p.stream) {
+        const u64 *t0 = nullptr;
+        if (p.pre_slices > 0) {      // sampled pre-pass: k-th best key of ~64 K rows -> initial bound of the full scan
+            DCNR_TRY(launch_stream_any(d, catalog_hat, n, queries_hat, n_queries, k, p, p.pre_slices, p.pre_groups_per_slice,
+                                       p.pre_gstride, nullptr, pre_lists, st));
+            DCNR_TRY(launch_merge_select(pre_lists, p.pre_slices, n_queries, p.kp, k, nullptr, nullptr, 0, tau0, st));
+            t0 = tau0;
+        }
+        DCNR_TRY(launch_stream_any(d, catalog_hat, n, queries_hat, n_queries, k, p, p.slices, p.groups_per_slice, 1, t0, lists,
+                                   st));
+    } else {
+        const size_t smem = (size_t)kQT * kCap * 8 + kQT * 8 + kQT * 4 + (size_t)kQT * d * 4;
+        if (smem > 48 * 1024)
+            DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_knn_scan<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        dim3 grid((unsigned)p.slices, (unsigned)p.tiles);
+        k_knn_scan<0><<<grid, kTT, smem, st>>>(catalog_hat, n, d, queries_hat, n_queries, k, p.kp, p.groups_per_slice * 32,
+                                               lists);
         DCNR_LAUNCHED();
     }
-    return DCNR_OK;
+    return launch_merge_select(lists, p.slices, n_queries, p.kp, k, dist_out, idx_out, idx_base, nullptr, st);
 }
 
 extern "C" int dcnr_knn_merge(const float *dist_parts, const int64_t *idx_parts, int32_t n_parts, int32_t n_queries,
