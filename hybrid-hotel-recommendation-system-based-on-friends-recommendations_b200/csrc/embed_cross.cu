@@ -85,6 +85,19 @@ k_embed_cross_fwd(GatherArgs ga, const float *__restrict__ x_in, int64_t ldx_in,
     const int64_t warp_first = group0 - ((tid >> 3) & 3);
     bool bad_id = false;
 
+    // a column quad that lies inside one table segment at a 16-byte aligned offset is fetched with one id load and
+    // one 128-bit row load (user / item embeddings: 8 of the 16 quads of a P0 row); the rest goes element by element
+    int qseg[NV], qoff[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        qseg[j] = -1;
+        qoff[j] = 0;
+        if (x_in == nullptr && kind[4 * j] >= 0 && kind[4 * j] == kind[4 * j + 3] && (off[4 * j] & 3) == 0 &&
+            (ga.seg[kind[4 * j]].width & 3) == 0 && (reinterpret_cast<uintptr_t>(ga.seg[kind[4 * j]].table) & 15) == 0) {
+            qseg[j] = kind[4 * j];
+            qoff[j] = off[4 * j];
+        }
+    }
     for (int64_t base = warp_first; base < B; base += stride) {
         const int64_t row = base + ((tid >> 3) & 3);
         const bool active = row < B;
@@ -97,22 +110,40 @@ k_embed_cross_fwd(GatherArgs ga, const float *__restrict__ x_in, int64_t ldx_in,
             }
         } else {
 #pragma unroll
-            for (int k = 0; k < NE; ++k) {
-                float v = 0.f;
-                if (active) {
-                    if (kind[k] >= 0) {
-                        const SmemSeg &s = sseg[kind[k]];
+            for (int j = 0; j < NV; ++j) {
+                if (qseg[j] >= 0) {
+                    float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (active) {
+                        const SmemSeg &s = sseg[qseg[j]];
                         int64_t id = __ldg(s.ids + row * s.id_stride);
                         if ((uint64_t)id >= (uint64_t)s.rows) {
                             bad_id = true;
                             id = 0;
                         }
-                        v = __ldg(s.table + id * s.width + off[k]);
-                    } else if (kind[k] == -1) {
-                        v = __ldg(ga.num + row * ga.n_num + off[k]);
+                        v4 = ldg4(s.table + id * s.width + qoff[j]);
                     }
+                    x[4 * j] = v4.x; x[4 * j + 1] = v4.y; x[4 * j + 2] = v4.z; x[4 * j + 3] = v4.w;
+                    continue;
                 }
-                x[k] = v;
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const int k = 4 * j + e;
+                    float v = 0.f;
+                    if (active) {
+                        if (kind[k] >= 0) {
+                            const SmemSeg &s = sseg[kind[k]];
+                            int64_t id = __ldg(s.ids + row * s.id_stride);
+                            if ((uint64_t)id >= (uint64_t)s.rows) {
+                                bad_id = true;
+                                id = 0;
+                            }
+                            v = __ldg(s.table + id * s.width + off[k]);
+                        } else if (kind[k] == -1) {
+                            v = __ldg(ga.num + row * ga.n_num + off[k]);
+                        }
+                    }
+                    x[k] = v;
+                }
             }
             if (x0_out != nullptr && active) {
                 if (x0_vec) {
