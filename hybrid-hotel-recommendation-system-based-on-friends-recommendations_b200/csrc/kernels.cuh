@@ -88,6 +88,11 @@ int gemm_any(int precision, const float *A, int64_t lda, bool a_kmajor, const fl
 // true when gemm_any would run this forward GEMM on the tensor-core kernel (so a FusedDot may be passed)
 bool gemm_any_uses_tc(int precision, int64_t lda, int64_t ldc, int64_t m, int64_t n, int64_t k, const WeightOp *wop,
                       int64_t ldb);
+// tcgen05 weight gradient (gemm_wgrad_tc.cu): dW[n, k] = dy^T x with both operands MN-major, per-slab partials
+bool wgrad_tc_supported(int precision, int64_t lddy, int64_t ldx, int64_t m, int32_t n, int32_t k);
+int wgrad_tc_slabs(int64_t m, int32_t n);
+int launch_wgrad_tc(int precision, const float *dy, int64_t lddy, const float *x, int64_t ldx, float *slabs, int64_t m,
+                    int32_t n, int32_t k, cudaStream_t stream);
 int64_t wgrad_scratch_floats(int64_t m, int32_t n, int32_t k);
 // dW[n, 0:k_valid] (ld lddw) = dy^T x over k (padded) columns; db = column sums of dy (may be NULL)
 int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const float *x, int64_t ldx, float *dw,

@@ -77,7 +77,9 @@ int wgrad_splits(int64_t m, int32_t n, int32_t k) {
 }
 
 int64_t wgrad_scratch_floats(int64_t m, int32_t n, int32_t k) {
-    return (int64_t)wgrad_splits(m, n, k) * n * (int64_t)round_up(k, 4) + bn_scratch_floats(m, n);
+    int64_t slabs = wgrad_splits(m, n, k);
+    if (n % 128 == 0 && k % 32 == 0) slabs = std::max<int64_t>(slabs, wgrad_tc_slabs(m, n));   // tensor-core path
+    return slabs * n * (int64_t)round_up(k, 4) + bn_scratch_floats(m, n);
 }
 
 int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const float *x, int64_t ldx, float *dw,
@@ -86,8 +88,13 @@ int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const floa
     // dW[n_out, k_in] = sum_b dy[b, n_out] * x[b, k_in] : both operands have the reduction index as the row
     const int splits = wgrad_splits(m, n, k);
     float *slabs = scratch;                                           // [splits][n][k]
-    float *colsum_scratch = scratch + (int64_t)splits * n * (int64_t)round_up(k, 4);
-    if (dw != nullptr) {
+    float *colsum_scratch = scratch + wgrad_scratch_floats(m, n, k) - bn_scratch_floats(m, n);
+    if (precision == DCNR_PREC_BF16) precision = DCNR_PREC_TF32;
+    if (dw != nullptr && wgrad_tc_supported(precision, lddy, ldx, m, n, k)) {
+        // tcgen05 path: MN-major operands straight from dy / x, one [n, k] partial per batch slab, slabs added in order
+        DCNR_TRY(launch_wgrad_tc(precision, dy, lddy, x, ldx, slabs, m, n, k, stream));
+        DCNR_TRY(launch_sum_partials_2d(slabs, wgrad_tc_slabs(m, n), n, k, k_valid, dw, lddw, stream));
+    } else if (dw != nullptr) {
         GemmEpilogue none{nullptr, nullptr, nullptr, 0, 0};
         if (splits == 1 && k_valid == k) {
             DCNR_TRY(gemm_any(precision, dy, lddy, false, x, ldx, false, dw, lddw, n, k, m, 1, none, stream));

@@ -35,25 +35,40 @@ int sm_count() {
     return cached;
 }
 
-// One thread per output column; partial rows are added in ascending order in double so the
-// result does not depend on how the producing grid was scheduled.
-__global__ void k_sum_partials(const float *__restrict__ partials, int64_t n_partials, int64_t ld, SegPtrs seg) {
-    int s = blockIdx.y;
-    if (s >= seg.n || seg.out[s] == nullptr) return;
-    int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= seg.len[s]) return;
-    const float *p = partials + seg.offset[s] + c;
+// 32 columns x 8 slices per CTA: slice y adds its contiguous range of partial rows in ascending order in double,
+// then the 8 slice sums are added in slice order -- a fixed association, so the result does not depend on how the
+// producing grid was scheduled.  (One thread per column over ALL partials was a 20 us latency chain per call.)
+constexpr int kSumSlices = 8;
+__global__ void __launch_bounds__(32 * kSumSlices)
+k_sum_partials(const float *__restrict__ partials, int64_t n_partials, int64_t ld, SegPtrs seg) {
+    __shared__ double sh[kSumSlices][33];
+    const int s = blockIdx.y;
+    if (s >= seg.n || seg.out[s] == nullptr) return;                 // CTA-uniform
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    const int64_t per = (n_partials + kSumSlices - 1) / kSumSlices;
+    const int64_t i0 = min(n_partials, ty * per), i1 = min(n_partials, i0 + per);
     double acc = 0.0;
-    int64_t i = 0;
-    for (; i + 8 <= n_partials; i += 8) {      // 8 loads in flight, added in ascending order (same result as the plain loop)
-        float v[8];
+    if (c < seg.len[s]) {
+        const float *p = partials + seg.offset[s] + c;
+        int64_t i = i0;
+        for (; i + 8 <= i1; i += 8) {      // 8 loads in flight, added in ascending order
+            float v[8];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = __ldg(p + (i + j) * ld);
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(p + (i + j) * ld);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) acc += (double)v[j];
+            for (int j = 0; j < 8; ++j) acc += (double)v[j];
+        }
+        for (; i < i1; ++i) acc += (double)__ldg(p + i * ld);
     }
-    for (; i < n_partials; ++i) acc += (double)p[i * ld];
-    seg.out[s][c] = (float)acc;
+    sh[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < seg.len[s]) {
+        double t = sh[0][tx];
+#pragma unroll
+        for (int y = 1; y < kSumSlices; ++y) t += sh[y][tx];
+        seg.out[s][c] = (float)t;
+    }
 }
 
 int launch_sum_partials(const float *partials, int64_t n_partials, int64_t ld, const SegPtrs &seg,
@@ -62,8 +77,8 @@ int launch_sum_partials(const float *partials, int64_t n_partials, int64_t ld, c
     for (int i = 0; i < seg.n; ++i)
         if (seg.out[i] && seg.len[i] > maxlen) maxlen = seg.len[i];
     if (maxlen == 0) return DCNR_OK;
-    dim3 grid((unsigned)ceil_div(maxlen, 128), (unsigned)seg.n);
-    k_sum_partials<<<grid, 128, 0, stream>>>(partials, n_partials, ld, seg);
+    dim3 grid((unsigned)ceil_div(maxlen, 32), (unsigned)seg.n);
+    k_sum_partials<<<grid, 32 * kSumSlices, 0, stream>>>(partials, n_partials, ld, seg);
     DCNR_LAUNCHED();
     return DCNR_OK;
 }
