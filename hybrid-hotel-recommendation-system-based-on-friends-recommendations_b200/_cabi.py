@@ -24,7 +24,7 @@ class Dims(Structure):
                 ("n_cross", c_int32), ("n_res", c_int32), ("in_dim", c_int32), ("in_dim_pad", c_int32),
                 ("n_users", c_int64), ("n_items", c_int64), ("cat_rows", c_int64 * MAX_CAT),
                 ("cat_width", c_int32 * MAX_CAT), ("dropout_p", c_float), ("bn_eps", c_float),
-                ("bn_momentum", c_float), ("precision", c_int32), ("reserved", c_int32)]
+                ("bn_momentum", c_float), ("precision", c_int32), ("reserved", c_int32), ("comm", c_void_p)]
 
 
 def _ptr_fields(spec):
@@ -103,6 +103,17 @@ _SIGS = {
     "dcnr_knn_topk": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p,
                               c_void_p, c_int64, c_void_p]),
     "dcnr_knn_merge": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "dcnr_comm_unique_id": (c_int, [c_void_p]),
+    "dcnr_comm_create": (c_int, [c_void_p, c_int32, c_int32, POINTER(c_void_p)]),
+    "dcnr_comm_destroy": (c_int, [c_void_p]),
+    "dcnr_comm_info": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32)]),
+    "dcnr_comm_allreduce_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
+    "dcnr_comm_allgather": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
+    "dcnr_comm_alltoallv": (c_int, [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p, POINTER(c_int64),
+                                    POINTER(c_int64), c_void_p]),
+    "dcnr_gather_rows": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p]),
+    "dcnr_scatter_rows": (c_int, [c_void_p, c_int64, c_int64, c_int32, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                  c_void_p]),
 }
 
 EXPORTS = tuple(_SIGS)
@@ -121,7 +132,7 @@ def lib():
         for name, (res, args) in _SIGS.items():
             fn = getattr(L, name)          # AttributeError here = header/library mismatch
             fn.restype, fn.argtypes = res, args
-        if L.dcnr_abi_version() != 1:
+        if L.dcnr_abi_version() != 2:
             raise RuntimeError("libdcnr_sm100a.so ABI version mismatch")
         _lib = L
     return _lib

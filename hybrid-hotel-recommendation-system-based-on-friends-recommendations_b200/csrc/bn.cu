@@ -109,17 +109,27 @@ __global__ void k_bn_stats_merge1(const double *__restrict__ pmean, const double
     if (c == 0) gcnt[blockIdx.x] = acc.n;
 }
 
-// Level 2: fold the groups in order (<= chunks / 32 of them) and emit mean / rstd / running statistics.
-// `parts` > 1: the groups of all data-parallel ranks, gathered rank by rank (SyncBN); m_total = rows over all ranks.
+// Level 2: fold the groups in order (<= chunks / 16 of them) and emit mean / rstd / running statistics.
+// Group k's (mean, M2, count) are gmean[k*stride + c], gm2[k*stride + c], gcnt[k*cnt_stride].  With pack_out != NULL
+// the folded (mean[n] | M2[n] | count) is written as doubles instead: this rank's contribution to the SyncBN
+// all-gather, whose result is folded by the same kernel with one "group" per rank (stride 2n + 2).
 __global__ void k_bn_stats_finalize(const double *__restrict__ gmean, const double *__restrict__ gm2,
-                                    const double *__restrict__ gcnt, int64_t groups, int n, float eps, float momentum,
-                                    float *__restrict__ mean_out, float *__restrict__ rstd_out, float *running_mean,
-                                    float *running_var, int64_t *nbt) {
+                                    const double *__restrict__ gcnt, int64_t groups, int64_t stride, int64_t cnt_stride,
+                                    int n, float eps, float momentum, float *__restrict__ mean_out,
+                                    float *__restrict__ rstd_out, float *running_mean, float *running_var, int64_t *nbt,
+                                    double *__restrict__ pack_out) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c == 0 && nbt != nullptr) *nbt += 1;
+    if (c == 0 && nbt != nullptr && pack_out == nullptr) *nbt += 1;
     if (c >= n) return;
     Moments acc{0.0, 0.0, 0.0};
-    for (int64_t k = 0; k < groups; ++k) merge_moments(acc, Moments{gcnt[k], gmean[k * n + c], gm2[k * n + c]});
+    for (int64_t k = 0; k < groups; ++k)
+        merge_moments(acc, Moments{gcnt[k * cnt_stride], gmean[k * stride + c], gm2[k * stride + c]});
+    if (pack_out != nullptr) {
+        pack_out[c] = acc.mean;
+        pack_out[n + c] = acc.m2;
+        if (c == 0) pack_out[2 * n] = acc.n;
+        return;
+    }
     const double m = acc.n;
     const double var_b = acc.m2 / m;
     mean_out[c] = (float)acc.mean;
@@ -131,16 +141,33 @@ __global__ void k_bn_stats_finalize(const double *__restrict__ gmean, const doub
     }
 }
 
+// SyncBN backward: pack this rank's (sum dy | sum dy*xhat | rows) as doubles; after the all-gather, add the ranks in
+// rank order and leave the global sums and 1 / global rows for k_bn_bwd_apply.
+__global__ void k_bn_bwd_pack(const float *__restrict__ sums, int n2, double rows, double *__restrict__ pack) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c < n2) pack[c] = (double)sums[c];
+    if (c == 0) pack[n2] = rows;
+}
+__global__ void k_bn_bwd_unpack(const double *__restrict__ all, int world, int n2, float *__restrict__ sums) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c > n2) return;
+    double acc = 0.0;
+    for (int r = 0; r < world; ++r) acc += all[(int64_t)r * (n2 + 2) + c];
+    sums[c] = c < n2 ? (float)acc : (float)(1.0 / acc);      // sums[n2] = 1 / global batch rows
+}
+
 int64_t bn_scratch_floats(int64_t m, int32_t n) {
     const int64_t chunks = std::max<int64_t>(ceil_div(m, kChunkRows), 1);
     const int64_t groups = ceil_div(chunks, kMergeFan);
-    // two double rows per chunk, two double rows + a count per merge group, then 2 float rows of sums
-    return chunks * 4 * (int64_t)n + groups * (4 * (int64_t)n + 2) + 4 * (int64_t)n + 64;
+    // two double rows per chunk, two double rows + a count per merge group, 2 float rows of sums (+ 1 / rows), and the
+    // SyncBN exchange buffers: (2n + 2) doubles for this rank and for each of up to kMaxWorld ranks
+    return chunks * 4 * (int64_t)n + groups * (4 * (int64_t)n + 2) + 4 * (int64_t)n + 64 +
+           2 * (int64_t)(kMaxWorld + 1) * (2 * (int64_t)n + 2);
 }
 
 int launch_bn_stats(const float *z, int64_t ldz, int64_t m, int32_t n, float eps, float momentum, float *mean,
                     float *rstd, float *running_mean, float *running_var, int64_t *nbt, float *scratch,
-                    cudaStream_t stream) {
+                    cudaStream_t stream, const void *comm) {
     DCNR_REQUIRE(n % 4 == 0 && n >= 4 && (ldz & 3) == 0, "bn: n=%d / ld must be multiples of 4", n);
     DCNR_REQUIRE(m >= 1, "bn: empty batch");
     const int64_t chunks = ceil_div(m, kChunkRows);
@@ -157,8 +184,22 @@ int launch_bn_stats(const float *z, int64_t ldz, int64_t m, int32_t n, float eps
     dim3 g1((unsigned)groups, (unsigned)ceil_div(n, 128));
     k_bn_stats_merge1<<<g1, 128, 0, stream>>>(pmean, pm2, chunks, m, n, gmean, gm2, gcnt);
     DCNR_LAUNCHED();
-    k_bn_stats_finalize<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(gmean, gm2, gcnt, groups, n, eps, momentum, mean,
-                                                                      rstd, running_mean, running_var, nbt);
+    const int world = comm_world(comm);
+    if (world > 1) {
+        DCNR_REQUIRE(world <= kMaxWorld, "data-parallel group larger than %d ranks", kMaxWorld);
+        double *mine = gcnt + groups, *all = mine + (2 * n + 2);              // exchange buffers (see bn_scratch_floats)
+        k_bn_stats_finalize<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(gmean, gm2, gcnt, groups, n, 1, n, eps, momentum,
+                                                                          nullptr, nullptr, nullptr, nullptr, nullptr, mine);
+        DCNR_LAUNCHED();
+        DCNR_TRY(comm_allgather(comm, mine, all, (2 * (int64_t)n + 2) * 8, stream));
+        k_bn_stats_finalize<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(all, all + n, all + 2 * n, world, 2 * n + 2,
+                                                                          2 * n + 2, n, eps, momentum, mean, rstd,
+                                                                          running_mean, running_var, nbt, nullptr);
+        DCNR_LAUNCHED();
+        return DCNR_OK;
+    }
+    k_bn_stats_finalize<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(gmean, gm2, gcnt, groups, n, 1, n, eps, momentum, mean,
+                                                                      rstd, running_mean, running_var, nbt, nullptr);
     DCNR_LAUNCHED();
     return DCNR_OK;
 }
@@ -275,13 +316,13 @@ k_bn_bwd_apply(const float *g, int64_t ldg, const float *__restrict__ out, int64
                const float *__restrict__ z, int64_t ldz, const float *__restrict__ mean,
                const float *__restrict__ rstd, const float *__restrict__ gamma, const float *__restrict__ sums,
                float post_scale, float *dz, int64_t lddz, float *dy_out, int64_t lddy, int64_t m, int n, int tx_n,
-               int ty_n, float *__restrict__ partials) {
+               int ty_n, float *__restrict__ partials, int global_rows) {
     extern __shared__ __align__(16) float sm[];   // [ty_n][n]
     const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
     const int64_t r0 = (int64_t)blockIdx.x * kChunkRows;
     const int64_t r1 = min(r0 + kChunkRows, m);
     const int cq = n >> 2;
-    const float inv_m = 1.f / (float)m;
+    const float inv_m = global_rows ? __ldg(sums + 2 * n) : 1.f / (float)m;     // SyncBN: sums and rows are global
     for (int q = tx; q < cq; q += tx_n) {
         const float4 mu = ldg4(mean + 4 * q), rs = ldg4(rstd + 4 * q), ga = ldg4(gamma + 4 * q);
         const float4 sa = ldg4(sums + 4 * q), sb = ldg4(sums + n + 4 * q);
@@ -318,7 +359,7 @@ k_bn_bwd_apply(const float *g, int64_t ldg, const float *__restrict__ out, int64
 int launch_bn_act_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo, const float *z, int64_t ldz,
                       const float *mean, const float *rstd, const float *gamma, float post_scale, float *dz,
                       int64_t lddz, float *dy_out, int64_t lddy, float *dgamma, float *dbeta, float *dbias,
-                      int64_t m, int32_t n, float *scratch, cudaStream_t stream) {
+                      int64_t m, int32_t n, float *scratch, cudaStream_t stream, const void *comm) {
     DCNR_REQUIRE(n % 4 == 0 && (ldg & 3) == 0 && (ldo & 3) == 0 && (ldz & 3) == 0 && (lddz & 3) == 0 &&
                      (dy_out == nullptr || (lddy & 3) == 0),
                  "bn_act_bwd: n / ld must be multiples of 4");
@@ -341,12 +382,23 @@ int launch_bn_act_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo
     seg.out[2] = dbeta;      seg.offset[2] = 0; seg.len[2] = n;
     seg.out[3] = dgamma;     seg.offset[3] = n; seg.len[3] = n;
     DCNR_TRY(launch_sum_partials(partials, chunks, 2 * (int64_t)n, seg, stream));
+    const int world = comm_world(comm);
+    if (world > 1) {            // dgamma / dbeta stay this rank's sums (they are all-reduced with the other gradients)
+        DCNR_REQUIRE(world <= kMaxWorld, "data-parallel group larger than %d ranks", kMaxWorld);
+        double *mine = reinterpret_cast<double *>(scratch + bn_scratch_floats(m, n) - 2 * (int64_t)(kMaxWorld + 1) * (2 * (int64_t)n + 2));
+        double *all = mine + (2 * n + 2);
+        k_bn_bwd_pack<<<(unsigned)ceil_div(2 * n + 1, 128), 128, 0, stream>>>(sums, 2 * n, (double)m, mine);
+        DCNR_LAUNCHED();
+        DCNR_TRY(comm_allgather(comm, mine, all, (2 * (int64_t)n + 2) * 8, stream));
+        k_bn_bwd_unpack<<<(unsigned)ceil_div(2 * n + 1, 128), 128, 0, stream>>>(all, world, 2 * n, sums);
+        DCNR_LAUNCHED();
+    }
     smem = (size_t)cm.ty_n * n * sizeof(float);
     if (smem > 48 * 1024)
         DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_bn_bwd_apply, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     float *p2 = dbias != nullptr ? partials : nullptr;   // pass-1 partials are dead once sums exist
     k_bn_bwd_apply<<<(unsigned)chunks, kT, smem, stream>>>(g, ldg, out, ldo, z, ldz, mean, rstd, gamma, sums, post_scale,
-                                                         dz, lddz, dy_out, lddy, m, n, cm.tx_n, cm.ty_n, p2);
+                                                         dz, lddz, dy_out, lddy, m, n, cm.tx_n, cm.ty_n, p2, world > 1 ? 1 : 0);
     DCNR_LAUNCHED();
     if (dbias != nullptr) {
         memset(&seg, 0, sizeof(seg));

@@ -241,3 +241,42 @@ extern "C" int dcnr_embed_scatter_bwd(const dcnr_dims *dims, const dcnr_batch *b
     }
     return DCNR_OK;
 }
+
+// ---- owner side of the row-sharded embedding exchange --------------------------------------------------------
+namespace dcnr {
+// one float4 (or one float when the width is not a multiple of 4) per thread; rows are contiguous so a warp
+// reads whole 64..256-byte table rows and writes a contiguous output
+template <typename T>
+__global__ void k_gather_rows(const T *__restrict__ table, int64_t rows, int wv, const int64_t *__restrict__ ids, int64_t n,
+                              T *__restrict__ out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= n * wv) return;
+    const int64_t i = e / wv;
+    const int c = (int)(e % wv);
+    int64_t id = __ldg(ids + i);
+    id = id < 0 ? 0 : (id >= rows ? rows - 1 : id);
+    out[e] = __ldg(table + id * wv + c);
+}
+}  // namespace dcnr
+
+extern "C" int dcnr_gather_rows(const float *table, int64_t rows, int32_t width, const int64_t *ids, int64_t n, float *out,
+                                dcnr_stream_t stream) {
+    DCNR_REQUIRE(table && ids && out && rows >= 1 && width >= 1, "bad argument");
+    if (n <= 0) return DCNR_OK;
+    cudaStream_t st = as_stream(stream);
+    if (width % 4 == 0 && ((reinterpret_cast<uintptr_t>(table) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+        const int wv = width / 4;
+        k_gather_rows<float4><<<(unsigned)ceil_div(n * wv, 256), 256, 0, st>>>(reinterpret_cast<const float4 *>(table), rows, wv, ids,
+                                                                            n, reinterpret_cast<float4 *>(out));
+    } else {
+        k_gather_rows<float><<<(unsigned)ceil_div(n * width, 256), 256, 0, st>>>(table, rows, width, ids, n, out);
+    }
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}
+
+extern "C" int dcnr_scatter_rows(const int64_t *ids, int64_t n, int64_t rows, int32_t width, const float *g, int64_t ldg,
+                                 float *grad_table, void *scratch, int64_t scratch_bytes, dcnr_stream_t stream) {
+    DCNR_REQUIRE(ids && g && grad_table && scratch && ldg >= width, "bad argument");
+    return launch_embed_scatter(ids, 1, n, rows, width, g, ldg, 0, grad_table, scratch, scratch_bytes, as_stream(stream));
+}

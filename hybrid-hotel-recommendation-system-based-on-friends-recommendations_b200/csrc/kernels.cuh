@@ -99,11 +99,19 @@ int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const floa
                         int64_t lddw, float *db, int64_t m, int32_t n, int32_t k, int32_t k_valid, float *scratch,
                         cudaStream_t stream);
 
+// ---- data-parallel communicator (comm.cu); `comm` is the opaque handle of dcnr_comm_create or NULL ----
+int comm_world(const void *comm);
+int comm_rank(const void *comm);
+int comm_allgather(const void *comm, const void *send, void *recv, int64_t bytes_per_rank, cudaStream_t stream);
+constexpr int kMaxWorld = 64;
+
 // ---- batch norm / elementwise (bn.cu) -------------------------------------------------------
+// `comm` != NULL: statistics (forward) and the two backward column sums are taken over the batches of ALL ranks
+// (SyncBN), so an N-rank step equals the single-device step on the concatenated batch.
 int64_t bn_scratch_floats(int64_t m, int32_t n);
 int launch_bn_stats(const float *z, int64_t ldz, int64_t m, int32_t n, float eps, float momentum, float *mean,
                     float *rstd, float *running_mean, float *running_var, int64_t *nbt, float *scratch,
-                    cudaStream_t stream);
+                    cudaStream_t stream, const void *comm = nullptr);
 int launch_bn_act_fwd(const float *z, int64_t ldz, const float *mean, const float *rstd, const float *gamma,
                       const float *beta, const float *residual, int64_t ldr, const uint8_t *keep, float drop_p,
                       uint64_t seed, uint32_t layer_tag, float *out, int64_t ldo, int64_t m, int32_t n,
@@ -111,7 +119,7 @@ int launch_bn_act_fwd(const float *z, int64_t ldz, const float *mean, const floa
 int launch_bn_act_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo, const float *z, int64_t ldz,
                       const float *mean, const float *rstd, const float *gamma, float post_scale, float *dz,
                       int64_t lddz, float *dy_out, int64_t lddy, float *dgamma, float *dbeta, float *dbias,
-                      int64_t m, int32_t n, float *scratch, cudaStream_t stream);
+                      int64_t m, int32_t n, float *scratch, cudaStream_t stream, const void *comm = nullptr);
 // eval: scale[c] = gamma*rsqrt(rv+eps), shift[c] = beta + (b_lin - rm)*scale   (folded in double)
 int launch_bn_fold(const float *gamma, const float *beta, const float *rm, const float *rv, const float *lin_bias,
                    float eps, float *scale, float *shift, int32_t n, cudaStream_t stream);

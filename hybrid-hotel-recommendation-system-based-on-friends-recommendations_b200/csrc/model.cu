@@ -254,14 +254,14 @@ extern "C" int dcnr_forward_train(const dcnr_dims *dims, const dcnr_params *para
         GemmEpilogue e1{nullptr, params->res_b1[r], nullptr, 0, 0};
         DCNR_TRY(gemm_any(prec, s.h[r], H, true, params->res_w1[r], H, true, s.z1[r], H, B, H, H, 1, e1, st, wo.get(wo.w1[r])));
         DCNR_TRY(launch_bn_stats(s.z1[r], H, B, H, dims->bn_eps, dims->bn_momentum, mean1, rstd1, params->res_rm1[r],
-                                 params->res_rv1[r], params->res_nbt1[r], s.bn_scratch, st));
+                                 params->res_rv1[r], params->res_nbt1[r], s.bn_scratch, st, dims->comm));
         const uint8_t *keep = drop_keep_mask ? drop_keep_mask + (int64_t)r * B * H : nullptr;
         DCNR_TRY(launch_bn_act_fwd(s.z1[r], H, mean1, rstd1, params->res_g1[r], params->res_be1[r], nullptr, 0, keep,
                                    dims->dropout_p, dropout_seed, (uint32_t)r, s.d1[r], H, B, H, st));
         GemmEpilogue e2{nullptr, params->res_b2[r], nullptr, 0, 0};
         DCNR_TRY(gemm_any(prec, s.d1[r], H, true, params->res_w2[r], H, true, s.z2[r], H, B, H, H, 1, e2, st, wo.get(wo.w2[r])));
         DCNR_TRY(launch_bn_stats(s.z2[r], H, B, H, dims->bn_eps, dims->bn_momentum, mean2, rstd2, params->res_rm2[r],
-                                 params->res_rv2[r], params->res_nbt2[r], s.bn_scratch, st));
+                                 params->res_rv2[r], params->res_nbt2[r], s.bn_scratch, st, dims->comm));
         DCNR_TRY(launch_bn_act_fwd(s.z2[r], H, mean2, rstd2, params->res_g2[r], params->res_be2[r], s.h[r], H, nullptr,
                                    0.f, 0, 0, s.h[r + 1], H, B, H, st));
     }
@@ -300,14 +300,14 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
         const float *mean1 = s.stats[r], *rstd1 = mean1 + H, *mean2 = mean1 + 2 * H, *rstd2 = mean1 + 3 * H;
         // out = relu(BN2(z2) + h_in): dy2 (kept in g for the identity path), dz2 -> g2
         DCNR_TRY(launch_bn_act_bwd(g, H, s.h[r + 1], H, s.z2[r], H, mean2, rstd2, params->res_g2[r], 1.f, g2, H, g, H,
-                                   grads->res_g2[r], grads->res_be2[r], grads->res_b2[r], B, H, w.bn, st));
+                                   grads->res_g2[r], grads->res_be2[r], grads->res_b2[r], B, H, w.bn, st, dims->comm));
         if (grads->res_w2[r])
             DCNR_TRY(launch_linear_wgrad(prec, g2, H, s.d1[r], H, grads->res_w2[r], H, nullptr, B, H, H, H, w.wgrad, st));
         GemmEpilogue none{nullptr, nullptr, nullptr, 0, 0};
         DCNR_TRY(gemm_any(prec, g2, H, true, params->res_w2[r], H, false, g3, H, B, H, H, 1, none, st, wt.get(wt.w2[r])));   // dd1
         // d1 = dropout(relu(BN1(z1))): dz1 in place in g3
         DCNR_TRY(launch_bn_act_bwd(g3, H, s.d1[r], H, s.z1[r], H, mean1, rstd1, params->res_g1[r], post, g3, H, nullptr,
-                                   0, grads->res_g1[r], grads->res_be1[r], grads->res_b1[r], B, H, w.bn, st));
+                                   0, grads->res_g1[r], grads->res_be1[r], grads->res_b1[r], B, H, w.bn, st, dims->comm));
         if (grads->res_w1[r])
             DCNR_TRY(launch_linear_wgrad(prec, g3, H, s.h[r], H, grads->res_w1[r], H, nullptr, B, H, H, H, w.wgrad, st));
         GemmEpilogue idn{nullptr, nullptr, g, H, 0};                                                      // + dy2

@@ -163,11 +163,18 @@ class DCN_RecSys(nn.Module):
         d.bn_eps = blk.bn1.eps if blk is not None else 1e-5
         d.bn_momentum = blk.bn1.momentum if blk is not None else 0.1
         d.precision = C.PRECISIONS[self.precision]
+        comm = getattr(self, "_comm", None)
+        d.comm = comm.handle if (comm is not None and comm.world > 1 and self.training) else None
+        rows = getattr(self, "_row_override", None)
+        if rows is not None:                     # per-sample tables (row-sharded exchange): id = batch position
+            d.n_users, d.n_items = rows[0].shape[0], rows[1].shape[0]
         return d
 
     def _ordered_params(self):
         """Parameters in the fixed order used by the autograd Function and dcnr_grads."""
-        ps = [self.user_embedding.weight, self.item_embedding.weight] + [e.weight for e in self.cat_embeddings]
+        rows = getattr(self, "_row_override", None)
+        tables = [self.user_embedding.weight, self.item_embedding.weight] if rows is None else list(rows)
+        ps = tables + [e.weight for e in self.cat_embeddings]
         ps += [self.initial_deep_layer.weight, self.initial_deep_layer.bias]
         for blk in self.res_blocks:
             ps += [blk.layer1.weight, blk.layer1.bias, blk.bn1.weight, blk.bn1.bias,
@@ -184,7 +191,7 @@ class DCN_RecSys(nn.Module):
             if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
                 raise RuntimeError("DCN_RecSys parameters must be contiguous float32 CUDA tensors "
                                    "(call model.cuda(); there is no CPU path)")
-        p.user_table, p.item_table = C.ptr(self.user_embedding.weight), C.ptr(self.item_embedding.weight)
+        p.user_table, p.item_table = C.ptr(ps[0]), C.ptr(ps[1])
         for i, e in enumerate(self.cat_embeddings):
             p.cat_table[i] = C.ptr(e.weight)
         p.w0, p.b0 = C.ptr(self.initial_deep_layer.weight), C.ptr(self.initial_deep_layer.bias)
@@ -232,6 +239,20 @@ class DCN_RecSys(nn.Module):
         cat_features = cat_features[:, :n_cat].to(torch.int64).contiguous()
         num_features = num_features.to(torch.float32).contiguous()
         return user_ids, item_ids, cat_features, num_features
+
+    def forward_rows(self, user_rows: torch.Tensor, item_rows: torch.Tensor, cat_features: torch.Tensor,
+                     num_features: torch.Tensor) -> torch.Tensor:
+        """forward() with the user / item embedding rows already fetched ([B, emb_dim] each, batch order) -- the
+        entry used by ``distributed.RowShardedDCN`` after the all-to-all exchange.  The rows act as per-sample
+        tables (id = batch position); gradients flow back into them."""
+        C.require_cuda(user_rows, item_rows)
+        B = user_rows.shape[0]
+        ar = torch.arange(B, dtype=torch.int64, device=user_rows.device)
+        self._row_override = (user_rows.contiguous(), item_rows.contiguous())
+        try:
+            return self.forward(ar, ar, cat_features, num_features)
+        finally:
+            self._row_override = None
 
     # ---- forward ---------------------------------------------------------------------------
     def forward(self, user_ids: torch.Tensor, item_ids: torch.Tensor, cat_features: torch.Tensor,

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DCNR_ABI_VERSION 1
+#define DCNR_ABI_VERSION 2
 #define DCNR_MAX_CAT 8     /* categorical tables (reference uses 2: city, hotel_type; train.py:290) */
 #define DCNR_MAX_RES 8     /* ResBlocks          (search space 1..4; train.py:183) */
 #define DCNR_MAX_CROSS 8   /* CrossLayers        (search space 1..6; train.py:182) */
@@ -71,6 +71,9 @@ typedef struct dcnr_dims {
     float bn_eps, bn_momentum;  /* nn.BatchNorm1d defaults 1e-5 / 0.1 */
     int32_t precision;          /* dcnr_precision for the dense layers */
     int32_t reserved;
+    void *comm;                 /* data-parallel group (dcnr_comm_create) or NULL.  When set, train-mode BatchNorm
+                                 * statistics and the BatchNorm backward reductions cover the batches of ALL ranks, so an
+                                 * N-rank step equals the reference's single-device step on the concatenated batch */
 } dcnr_dims;
 
 /* Parameters in the reference's state_dict layouts, fp32, device memory. */
@@ -265,6 +268,36 @@ int dcnr_knn_topk(const float *catalog_hat, int64_t n, int32_t d, const float *q
  * in the same total order, so the result does not depend on the shard count. */
 int dcnr_knn_merge(const float *dist_parts, const int64_t *idx_parts, int32_t n_parts, int32_t n_queries,
                    int32_t k, float *dist_out, int64_t *idx_out, dcnr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
+ * Data parallelism (no counterpart in the reference, which is single-process).
+ * One process per GPU; the communicator is NCCL over NVLink / NVSwitch, reached through dlopen.
+ * ------------------------------------------------------------------------------------------ */
+
+/* Rank 0 creates a 128-byte id and distributes it (e.g. torch.distributed broadcast); every rank then calls
+ * dcnr_comm_create with the same id.  The handle goes into dcnr_dims.comm and the calls below. */
+int dcnr_comm_unique_id(uint8_t *id_host /* [128] */);
+int dcnr_comm_create(const uint8_t *id_host, int32_t rank, int32_t world, void **comm_out);
+int dcnr_comm_destroy(void *comm);
+int dcnr_comm_info(const void *comm, int32_t *rank, int32_t *world);
+/* In-place sum over the ranks (gradient all-reduce after dcnr_backward). */
+int dcnr_comm_allreduce_f32(void *comm, float *buf, int64_t count, dcnr_stream_t stream);
+/* recv[r*bytes_per_rank ..] = rank r's send buffer (sparse embedding-gradient segments, top-k lists). */
+int dcnr_comm_allgather(void *comm, const void *send, void *recv, int64_t bytes_per_rank, dcnr_stream_t stream);
+/* Variable all-to-all (row-sharded embedding tables: ids to the owning rank, rows back; gradient rows to the
+ * owner in backward).  The four arrays are HOST arrays with one entry per rank (bytes / byte offsets). */
+int dcnr_comm_alltoallv(void *comm, const void *send, const int64_t *send_bytes_host, const int64_t *send_off_host,
+                        void *recv, const int64_t *recv_bytes_host, const int64_t *recv_off_host, dcnr_stream_t stream);
+
+/* out[i] = table[ids[i]] for a [rows, width] fp32 table (the owner-side lookup of a row-sharded embedding
+ * exchange; ids are LOCAL row numbers).  Bit-exact copy. */
+int dcnr_gather_rows(const float *table, int64_t rows, int32_t width, const int64_t *ids, int64_t n, float *out,
+                     dcnr_stream_t stream);
+/* Dense gradient of ONE table from per-sample gradient rows g [n, width] and LOCAL ids [n]: the sorted-segment
+ * scatter-add of dcnr_embed_scatter_bwd for a single table (owner side of the sharded exchange).
+ * scratch: dcnr_workspace_bytes(kind = 2) for a batch of n rows. */
+int dcnr_scatter_rows(const int64_t *ids, int64_t n, int64_t rows, int32_t width, const float *g, int64_t ldg,
+                      float *grad_table, void *scratch, int64_t scratch_bytes, dcnr_stream_t stream);
 
 #ifdef __cplusplus
 }
