@@ -12,8 +12,10 @@ A "step" is one pass of the ranking forward over all rows.
   roofline  the dominant kernel (the H x H dense layer of the ResBlocks) timed live
   cpu_baseline / --impl reference: the oracle port of the reference's CPU PyTorch path
             (oracle/dcnr_oracle.py, same ATen ops) on the box's host cores, bounded sample
-Extra (not part of the contract line's headline): "train" = configs[2] training step, "similarity"
-= configs[3] cosine top-k, both single-GPU-per-rank measurements with their own units.
+Extra (not part of the contract line's headline): "train" = configs[2] training step (data parallel with
+global-batch BatchNorm + NCCL gradient all-reduce when N > 1), "similarity" = configs[3] cosine top-k,
+"sharded" = configs[4] row-sharded 100 M-row tables with the all-to-all exchange, "kernels" = the HBM-bound
+kernels (gather, scatter, top-k scan) against their algorithmic bytes -- each with its own unit.
 
 N > 1 (torchrun): requests are sharded, every rank scores its own 32 768 000 rows (weak scaling),
 no collective on the data path; value = all ranks' rows / max-over-ranks time.
@@ -166,7 +168,7 @@ def reference_arm(args):
     dt = time.perf_counter() - t0
     value = rows * args.steps / dt
     sample = f"{n_req} requests x {CANDIDATES} candidates = {rows} rows per step (of {REQUESTS * CANDIDATES})"
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": "ranking_candidates_per_s", "value": value, "unit": "candidates/s",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
@@ -175,16 +177,30 @@ def reference_arm(args):
         "cpu_baseline": {"value": value, "unit": "candidates/s", "cores": torch.get_num_threads(), "kind": "port",
                          "sample": sample},
         "e2e": {"value": value, "unit": "candidates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-    }))
+    })
+
+
+def _emit(obj):
+    """The contract line goes to the process's ORIGINAL stdout; everything else that writes to fd 1 while the bench
+    runs (NCCL prints its version banner there) has been redirected to stderr by main()."""
+    os.write(_REAL_STDOUT, (json.dumps(obj) + "\n").encode())
+
+
+_REAL_STDOUT = 1
 
 
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="dcnr_b200", choices=["dcnr_b200", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("DCNR_PRECISION", "fp32"))
+    ap.add_argument("--precision", default=os.environ.get("DCNR_PRECISION", "tf32x3"),
+                    help="dense-layer arithmetic: tf32x3 (tcgen05, fp32-parity split; default), fp32 (CUDA cores), tf32")
     ap.add_argument("--requests", type=int, default=REQUESTS)
     ap.add_argument("--skip-extras", action="store_true", help="skip the train / similarity side measurements")
     args = ap.parse_args()
@@ -283,24 +299,47 @@ def main():
         "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "checksum": checksum,
     }
 
+    traffic_file = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(traffic_file):                        # dram bytes per launch of the same kernel from the ncu --set full capture
+        t = json.load(open(traffic_file)).get(args.precision)
+        if t:
+            roofline["traffic"] = t["dram_bytes_per_launch"]
+            roofline["traffic_note"] = t["note"]
     if not args.skip_extras:
-        result["train"] = bench_train(model, dev, world, rank, dist, barrier, max_over_ranks)
+        comm = None
+        if world > 1:
+            comm = dcnr_b200.distributed.Communicator()
+        result["train"] = bench_train(model, dev, world, rank, comm, barrier, max_over_ranks)
+        del model
+        torch.cuda.empty_cache()
+        result["sharded"] = bench_sharded(dev, world, rank, comm, barrier, max_over_ranks, args.precision)
+        torch.cuda.empty_cache()
         if world == 1:
             result["similarity"] = bench_similarity(dev, pk)
+            sys.path.insert(0, os.path.join(ROOT, "scripts"))
+            import kernel_probe
+            result["kernels"] = {k: {kk: vv for kk, vv in v.items() if kk != "note"} for k, v in
+                                 kernel_probe.probe(65_536, pk["hbm"]).items()}
+            result["kernels"]["how"] = ("C-ABI operator calls at the configs[2] shape (B = 65536, tables 1M x 100K), CUDA events, "
+                                        "algorithmic bytes per row from SURVEY.md 8d; hbm_frac = GB/s / measured copy bandwidth")
+        if comm is not None:
+            comm.close()
     if rank == 0 and world == 1:
         result["cpu_baseline"] = cpu_baseline()
     if rank == 0:
-        print(json.dumps(result))
+        _emit(result)
     if dist is not None:
         dist.destroy_process_group()
 
 
-def bench_train(model, dev, world, rank, dist, barrier, max_over_ranks, global_batch=65_536, steps=10):
-    """BASELINE configs[2]: P0 training step (fwd + bwd + gradient all-reduce), global batch 65 536
-    split over the ranks (strong scaling), 1 M x 100 K tables, dropout 0.6, dense embedding grads."""
+def bench_train(model, dev, world, rank, comm, barrier, max_over_ranks, global_batch=65_536, steps=10):
+    """BASELINE configs[2]: P0 training step (fwd + BCE + bwd + gradient all-reduce), global batch 65 536
+    split over the ranks (strong scaling), 1 M x 100 K tables, dropout 0.6, dense embedding grads.  With N > 1
+    the BatchNorm statistics cover the global batch (library communicator), the loss gradient is scaled by the
+    global batch and the gradients are SUMMED over ranks: the step is the single-device step on 65 536 rows."""
     import dcnr_b200
     from dcnr_b200 import _cabi as C
-    from dcnr_b200.distributed import allreduce_gradients
+    from dcnr_b200.distributed import allreduce_gradients, attach
     B = global_batch // world
     g = torch.Generator(device=dev).manual_seed(99 + rank)
     u = torch.randint(0, N_USERS, (B,), generator=g, device=dev)
@@ -309,6 +348,7 @@ def bench_train(model, dev, world, rank, dist, barrier, max_over_ranks, global_b
     x = torch.rand((B, N_NUM), generator=g, device=dev)
     y = (torch.rand(B, generator=g, device=dev) < 0.3).float()
     model.train()
+    attach(model, comm)
     params = list(model.parameters())
 
     def step():
@@ -316,31 +356,91 @@ def bench_train(model, dev, world, rank, dist, barrier, max_over_ranks, global_b
             p.grad = None
         logits = model(u, i, c, x)
         _, dl = dcnr_b200.functional.bce_with_logits(logits.detach(), y)
+        if world > 1:
+            dl = dl / world                                   # mean over the GLOBAL batch
         logits.backward(gradient=dl)
-        allreduce_gradients(params)
+        allreduce_gradients(model.parameters_to_allreduce(), comm=comm, average=False)
     C.launch_count(reset=True)
     step(); torch.cuda.synchronize()
     per_step = C.launch_count()
     secs = max_over_ranks(time_steps(step, steps, 3, barrier))
     model.eval()
+    attach(model, None)
+    flops = 3 * FLOP_PER_ROW * global_batch
     return {"metric": "train_samples_per_s", "value": global_batch * steps / secs, "unit": "samples/s",
             "global_batch": global_batch, "per_gpu_batch": B, "ms_per_step": secs / steps * 1e3, "scaling": "strong",
-            "includes": "forward + BCE + backward + NCCL gradient all-reduce (optimizer excluded)",
+            "algorithmic_tflops": flops * steps / secs / 1e12,
+            "includes": "forward + BCE + backward + NCCL all-reduce of the dense gradients; when N > 1 also global-batch "
+                        "BatchNorm and the all-gather of (id, gradient row) pairs that builds the table gradients "
+                        "(optimizer excluded)",
             "gpu_launches_per_step": per_step}
 
 
+def bench_sharded(dev, world, rank, comm, barrier, max_over_ranks, precision, global_batch=262_144, rows=100_000_000,
+                  steps=5):
+    """BASELINE configs[4]: user / item tables of 100 M rows x 16 (6.4 GB each) row-sharded over the ranks by
+    row % N, global batch 262 144 split over the ranks, forward + backward with the NCCL all-to-all exchange of
+    ids / rows / gradient rows and the owner-side sorted-segment scatter-add; dense part data parallel."""
+    import dcnr_b200
+    from dcnr_b200.distributed import Communicator, RowShardedDCN, allreduce_gradients
+    own = comm is None
+    if own:
+        comm = Communicator()                                 # world 1: no NCCL traffic, same code path
+    B = global_batch // world
+    model = RowShardedDCN(rows, rows, CAT_DIMS, N_NUM, P0, comm, precision=precision, device=dev).train()
+    with torch.no_grad():
+        model.user_table.weight.mul_(0.1); model.item_table.weight.mul_(0.1)
+    g = torch.Generator(device=dev).manual_seed(321 + rank)
+    u = torch.randint(0, rows, (B,), generator=g, device=dev)
+    i = torch.randint(0, rows, (B,), generator=g, device=dev)
+    c = torch.stack([torch.randint(0, n, (B,), generator=g, device=dev) for n in CAT_DIMS.values()], 1)
+    x = torch.rand((B, N_NUM), generator=g, device=dev)
+    y = (torch.rand(B, generator=g, device=dev) < 0.3).float()
+    dense = model.dense_parameters()
+    every = list(model.parameters())
+
+    def step():
+        for p in every:
+            p.grad = None
+        logits = model(u, i, c, x)
+        _, dl = dcnr_b200.functional.bce_with_logits(logits.detach(), y)
+        logits.backward(gradient=dl / world)
+        allreduce_gradients(dense, comm=comm, average=False)
+    secs = max_over_ranks(time_steps(step, steps, 2, barrier))
+    exch = model.user_table.last_exchange_bytes + model.item_table.last_exchange_bytes
+    out = {"metric": "sharded_train_samples_per_s", "value": global_batch * steps / secs, "unit": "samples/s",
+           "global_batch": global_batch, "per_gpu_batch": B, "table_rows": rows, "rows_per_rank": model.user_table.weight.shape[0],
+           "ms_per_step": secs / steps * 1e3, "scaling": "strong",
+           "alltoall_bytes_per_rank_fwd": exch, "includes": "ids/rows all-to-all fwd, gradient rows all-to-all + owner-side "
+           "scatter-add bwd (dense shard gradients, zero-filled every step), dense all-reduce; optimizer excluded"}
+    del model
+    if own:
+        comm.close()
+    return out
+
+
 def bench_similarity(dev, pk, n=10_000_000, d=16, k=201):
-    """BASELINE configs[3] on one GPU: cosine top-201 over a 10 M x 16 catalog (640 MB scan per query batch)."""
+    """BASELINE configs[3] on one GPU: cosine top-201 over a 10 M x 16 catalog (640 MB scan per query batch).
+    hbm_frac = one catalog read / whole-call time (normalise + scan + merge), replayed from a CUDA graph."""
     import dcnr_b200
     g = torch.Generator(device=dev).manual_seed(7)
     E = torch.randn(n, d, device=dev, generator=g)
     model = dcnr_b200.NearestNeighbors().fit(E)
     out = {}
-    for nq in (1, 32):
-        Q = E[torch.randint(0, n, (nq,), device=dev, generator=g)]
-        secs = time_steps(lambda: model.kneighbors_tensor(Q, k), 5, 2, lambda: None) / 5
-        out[f"q{nq}"] = {"ms": secs * 1e3, "pairs_per_s": nq * n / secs,
-                         "hbm_frac": (n * d * 4 * ((nq + 7) // 8)) / secs / 1e9 / pk["hbm"]}
+    for nq in (1, 8, 32):
+        Q = E[torch.randint(0, n, (nq,), device=dev, generator=g)].contiguous()
+        s = torch.cuda.Stream()
+        with torch.cuda.stream(s):
+            model.kneighbors_tensor(Q, k)
+            gr = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gr, stream=s):
+                model.kneighbors_tensor(Q, k)
+        torch.cuda.synchronize()
+        secs = time_steps(gr.replay, 10, 3, lambda: None) / 10
+        passes = 1 if nq == 1 else (nq + 7) // 8
+        out[f"q{nq}"] = {"ms": secs * 1e3, "pairs_per_s": nq * n / secs, "catalog_passes": passes,
+                         "hbm_frac": (n * d * 4) / secs / 1e9 / pk["hbm"],
+                         "hbm_frac_per_pass": passes * (n * d * 4) / secs / 1e9 / pk["hbm"]}
     return {"metric": "similarity_query_candidate_pairs_per_s", "catalog": f"{n} x {d} f32", "k": k, **out}
 
 

@@ -137,6 +137,27 @@ static int small_subs_per_cta(int64_t n_rows, int32_t width) {
 }
 static int64_t small_ctas(int64_t B, int subs) { return ceil_div(ceil_div(std::max<int64_t>(B, 1), kSubRows), subs); }
 
+__global__ void k_pack_embed_grads(const int64_t *__restrict__ user_ids, const int64_t *__restrict__ item_ids,
+                                   const float *__restrict__ dx0, int64_t lddx, int64_t B, int w2, int64_t *__restrict__ ids_out,
+                                   float *__restrict__ rows_out) {
+    const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= B * w2) return;
+    const int64_t b = e / w2;
+    const int c = (int)(e % w2);
+    rows_out[e] = __ldg(dx0 + b * lddx + c);
+    if (c == 0) ids_out[2 * b] = user_ids[b];
+    if (c == 1) ids_out[2 * b + 1] = item_ids[b];
+}
+
+int launch_pack_embed_grads(const int64_t *user_ids, const int64_t *item_ids, const float *dx0, int64_t lddx, int64_t B,
+                            int32_t emb_dim, int64_t *ids_out, float *rows_out, cudaStream_t stream) {
+    if (B <= 0) return DCNR_OK;
+    const int w2 = 2 * emb_dim;
+    k_pack_embed_grads<<<(unsigned)ceil_div(B * w2, 256), 256, 0, stream>>>(user_ids, item_ids, dx0, lddx, B, w2, ids_out, rows_out);
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}
+
 static int sort_bits(int64_t n_rows) {
     int b = 1;
     while (((int64_t)1 << b) < n_rows && b < 32) ++b;

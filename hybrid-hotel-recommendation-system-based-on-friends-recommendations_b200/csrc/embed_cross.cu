@@ -98,6 +98,24 @@ k_embed_cross_fwd(GatherArgs ga, const float *__restrict__ x_in, int64_t ldx_in,
             qoff[j] = off[4 * j];
         }
     }
+    // the element-wise metadata is only needed on the mixed quads: keep it in shared memory, not in 2 * NE registers
+    __shared__ int smeta[8][NV * 4];
+    if ((tid >> 3) == 0) {
+#pragma unroll
+        for (int k = 0; k < NE; ++k) smeta[lane8][k] = ((kind[k] + 2) & 0xff) | (off[k] << 8);
+    }
+    __syncthreads();
+    // ids of the vector quads are fetched one row AHEAD, so a row costs one exposed memory round trip (the table
+    // rows) instead of two dependent ones (id, then row)
+    int64_t idv[NV];
+    auto load_ids = [&](int64_t r, int64_t (&dst)[NV]) {
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+            dst[j] = 0;
+            if (qseg[j] >= 0 && r < B) dst[j] = __ldg(sseg[qseg[j]].ids + r * sseg[qseg[j]].id_stride);
+        }
+    };
+    if (x_in == nullptr) load_ids(warp_first + ((tid >> 3) & 3), idv);
     for (int64_t base = warp_first; base < B; base += stride) {
         const int64_t row = base + ((tid >> 3) & 3);
         const bool active = row < B;
@@ -109,13 +127,15 @@ k_embed_cross_fwd(GatherArgs ga, const float *__restrict__ x_in, int64_t ldx_in,
                 x[k] = (active && col < D) ? __ldg(x_in + row * ldx_in + col) : 0.f;
             }
         } else {
+            int64_t idn[NV];
+            load_ids(row + stride, idn);
 #pragma unroll
             for (int j = 0; j < NV; ++j) {
                 if (qseg[j] >= 0) {
                     float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
                     if (active) {
                         const SmemSeg &s = sseg[qseg[j]];
-                        int64_t id = __ldg(s.ids + row * s.id_stride);
+                        int64_t id = idv[j];
                         if ((uint64_t)id >= (uint64_t)s.rows) {
                             bad_id = true;
                             id = 0;
@@ -128,23 +148,27 @@ k_embed_cross_fwd(GatherArgs ga, const float *__restrict__ x_in, int64_t ldx_in,
 #pragma unroll
                 for (int e = 0; e < 4; ++e) {
                     const int k = 4 * j + e;
+                    const int meta = smeta[lane8][k];
+                    const int kd = (meta & 0xff) - 2, of = meta >> 8;
                     float v = 0.f;
                     if (active) {
-                        if (kind[k] >= 0) {
-                            const SmemSeg &s = sseg[kind[k]];
+                        if (kd >= 0) {
+                            const SmemSeg &s = sseg[kd];
                             int64_t id = __ldg(s.ids + row * s.id_stride);
                             if ((uint64_t)id >= (uint64_t)s.rows) {
                                 bad_id = true;
                                 id = 0;
                             }
-                            v = __ldg(s.table + id * s.width + off[k]);
-                        } else if (kind[k] == -1) {
-                            v = __ldg(ga.num + row * ga.n_num + off[k]);
+                            v = __ldg(s.table + id * s.width + of);
+                        } else if (kd == -1) {
+                            v = __ldg(ga.num + row * ga.n_num + of);
                         }
                     }
                     x[k] = v;
                 }
             }
+#pragma unroll
+            for (int j = 0; j < NV; ++j) idv[j] = idn[j];
             if (x0_out != nullptr && active) {
                 if (x0_vec) {
 #pragma unroll

@@ -78,10 +78,17 @@ struct TrainSaved {
     }
 };
 
+// true when the user / item table gradients are built from the GLOBAL batch: every rank all-gathers the (ids, gradient
+// rows) of all ranks and runs the same sorted-segment scatter-add, so the dense gradients come out identical on all
+// ranks, in the single-device summation order, for ~150 B per sample instead of a 70 MB dense all-reduce per step
+static bool dp_sparse_tables(const dcnr_dims *d) { return comm_world(d->comm) > 1 && d->dp_sparse_tables != 0; }
+
 struct BwdScratch {
     float *ga, *gb, *gc, *dx0, *cross_partials, *wgrad, *bn, *wsplit;
     void *scatter;
     int64_t scatter_bytes;
+    int64_t *pack_ids, *all_ids;       // [B][2] (user, item) of this rank / [world*B][2] of all ranks
+    float *pack_rows, *all_rows;       // [B][2E] / [world*B][2E]
     void layout(const dcnr_dims *d, int64_t B, Arena &a, bool with_scatter) {
         const int64_t H = d->hidden, Dp = d->in_dim_pad;
         ga = a.take<float>(B * H);
@@ -93,8 +100,17 @@ struct BwdScratch {
                                        wgrad_scratch_floats(B, (int32_t)H, (int32_t)Dp)));
         bn = a.take<float>(bn_scratch_floats(B, (int32_t)H));
         wsplit = a.take<float>(WeightOps::floats(d));
-        scatter_bytes = with_scatter ? scatter_scratch_bytes(B) : 0;
+        const int world = dp_sparse_tables(d) ? comm_world(d->comm) : 1;
+        scatter_bytes = with_scatter ? scatter_scratch_bytes(B * world) : 0;
         scatter = a.take<char>(scatter_bytes);
+        pack_ids = all_ids = nullptr;
+        pack_rows = all_rows = nullptr;
+        if (with_scatter && world > 1) {
+            pack_ids = a.take<int64_t>(B * 2);
+            all_ids = a.take<int64_t>(B * 2 * world);
+            pack_rows = a.take<float>(B * 2 * d->emb_dim);
+            all_rows = a.take<float>(B * 2 * d->emb_dim * world);
+        }
     }
 };
 
@@ -323,7 +339,24 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
     const CrossArgs ca = cross_args(dims, params);
     DCNR_TRY(launch_cross_bwd(s.x0p, Dp, B, ca, Dp, nullptr, 0, grad_logits, params->wf + H, w.dx0, Dp, 1, grads->cross_w,
                               grads->cross_b, grads->wf ? grads->wf + H : nullptr, w.cross_partials, st));
-    if (want_tables)
+    if (want_tables && dp_sparse_tables(dims)) {
+        // data parallel: user / item gradients from the global batch (rank-major = the concatenated batch order);
+        // the tiny categorical tables stay local and are summed by the dense gradient all-reduce
+        const int world = comm_world(dims->comm), E = dims->emb_dim;
+        DCNR_TRY(launch_pack_embed_grads(batch->user_ids, batch->item_ids, w.dx0, Dp, B, E, w.pack_ids, w.pack_rows, st));
+        DCNR_TRY(comm_allgather(dims->comm, w.pack_ids, w.all_ids, B * 2 * (int64_t)sizeof(int64_t), st));
+        DCNR_TRY(comm_allgather(dims->comm, w.pack_rows, w.all_rows, B * 2 * E * (int64_t)sizeof(float), st));
+        if (grads->user_table)
+            DCNR_TRY(launch_embed_scatter(w.all_ids, 2, B * world, dims->n_users, E, w.all_rows, 2 * E, 0, grads->user_table,
+                                          w.scatter, w.scatter_bytes, st));
+        if (grads->item_table)
+            DCNR_TRY(launch_embed_scatter(w.all_ids + 1, 2, B * world, dims->n_items, E, w.all_rows, 2 * E, E, grads->item_table,
+                                          w.scatter, w.scatter_bytes, st));
+        dcnr_grads cat_only = *grads;
+        cat_only.user_table = cat_only.item_table = nullptr;
+        DCNR_TRY(dcnr_embed_scatter_bwd(dims, batch, w.dx0, Dp, &cat_only, w.scatter, w.scatter_bytes, stream));
+    } else if (want_tables) {
         DCNR_TRY(dcnr_embed_scatter_bwd(dims, batch, w.dx0, Dp, grads, w.scatter, w.scatter_bytes, stream));
+    }
     return DCNR_OK;
 }

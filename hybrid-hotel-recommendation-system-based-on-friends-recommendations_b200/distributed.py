@@ -154,29 +154,43 @@ def owner_of(ids: torch.Tensor, world: int):
     return ids % world, ids // world
 
 
+def _gather_rows_device(shard: torch.Tensor, ids_here: torch.Tensor) -> torch.Tensor:
+    from . import _cabi as C
+    rows_here = torch.empty((ids_here.numel(), shard.shape[1]), dtype=torch.float32, device=shard.device)
+    C.check(C.lib().dcnr_gather_rows(C.ptr(shard), shard.shape[0], shard.shape[1], C.ptr(ids_here), ids_here.numel(),
+                                     C.ptr(rows_here), C.stream()))
+    return rows_here
+
+
+def exchange_lookup(comm, shard: torch.Tensor, ids: torch.Tensor, gather_rows=_gather_rows_device):
+    """Forward half of the row-sharded exchange (host logic; ``comm`` needs rank / world / allgather / alltoallv,
+    ``gather_rows(shard, local_ids)`` is the owner-side lookup -- the library kernel in the product, injectable so
+    the world_size-2 gloo tests can run this logic on CPU).  Returns (rows in batch order, plan for backward)."""
+    world, rank = comm.world, comm.rank
+    owner, local = owner_of(ids, world)
+    order = torch.sort(owner, stable=True).indices
+    counts = torch.bincount(owner, minlength=world)
+    matrix = comm.allgather(counts).cpu() if world > 1 else counts.reshape(1, 1).cpu()   # one host sync: message sizes
+    send_rows = [int(v) for v in matrix[rank]]               # ids this rank asks rank p for
+    recv_rows = [int(v) for v in matrix[:, rank]]            # ids rank p asks this rank for
+    ids_sorted = local[order].contiguous()
+    ids_here = comm.alltoallv(ids_sorted, send_rows, recv_rows) if world > 1 else ids_sorted
+    rows_here = gather_rows(shard, ids_here)
+    rows_sorted = comm.alltoallv(rows_here, recv_rows, send_rows) if world > 1 else rows_here
+    rows = torch.empty_like(rows_sorted)
+    rows[order] = rows_sorted                                # back to batch order
+    return rows, dict(order=order, ids_here=ids_here, send_rows=send_rows, recv_rows=recv_rows)
+
+
 class _LookupFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, table: "RowShardedTable", shard: torch.Tensor, ids: torch.Tensor):
-        from . import _cabi as C
-        comm = table.comm
-        world, rank = comm.world, comm.rank
-        owner, local = owner_of(ids, world)
-        order = torch.sort(owner, stable=True).indices
-        counts = torch.bincount(owner, minlength=world)
-        matrix = comm.allgather(counts).cpu() if world > 1 else counts.reshape(1, 1).cpu()
-        send_rows = [int(v) for v in matrix[rank]]               # ids this rank asks rank p for
-        recv_rows = [int(v) for v in matrix[:, rank]]            # ids rank p asks this rank for
-        ids_sorted = local[order].contiguous()
-        ids_here = comm.alltoallv(ids_sorted, send_rows, recv_rows) if world > 1 else ids_sorted
-        rows_here = torch.empty((ids_here.numel(), shard.shape[1]), dtype=torch.float32, device=shard.device)
-        C.check(C.lib().dcnr_gather_rows(C.ptr(shard), shard.shape[0], shard.shape[1], C.ptr(ids_here), ids_here.numel(),
-                                         C.ptr(rows_here), C.stream()))
-        rows_sorted = comm.alltoallv(rows_here, recv_rows, send_rows) if world > 1 else rows_here
-        rows = torch.empty_like(rows_sorted)
-        rows[order] = rows_sorted                                # back to batch order
-        ctx.table, ctx.order, ctx.ids_here = table, order, ids_here
-        ctx.send_rows, ctx.recv_rows, ctx.shard_shape = send_rows, recv_rows, tuple(shard.shape)
-        table.last_exchange_bytes = (sum(send_rows) - send_rows[rank]) * 8 + (sum(recv_rows) - recv_rows[rank]) * shard.shape[1] * 4
+        rows, plan = exchange_lookup(table.comm, shard, ids)
+        rank = table.comm.rank
+        ctx.table, ctx.order, ctx.ids_here = table, plan["order"], plan["ids_here"]
+        ctx.send_rows, ctx.recv_rows, ctx.shard_shape = plan["send_rows"], plan["recv_rows"], tuple(shard.shape)
+        table.last_exchange_bytes = ((sum(ctx.send_rows) - ctx.send_rows[rank]) * 8 +
+                                     (sum(ctx.recv_rows) - ctx.recv_rows[rank]) * shard.shape[1] * 4)
         return rows
 
     @staticmethod

@@ -165,6 +165,8 @@ class DCN_RecSys(nn.Module):
         d.precision = C.PRECISIONS[self.precision]
         comm = getattr(self, "_comm", None)
         d.comm = comm.handle if (comm is not None and comm.world > 1 and self.training) else None
+        d.dp_sparse_tables = 1 if (d.comm and getattr(self, "dp_sparse_embedding_grads", True) and
+                                   getattr(self, "_row_override", None) is None) else 0
         rows = getattr(self, "_row_override", None)
         if rows is not None:                     # per-sample tables (row-sharded exchange): id = batch position
             d.n_users, d.n_items = rows[0].shape[0], rows[1].shape[0]
@@ -239,6 +241,14 @@ class DCN_RecSys(nn.Module):
         cat_features = cat_features[:, :n_cat].to(torch.int64).contiguous()
         num_features = num_features.to(torch.float32).contiguous()
         return user_ids, item_ids, cat_features, num_features
+
+    def parameters_to_allreduce(self):
+        """Parameters whose ``.grad`` still has to be summed over the data-parallel ranks after backward(): all of
+        them, except the user / item tables when their gradients were already built from the global batch."""
+        comm = getattr(self, "_comm", None)
+        sparse = comm is not None and comm.world > 1 and getattr(self, "dp_sparse_embedding_grads", True)
+        skip = {id(self.user_embedding.weight), id(self.item_embedding.weight)} if sparse else set()
+        return [p for p in self.parameters() if id(p) not in skip]
 
     def forward_rows(self, user_rows: torch.Tensor, item_rows: torch.Tensor, cat_features: torch.Tensor,
                      num_features: torch.Tensor) -> torch.Tensor:

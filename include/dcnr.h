@@ -70,7 +70,9 @@ typedef struct dcnr_dims {
     float dropout_p;            /* nn.Dropout(p) inside each ResBlock (train.py:108) */
     float bn_eps, bn_momentum;  /* nn.BatchNorm1d defaults 1e-5 / 0.1 */
     int32_t precision;          /* dcnr_precision for the dense layers */
-    int32_t reserved;
+    int32_t dp_sparse_tables;   /* with comm: 1 = build the user / item table gradients from the all-gathered (id, gradient
+                                 * row) pairs of ALL ranks (identical dense gradients on every rank, single-device summation
+                                 * order, ~150 B per sample on the wire); 0 = local gradients, all-reduce them yourself */
     void *comm;                 /* data-parallel group (dcnr_comm_create) or NULL.  When set, train-mode BatchNorm
                                  * statistics and the BatchNorm backward reductions cover the batches of ALL ranks, so an
                                  * N-rank step equals the reference's single-device step on the concatenated batch */

@@ -76,3 +76,47 @@ def _topk_job(rank, world):
 
 def test_sharded_topk_gather_and_merge_equals_unsharded():
     assert all(_run(_topk_job))
+
+
+class _GlooComm:
+    """Same interface as distributed.Communicator, over gloo (CPU): the stand-in transport for the host logic."""
+
+    def __init__(self):
+        self.rank, self.world = dist.get_rank(), dist.get_world_size()
+
+    def allgather(self, t):
+        parts = [torch.empty_like(t) for _ in range(self.world)]
+        dist.all_gather(parts, t.contiguous())
+        return torch.stack(parts)
+
+    def alltoallv(self, send, send_rows, recv_rows):
+        outs = [torch.empty((r,) + tuple(send.shape[1:]), dtype=send.dtype) for r in recv_rows]
+        ins = list(torch.split(send.contiguous(), list(send_rows)))
+        reqs = []
+        for p in range(self.world):
+            if p == self.rank:
+                outs[p].copy_(ins[p])
+            else:
+                reqs.append(dist.isend(ins[p], p)); reqs.append(dist.irecv(outs[p], p))
+        for r in reqs:
+            r.wait()
+        return torch.cat(outs)
+
+
+def _exchange_job(rank, world):
+    torch.manual_seed(0)
+    full = torch.randn(1001, 8)                                   # odd row count: shards differ in size
+    shard = full[rank::world].contiguous()
+    g = torch.Generator().manual_seed(7 + rank)
+    ids = torch.cat([torch.randint(0, 1001, (300 + 17 * rank,), generator=g), torch.tensor([0, 1000, 1000, 5])])
+    rows, plan = D.exchange_lookup(_GlooComm(), shard, ids, gather_rows=lambda s, i: s[i])
+    ok_rows = bool(torch.equal(rows, full[ids]))
+    owner, local = D.owner_of(ids, world)
+    ok_plan = sum(plan["send_rows"]) == ids.numel() and plan["send_rows"][rank] == int((owner == rank).sum())
+    ok_local = bool((plan["ids_here"] < shard.shape[0]).all())
+    return ok_rows and ok_plan and ok_local
+
+
+def test_row_sharded_exchange_returns_the_right_rows_in_batch_order():
+    assert all(_run(_exchange_job))
+    assert all(_run(_exchange_job, world=3))

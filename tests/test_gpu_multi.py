@@ -66,7 +66,7 @@ def _worker(rank, world, port, ret):
             lo_full = run(full, slice(0, B), False)
             part = dcnr_b200.DCN_RecSys(N_USERS, N_ITEMS, CAT, N_NUM, P, precision=prec)
             lo_part = run(part, slice(b0, b1), True)
-            D.allreduce_gradients(list(part.parameters()), comm=comm, average=False)
+            D.allreduce_gradients(part.parameters_to_allreduce(), comm=comm, average=False)   # tables: already global
             errs = {"logits": _err(lo_part, lo_full[b0:b1])}
             scale = max(float(p.grad.abs().max()) for p in full.parameters())
             for (n, pf), (_, pp) in zip(full.named_parameters(), part.named_parameters()):
