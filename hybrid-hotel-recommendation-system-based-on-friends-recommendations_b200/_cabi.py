@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes
 import os
-from ctypes import POINTER, Structure, c_char_p, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_uint64, c_void_p
+from ctypes import POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint8, c_uint32, c_uint64, c_void_p
 
 import torch
 
@@ -70,8 +70,8 @@ _SIGS = {
     "dcnr_backward": (c_int, [POINTER(Dims), POINTER(Params), POINTER(Batch), c_void_p, c_void_p, c_int64,
                               POINTER(Grads), c_void_p, c_int64, c_void_p]),
     "dcnr_bce_with_logits": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p]),
-    "dcnr_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_float, c_float, c_float, c_float,
-                               c_float, c_int, c_int64, c_void_p]),
+    "dcnr_adam_step": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_double, c_double, c_double, c_double,
+                               c_double, c_int, c_int64, c_void_p]),
     "dcnr_check_ids": (c_int, [POINTER(Dims), POINTER(Batch), c_void_p, c_void_p]),
     "dcnr_embed_concat_fwd": (c_int, [POINTER(Dims), POINTER(Params), POINTER(Batch), c_void_p, c_int64, c_void_p]),
     "dcnr_embed_scatter_bwd": (c_int, [POINTER(Dims), POINTER(Batch), c_void_p, c_int64, POINTER(Grads), c_void_p,

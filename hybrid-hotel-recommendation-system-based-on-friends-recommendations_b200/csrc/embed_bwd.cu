@@ -18,15 +18,38 @@ namespace dcnr {
 
 constexpr int kWin = 32;
 
-__global__ void k_scatter_prep(const int64_t *__restrict__ ids, int64_t id_stride, int64_t B, int64_t n_rows,
+// Two tables of the same width can share ONE sort: positions B..2B-1 carry table 1's ids with bit `tbit` set, so the
+// sorted order is table 0's segments, then table 1's (tbit = 32: single table).
+struct ScatterTables {
+    float *grad[2];
+    int32_t col0[2];
+    int32_t tbit;          // key bit that selects the table (32 = one table)
+    int64_t B;             // batch rows per table
+};
+
+__global__ void k_scatter_prep(const int64_t *__restrict__ ids0, int64_t stride0, int64_t rows0,
+                               const int64_t *__restrict__ ids1, int64_t stride1, int64_t rows1, int64_t B, int tbit,
                                uint32_t *__restrict__ keys, uint32_t *__restrict__ vals) {
     const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= B) return;
-    int64_t id = ids[i * id_stride];
+    if (i >= (ids1 != nullptr ? 2 * B : B)) return;
+    const bool second = i >= B;
+    int64_t id = second ? ids1[(i - B) * stride1] : ids0[i * stride0];
+    const int64_t n_rows = second ? rows1 : rows0;
     if (id < 0) id = 0;
     if (id >= n_rows) id = n_rows - 1;     // out-of-range ids are reported by dcnr_check_ids; stay memory-safe here
-    keys[i] = (uint32_t)id;
+    keys[i] = (uint32_t)id | (second ? (1u << tbit) : 0u);
     vals[i] = (uint32_t)i;
+}
+
+__device__ __forceinline__ float *scatter_dst(const ScatterTables &t, uint32_t key, int width, int col) {
+    const uint32_t tb = t.tbit < 32 ? (key >> t.tbit) : 0u;
+    const uint32_t id = t.tbit < 32 ? (key & ((1u << t.tbit) - 1u)) : key;
+    return t.grad[tb] + (int64_t)id * width + col;
+}
+__device__ __forceinline__ float scatter_src(const ScatterTables &t, uint32_t key, uint32_t val, const float *dx0, int64_t lddx,
+                                             int col) {
+    const uint32_t tb = t.tbit < 32 ? (key >> t.tbit) : 0u;
+    return __ldg(dx0 + ((int64_t)val - (int64_t)tb * t.B) * lddx + t.col0[tb] + col);
 }
 
 // flags[w]: bit0 = first segment continues from window w-1 (head partial in carry[w][0])
@@ -34,7 +57,7 @@ __global__ void k_scatter_prep(const int64_t *__restrict__ ids, int64_t id_strid
 //           bit2 = last segment starts here and continues into window w+1 (tail partial in carry[w][1])
 __global__ void __launch_bounds__(128)
 k_scatter_window(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int64_t B, int width,
-                 const float *__restrict__ dx0, int64_t lddx, int col0, float *__restrict__ grad,
+                 const float *__restrict__ dx0, int64_t lddx, ScatterTables tabs,
                  float *__restrict__ carry, uint8_t *__restrict__ flags, int64_t n_windows) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_windows * width) return;
@@ -54,13 +77,13 @@ k_scatter_window(const uint32_t *__restrict__ keys, const uint32_t *__restrict__
                 carry[(w * 2 + 0) * width + col] = acc;
                 fl |= 1;
             } else {
-                grad[(int64_t)cur * width + col] = acc;
+                *scatter_dst(tabs, cur, width, col) = acc;
             }
             cur = id;
             acc = 0.f;
             first = false;
         }
-        acc += __ldg(dx0 + (int64_t)vals[p] * lddx + col0 + col);
+        acc += scatter_src(tabs, id, vals[p], dx0, lddx, col);
     }
     const bool left_open = first && has_left && cur == left_id;
     const bool right_open = has_right && cur == right_id;
@@ -72,13 +95,13 @@ k_scatter_window(const uint32_t *__restrict__ keys, const uint32_t *__restrict__
         carry[(w * 2 + 1) * width + col] = acc;
         fl |= 4;
     } else {
-        grad[(int64_t)cur * width + col] = acc;
+        *scatter_dst(tabs, cur, width, col) = acc;
     }
     if (col == 0) flags[w] = fl;
 }
 
 __global__ void __launch_bounds__(128)
-k_scatter_fixup(const uint32_t *__restrict__ keys, int64_t B, int width, float *__restrict__ grad,
+k_scatter_fixup(const uint32_t *__restrict__ keys, int64_t B, int width, ScatterTables tabs,
                 const float *__restrict__ carry, const uint8_t *__restrict__ flags, int64_t n_windows) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= n_windows * width) return;
@@ -92,7 +115,7 @@ k_scatter_fixup(const uint32_t *__restrict__ keys, int64_t B, int width, float *
         acc += carry[(w2 * 2 + 0) * width + col];
         if (!(flags[w2] & 2)) break;
     }
-    grad[(int64_t)id * width + col] = acc;
+    *scatter_dst(tabs, id, width, col) = acc;
 }
 
 // ---- tiny tables (city: 100 rows, hotel_type: 6 rows => thousands of duplicates per row) -----------------------
@@ -117,10 +140,22 @@ k_scatter_small(const int64_t *__restrict__ ids, int64_t id_stride, int64_t B, i
     if (s < subs_per_cta) {
         const int64_t b0 = ((int64_t)blockIdx.x * subs_per_cta + s) * kSubRows, b1 = min(B, b0 + kSubRows);
         float *mine = tab + (size_t)s * tsz + j;
-        for (int64_t b = b0; b < b1; ++b) {
-            int64_t id = __ldg(ids + b * id_stride);
-            id = id < 0 ? 0 : (id >= n_rows ? n_rows - 1 : id);      // dcnr_check_ids reports bad ids; stay memory-safe
-            mine[id * width] += __ldg(dx0 + b * lddx + col0 + j);
+        for (int64_t bb = b0; bb < b1; bb += 8) {                    // 8 (id, value) pairs in flight, added in batch order
+            int64_t id[8];
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int64_t b = min(bb + q, b1 - 1);
+                id[q] = __ldg(ids + b * id_stride);
+                v[q] = __ldg(dx0 + b * lddx + col0 + j);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (bb + q < b1) {
+                    const int64_t r = id[q] < 0 ? 0 : (id[q] >= n_rows ? n_rows - 1 : id[q]);   // dcnr_check_ids reports bad ids
+                    mine[r * width] += v[q];
+                }
+            }
         }
     }
     __syncthreads();
@@ -181,6 +216,51 @@ int64_t scatter_scratch_bytes(int64_t B) {
     return bytes;      // (the tiny-table path's partial tables need <= 32 B per batch row: they reuse this space)
 }
 
+// Sorted-segment path for one table, or for two tables of equal width sharing one radix sort (ids1 != NULL).
+static int launch_scatter_sorted(const int64_t *ids0, int64_t stride0, int64_t rows0, float *grad0, int32_t col0,
+                                 const int64_t *ids1, int64_t stride1, int64_t rows1, float *grad1, int32_t col1, int64_t B,
+                                 int32_t width, const float *dx0, int64_t lddx, void *scratch, int64_t scratch_bytes,
+                                 cudaStream_t stream) {
+    const bool two = ids1 != nullptr;
+    const int64_t n = two ? 2 * B : B;
+    DCNR_REQUIRE(n < 0x7fffffffLL, "batch too large for one scatter");
+    if (scratch_bytes < scatter_scratch_bytes(n)) {
+        set_error("scatter scratch too small (%lld < %lld)", (long long)scratch_bytes, (long long)scatter_scratch_bytes(n));
+        return DCNR_ERR_WORKSPACE;
+    }
+    int tbit = 32;
+    if (two) {
+        tbit = std::max(sort_bits(rows0), sort_bits(rows1));
+        DCNR_REQUIRE(tbit < 32, "tables too large to share a sort");
+    }
+    Arena ar(scratch, scratch_bytes);
+    const int64_t n_windows = ceil_div(n, kWin);
+    uint32_t *k0 = ar.take<uint32_t>(n), *k1 = ar.take<uint32_t>(n);
+    uint32_t *v0 = ar.take<uint32_t>(n), *v1 = ar.take<uint32_t>(n);
+    float *carry = ar.take<float>(n_windows * 2 * 256);
+    uint8_t *flags = ar.take<uint8_t>(n_windows);
+    const int64_t temp_bytes = cub_temp_bytes(n);
+    void *temp = ar.take<char>(temp_bytes);
+
+    k_scatter_prep<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(ids0, stride0, rows0, ids1, stride1, rows1, B, tbit, k0, v0);
+    DCNR_LAUNCHED();
+    cub::DoubleBuffer<uint32_t> kb(k0, k1), vb(v0, v1);
+    size_t tb = (size_t)temp_bytes;
+    DCNR_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(temp, tb, kb, vb, (int)n, 0, two ? tbit + 1 : sort_bits(rows0), stream));
+    count_launch(3);
+    ScatterTables tabs;
+    tabs.grad[0] = grad0; tabs.grad[1] = two ? grad1 : grad0;
+    tabs.col0[0] = col0; tabs.col0[1] = two ? col1 : col0;
+    tabs.tbit = tbit; tabs.B = B;
+    const int64_t threads = n_windows * width;
+    k_scatter_window<<<(unsigned)ceil_div(threads, 128), 128, 0, stream>>>(kb.Current(), vb.Current(), n, width, dx0, lddx, tabs,
+                                                                         carry, flags, n_windows);
+    DCNR_LAUNCHED();
+    k_scatter_fixup<<<(unsigned)ceil_div(threads, 128), 128, 0, stream>>>(kb.Current(), n, width, tabs, carry, flags, n_windows);
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}
+
 int launch_embed_scatter(const int64_t *ids, int64_t id_stride, int64_t B, int64_t n_rows, int32_t width,
                          const float *dx0, int64_t lddx, int32_t col0, float *grad_table, void *scratch,
                          int64_t scratch_bytes, cudaStream_t stream) {
@@ -205,34 +285,29 @@ int launch_embed_scatter(const int64_t *ids, int64_t id_stride, int64_t B, int64
     }
     DCNR_CUDA_CHECK(cudaMemsetAsync(grad_table, 0, (size_t)n_rows * width * sizeof(float), stream));
     if (B <= 0) return DCNR_OK;
-    DCNR_REQUIRE(B < 0x7fffffffLL, "batch too large for one scatter");
-    if (scratch_bytes < scatter_scratch_bytes(B)) {
-        set_error("scatter scratch too small (%lld < %lld)", (long long)scratch_bytes, (long long)scatter_scratch_bytes(B));
-        return DCNR_ERR_WORKSPACE;
-    }
-    Arena ar(scratch, scratch_bytes);
-    const int64_t n_windows = ceil_div(B, kWin);
-    uint32_t *k0 = ar.take<uint32_t>(B), *k1 = ar.take<uint32_t>(B);
-    uint32_t *v0 = ar.take<uint32_t>(B), *v1 = ar.take<uint32_t>(B);
-    float *carry = ar.take<float>(n_windows * 2 * 256);
-    uint8_t *flags = ar.take<uint8_t>(n_windows);
-    const int64_t temp_bytes = cub_temp_bytes(B);
-    void *temp = ar.take<char>(temp_bytes);
+    return launch_scatter_sorted(ids, id_stride, n_rows, grad_table, col0, nullptr, 0, 0, nullptr, 0, B, width, dx0, lddx, scratch,
+                                 scratch_bytes, stream);
+}
 
-    k_scatter_prep<<<(unsigned)ceil_div(B, 256), 256, 0, stream>>>(ids, id_stride, B, n_rows, k0, v0);
-    DCNR_LAUNCHED();
-    cub::DoubleBuffer<uint32_t> kb(k0, k1), vb(v0, v1);
-    size_t tb = (size_t)temp_bytes;
-    DCNR_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(temp, tb, kb, vb, (int)B, 0, sort_bits(n_rows), stream));
-    count_launch(3);
-    const int64_t threads = n_windows * width;
-    k_scatter_window<<<(unsigned)ceil_div(threads, 128), 128, 0, stream>>>(kb.Current(), vb.Current(), B, width, dx0, lddx,
-                                                                         col0, grad_table, carry, flags, n_windows);
-    DCNR_LAUNCHED();
-    k_scatter_fixup<<<(unsigned)ceil_div(threads, 128), 128, 0, stream>>>(kb.Current(), B, width, grad_table, carry, flags,
-                                                                        n_windows);
-    DCNR_LAUNCHED();
-    return DCNR_OK;
+// user + item tables (same width, both too large for the tiny-table path): one shared sort
+int launch_embed_scatter_pair(const int64_t *ids0, int64_t stride0, int64_t rows0, float *grad0, int32_t col0,
+                              const int64_t *ids1, int64_t stride1, int64_t rows1, float *grad1, int32_t col1, int64_t B,
+                              int32_t width, const float *dx0, int64_t lddx, void *scratch, int64_t scratch_bytes,
+                              cudaStream_t stream) {
+    const bool shareable = grad0 != nullptr && grad1 != nullptr && B > 0 && small_subs_per_cta(rows0, width) == 0 &&
+                           small_subs_per_cta(rows1, width) == 0 && std::max(sort_bits(rows0), sort_bits(rows1)) < 31 &&
+                           2 * B < 0x7fffffffLL && scratch_bytes >= scatter_scratch_bytes(2 * B);
+    if (!shareable) {
+        if (grad0 != nullptr)
+            DCNR_TRY(launch_embed_scatter(ids0, stride0, B, rows0, width, dx0, lddx, col0, grad0, scratch, scratch_bytes, stream));
+        if (grad1 != nullptr)
+            DCNR_TRY(launch_embed_scatter(ids1, stride1, B, rows1, width, dx0, lddx, col1, grad1, scratch, scratch_bytes, stream));
+        return DCNR_OK;
+    }
+    DCNR_CUDA_CHECK(cudaMemsetAsync(grad0, 0, (size_t)rows0 * width * sizeof(float), stream));
+    DCNR_CUDA_CHECK(cudaMemsetAsync(grad1, 0, (size_t)rows1 * width * sizeof(float), stream));
+    return launch_scatter_sorted(ids0, stride0, rows0, grad0, col0, ids1, stride1, rows1, grad1, col1, B, width, dx0, lddx, scratch,
+                                 scratch_bytes, stream);
 }
 
 }  // namespace dcnr
@@ -246,12 +321,8 @@ extern "C" int dcnr_embed_scatter_bwd(const dcnr_dims *dims, const dcnr_batch *b
     DCNR_REQUIRE(lddx >= dims->in_dim, "lddx too small");
     cudaStream_t st = as_stream(stream);
     const int E = dims->emb_dim;
-    if (grads->user_table)
-        DCNR_TRY(launch_embed_scatter(batch->user_ids, 1, batch->batch, dims->n_users, E, dx0, lddx, 0, grads->user_table,
-                                      scratch, scratch_bytes, st));
-    if (grads->item_table)
-        DCNR_TRY(launch_embed_scatter(batch->item_ids, 1, batch->batch, dims->n_items, E, dx0, lddx, E, grads->item_table,
-                                      scratch, scratch_bytes, st));
+    DCNR_TRY(launch_embed_scatter_pair(batch->user_ids, 1, dims->n_users, grads->user_table, 0, batch->item_ids, 1, dims->n_items,
+                                       grads->item_table, E, batch->batch, E, dx0, lddx, scratch, scratch_bytes, st));
     int col = 2 * E;
     for (int i = 0; i < dims->n_cat; ++i) {
         if (grads->cat_table[i])

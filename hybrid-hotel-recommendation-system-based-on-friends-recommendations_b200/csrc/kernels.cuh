@@ -140,6 +140,10 @@ int launch_rowdot_bwd(const float *dlogit, const float *a, int64_t lda, const fl
 
 // ---- embedding backward (embed_bwd.cu) ----------------------------------------------------------
 int64_t scatter_scratch_bytes(int64_t B);
+int launch_embed_scatter_pair(const int64_t *ids0, int64_t stride0, int64_t rows0, float *grad0, int32_t col0,
+                              const int64_t *ids1, int64_t stride1, int64_t rows1, float *grad1, int32_t col1, int64_t B,
+                              int32_t width, const float *dx0, int64_t lddx, void *scratch, int64_t scratch_bytes,
+                              cudaStream_t stream);
 // ids_out[b] = (user_ids[b], item_ids[b]); rows_out[b] = dx0[b, 0 : 2*emb_dim]  (the payload of the sparse gradient all-gather)
 int launch_pack_embed_grads(const int64_t *user_ids, const int64_t *item_ids, const float *dx0, int64_t lddx, int64_t B,
                             int32_t emb_dim, int64_t *ids_out, float *rows_out, cudaStream_t stream);

@@ -101,7 +101,7 @@ struct BwdScratch {
         bn = a.take<float>(bn_scratch_floats(B, (int32_t)H));
         wsplit = a.take<float>(WeightOps::floats(d));
         const int world = dp_sparse_tables(d) ? comm_world(d->comm) : 1;
-        scatter_bytes = with_scatter ? scatter_scratch_bytes(B * world) : 0;
+        scatter_bytes = with_scatter ? scatter_scratch_bytes(2 * B * world) : 0;      // user + item share one sort
         scatter = a.take<char>(scatter_bytes);
         pack_ids = all_ids = nullptr;
         pack_rows = all_rows = nullptr;
@@ -346,12 +346,8 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
         DCNR_TRY(launch_pack_embed_grads(batch->user_ids, batch->item_ids, w.dx0, Dp, B, E, w.pack_ids, w.pack_rows, st));
         DCNR_TRY(comm_allgather(dims->comm, w.pack_ids, w.all_ids, B * 2 * (int64_t)sizeof(int64_t), st));
         DCNR_TRY(comm_allgather(dims->comm, w.pack_rows, w.all_rows, B * 2 * E * (int64_t)sizeof(float), st));
-        if (grads->user_table)
-            DCNR_TRY(launch_embed_scatter(w.all_ids, 2, B * world, dims->n_users, E, w.all_rows, 2 * E, 0, grads->user_table,
-                                          w.scatter, w.scatter_bytes, st));
-        if (grads->item_table)
-            DCNR_TRY(launch_embed_scatter(w.all_ids + 1, 2, B * world, dims->n_items, E, w.all_rows, 2 * E, E, grads->item_table,
-                                          w.scatter, w.scatter_bytes, st));
+        DCNR_TRY(launch_embed_scatter_pair(w.all_ids, 2, dims->n_users, grads->user_table, 0, w.all_ids + 1, 2, dims->n_items,
+                                           grads->item_table, E, B * world, E, w.all_rows, 2 * E, w.scatter, w.scatter_bytes, st));
         dcnr_grads cat_only = *grads;
         cat_only.user_table = cat_only.item_table = nullptr;
         DCNR_TRY(dcnr_embed_scatter_bwd(dims, batch, w.dx0, Dp, &cat_only, w.scatter, w.scatter_bytes, stream));

@@ -154,9 +154,10 @@ int dcnr_bce_with_logits(const float *logits, const float *labels, int64_t batch
                          float *grad_logits, float *scratch, dcnr_stream_t stream);
 
 /* One fused dense Adam (decoupled_weight_decay = 0) / AdamW (= 1) update of a flat fp32 tensor,
- * torch.optim semantics (train.py:201-204, :226); step counts from 1.   */
-int dcnr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, float lr,
-                   float beta1, float beta2, float eps, float weight_decay, int decoupled_weight_decay,
+ * torch.optim semantics (train.py:201-204, :226); step counts from 1.  The hyper-parameters are doubles (Python floats)
+ * so that 1 - beta, lr / bias_correction are formed exactly like torch forms them.   */
+int dcnr_adam_step(float *param, const float *grad, float *exp_avg, float *exp_avg_sq, int64_t n, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, int decoupled_weight_decay,
                    int64_t step, dcnr_stream_t stream);
 
 /* Sets *flag_host != 0 (and returns DCNR_ERR_INDEX) if any id is outside its table

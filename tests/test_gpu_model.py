@@ -349,3 +349,27 @@ def test_scatter_heavy_duplicates_and_order():
         ref = torch.zeros(got.shape, dtype=torch.float64)
         ref.index_add_(0, ids, dx0[:, c0:c0 + width].double())
         assert orc.max_abs_normalised(got.cpu(), ref) < 2e-6
+
+
+@pytest.mark.parametrize("decoupled,wd", [(False, 0.0), (False, 1e-4), (True, 1e-2)])
+def test_adam_step_matches_torch_optim(decoupled, wd):
+    """dcnr_adam_step == torch.optim.Adam / AdamW (train.py:201-204, :226) over several steps of one dense tensor
+    (dense semantics -- every row's moments decay every step)."""
+    import dcnr_b200
+    F_ = dcnr_b200.functional
+    g = torch.Generator(device="cuda").manual_seed(17)
+    p0 = torch.randn(10007, 16, device="cuda", generator=g) * 0.1
+    ref = torch.nn.Parameter(p0.clone())
+    opt = (torch.optim.AdamW if decoupled else torch.optim.Adam)([ref], lr=3e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=wd)
+    ours, m, v = p0.clone(), torch.zeros_like(p0), torch.zeros_like(p0)
+    for step in range(1, 6):
+        grad = torch.randn(p0.shape, device="cuda", generator=g) * (0.5 if step % 2 else 1e-3)
+        grad[::7] = 0.0                                     # untouched rows still decay their moments (dense Adam)
+        ref.grad = grad.clone()
+        opt.step()
+        F_.adam_step_(ours, grad, m, v, step, 3e-3, (0.9, 0.999), 1e-8, wd, decoupled)
+        err = float((ours - ref.detach()).abs().max() / ref.detach().abs().max())
+        assert err < 2e-6, (step, err)
+    st = opt.state[ref]
+    assert float((m - st["exp_avg"]).abs().max()) <= 1e-6 * float(st["exp_avg"].abs().max())
+    assert float((v - st["exp_avg_sq"]).abs().max()) <= 1e-6 * float(st["exp_avg_sq"].abs().max())
