@@ -325,7 +325,7 @@ def main():
         if comm is not None:
             comm.close()
     if rank == 0 and world == 1:
-        result["cpu_baseline"] = cpu_baseline()
+        result["cpu_baseline"] = cpu_baseline(dev=dev)
     if rank == 0:
         _emit(result)
     if dist is not None:
@@ -444,8 +444,11 @@ def bench_similarity(dev, pk, n=10_000_000, d=16, k=201):
     return {"metric": "similarity_query_candidate_pairs_per_s", "catalog": f"{n} x {d} f32", "k": k, **out}
 
 
-def cpu_baseline(budget_s=12.0):
-    """Oracle port of the reference's CPU path on this box's host cores, bounded sample."""
+def cpu_baseline(budget_s=12.0, dev=None):
+    """Oracle port of the reference's CPU path on this box's host cores, bounded sample.  Two side numbers ride
+    along, both with the same port (oracle/dcnr_oracle.py = the reference's ATen op sequence): the configs[0] training
+    step (B = 4096, forward + backward) on the host cores, and the ranking forward in torch EAGER on this GPU (fp32,
+    TF32 off) -- what the unmodified reference would do if its device line said cuda."""
     from oracle import dcnr_oracle as orc
     torch.set_num_threads(os.cpu_count() or 1)
     state = make_state()
@@ -457,9 +460,36 @@ def cpu_baseline(budget_s=12.0):
         while time.perf_counter() - t0 < budget_s:
             orc.forward(state, u, i, c, x, training=False); n += 1
     dt = time.perf_counter() - t0
-    return {"value": n * u.numel() / dt, "unit": "candidates/s", "cores": torch.get_num_threads(), "kind": "port",
-            "sample": f"{n} passes over {n_req} requests x {CANDIDATES} candidates ({u.numel()} rows each), {dt:.1f} s, "
-                      "torch CPU fp32, eval mode"}
+    out = {"value": n * u.numel() / dt, "unit": "candidates/s", "cores": torch.get_num_threads(), "kind": "port",
+           "sample": f"{n} passes over {n_req} requests x {CANDIDATES} candidates ({u.numel()} rows each), {dt:.1f} s, "
+                     "torch CPU fp32, eval mode"}
+    # configs[0]: training step on the host cores
+    B = 4096
+    g = torch.Generator().manual_seed(5)
+    tu = torch.randint(0, N_USERS, (B,), generator=g); ti = torch.randint(0, N_ITEMS, (B,), generator=g)
+    tc = torch.stack([torch.randint(0, k, (B,), generator=g) for k in CAT_DIMS.values()], 1)
+    tx = torch.rand(B, N_NUM, generator=g); ty = (torch.rand(B, generator=g) < 0.3).float()
+    orc.forward_backward(state, tu, ti, tc, tx, labels=ty, dropout_p=0.0)
+    t0 = time.perf_counter(); n = 0
+    while time.perf_counter() - t0 < 5.0:
+        orc.forward_backward(state, tu, ti, tc, tx, labels=ty, dropout_p=0.0); n += 1
+    dt = time.perf_counter() - t0
+    out["train_step_cpu"] = {"value": n * B / dt, "unit": "samples/s", "batch": B, "ms_per_step": dt / n * 1e3,
+                             "what": "configs[0]: forward + BCE + backward (dense table gradients), torch CPU fp32"}
+    if dev is not None:
+        try:
+            torch.backends.cuda.matmul.allow_tf32 = False
+            st = {k: v.to(dev) for k, v in state.items()}
+            gu, gi, gc, gx = synth_requests(2048, CANDIDATES, 1234, dev)          # 1 024 000 rows per pass
+            with torch.no_grad():
+                for _ in range(2):
+                    orc.forward(st, gu, gi, gc, gx, training=False)
+                secs = time_steps(lambda: orc.forward(st, gu, gi, gc, gx, training=False), 5, 1, lambda: None)
+            out["torch_eager_cuda"] = {"value": 5 * gu.numel() / secs, "unit": "candidates/s",
+                                       "what": "same port in torch eager on this GPU, fp32 (allow_tf32 = False), 1 024 000 rows per pass"}
+        except Exception as e:                                 # a baseline must never sink the bench line
+            out["torch_eager_cuda"] = {"error": str(e)[:200]}
+    return out
 
 
 if __name__ == "__main__":
