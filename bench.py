@@ -364,12 +364,25 @@ def bench_train(model, dev, world, rank, comm, barrier, max_over_ranks, global_b
     step(); torch.cuda.synchronize()
     per_step = C.launch_count()
     secs = max_over_ranks(time_steps(step, steps, 3, barrier))
+    # the same step captured once as a CUDA graph (dcnr_b200.training.GraphedTrainStep) and replayed
+    graphed = None
+    try:
+        gs = dcnr_b200.training.GraphedTrainStep(model, B, comm)
+        gs.load(u, i, c, x, y)
+        gs.capture()
+        gsecs = max_over_ranks(time_steps(lambda: gs(), 2 * steps, 3, barrier))
+        graphed = {"value": global_batch * 2 * steps / gsecs, "unit": "samples/s", "ms_per_step": gsecs / (2 * steps) * 1e3,
+                   "loss": float(gs.loss)}
+        del gs
+    except Exception as e:                                      # the eager number above stands on its own
+        graphed = {"error": str(e)[:300]}
+    model._dropout_step = None
     model.eval()
     attach(model, None)
     flops = 3 * FLOP_PER_ROW * global_batch
     return {"metric": "train_samples_per_s", "value": global_batch * steps / secs, "unit": "samples/s",
             "global_batch": global_batch, "per_gpu_batch": B, "ms_per_step": secs / steps * 1e3, "scaling": "strong",
-            "algorithmic_tflops": flops * steps / secs / 1e12,
+            "algorithmic_tflops": flops * steps / secs / 1e12, "cuda_graph": graphed,
             "includes": "forward + BCE + backward + NCCL all-reduce of the dense gradients; when N > 1 also global-batch "
                         "BatchNorm and the all-gather of (id, gradient row) pairs that builds the table gradients "
                         "(optimizer excluded)",

@@ -13,9 +13,10 @@ from .model import DCN_RecSys, CrossLayer, ResBlock
 from . import functional
 from . import serving
 from . import distributed
+from . import training
 
 __all__ = ["DCN_RecSys", "CrossLayer", "ResBlock", "NearestNeighbors", "merge_shards", "functional", "serving",
-           "distributed", "library_path", "launch_count"]
+           "distributed", "training", "library_path", "launch_count"]
 
 
 def library_path() -> str:

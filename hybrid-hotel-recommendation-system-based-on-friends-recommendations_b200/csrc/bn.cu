@@ -225,13 +225,14 @@ k_bn_act_fwd(const float *__restrict__ z, int64_t ldz, const float *__restrict__
              const float *__restrict__ rstd, const float *__restrict__ gamma, const float *__restrict__ beta,
              const float *__restrict__ residual, int64_t ldr, const uint8_t *__restrict__ keep, float drop_p,
              uint64_t seed, uint32_t layer_tag, float *__restrict__ out, int64_t ldo, int64_t m, int n, int tx_n,
-             int ty_n) {
+             int ty_n, const uint64_t *__restrict__ seed_step) {
     const int tx = threadIdx.x % tx_n, ty = threadIdx.x / tx_n;
     const int64_t r0 = (int64_t)blockIdx.x * kChunkRows;
     const int64_t r1 = min(r0 + kChunkRows, m);
     const int cq = n >> 2;
     const bool philox = keep == nullptr && drop_p > 0.f;
     const float post = (keep != nullptr || philox) ? 1.f / (1.f - drop_p) : 1.f;
+    if (seed_step != nullptr) seed += __ldg(seed_step);           // device-side step counter (CUDA-graph replays)
     const uint2 key = make_uint2((uint32_t)seed, (uint32_t)(seed >> 32));
     for (int q = tx; q < cq; q += tx_n) {
         const float4 mu = ldg4(mean + 4 * q), rs = ldg4(rstd + 4 * q), ga = ldg4(gamma + 4 * q), be = ldg4(beta + 4 * q);
@@ -263,7 +264,7 @@ k_bn_act_fwd(const float *__restrict__ z, int64_t ldz, const float *__restrict__
 int launch_bn_act_fwd(const float *z, int64_t ldz, const float *mean, const float *rstd, const float *gamma,
                       const float *beta, const float *residual, int64_t ldr, const uint8_t *keep, float drop_p,
                       uint64_t seed, uint32_t layer_tag, float *out, int64_t ldo, int64_t m, int32_t n,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, const uint64_t *seed_step) {
     DCNR_REQUIRE(n % 4 == 0 && (ldz & 3) == 0 && (ldo & 3) == 0 && (residual == nullptr || (ldr & 3) == 0),
                  "bn_act: n / ld must be multiples of 4");
     DCNR_REQUIRE(drop_p >= 0.f && drop_p < 1.f, "dropout p must be in [0,1)");
@@ -271,7 +272,7 @@ int launch_bn_act_fwd(const float *z, int64_t ldz, const float *mean, const floa
     const ColMap cm = col_map(n);
     k_bn_act_fwd<<<(unsigned)ceil_div(m, kChunkRows), kT, 0, stream>>>(z, ldz, mean, rstd, gamma, beta, residual, ldr,
                                                                      keep, drop_p, seed, layer_tag, out, ldo, m, n,
-                                                                     cm.tx_n, cm.ty_n);
+                                                                     cm.tx_n, cm.ty_n, seed_step);
     DCNR_LAUNCHED();
     return DCNR_OK;
 }
@@ -479,6 +480,13 @@ __global__ void k_pad_rows(const float *__restrict__ src, int64_t lds, float *__
     dst[(int64_t)r * ldd + c] = c < cols ? src[(int64_t)r * lds + c] : 0.f;
 }
 
+__global__ void k_inc_u64(uint64_t *p) { *p += 1; }
+int launch_inc_u64(uint64_t *p, cudaStream_t stream) {
+    k_inc_u64<<<1, 1, 0, stream>>>(p);
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}
+
 int launch_pad_rows(const float *src, int64_t lds, float *dst, int64_t ldd, int32_t rows, int32_t cols,
                     int32_t cols_pad, cudaStream_t stream) {
     const int64_t total = (int64_t)rows * cols_pad;
@@ -513,7 +521,7 @@ extern "C" int dcnr_bn_act_fwd(const float *z, int64_t ldz, const float *mean, c
                                dcnr_stream_t stream) {
     DCNR_REQUIRE(z && mean && rstd && gamma && beta && out, "null argument");
     return launch_bn_act_fwd(z, ldz, mean, rstd, gamma, beta, residual, ldr, keep, drop_p, seed, layer_tag, out, ldo, m,
-                             n, as_stream(stream));
+                             n, as_stream(stream), nullptr);
 }
 
 extern "C" int dcnr_bn_act_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo, const float *z, int64_t ldz,

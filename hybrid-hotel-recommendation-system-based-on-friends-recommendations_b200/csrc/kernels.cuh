@@ -115,7 +115,8 @@ int launch_bn_stats(const float *z, int64_t ldz, int64_t m, int32_t n, float eps
 int launch_bn_act_fwd(const float *z, int64_t ldz, const float *mean, const float *rstd, const float *gamma,
                       const float *beta, const float *residual, int64_t ldr, const uint8_t *keep, float drop_p,
                       uint64_t seed, uint32_t layer_tag, float *out, int64_t ldo, int64_t m, int32_t n,
-                      cudaStream_t stream);
+                      cudaStream_t stream, const uint64_t *seed_step = nullptr);
+int launch_inc_u64(uint64_t *p, cudaStream_t stream);
 int launch_bn_act_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo, const float *z, int64_t ldz,
                       const float *mean, const float *rstd, const float *gamma, float post_scale, float *dz,
                       int64_t lddz, float *dy_out, int64_t lddy, float *dgamma, float *dbeta, float *dbias,

@@ -273,7 +273,7 @@ extern "C" int dcnr_forward_train(const dcnr_dims *dims, const dcnr_params *para
                                  params->res_rv1[r], params->res_nbt1[r], s.bn_scratch, st, dims->comm));
         const uint8_t *keep = drop_keep_mask ? drop_keep_mask + (int64_t)r * B * H : nullptr;
         DCNR_TRY(launch_bn_act_fwd(s.z1[r], H, mean1, rstd1, params->res_g1[r], params->res_be1[r], nullptr, 0, keep,
-                                   dims->dropout_p, dropout_seed, (uint32_t)r, s.d1[r], H, B, H, st));
+                                   dims->dropout_p, dropout_seed, (uint32_t)r, s.d1[r], H, B, H, st, dims->dropout_step));
         GemmEpilogue e2{nullptr, params->res_b2[r], nullptr, 0, 0};
         DCNR_TRY(gemm_any(prec, s.d1[r], H, true, params->res_w2[r], H, true, s.z2[r], H, B, H, H, 1, e2, st, wo.get(wo.w2[r])));
         DCNR_TRY(launch_bn_stats(s.z2[r], H, B, H, dims->bn_eps, dims->bn_momentum, mean2, rstd2, params->res_rm2[r],
@@ -281,7 +281,9 @@ extern "C" int dcnr_forward_train(const dcnr_dims *dims, const dcnr_params *para
         DCNR_TRY(launch_bn_act_fwd(s.z2[r], H, mean2, rstd2, params->res_g2[r], params->res_be2[r], s.h[r], H, nullptr,
                                    0.f, 0, 0, s.h[r + 1], H, B, H, st));
     }
-    return launch_rowdot_fwd(s.h[dims->n_res], H, params->wf, s.logit_cross, params->bf, logits, B, H, st);
+    DCNR_TRY(launch_rowdot_fwd(s.h[dims->n_res], H, params->wf, s.logit_cross, params->bf, logits, B, H, st));
+    if (dims->dropout_step != nullptr) DCNR_TRY(launch_inc_u64(dims->dropout_step, st));
+    return DCNR_OK;
 }
 
 extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, const dcnr_batch *batch,

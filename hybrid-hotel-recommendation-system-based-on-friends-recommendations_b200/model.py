@@ -163,6 +163,8 @@ class DCN_RecSys(nn.Module):
         d.bn_eps = blk.bn1.eps if blk is not None else 1e-5
         d.bn_momentum = blk.bn1.momentum if blk is not None else 0.1
         d.precision = C.PRECISIONS[self.precision]
+        step = getattr(self, "_dropout_step", None)        # device counter (training.GraphedTrainStep)
+        d.dropout_step = C.ptr(step) if step is not None else None
         comm = getattr(self, "_comm", None)
         d.comm = comm.handle if (comm is not None and comm.world > 1 and self.training) else None
         d.dp_sparse_tables = 1 if (d.comm and getattr(self, "dp_sparse_embedding_grads", True) and

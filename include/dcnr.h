@@ -73,6 +73,9 @@ typedef struct dcnr_dims {
     int32_t dp_sparse_tables;   /* with comm: 1 = build the user / item table gradients from the all-gathered (id, gradient
                                  * row) pairs of ALL ranks (identical dense gradients on every rank, single-device summation
                                  * order, ~150 B per sample on the wire); 0 = local gradients, all-reduce them yourself */
+    uint64_t *dropout_step;     /* optional DEVICE counter: its value is added to dropout_seed and every dcnr_forward_train
+                                 * increments it, so a captured CUDA graph of the training step draws a fresh dropout mask
+                                 * on every replay (NULL: the seed argument alone decides the mask) */
     void *comm;                 /* data-parallel group (dcnr_comm_create) or NULL.  When set, train-mode BatchNorm
                                  * statistics and the BatchNorm backward reductions cover the batches of ALL ranks, so an
                                  * N-rank step equals the reference's single-device step on the concatenated batch */
