@@ -20,6 +20,7 @@
 // by k_split_tf32 and both halves are streamed by TMA (they stay L2 resident).
 #include <cuda.h>
 
+#include <cstdio>
 #include <cstdlib>
 
 #include "kernels.cuh"
@@ -103,6 +104,14 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *tm,
         ::"r"(dst), "l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(bar)
         : "memory");
 }
+// One lane of a fully converged warp.  The TMA / MMA issuing warps run their loops with ALL lanes (warp-uniform control
+// flow, so addresses and descriptors live in uniform registers) and only predicate the issue itself: inside an
+// `if (lane == 0)` region the compiler wraps every UTCHMMA / UTMALDG in an elect + 4x R2UR.BROADCAST loop (~90 clk per MMA).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
                  ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1), "r"(src)
@@ -127,6 +136,36 @@ __device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *tm, int c0, i
     asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
                  ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1)
                  : "memory");
+}
+// A operand from tensor memory (rows = TMEM lanes, K = 8 consecutive 32-bit columns), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma_tf32_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,"
+        "%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+        : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -175,7 +214,9 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 struct Params {
     int64_t M;
     int32_t N_total, K, block_n, terms, stages, acc_cols, acc_stages, corr_sep, tmem_cols;
+    int32_t a_tmem, a_col0;   // TF32X3: A hi / lo in a tensor-memory ring (64 columns per stage) starting at column a_col0
     int32_t num_m_tiles, num_n_tiles;
+    long long *dbg;           // DCNR_GEMM_DEBUG bit 16: clock64 stamps of CTA 0's pipeline (first 64 k-blocks)
     int32_t debug;            // timing experiments only (DCNR_GEMM_DEBUG): bit0 skip the split arithmetic, bit1 hi.hi MMA only
     float *C;                 // may be NULL when only the fused row dot is wanted
     int64_t ldc;
@@ -213,7 +254,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const bool leader = rank == 0;
     const int bn_cta = p.block_n / CTAS;                 // weight rows staged by this CTA
     const int b_tile_bytes = bn_cta * BLOCK_K * 4;
-    const int stage_bytes = (p.terms == 3 ? 2 : 1) * (A_TILE_BYTES + b_tile_bytes);
+    // stage: [A (raw -> hi)][A lo][B hi][B lo] (TF32X3), [A][B hi][B lo] (TF32X3 with A in tensor memory), [A][B] (TF32)
+    const int b_off = (p.terms == 3 && !p.a_tmem) ? 2 * A_TILE_BYTES : A_TILE_BYTES;
+    const int stage_bytes = b_off + (p.terms == 3 ? 2 : 1) * b_tile_bytes;
     const int stages = p.stages, acc_stages = p.acc_stages;
     uint8_t *epi_slots = smem + (size_t)stages * stage_bytes;            // 1024-aligned (stage sizes are multiples of 1 KB)
     uint64_t *bars = reinterpret_cast<uint64_t *>(epi_slots + kEpiBytes);
@@ -275,7 +318,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
     if (warp == 0) {
         // ---------------- TMA producer (both CTAs of a pair) ----------------
-        if (lane == 0) {
+        {
             uint32_t it = 0;
             for (int t = tile0; t < num_tiles; t += tile_step) {
                 const int m0 = (t / p.num_n_tiles) * (BLOCK_M * CTAS) + (int)rank * BLOCK_M;
@@ -286,17 +329,19 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     wait_x(empty0 + 8 * s, ph ^ 1);
                     uint8_t *st = smem + (size_t)s * stage_bytes;
                     const uint32_t fb = L_fullB0 + 8 * s;
+                    if (elect_one()) {
+                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64) p.dbg[it * 8 + 0] = clock64();
                     if (p.terms == 3) {
                         // A lands on this CTA's own barrier (its split warps wait for it), the weight halves on the leader's
                         mbar_expect_tx(fullA0 + 8 * s, (uint32_t)A_TILE_BYTES);
                         tma_load_2d(smem_u32(st), &tmA, kb * BLOCK_K, m0, fullA0 + 8 * s);
                         if (leader) mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(CTAS * 2 * b_tile_bytes));
                         if (CTAS == 2) {
-                            tma_load_2d_pair(smem_u32(st + 2 * A_TILE_BYTES), &tmBhi, kb * BLOCK_K, n0, fb);
-                            tma_load_2d_pair(smem_u32(st + 2 * A_TILE_BYTES + b_tile_bytes), &tmBlo, kb * BLOCK_K, n0, fb);
+                            tma_load_2d_pair(smem_u32(st + b_off), &tmBhi, kb * BLOCK_K, n0, fb);
+                            tma_load_2d_pair(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * BLOCK_K, n0, fb);
                         } else {
-                            tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES), &tmBhi, kb * BLOCK_K, n0, fb);
-                            tma_load_2d(smem_u32(st + 2 * A_TILE_BYTES + b_tile_bytes), &tmBlo, kb * BLOCK_K, n0, fb);
+                            tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * BLOCK_K, n0, fb);
+                            tma_load_2d(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * BLOCK_K, n0, fb);
                         }
                     } else {
                         if (leader) mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(CTAS * (A_TILE_BYTES + b_tile_bytes)));
@@ -308,17 +353,26 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             tma_load_2d(smem_u32(st + A_TILE_BYTES), &tmBhi, kb * BLOCK_K, n0, fb);
                         }
                     }
+                    }
+                    __syncwarp();
                 }
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer (leader CTA only) ----------------
-        if (lane == 0 && leader) {
+        // ---------------- MMA issuer (leader CTA only; all lanes loop, one elected lane issues) ----------------
+        if (leader) {
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(p.block_n >> 3) << 17) |
                                    ((uint32_t)((BLOCK_M * CTAS) >> 4) << 24);
-            auto mma = [&](uint32_t d, uint32_t a, uint32_t b, uint32_t acc) {
-                if (CTAS == 2) umma_tf32_pair(d, make_desc(a), make_desc(b), idesc, acc);
-                else umma_tf32(d, make_desc(a), make_desc(b), idesc, acc);
+            // descriptors are built once per operand per k-block; a k-step only adds 32 bytes (2 in the >>4 address field),
+            // which keeps the single issuing thread at a few instructions per MMA (it was ~90 clk per MMA, i.e. issue-bound
+            // for 128-column tiles and close to it for 256-column ones)
+            auto mma = [&](uint32_t d, uint64_t a, uint64_t b, uint32_t acc) {
+                if (CTAS == 2) umma_tf32_pair(d, a, b, idesc, acc);
+                else umma_tf32(d, a, b, idesc, acc);
+            };
+            auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t acc) {
+                if (CTAS == 2) umma_tf32_ts_pair(d, a, b, idesc, acc);
+                else umma_tf32_ts(d, a, b, idesc, acc);
             };
             uint32_t it = 0, tl = 0;
             for (int t = tile0; t < num_tiles; t += tile_step, ++tl) {
@@ -332,41 +386,107 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     wait_x(fullB0 + 8 * s, ph);
                     if (p.terms == 3) wait_x(ready0 + 8 * s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                    uint8_t *st = smem + (size_t)s * stage_bytes;
-                    const uint32_t a_hi = smem_u32(st);
-                    if (p.terms == 3) {
-                        const uint32_t a_lo = a_hi + A_TILE_BYTES, b_hi = a_hi + 2 * A_TILE_BYTES, b_lo = b_hi + b_tile_bytes;
+                    const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                    if (elect_one()) {
+                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64) p.dbg[it * 8 + 3] = clock64();
+                    if (p.terms == 3 && p.a_tmem) {
+                        // A hi / lo of this k-block sit in the TMEM ring slot the split warps just filled
+                        const uint32_t t_hi = tmem_base + (uint32_t)p.a_col0 + (uint32_t)s * 64u, t_lo = t_hi + 32u;
+                        const uint64_t db_hi = make_desc(a_hi + b_off), db_lo = make_desc(a_hi + b_off + b_tile_bytes);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            const uint32_t off = k * UMMA_K * 4;
-                            // lo terms first; with a separate accumulator (corr_sep) the long-running main sum
-                            // sees a third of the additions (the tensor core's fp32 accumulate truncates)
+                            const uint64_t o = (uint64_t)(k * UMMA_K * 4 >> 4);
+                            const uint32_t tk = k * UMMA_K;
                             if (p.debug & 2) {
-                                mma(d_main, a_hi + off, b_hi + off, (uint32_t)((kb | k) != 0));
+                                mma_ts(d_main, t_hi + tk, db_hi + o, (uint32_t)((kb | k) != 0));
                                 continue;
                             }
-                            mma(d_corr, a_lo + off, b_hi + off, (kb | k) != 0);
-                            mma(d_corr, a_hi + off, b_lo + off, 1);
-                            mma(d_main, a_hi + off, b_hi + off, p.corr_sep ? (uint32_t)((kb | k) != 0) : 1u);
+                            mma_ts(d_corr, t_lo + tk, db_hi + o, (kb | k) != 0);
+                            mma_ts(d_corr, t_hi + tk, db_lo + o, 1);
+                            mma_ts(d_main, t_hi + tk, db_hi + o, p.corr_sep ? (uint32_t)((kb | k) != 0) : 1u);
                         }
-                    } else {
-                        const uint32_t b_hi = a_hi + A_TILE_BYTES;
+                    } else if (p.terms == 3) {
+                        const uint64_t da_hi = make_desc(a_hi), da_lo = make_desc(a_hi + A_TILE_BYTES);
+                        const uint64_t db_hi = make_desc(a_hi + 2 * A_TILE_BYTES), db_lo = make_desc(a_hi + 2 * A_TILE_BYTES + b_tile_bytes);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            const uint32_t off = k * UMMA_K * 4;
-                            mma(d_main, a_hi + off, b_hi + off, (kb | k) != 0);
+                            const uint64_t o = (uint64_t)(k * UMMA_K * 4 >> 4);
+                            if (p.debug & 2) {
+                                mma(d_main, da_hi + o, db_hi + o, (uint32_t)((kb | k) != 0));
+                                continue;
+                            }
+                            // lo terms first; with a separate accumulator (corr_sep) the long-running main sum
+                            // sees a third of the additions (the tensor core's fp32 accumulate truncates)
+                            mma(d_corr, da_lo + o, db_hi + o, (kb | k) != 0);
+                            mma(d_corr, da_hi + o, db_lo + o, 1);
+                            mma(d_main, da_hi + o, db_hi + o, p.corr_sep ? (uint32_t)((kb | k) != 0) : 1u);
+                        }
+                    } else {
+                        const uint64_t da = make_desc(a_hi), db = make_desc(a_hi + A_TILE_BYTES);
+#pragma unroll
+                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                            const uint64_t o = (uint64_t)(k * UMMA_K * 4 >> 4);
+                            mma(d_main, da + o, db + o, (kb | k) != 0);
                         }
                     }
                     if (CTAS == 2) umma_commit_pair(empty0 + 8 * s);
                     else umma_commit(empty0 + 8 * s);
+                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64) p.dbg[it * 8 + 4] = clock64();
+                    if (kb == num_kb - 1) {                // same elected lane: the commit covers every MMA of this tile
+                        if (CTAS == 2) umma_commit_pair(tfull0 + 8 * as);
+                        else umma_commit(tfull0 + 8 * as);
+                    }
+                    }
+                    __syncwarp();
                 }
-                if (CTAS == 2) umma_commit_pair(tfull0 + 8 * as);
-                else umma_commit(tfull0 + 8 * as);
             }
         }
     } else if (warp < 6) {
         // ---------------- warps 2..5: split the landed A tile into hi / lo (TF32X3) ----------------
-        if (p.terms == 3) {
+        if (p.terms == 3 && p.a_tmem) {
+            // One thread per tile row: it reads its 128-byte row of the k-block from the swizzled TMA tile (chunk c of
+            // row r sits at position c ^ (r & 7): conflict-free), splits it and writes hi / lo straight into the TMEM
+            // operand ring (tcgen05.st: lane = row).  No hi / lo tiles in shared memory and no shared-memory operand
+            // reads for A: the shared-memory traffic that bounds the all-shared-memory variant drops by a third.
+            const int quad = warp & 3;                     // TMEM lane quadrant of this warp = rows 32*quad .. +31
+            const int r = quad * 32 + lane;
+            const uint32_t swz = (uint32_t)(r & 7);
+            uint32_t it = 0;
+            for (int t = tile0; t < num_tiles; t += tile_step) {
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1;
+                    mbar_wait(fullA0 + 8 * s, ph);
+                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) p.dbg[it * 8 + 1] = clock64();
+                    const uint8_t *row = smem + (size_t)s * stage_bytes + r * 128;
+                    uint32_t hi[32], lo[32];
+#pragma unroll
+                    for (int c = 0; c < 8; ++c) {
+                        const float4 v = *reinterpret_cast<const float4 *>(row + (((uint32_t)c ^ swz) << 4));
+                        const float e[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t u;
+                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(e[q]));
+                            hi[4 * c + q] = u;
+                            lo[4 * c + q] = __float_as_uint(e[q] - __uint_as_float(u));
+                        }
+                    }
+                    const uint32_t t_hi = tmem_base + (uint32_t)p.a_col0 + (uint32_t)s * 64u + ((uint32_t)(quad * 32) << 16);
+                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) p.dbg[it * 8 + 6] = clock64();
+                    tmem_st32(t_hi, hi);
+                    tmem_st32(t_hi + 32u, lo);
+                    asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) p.dbg[it * 8 + 2] = clock64();
+                    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CTAS == 2) mbar_arrive_cluster(L_ready0 + 8 * s);
+                        else mbar_arrive(ready0 + 8 * s);
+                    }
+                }
+            }
+        } else if (p.terms == 3) {
             const int tt = threadIdx.x - 64;               // 0..127
             uint32_t it = 0;
             for (int t = tile0; t < num_tiles; t += tile_step) {
@@ -374,6 +494,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1;
                     mbar_wait(fullA0 + 8 * s, ph);
+                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && tt == 0) p.dbg[it * 8 + 1] = clock64();
                     float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * stage_bytes);
                     float4 *lo = hi + A_TILE_BYTES / 16;
 #pragma unroll
@@ -391,8 +512,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                     // every lane publishes its writes to the async proxy, then one lane per warp arrives
                     // (128 remote arrivals per k-block from the peer CTA were a measurable part of the hop)
+                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && tt == 0) p.dbg[it * 8 + 6] = clock64();
                     if (CTAS == 2) asm volatile("fence.proxy.async;" ::: "memory");
                     else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && tt == 0) p.dbg[it * 8 + 2] = clock64();
                     __syncwarp();
                     if (lane == 0) {
                         if (CTAS == 2) mbar_arrive_cluster(L_ready0 + 8 * s);
@@ -444,6 +567,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 __syncwarp();
             }
             wait_x(tfull0 + 8 * as, (tl / acc_stages) & 1);
+            if ((p.debug & 16) && blockIdx.x == 0 && tl < 8 && threadIdx.x == 192) p.dbg[512 + tl * 2] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int mw = m0 + quad * 32;                  // first row of this warp
             const uint32_t t_main = tmem_base + as * acc_stride + ((uint32_t)(quad * 32) << 16);
@@ -499,6 +623,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                 }
             }
+            if ((p.debug & 16) && blockIdx.x == 0 && tl < 8 && threadIdx.x == 192) p.dbg[512 + tl * 2 + 1] = clock64();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) {                                // one arrival per epilogue warp frees the accumulator stage
@@ -597,16 +722,28 @@ static int make_map(CUtensorMap *tm, const float *base, int64_t rows, int64_t co
     return DCNR_OK;
 }
 
-static int pick_block_n(int64_t n) {
-    for (int bn = 256; bn >= 32; bn -= 32)       // the epilogue moves 32-column boxes
+static int pick_block_n(int64_t n, int cap = 256) {
+    for (int bn = cap; bn >= 32; bn -= 32)       // the epilogue moves 32-column boxes
         if (n % bn == 0) return bn;
     return 0;
+}
+// TF32X3 takes the A operand from tensor memory (128-column tiles, single CTAs): measured 0.79 ms per 1 M x 256 x 256
+// layer against 0.89 ms for the all-shared-memory 2-CTA form, which DCNR_GEMM_ATMEM=0 selects.
+static bool atmem_enabled() {
+    static const bool on = [] {
+        const char *e = getenv("DCNR_GEMM_ATMEM");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    return on;
+}
+static int block_n_for(int precision, int64_t n) {
+    return pick_block_n(n, (precision == DCNR_PREC_TF32X3 && atmem_enabled()) ? 128 : 256);
 }
 
 }  // namespace tc
 
-int gemm_tc_n_tiles(int64_t n) {
-    const int bn = tc::pick_block_n(n);
+int gemm_tc_n_tiles(int64_t n, int precision) {
+    const int bn = tc::block_n_for(precision, n);
     return bn > 0 ? (int)(n / bn) : 1;
 }
 
@@ -653,8 +790,10 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
                  "bias / col_scale must be 16-byte aligned");
     Params p;
     p.M = m; p.N_total = (int32_t)n; p.K = (int32_t)k;
-    p.block_n = pick_block_n(n);
+    p.block_n = block_n_for(precision, n);
     p.terms = terms;
+    p.a_tmem = (terms == 3 && atmem_enabled()) ? 1 : 0;
+    p.a_col0 = 0;
     p.C = C; p.ldc = ldc; p.epi = epi;
     p.dot_w = dot_w; p.dot_out = dot_out;
     static const int debug_bits = [] {
@@ -662,13 +801,15 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
         return e != nullptr ? atoi(e) : 0;
     }();
     p.debug = debug_bits;
+    p.dbg = nullptr;
+    static long long *dbg_buf = nullptr;
+    if (debug_bits & 16) {
+        if (dbg_buf == nullptr) cudaMalloc(&dbg_buf, 1024 * sizeof(long long));
+        cudaMemsetAsync(dbg_buf, 0, 1024 * sizeof(long long), stream);
+        p.dbg = dbg_buf;
+    }
     p.acc_cols = 32;
     while (p.acc_cols < p.block_n) p.acc_cols <<= 1;
-    p.corr_sep = (terms == 3 && 4 * p.acc_cols <= 512) ? 1 : 0;      // room for main + lo accumulators, double buffered
-    const int per_stage_cols = p.corr_sep ? 2 * p.acc_cols : p.acc_cols;
-    p.acc_stages = 2 * per_stage_cols <= 512 ? 2 : 1;
-    p.tmem_cols = 32;
-    while (p.tmem_cols < p.acc_stages * per_stage_cols) p.tmem_cols <<= 1;
     p.num_n_tiles = (int32_t)(n / p.block_n);
 
     // CTA pairs (2-CTA MMA) whenever the tile splits evenly and a pair has work; DCNR_GEMM_CTAS=1 forces single CTAs
@@ -677,15 +818,24 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
         return e != nullptr ? atoi(e) : 0;
     }();
     int ctas = m > BLOCK_M ? 2 : 1;
-    if (forced_ctas == 1) ctas = 1;
+    if (forced_ctas == 1 || (p.a_tmem && forced_ctas != 2)) ctas = 1;     // A-in-TMEM: pairs measured slower (1.06 vs 0.79 ms)
     int max_pairs = 0;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     auto plan = [&](int c, size_t *smem_out) {
-        const int stage_bytes = (terms == 3 ? 2 : 1) * (A_TILE_BYTES + (p.block_n / c) * BLOCK_K * 4);
+        const int b_bytes = (p.block_n / c) * BLOCK_K * 4;
+        const int stage_bytes = ((terms == 3 && !p.a_tmem) ? 2 : 1) * A_TILE_BYTES + (terms == 3 ? 2 : 1) * b_bytes;
         const int budget = 227 * 1024 - 1024 - kBarBytes - kEpiVecBytes - kEpiBytes;
-        p.stages = std::max(1, std::min(6, budget / stage_bytes));
+        p.stages = std::max(1, std::min(p.a_tmem ? 4 : 6, budget / stage_bytes));
         *smem_out = (size_t)p.stages * stage_bytes + 1024 + kBarBytes + kEpiVecBytes + kEpiBytes;
+        // tensor memory: accumulator stage(s) first, then (A in TMEM) the operand ring, 64 columns (hi | lo) per stage
+        const int ring_cols = p.a_tmem ? p.stages * 64 : 0;
+        p.corr_sep = (terms == 3 && 4 * p.acc_cols + ring_cols <= 512) ? 1 : 0;   // separate accumulator for the lo terms
+        const int per_stage_cols = p.corr_sep ? 2 * p.acc_cols : p.acc_cols;
+        p.acc_stages = 2 * per_stage_cols + ring_cols <= 512 ? 2 : 1;
+        p.a_col0 = p.acc_stages * per_stage_cols;
+        p.tmem_cols = 32;
+        while (p.tmem_cols < p.a_col0 + ring_cols) p.tmem_cols <<= 1;
     };
     size_t smem = 0;
     if (ctas == 2) {
@@ -725,6 +875,22 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
         k_gemm_tc<1><<<grid, kThreadsP, smem, stream>>>(tmA, tmBhi, tmBlo, tmR, tmC, p);
     }
     DCNR_LAUNCHED();
+    if (debug_bits & 16) {              // timing experiment: dump the stamps of the first two launches
+        static int dumps = 0;
+        if (dumps++ < 2) {
+            long long h[1024];
+            cudaStreamSynchronize(stream);
+            cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
+            const long long t0 = h[0];
+            fprintf(stderr, "block_n %d stages %d a_tmem %d | it: TMA issue | +landed | +split loads/math | +st or fence | MMA start | issue done\n",
+                    p.block_n, p.stages, p.a_tmem);
+            for (int i = 8; i < 40; ++i)
+                fprintf(stderr, "%2d: %8lld  +%6lld  +%6lld  +%6lld  mma@%8lld  +%5lld\n", i, h[i * 8] - t0, h[i * 8 + 1] - h[i * 8],
+                        h[i * 8 + 6] - h[i * 8 + 1], h[i * 8 + 2] - h[i * 8 + 6], h[i * 8 + 3] - t0, h[i * 8 + 4] - h[i * 8 + 3]);
+            for (int t = 0; t < 8; ++t)
+                fprintf(stderr, "epilogue tile %d: start %8lld  took %6lld\n", t, h[512 + 2 * t] - t0, h[512 + 2 * t + 1] - h[512 + 2 * t]);
+        }
+    }
     return DCNR_OK;
 }
 

@@ -49,6 +49,12 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {      
         if (!ok && spins > (1u << 24)) __trap();
     }
 }
+// one lane of a converged warp (the issuing warps loop with all lanes so descriptors stay in uniform registers)
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *tm, int c0, int c1, int c2, uint32_t bar) {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
@@ -140,20 +146,21 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
-        if (lane == 0) {
-            for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % stages;
-                mbar_wait(empty0 + 8 * s, ((kb / stages) & 1) ^ 1);
-                uint8_t *st = smem + (size_t)s * stage_bytes;
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % stages;
+            mbar_wait(empty0 + 8 * s, ((kb / stages) & 1) ^ 1);
+            uint8_t *st = smem + (size_t)s * stage_bytes;
+            const int row = (int)(b0 + (int64_t)kb * BLOCK_K);           // rows past B are zero-filled: no contribution
+            if (elect_one()) {
                 mbar_expect_tx(full0 + 8 * s, (uint32_t)(a_bytes + b_bytes));
-                const int row = (int)(b0 + (int64_t)kb * BLOCK_K);       // rows past B are zero-filled: no contribution
                 tma_load_3d(smem_u32(st), &tmA, 0, row, mt * (BLOCK_M / 32), full0 + 8 * s);
                 tma_load_3d(smem_u32(st + a_bytes), &tmB, 0, row, 0, full0 + 8 * s);
             }
+            __syncwarp();
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer ----------------
-        if (lane == 0) {
+        // ---------------- MMA issuer (all lanes loop, one elected lane issues) ----------------
+        {
             // kind::tf32, fp32 accumulate, A and B MN-major (bits 15 / 16), N = k_in, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.k_in >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
@@ -162,24 +169,29 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 const int s = kb % stages;
                 mbar_wait((p.terms == 3 ? ready0 : full0) + 8 * s, (kb / stages) & 1);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                uint8_t *st = smem + (size_t)s * stage_bytes;
-                const uint32_t a_hi = smem_u32(st), b_hi = a_hi + a_bytes, a_lo = b_hi + b_bytes, b_lo = a_lo + a_bytes;
+                const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                if (elect_one()) {
+                    const uint64_t da_hi = make_desc_mn(a_hi, lbo), db_hi = make_desc_mn(a_hi + a_bytes, lbo);
+                    const uint64_t da_lo = make_desc_mn(a_hi + a_bytes + b_bytes, lbo);
+                    const uint64_t db_lo = make_desc_mn(a_hi + 2 * a_bytes + b_bytes, lbo);
 #pragma unroll
-                for (int k = 0; k < BLOCK_K / 8; ++k) {
-                    const uint32_t off = k * 1024;                    // next 8 batch rows (two 4-row atoms) of every block
-                    const uint32_t first = (uint32_t)((kb | k) != 0);
-                    if (p.terms == 3) {
-                        umma_tf32(d_corr, make_desc_mn(a_lo + off, lbo), make_desc_mn(b_hi + off, lbo), idesc, first);
-                        umma_tf32(d_corr, make_desc_mn(a_hi + off, lbo), make_desc_mn(b_lo + off, lbo), idesc, 1);
-                        umma_tf32(d_main, make_desc_mn(a_hi + off, lbo), make_desc_mn(b_hi + off, lbo), idesc,
-                                  p.corr_sep ? first : 1u);
-                    } else {
-                        umma_tf32(d_main, make_desc_mn(a_hi + off, lbo), make_desc_mn(b_hi + off, lbo), idesc, first);
+                    for (int k = 0; k < BLOCK_K / 8; ++k) {
+                        const uint64_t o = (uint64_t)(k * 1024 >> 4);        // next 8 batch rows (two 4-row atoms) of every block
+                        const uint32_t first = (uint32_t)((kb | k) != 0);
+                        if (p.terms == 3) {
+                            umma_tf32(d_corr, da_lo + o, db_hi + o, idesc, first);
+                            umma_tf32(d_corr, da_hi + o, db_lo + o, idesc, 1);
+                            umma_tf32(d_main, da_hi + o, db_hi + o, idesc, p.corr_sep ? first : 1u);
+                        } else {
+                            umma_tf32(d_main, da_hi + o, db_hi + o, idesc, first);
+                        }
                     }
+                    umma_commit(empty0 + 8 * s);
+                    if (kb == num_kb - 1) umma_commit(done0);
                 }
-                umma_commit(empty0 + 8 * s);
+                __syncwarp();
             }
-            umma_commit(done0);
+            if (num_kb == 0 && elect_one()) umma_commit(done0);
         }
     } else {
         // ---------------- warps 2..5: split both tiles (TF32X3), then the epilogue ----------------
