@@ -189,14 +189,24 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
         : "memory");
 }
 // K-major, SWIZZLE_128B canonical layout: 8-row groups 1024 B apart (SBO), LBO unused (1), version 1.
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+// bk = floats per k-block row: 32 -> 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart;
+//                               16 ->  64-byte rows, SWIZZLE_64B,  8-row groups  512 B apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, int bk = 32) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
     d |= (uint64_t)1 << 16;                             // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset, bits [32,46)
+    d |= (uint64_t)((8 * bk * 4) >> 4) << 32;           // stride byte offset, bits [32,46)
     d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
-    d |= (uint64_t)2 << 61;                             // layout type SWIZZLE_128B
+    d |= (uint64_t)(bk == 32 ? 2 : 4) << 61;            // layout type SWIZZLE_128B / SWIZZLE_64B
     return d;
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[32], int o) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+        ::"r"(taddr), "r"(r[o]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]),
+          "r"(r[o + 7]), "r"(r[o + 8]), "r"(r[o + 9]), "r"(r[o + 10]), "r"(r[o + 11]), "r"(r[o + 12]), "r"(r[o + 13]),
+          "r"(r[o + 14]), "r"(r[o + 15])
+        : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -214,6 +224,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 struct Params {
     int64_t M;
     int32_t N_total, K, block_n, terms, stages, acc_cols, acc_stages, corr_sep, tmem_cols;
+    int32_t bk;               // floats per k-block (32, or 16 with A in tensor memory: six finer pipeline stages)
     int32_t a_tmem, a_col0;   // TF32X3: A hi / lo in a tensor-memory ring (64 columns per stage) starting at column a_col0
     int32_t num_m_tiles, num_n_tiles;
     long long *dbg;           // DCNR_GEMM_DEBUG bit 16: clock64 stamps of CTA 0's pipeline (first 64 k-blocks)
@@ -253,9 +264,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
     const int bn_cta = p.block_n / CTAS;                 // weight rows staged by this CTA
-    const int b_tile_bytes = bn_cta * BLOCK_K * 4;
+    const int bk = p.bk;                                 // floats per k-block
+    const int a_tile_bytes = BLOCK_M * bk * 4;
+    const int b_tile_bytes = bn_cta * bk * 4;
     // stage: [A (raw -> hi)][A lo][B hi][B lo] (TF32X3), [A][B hi][B lo] (TF32X3 with A in tensor memory), [A][B] (TF32)
-    const int b_off = (p.terms == 3 && !p.a_tmem) ? 2 * A_TILE_BYTES : A_TILE_BYTES;
+    const int b_off = (p.terms == 3 && !p.a_tmem) ? 2 * a_tile_bytes : a_tile_bytes;
     const int stage_bytes = b_off + (p.terms == 3 ? 2 : 1) * b_tile_bytes;
     const int stages = p.stages, acc_stages = p.acc_stages;
     uint8_t *epi_slots = smem + (size_t)stages * stage_bytes;            // 1024-aligned (stage sizes are multiples of 1 KB)
@@ -272,7 +285,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     // the same barriers in the leader CTA, as shared::cluster addresses (identity for CTAS == 1)
     const uint32_t L_fullB0 = CTAS == 2 ? mapa(fullB0, 0) : fullB0, L_ready0 = CTAS == 2 ? mapa(ready0, 0) : ready0,
                    L_tempty0 = CTAS == 2 ? mapa(tempty0, 0) : tempty0;
-    const int num_kb = p.K / BLOCK_K;
+    const int num_kb = p.K / bk;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
 
@@ -333,24 +346,24 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64) p.dbg[it * 8 + 0] = clock64();
                     if (p.terms == 3) {
                         // A lands on this CTA's own barrier (its split warps wait for it), the weight halves on the leader's
-                        mbar_expect_tx(fullA0 + 8 * s, (uint32_t)A_TILE_BYTES);
-                        tma_load_2d(smem_u32(st), &tmA, kb * BLOCK_K, m0, fullA0 + 8 * s);
+                        mbar_expect_tx(fullA0 + 8 * s, (uint32_t)a_tile_bytes);
+                        tma_load_2d(smem_u32(st), &tmA, kb * bk, m0, fullA0 + 8 * s);
                         if (leader) mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(CTAS * 2 * b_tile_bytes));
                         if (CTAS == 2) {
-                            tma_load_2d_pair(smem_u32(st + b_off), &tmBhi, kb * BLOCK_K, n0, fb);
-                            tma_load_2d_pair(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * BLOCK_K, n0, fb);
+                            tma_load_2d_pair(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fb);
+                            tma_load_2d_pair(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * bk, n0, fb);
                         } else {
-                            tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * BLOCK_K, n0, fb);
-                            tma_load_2d(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * BLOCK_K, n0, fb);
+                            tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fb);
+                            tma_load_2d(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * bk, n0, fb);
                         }
                     } else {
-                        if (leader) mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(CTAS * (A_TILE_BYTES + b_tile_bytes)));
+                        if (leader) mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(CTAS * (a_tile_bytes + b_tile_bytes)));
                         if (CTAS == 2) {
-                            tma_load_2d_pair(smem_u32(st), &tmA, kb * BLOCK_K, m0, fb);
-                            tma_load_2d_pair(smem_u32(st + A_TILE_BYTES), &tmBhi, kb * BLOCK_K, n0, fb);
+                            tma_load_2d_pair(smem_u32(st), &tmA, kb * bk, m0, fb);
+                            tma_load_2d_pair(smem_u32(st + a_tile_bytes), &tmBhi, kb * bk, n0, fb);
                         } else {
-                            tma_load_2d(smem_u32(st), &tmA, kb * BLOCK_K, m0, fb);
-                            tma_load_2d(smem_u32(st + A_TILE_BYTES), &tmBhi, kb * BLOCK_K, n0, fb);
+                            tma_load_2d(smem_u32(st), &tmA, kb * bk, m0, fb);
+                            tma_load_2d(smem_u32(st + a_tile_bytes), &tmBhi, kb * bk, n0, fb);
                         }
                     }
                     }
@@ -391,10 +404,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64) p.dbg[it * 8 + 3] = clock64();
                     if (p.terms == 3 && p.a_tmem) {
                         // A hi / lo of this k-block sit in the TMEM ring slot the split warps just filled
-                        const uint32_t t_hi = tmem_base + (uint32_t)p.a_col0 + (uint32_t)s * 64u, t_lo = t_hi + 32u;
-                        const uint64_t db_hi = make_desc(a_hi + b_off), db_lo = make_desc(a_hi + b_off + b_tile_bytes);
-#pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
+                        const uint32_t t_hi = tmem_base + (uint32_t)p.a_col0 + (uint32_t)(s * 2 * bk), t_lo = t_hi + (uint32_t)bk;
+                        const uint64_t db_hi = make_desc(a_hi + b_off, bk), db_lo = make_desc(a_hi + b_off + b_tile_bytes, bk);
+#pragma unroll 4
+                        for (int k = 0; k < bk / UMMA_K; ++k) {
                             const uint64_t o = (uint64_t)(k * UMMA_K * 4 >> 4);
                             const uint32_t tk = k * UMMA_K;
                             if (p.debug & 2) {
@@ -406,8 +419,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             mma_ts(d_main, t_hi + tk, db_hi + o, p.corr_sep ? (uint32_t)((kb | k) != 0) : 1u);
                         }
                     } else if (p.terms == 3) {
-                        const uint64_t da_hi = make_desc(a_hi), da_lo = make_desc(a_hi + A_TILE_BYTES);
-                        const uint64_t db_hi = make_desc(a_hi + 2 * A_TILE_BYTES), db_lo = make_desc(a_hi + 2 * A_TILE_BYTES + b_tile_bytes);
+                        const uint64_t da_hi = make_desc(a_hi), da_lo = make_desc(a_hi + a_tile_bytes);
+                        const uint64_t db_hi = make_desc(a_hi + 2 * a_tile_bytes), db_lo = make_desc(a_hi + 2 * a_tile_bytes + b_tile_bytes);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                             const uint64_t o = (uint64_t)(k * UMMA_K * 4 >> 4);
@@ -422,7 +435,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             mma(d_main, da_hi + o, db_hi + o, p.corr_sep ? (uint32_t)((kb | k) != 0) : 1u);
                         }
                     } else {
-                        const uint64_t da = make_desc(a_hi), db = make_desc(a_hi + A_TILE_BYTES);
+                        const uint64_t da = make_desc(a_hi), db = make_desc(a_hi + a_tile_bytes);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                             const uint64_t o = (uint64_t)(k * UMMA_K * 4 >> 4);
@@ -458,24 +471,37 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint32_t ph = (it / stages) & 1;
                     mbar_wait(fullA0 + 8 * s, ph);
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) p.dbg[it * 8 + 1] = clock64();
-                    const uint8_t *row = smem + (size_t)s * stage_bytes + r * 128;
+                    // row pitch = the k-block width; chunk c of row r sits at c ^ (r & 7) (128-byte rows, SWIZZLE_128B) or at
+                    // c ^ ((r >> 1) & 3) (64-byte rows, SWIZZLE_64B): conflict-free either way
+                    const uint8_t *row = smem + (size_t)s * stage_bytes + r * (bk * 4);
+                    const uint32_t sw = bk == 32 ? swz : (uint32_t)((r >> 1) & 3);
                     uint32_t hi[32], lo[32];
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        const float4 v = *reinterpret_cast<const float4 *>(row + (((uint32_t)c ^ swz) << 4));
-                        const float e[4] = {v.x, v.y, v.z, v.w};
+                        if (4 * c < bk) {
+                            const float4 v = *reinterpret_cast<const float4 *>(row + (((uint32_t)c ^ sw) << 4));
+                            const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            uint32_t u;
-                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(e[q]));
-                            hi[4 * c + q] = u;
-                            lo[4 * c + q] = __float_as_uint(e[q] - __uint_as_float(u));
+                            for (int q = 0; q < 4; ++q) {
+                                uint32_t u;
+                                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(e[q]));
+                                hi[4 * c + q] = u;
+                                lo[4 * c + q] = __float_as_uint(e[q] - __uint_as_float(u));
+                            }
+                        } else {
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) hi[4 * c + q] = lo[4 * c + q] = 0u;
                         }
                     }
-                    const uint32_t t_hi = tmem_base + (uint32_t)p.a_col0 + (uint32_t)s * 64u + ((uint32_t)(quad * 32) << 16);
+                    const uint32_t t_hi = tmem_base + (uint32_t)p.a_col0 + (uint32_t)(s * 2 * bk) + ((uint32_t)(quad * 32) << 16);
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) p.dbg[it * 8 + 6] = clock64();
-                    tmem_st32(t_hi, hi);
-                    tmem_st32(t_hi + 32u, lo);
+                    if (bk == 32) {
+                        tmem_st32(t_hi, hi);
+                        tmem_st32(t_hi + 32u, lo);
+                    } else {
+                        tmem_st16(t_hi, hi, 0);
+                        tmem_st16(t_hi + 16u, lo, 0);
+                    }
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) p.dbg[it * 8 + 2] = clock64();
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -496,9 +522,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     mbar_wait(fullA0 + 8 * s, ph);
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && tt == 0) p.dbg[it * 8 + 1] = clock64();
                     float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * stage_bytes);
-                    float4 *lo = hi + A_TILE_BYTES / 16;
+                    float4 *lo = hi + a_tile_bytes / 16;
 #pragma unroll
-                    for (int i = 0; i < A_TILE_BYTES / 16 / 128; ++i) {
+                    for (int i = 0; i < a_tile_bytes / 16 / 128; ++i) {
                         if (p.debug & 1) break;
                         const float4 v = hi[tt + 128 * i];
                         float4 h, l;
@@ -701,7 +727,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int make_map(CUtensorMap *tm, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-                    int box_cols = BLOCK_K) {
+                    int box_cols = BLOCK_K) {       // box_cols 32 -> SWIZZLE_128B, 16 -> SWIZZLE_64B
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) {
         set_error("cuTensorMapEncodeTiled entry point not available");
@@ -712,8 +738,8 @@ static int make_map(CUtensorMap *tm, const float *base, int64_t rows, int64_t co
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): rows %lld cols %lld ld %lld", (int)r, (long long)rows,
                   (long long)cols, (long long)ld);
@@ -794,6 +820,13 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     p.terms = terms;
     p.a_tmem = (terms == 3 && atmem_enabled()) ? 1 : 0;
     p.a_col0 = 0;
+    static const int forced_bk = [] {
+        const char *e = getenv("DCNR_GEMM_BK");
+        return e != nullptr ? atoi(e) : 0;
+    }();
+    // 64-byte k-blocks (DCNR_GEMM_BK=16: six pipeline stages instead of three) are implemented and parity-clean but measured
+    // slower (1.15 vs 0.79 ms): the weight boxes become 64-byte rows and their TMA loads, not the A path, set the pace
+    p.bk = (p.a_tmem && forced_bk == 16) ? 16 : BLOCK_K;
     p.C = C; p.ldc = ldc; p.epi = epi;
     p.dot_w = dot_w; p.dot_out = dot_out;
     static const int debug_bits = [] {
@@ -823,13 +856,13 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     auto plan = [&](int c, size_t *smem_out) {
-        const int b_bytes = (p.block_n / c) * BLOCK_K * 4;
-        const int stage_bytes = ((terms == 3 && !p.a_tmem) ? 2 : 1) * A_TILE_BYTES + (terms == 3 ? 2 : 1) * b_bytes;
+        const int b_bytes = (p.block_n / c) * p.bk * 4;
+        const int stage_bytes = ((terms == 3 && !p.a_tmem) ? 2 : 1) * BLOCK_M * p.bk * 4 + (terms == 3 ? 2 : 1) * b_bytes;
         const int budget = 227 * 1024 - 1024 - kBarBytes - kEpiVecBytes - kEpiBytes;
-        p.stages = std::max(1, std::min(p.a_tmem ? 4 : 6, budget / stage_bytes));
+        p.stages = std::max(1, std::min(p.a_tmem ? 256 / (2 * p.bk) : 6, budget / stage_bytes));
         *smem_out = (size_t)p.stages * stage_bytes + 1024 + kBarBytes + kEpiVecBytes + kEpiBytes;
         // tensor memory: accumulator stage(s) first, then (A in TMEM) the operand ring, 64 columns (hi | lo) per stage
-        const int ring_cols = p.a_tmem ? p.stages * 64 : 0;
+        const int ring_cols = p.a_tmem ? p.stages * 2 * p.bk : 0;
         p.corr_sep = (terms == 3 && 4 * p.acc_cols + ring_cols <= 512) ? 1 : 0;   // separate accumulator for the lo terms
         const int per_stage_cols = p.corr_sep ? 2 * p.acc_cols : p.acc_cols;
         p.acc_stages = 2 * per_stage_cols + ring_cols <= 512 ? 2 : 1;
@@ -854,15 +887,15 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
         }
     }
     CUtensorMap tmA, tmBhi, tmBlo, tmR, tmC;
-    DCNR_TRY(make_map(&tmA, A, m, k, lda, BLOCK_M));
+    DCNR_TRY(make_map(&tmA, A, m, k, lda, BLOCK_M, p.bk));
     // epilogue boxes: 32 rows x 32 columns of the residual / output (rows and columns past the matrix are
     // zero-filled on load and clipped on store)
     if (C != nullptr) DCNR_TRY(make_map(&tmC, C, m, n, ldc, 32, 32));
     else tmC = tmA;                                  // never dereferenced
     if (epi.residual != nullptr) DCNR_TRY(make_map(&tmR, epi.residual, m, n, epi.ldr, 32, 32));
     else tmR = tmA;
-    DCNR_TRY(make_map(&tmBhi, B, n, k, ldb, p.block_n / ctas));
-    DCNR_TRY(make_map(&tmBlo, terms == 3 ? B_lo : B, n, k, ldb, p.block_n / ctas));
+    DCNR_TRY(make_map(&tmBhi, B, n, k, ldb, p.block_n / ctas, p.bk));
+    DCNR_TRY(make_map(&tmBlo, terms == 3 ? B_lo : B, n, k, ldb, p.block_n / ctas, p.bk));
     p.num_m_tiles = (int32_t)ceil_div(m, BLOCK_M * ctas);
     const int64_t num_tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
     if (ctas == 2) {
