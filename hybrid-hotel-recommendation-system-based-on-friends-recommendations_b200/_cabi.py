@@ -103,6 +103,8 @@ _SIGS = {
     "dcnr_knn_topk": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p,
                               c_void_p, c_int64, c_void_p]),
     "dcnr_knn_merge": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
+    "dcnr_mmr_rerank": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_float, c_int32, c_int32,
+                                c_void_p, c_void_p, c_void_p]),
     "dcnr_comm_unique_id": (c_int, [c_void_p]),
     "dcnr_comm_create": (c_int, [c_void_p, c_int32, c_int32, POINTER(c_void_p)]),
     "dcnr_comm_destroy": (c_int, [c_void_p]),

@@ -82,3 +82,55 @@ class RankingEngine:
             b["free"].record(compute)
         compute.synchronize()
         return out
+
+
+def rerank_with_mmr(ranked_items_with_scores, lambda_param: float, top_k: int = 20, *, item_embeddings: torch.Tensor,
+                    item_id_mapping) -> list:
+    """Drop-in for ``rerank_with_mmr`` (main.py:133-169) on the GPU: same arguments (the ranked ``[(score, item_id)]``
+    list, ``lambda_param``, ``top_k``) plus the two objects the reference reads from ``ml_artifacts``
+    (``item_embeddings`` as a CUDA tensor [n_items, d], ``artifacts['item_id_mapping']``).  Returns the re-ranked item ids."""
+    return rerank_with_mmr_batch([ranked_items_with_scores], lambda_param, top_k, item_embeddings=item_embeddings,
+                                 item_id_mapping=item_id_mapping)[0]
+
+
+def rerank_with_mmr_batch(requests, lambda_param: float, top_k: int = 20, *, item_embeddings: torch.Tensor,
+                          item_id_mapping) -> list:
+    """Many requests in one launch (one CTA per request).  ``requests``: list of ranked ``[(score, item_id)]`` lists."""
+    from . import _cabi as C
+    C.require_cuda(item_embeddings)
+    emb = item_embeddings.to(torch.float32).contiguous()
+    dev = emb.device
+    offsets, scores, idx = [0], [], []
+    for req in requests:
+        for score, item_id in req:
+            scores.append(float(score))
+            j = item_id_mapping.get(item_id)
+            idx.append(-1 if j is None else int(j))
+        offsets.append(len(scores))
+    n_req = len(requests)
+    if n_req == 0:
+        return []
+    max_c = max(b - a for a, b in zip(offsets[:-1], offsets[1:]))
+    s_dev = torch.tensor(scores, dtype=torch.float32, device=dev)
+    i_dev = torch.tensor(idx, dtype=torch.int64, device=dev)
+    o_dev = torch.tensor(offsets, dtype=torch.int32, device=dev)
+    order = torch.empty((n_req, top_k), dtype=torch.int32, device=dev)
+    count = torch.empty(n_req, dtype=torch.int32, device=dev)
+    with torch.cuda.device(dev):
+        C.check(C.lib().dcnr_mmr_rerank(C.ptr(emb), emb.shape[0], emb.shape[1], C.ptr(s_dev), C.ptr(i_dev), C.ptr(o_dev), n_req,
+                                        float(lambda_param), int(top_k), int(max_c), C.ptr(order), C.ptr(count), C.stream()))
+    order, count = order.cpu().numpy(), count.cpu().numpy()
+    return [[requests[r][int(p)][1] for p in order[r, :count[r]]] for r in range(n_req)]
+
+
+def expand_candidates(nn_model, item_embeddings: torch.Tensor, positive_rows, n_neighbors: int = 11):
+    """The per-positive-hotel kNN loop of ``_generate_candidates`` (main.py:196-203) as ONE batched query: for every
+    internal row in ``positive_rows`` the ``n_neighbors - 1`` nearest catalog rows with position 0 (the hotel itself)
+    dropped, exactly what ``indices.squeeze()[1:]`` keeps at main.py:201.  Returns an int64 array [len(positive_rows),
+    n_neighbors - 1] of internal rows; the caller maps them through ``reverse_item_map`` and unions them into the
+    candidate set like the reference does."""
+    rows = torch.as_tensor(positive_rows, dtype=torch.int64, device=item_embeddings.device).reshape(-1)
+    if rows.numel() == 0:
+        return np.empty((0, max(n_neighbors - 1, 0)), dtype=np.int64)
+    _, ind = nn_model.kneighbors_tensor(item_embeddings[rows].to(torch.float32), n_neighbors)
+    return ind[:, 1:].cpu().numpy()

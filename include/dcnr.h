@@ -276,6 +276,18 @@ int dcnr_knn_merge(const float *dist_parts, const int64_t *idx_parts, int32_t n_
                    int32_t k, float *dist_out, int64_t *idx_out, dcnr_stream_t stream);
 
 /* ------------------------------------------------------------------------------------------
+ * MMR re-rank (rerank_with_mmr, main.py:133-169), one CTA per request.
+ * scores / emb_idx: the candidates of all requests back to back, each request in ranked (score-descending) order;
+ * offsets: [n_requests + 1] prefix offsets; emb_idx: row of item_emb per candidate, < 0 = item unknown to the id map
+ * (skipped, main.py:150).  order_out: [n_requests, top_k] positions INSIDE each request's candidate list (-1 padded),
+ * count_out: [n_requests].  max_candidates: the largest request (host value, sizes the shared memory).
+ * Bit-exact with oracle/mmr_oracle.c (sequential-fma cosine, fp32 mmr, first maximum wins).
+ * ------------------------------------------------------------------------------------------ */
+int dcnr_mmr_rerank(const float *item_emb, int64_t n_items, int32_t d, const float *scores, const int64_t *emb_idx,
+                    const int32_t *offsets, int32_t n_requests, float lambda, int32_t top_k, int32_t max_candidates,
+                    int32_t *order_out, int32_t *count_out, dcnr_stream_t stream);
+
+/* ------------------------------------------------------------------------------------------
  * Data parallelism (no counterpart in the reference, which is single-process).
  * One process per GPU; the communicator is NCCL over NVLink / NVSwitch, reached through dlopen.
  * ------------------------------------------------------------------------------------------ */

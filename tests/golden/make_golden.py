@@ -151,6 +151,27 @@ def knn_case(name, n, d, nq, k, seed):
     print("knn", name, "dist dtype", dists[0].dtype, "ind dtype", inds[0].dtype)
 
 
+def mmr_case(name, n_items, d, C, lam, top_k, seed, unmapped=()):
+    """rerank_with_mmr (main.py:133-169) on random embeddings / scores; external ids are idx * 7 + 3 so that the id
+    mapping is exercised; `unmapped` candidate positions get ids the mapping does not know (skipped at main.py:150)."""
+    rng = np.random.default_rng(seed)
+    E = rng.standard_normal((n_items, d)).astype(np.float32)
+    idx = rng.choice(n_items, size=C, replace=False)
+    scores = np.sort(rng.standard_normal(C).astype(np.float32))[::-1].copy()       # ranked order (main.py:325)
+    ext = [int(i) * 7 + 3 for i in idx]
+    for pos in unmapped:
+        ext[pos] = -1000 - pos
+    ref_main.ml_artifacts["item_embeddings"] = E
+    ref_main.ml_artifacts["artifacts"] = {"item_id_mapping": {int(i) * 7 + 3: int(i) for i in range(n_items)}}
+    ranked = [(scores[c], ext[c]) for c in range(C)]         # numpy float32 scores, as zip(scores, ids) yields at main.py:325
+    chosen = ref_main.rerank_with_mmr(ranked, lam, top_k)
+    pos_of = {e: c for c, e in enumerate(ext)}
+    emb_idx = np.array([-1 if c in unmapped else int(idx[c]) for c in range(C)], dtype=np.int64)
+    np.savez_compressed(os.path.join(HERE, f"mmr_{name}.npz"), E=E, scores=scores, emb_idx=emb_idx, lam=np.array(lam),
+                        top_k=np.array(top_k), order=np.array([pos_of[e] for e in chosen], dtype=np.int32))
+    print("mmr", name, "selected", len(chosen))
+
+
 if __name__ == "__main__":
     P0 = dict(emb_dim=16, hidden_dim=256, n_cross_layers=3, n_res_blocks=2, dropout=0.0,
               lr=1e-3, batch_size=512)   # extra keys must be ignored (train.py:186-192)
@@ -167,3 +188,6 @@ if __name__ == "__main__":
     knn_case("small", 3000, 16, 8, 11, 5)
     knn_case("k51", 5000, 16, 4, 51, 6)
     knn_case("d64", 2000, 64, 4, 11, 7)
+    mmr_case("c300", 2000, 16, 300, 0.7, 20, 8)
+    mmr_case("c40_unmapped", 500, 16, 40, 0.3, 20, 9, unmapped=(0, 5, 17))
+    mmr_case("c12", 200, 64, 12, 0.5, 20, 10)

@@ -1,0 +1,62 @@
+"""GPU parity of the rows after the ranking forward through the C ABI:
+MMR re-rank vs the reference's own outputs (golden) and vs the oracle on larger random requests;
+batched candidate expansion vs the reference's one-query-per-positive-hotel loop."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+@pytest.mark.parametrize("name", ["c300", "c40_unmapped", "c12"])
+def test_mmr_matches_reference_golden(name):
+    import dcnr_b200
+    z = np.load(os.path.join(GOLD, f"mmr_{name}.npz"))
+    E = torch.from_numpy(z["E"]).cuda()
+    C = len(z["scores"])
+    ids = [int(i) * 7 + 3 if i >= 0 else -1000 - c for c, i in enumerate(z["emb_idx"])]
+    mapping = {int(i) * 7 + 3: int(i) for i in range(E.shape[0])}
+    ranked = [(float(z["scores"][c]), ids[c]) for c in range(C)]
+    got = dcnr_b200.serving.rerank_with_mmr(ranked, float(z["lam"]), int(z["top_k"]), item_embeddings=E, item_id_mapping=mapping)
+    assert got == [ids[p] for p in z["order"]]
+
+
+def test_mmr_batch_matches_oracle():
+    import dcnr_b200
+    from oracle import mmr_oracle
+    rng = np.random.default_rng(3)
+    E = rng.standard_normal((20000, 16)).astype(np.float32)
+    E[77] = 0.0                                             # zero vector: norm 0 -> 1 like sklearn's normalize
+    mapping = {i: i for i in range(E.shape[0])}
+    reqs, want = [], []
+    for r in range(64):
+        C = int(rng.integers(1, 700))
+        idx = rng.choice(E.shape[0], size=C, replace=False)
+        if r % 5 == 0:
+            idx[0] = 77
+        sc = np.sort(rng.standard_normal(C).astype(np.float32))[::-1].copy()
+        if r % 7 == 0 and C > 4:
+            sc[2] = sc[1]                                   # exact score tie: the earlier candidate must win
+        reqs.append([(sc[c], int(idx[c])) for c in range(C)])
+        want.append([int(idx[p]) for p in mmr_oracle.mmr_rerank(E, sc, idx.astype(np.int64), 0.7, 20)])
+    got = dcnr_b200.serving.rerank_with_mmr_batch(reqs, 0.7, 20, item_embeddings=torch.from_numpy(E).cuda(), item_id_mapping=mapping)
+    assert got == want
+
+
+def test_expand_candidates_equals_per_hotel_queries():
+    """main.py:196-203: one kneighbors(vec, 11) per positive hotel, position 0 dropped -- batched here."""
+    import dcnr_b200
+    from oracle import knn_oracle
+    rng = np.random.default_rng(11)
+    E = rng.standard_normal((30000, 16)).astype(np.float32)
+    positives = rng.choice(E.shape[0], size=37, replace=False)
+    nn_model = dcnr_b200.NearestNeighbors(n_neighbors=16, metric="cosine", algorithm="brute").fit(E)
+    got = dcnr_b200.serving.expand_candidates(nn_model, torch.from_numpy(E).cuda(), positives, 11)
+    ref = knn_oracle.OracleNearestNeighbors().fit(E)
+    for r, row in enumerate(positives):
+        _, ind = ref.kneighbors(E[row].reshape(1, -1), n_neighbors=11)
+        assert np.array_equal(got[r], ind[0][1:])
+    assert set(got.reshape(-1)) == set(np.concatenate([ref.kneighbors(E[p].reshape(1, -1), n_neighbors=11)[1][0][1:] for p in positives]))

@@ -152,3 +152,13 @@ def test_knn_oracle_ties_by_index_and_merge():
         parts = [knn_oracle.cosine_topk(ehat[a:b], q, 20, idx_base=int(a)) for a, b in zip(bounds[:-1], bounds[1:])]
         d, i = knn_oracle.merge_topk(np.stack([p[0] for p in parts]), np.stack([p[1] for p in parts]))
         assert (i == full[1]).all() and (d == full[0]).all()
+
+
+@pytest.mark.parametrize("name", ["c300", "c40_unmapped", "c12"])
+def test_mmr_oracle_matches_reference_rerank(name):
+    """oracle/mmr_oracle.c == the reference's rerank_with_mmr (main.py:133-169) on the committed fixtures
+    (tests/golden/make_golden.py ran the unmodified function; includes an unmapped best item and C < top_k)."""
+    from oracle import mmr_oracle
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"mmr_{name}.npz"))
+    got = mmr_oracle.mmr_rerank(z["E"], z["scores"], z["emb_idx"], float(z["lam"]), int(z["top_k"]))
+    assert np.array_equal(got, z["order"])
