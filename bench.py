@@ -315,6 +315,7 @@ def main():
         result["sharded"] = bench_sharded(dev, world, rank, comm, barrier, max_over_ranks, args.precision)
         torch.cuda.empty_cache()
         if world == 1:
+            result["mmr"] = bench_mmr(dev)
             result["similarity"] = bench_similarity(dev, pk)
             sys.path.insert(0, os.path.join(ROOT, "scripts"))
             import kernel_probe
@@ -455,6 +456,37 @@ def bench_similarity(dev, pk, n=10_000_000, d=16, k=201):
                          "hbm_frac": (n * d * 4) / secs / 1e9 / pk["hbm"],
                          "hbm_frac_per_pass": passes * (n * d * 4) / secs / 1e9 / pk["hbm"]}
     return {"metric": "similarity_query_candidate_pairs_per_s", "catalog": f"{n} x {d} f32", "k": k, **out}
+
+
+def bench_mmr(dev, n_req=4096, n_cand=CANDIDATES):
+    """the greedy MMR re-rank (main.py:327-332, top_k 20, lambda 0.7) of n_req requests x 500 scored
+    candidates in one launch (one CTA per request), next to the oracle's C restatement on one host core."""
+    import numpy as np
+    from dcnr_b200 import _cabi as C
+    g = torch.Generator(device=dev).manual_seed(11)
+    emb = torch.randn(N_ITEMS, P0["emb_dim"], generator=g, device=dev)
+    idx = torch.randint(0, N_ITEMS, (n_req * n_cand,), generator=g, device=dev)
+    scores = torch.sort(torch.randn(n_req, n_cand, generator=g, device=dev), dim=1, descending=True).values.reshape(-1).contiguous()
+    offsets = torch.arange(0, (n_req + 1) * n_cand, n_cand, dtype=torch.int32, device=dev)
+    order = torch.empty((n_req, 20), dtype=torch.int32, device=dev); count = torch.empty(n_req, dtype=torch.int32, device=dev)
+
+    def run():
+        C.check(C.lib().dcnr_mmr_rerank(C.ptr(emb), N_ITEMS, P0["emb_dim"], C.ptr(scores), C.ptr(idx), C.ptr(offsets), n_req, 0.7, 20,
+                                        n_cand, C.ptr(order), C.ptr(count), C.stream()))
+    secs = time_steps(run, 5, 2, lambda: None) / 5
+    out = {"metric": "mmr_requests_per_s", "value": n_req / secs, "unit": "requests/s", "requests": n_req, "candidates": n_cand,
+           "ms": secs * 1e3}
+    try:
+        from oracle import mmr_oracle
+        E = emb.cpu().numpy(); sc = scores[: 16 * n_cand].cpu().numpy().reshape(16, n_cand); ix = idx[: 16 * n_cand].cpu().numpy().reshape(16, n_cand)
+        t0 = time.perf_counter()
+        ref = [mmr_oracle.mmr_rerank(E, sc[r], ix[r], 0.7, 20) for r in range(16)]
+        dt = time.perf_counter() - t0
+        out["cpu_oracle_requests_per_s"] = 16 / dt
+        out["matches_oracle"] = bool(all(np.array_equal(ref[r], order[r].cpu().numpy()[: len(ref[r])]) for r in range(16)))
+    except Exception as e:
+        out["cpu_oracle_error"] = str(e)[:200]
+    return out
 
 
 def cpu_baseline(budget_s=12.0, dev=None):
