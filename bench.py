@@ -326,7 +326,8 @@ def main():
         if comm is not None:
             comm.close()
     if rank == 0 and world == 1:
-        result["cpu_baseline"] = cpu_baseline(dev=dev)
+        # (--skip-extras is the profiling form of the command: keep torch's own kernels out of its launch list)
+        result["cpu_baseline"] = cpu_baseline(dev=None if args.skip_extras else dev)
     if rank == 0:
         _emit(result)
     if dist is not None:
