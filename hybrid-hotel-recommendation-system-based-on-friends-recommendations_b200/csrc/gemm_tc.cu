@@ -260,7 +260,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
           const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmR,
           const __grid_constant__ CUtensorMap tmC, Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by OFFSETTING the __shared__ array: a round trip through uintptr_t loses the address space and
+    // every shared-memory access below became a generic LD / ST (the split and the epilogue ran 3-4x slower)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
     const int bn_cta = p.block_n / CTAS;                 // weight rows staged by this CTA
@@ -601,14 +603,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             for (int c0 = 0; c0 < p.block_n; c0 += 32, ++g) {
                 const uint32_t sl = g % kEpiSlots;
                 uint8_t *row = slots + sl * kEpiSlotBytes + lane * 128;
+                const bool stamp = (p.debug & 16) && blockIdx.x == 0 && threadIdx.x == 192 && g >= 16 && g < 48;
+                if (stamp) p.dbg[600 + (g - 16) * 6 + 0] = clock64();
                 if (has_res) {
                     mbar_wait(rf0 + 8 * sl, (g / kEpiSlots) & 1);
                 } else if (has_c) {                         // the store that last used this slot has finished reading it
                     if (lane == 0) bulk_wait_read<kEpiSlots - 1>();
                     __syncwarp();
                 }
+                if (stamp) p.dbg[600 + (g - 16) * 6 + 1] = clock64();
                 uint32_t r[32];
                 tmem_ld32(t_main + (uint32_t)c0, r);
+                if (stamp) p.dbg[600 + (g - 16) * 6 + 2] = clock64();
                 if (p.corr_sep) {
                     uint32_t r2[32];
                     tmem_ld32(t_main + corr_off + (uint32_t)c0, r2);
@@ -636,8 +642,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                     if (has_c) *cell = v;
                 }
+                if (stamp) p.dbg[600 + (g - 16) * 6 + 3] = clock64();
                 if (has_c) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
+                if (stamp) p.dbg[600 + (g - 16) * 6 + 4] = clock64();
                 if (lane == 0) {
                     if (has_c) {
                         tma_store_2d(&tmC, smem_u32(slots + sl * kEpiSlotBytes), n0 + c0, mw);
@@ -648,6 +656,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         issue_res_load(g + kEpiSlots - 1);
                     }
                 }
+                if (stamp) p.dbg[600 + (g - 16) * 6 + 5] = clock64();
             }
             if ((p.debug & 16) && blockIdx.x == 0 && tl < 8 && threadIdx.x == 192) p.dbg[512 + tl * 2 + 1] = clock64();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -922,6 +931,12 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
                         h[i * 8 + 6] - h[i * 8 + 1], h[i * 8 + 2] - h[i * 8 + 6], h[i * 8 + 3] - t0, h[i * 8 + 4] - h[i * 8 + 3]);
             for (int t = 0; t < 8; ++t)
                 fprintf(stderr, "epilogue tile %d: start %8lld  took %6lld\n", t, h[512 + 2 * t] - t0, h[512 + 2 * t + 1] - h[512 + 2 * t]);
+            fprintf(stderr, "epilogue chunk: start | slot wait | tmem ld | math+sts | fence | store/prefetch\n");
+            for (int c = 0; c < 32; ++c) {
+                const long long *e = h + 600 + c * 6;
+                fprintf(stderr, "%2d: %8lld  +%5lld +%5lld +%5lld +%5lld +%5lld\n", c + 16, e[0] - t0, e[1] - e[0], e[2] - e[1], e[3] - e[2],
+                        e[4] - e[3], e[5] - e[4]);
+            }
         }
     }
     return DCNR_OK;

@@ -108,7 +108,9 @@ struct Params {
 __global__ void __launch_bounds__(kThreads, 1)
 k_wgrad_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, Params p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t *smem = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+    // 1024-byte alignment by OFFSETTING the __shared__ array: a round trip through uintptr_t loses the address space and
+    // every shared-memory access below became a generic LD / ST (the split and the epilogue ran 3-4x slower)
+    uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int a_bytes = BLOCK_M * BLOCK_K * 4;                 // 16 KB: 4 blocks of [32 rows x 128 B]
     const int b_bytes = p.k_in * BLOCK_K * 4;                  // k_in / 32 blocks
     const int stage_bytes = (p.terms == 3 ? 2 : 1) * (a_bytes + b_bytes);      // [A hi][B hi]([A lo][B lo])
