@@ -225,6 +225,7 @@ struct Params {
     int64_t M;
     int32_t N_total, K, block_n, terms, stages, acc_cols, acc_stages, corr_sep, tmem_cols;
     int32_t bk;               // floats per k-block (32, or 16 with A in tensor memory: six finer pipeline stages)
+    int32_t epi_slots;        // epilogue slots per warp (2 or 4)
     int32_t a_tmem, a_col0;   // TF32X3: A hi / lo in a tensor-memory ring (64 columns per stage) starting at column a_col0
     int32_t num_m_tiles, num_n_tiles;
     long long *dbg;           // DCNR_GEMM_DEBUG bit 16: clock64 stamps of CTA 0's pipeline (first 64 k-blocks)
@@ -238,9 +239,7 @@ struct Params {
 
 constexpr int kThreadsP = 320;                      // warp 0 TMA, warp 1 MMA, warps 2-5 operand split, warps 6-9 epilogue
 constexpr int kEpiSlotBytes = 32 * 32 * 4;          // one epilogue slot: 32 rows x 32 fp32 columns, 128B-swizzled
-constexpr int kEpiSlots = 4;                        // slots per epilogue warp (residual prefetch depth 3)
-constexpr int kEpiBytes = 4 * kEpiSlots * kEpiSlotBytes;
-constexpr int kEpiVecBytes = 4 * 3 * 256 * 4;       // per-warp copies of col_scale / bias / dot_w for the tile's columns
+constexpr int kEpiSlotsMax = 4;                     // slots per epilogue warp: 4 (residual prefetch depth 3) or 2 (one more operand stage)
 constexpr int kBarBytes = 512;                      // mbarriers + the TMEM base slot
 
 // Persistent, warp-specialised: every CTA (CTAS = 1) or CTA pair (CTAS = 2, a 2-CTA cluster) walks
@@ -274,10 +273,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int stage_bytes = b_off + (p.terms == 3 ? 2 : 1) * b_tile_bytes;
     const int stages = p.stages, acc_stages = p.acc_stages;
     uint8_t *epi_slots = smem + (size_t)stages * stage_bytes;            // 1024-aligned (stage sizes are multiples of 1 KB)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_slots + kEpiBytes);
+    const int kEpiSlots = p.epi_slots;
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_slots + 4 * kEpiSlots * kEpiSlotBytes);
     // bars: fullA[stages], fullB[stages], ready[stages], empty[stages], tfull[acc_stages], tempty[acc_stages], rfull[4][kEpiSlots]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * stages + 2 * acc_stages + 4 * kEpiSlots);
-    float *epi_vecs = reinterpret_cast<float *>(reinterpret_cast<uint8_t *>(bars) + kBarBytes);
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * stages + 2 * acc_stages + 4 * kEpiSlotsMax);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t fullA0 = smem_u32(bars), fullB0 = smem_u32(bars + stages), ready0 = smem_u32(bars + 2 * stages),
@@ -565,7 +564,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
         uint8_t *slots = epi_slots + (size_t)ew * kEpiSlots * kEpiSlotBytes;
         const uint32_t rf0 = rfull0 + 8 * ew * kEpiSlots;
-        float *vscale = epi_vecs + ew * 3 * 256, *vbias = vscale + 256, *vdot = vbias + 256;
         const bool has_res = p.epi.residual != nullptr, has_c = p.C != nullptr;
         const int cpt = (p.block_n + 31) / 32;             // chunks per tile
         const uint32_t swz = (uint32_t)(lane & 7);
@@ -585,15 +583,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int as = tl % acc_stages;
             const int m0 = (t / p.num_n_tiles) * (BLOCK_M * CTAS) + (int)rank * BLOCK_M;
             const int n_tile = t % p.num_n_tiles, n0 = n_tile * p.block_n;
-            if (tl == 0 || p.num_n_tiles > 1) {            // this tile's per-column vectors (private copy per warp)
-                __syncwarp();
-                for (int c = lane; c < p.block_n; c += 32) {
-                    vscale[c] = p.epi.col_scale != nullptr ? __ldg(p.epi.col_scale + n0 + c) : 1.f;
-                    vbias[c] = p.epi.bias != nullptr ? __ldg(p.epi.bias + n0 + c) : 0.f;
-                    vdot[c] = p.dot_w != nullptr ? __ldg(p.dot_w + n0 + c) : 0.f;
-                }
-                __syncwarp();
-            }
             wait_x(tfull0 + 8 * as, (tl / acc_stages) & 1);
             if ((p.debug & 16) && blockIdx.x == 0 && tl < 8 && threadIdx.x == 192) p.dbg[512 + tl * 2] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -608,7 +597,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 if (has_res) {
                     mbar_wait(rf0 + 8 * sl, (g / kEpiSlots) & 1);
                 } else if (has_c) {                         // the store that last used this slot has finished reading it
-                    if (lane == 0) bulk_wait_read<kEpiSlots - 1>();
+                    if (lane == 0) {
+                        if (kEpiSlots == 4) bulk_wait_read<3>();
+                        else bulk_wait_read<1>();
+                    }
                     __syncwarp();
                 }
                 if (stamp) p.dbg[600 + (g - 16) * 6 + 1] = clock64();
@@ -624,8 +616,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     float4 *cell = reinterpret_cast<float4 *>(row + (((uint32_t)j ^ swz) << 4));
-                    const float4 s4 = *reinterpret_cast<const float4 *>(vscale + c0 + 4 * j);
-                    const float4 b4 = *reinterpret_cast<const float4 *>(vbias + c0 + 4 * j);
+                    // per-column vectors straight from global memory: warp-uniform addresses, L1 hits after the first tile
+                    const float4 s4 = p.epi.col_scale != nullptr ? ldg4(p.epi.col_scale + n0 + c0 + 4 * j) : make_float4(1.f, 1.f, 1.f, 1.f);
+                    const float4 b4 = p.epi.bias != nullptr ? ldg4(p.epi.bias + n0 + c0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
                     float4 v;
                     v.x = fmaf(__uint_as_float(r[4 * j]), s4.x, b4.x); v.y = fmaf(__uint_as_float(r[4 * j + 1]), s4.y, b4.y);
                     v.z = fmaf(__uint_as_float(r[4 * j + 2]), s4.z, b4.z); v.w = fmaf(__uint_as_float(r[4 * j + 3]), s4.w, b4.w);
@@ -637,7 +630,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
                     }
                     if (p.dot_w != nullptr) {
-                        const float4 w4 = *reinterpret_cast<const float4 *>(vdot + c0 + 4 * j);
+                        const float4 w4 = ldg4(p.dot_w + n0 + c0 + 4 * j);
                         dot = fmaf(v.x, w4.x, fmaf(v.y, w4.y, fmaf(v.z, w4.z, fmaf(v.w, w4.w, dot))));
                     }
                     if (has_c) *cell = v;
@@ -867,9 +860,19 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     auto plan = [&](int c, size_t *smem_out) {
         const int b_bytes = (p.block_n / c) * p.bk * 4;
         const int stage_bytes = ((terms == 3 && !p.a_tmem) ? 2 : 1) * BLOCK_M * p.bk * 4 + (terms == 3 ? 2 : 1) * b_bytes;
-        const int budget = 227 * 1024 - 1024 - kBarBytes - kEpiVecBytes - kEpiBytes;
-        p.stages = std::max(1, std::min(p.a_tmem ? 256 / (2 * p.bk) : 6, budget / stage_bytes));
-        *smem_out = (size_t)p.stages * stage_bytes + 1024 + kBarBytes + kEpiVecBytes + kEpiBytes;
+        // four epilogue slots per warp (residual prefetch depth 3) unless two slots buy another operand stage
+        static const int forced_slots = [] {
+            const char *e = getenv("DCNR_GEMM_EPI_SLOTS");
+            return e != nullptr ? atoi(e) : 0;
+        }();
+        const int cap = p.a_tmem ? 256 / (2 * p.bk) : 6;
+        auto stages_for = [&](int slots) {
+            const int budget = 227 * 1024 - 1024 - kBarBytes - 4 * slots * kEpiSlotBytes;
+            return std::max(1, std::min(cap, budget / stage_bytes));
+        };
+        p.epi_slots = (forced_slots == 2 || forced_slots == 4) ? forced_slots : (stages_for(2) > stages_for(4) && p.a_tmem ? 2 : 4);
+        p.stages = stages_for(p.epi_slots);
+        *smem_out = (size_t)p.stages * stage_bytes + 1024 + kBarBytes + 4 * p.epi_slots * kEpiSlotBytes;
         // tensor memory: accumulator stage(s) first, then (A in TMEM) the operand ring, 64 columns (hi | lo) per stage
         const int ring_cols = p.a_tmem ? p.stages * 2 * p.bk : 0;
         p.corr_sep = (terms == 3 && 4 * p.acc_cols + ring_cols <= 512) ? 1 : 0;   // separate accumulator for the lo terms
