@@ -227,9 +227,11 @@ struct Params {
     int32_t bk;               // floats per k-block (32, or 16 with A in tensor memory: six finer pipeline stages)
     int32_t epi_slots;        // epilogue slots per warp (2 or 4)
     int32_t a_tmem, a_col0;   // TF32X3: A hi / lo in a tensor-memory ring (64 columns per stage) starting at column a_col0
+    int32_t b_split;          // TF32X3: the weight arrives as raw fp32 and warps 10-13 split it in shared memory (half the L2 stream)
     int32_t num_m_tiles, num_n_tiles;
     long long *dbg;           // DCNR_GEMM_DEBUG bit 16: clock64 stamps of CTA 0's pipeline (first 64 k-blocks)
-    int32_t debug;            // timing experiments only (DCNR_GEMM_DEBUG): bit0 skip the split arithmetic, bit1 hi.hi MMA only
+    int32_t debug;            // timing experiments only (DCNR_GEMM_DEBUG): bit0 skip the split arithmetic, bit1 hi.hi MMA only,
+                              // bit2 skip the in-kernel weight split, bit3 skip the A split (tensor-memory form)
     float *C;                 // may be NULL when only the fused row dot is wanted
     int64_t ldc;
     GemmEpilogue epi;
@@ -237,7 +239,7 @@ struct Params {
     float *dot_out;           // [num_n_tiles][M] partial dots (summed by the caller)
 };
 
-constexpr int kThreadsP = 320;                      // warp 0 TMA, warp 1 MMA, warps 2-5 operand split, warps 6-9 epilogue
+constexpr int kThreadsP = 448;                      // warp 0 TMA, warp 1 MMA, warps 2-5 A split, warps 6-9 epilogue, warps 10-13 weight split
 constexpr int kEpiSlotBytes = 32 * 32 * 4;          // one epilogue slot: 32 rows x 32 fp32 columns, 128B-swizzled
 constexpr int kEpiSlotsMax = 4;                     // slots per epilogue warp: 4 (residual prefetch depth 3) or 2 (one more operand stage)
 constexpr int kBarBytes = 512;                      // mbarriers + the TMEM base slot
@@ -294,7 +296,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int s = 0; s < stages; ++s) {
             mbar_init(fullA0 + 8 * s, 1);
             mbar_init(fullB0 + 8 * s, 1);
-            mbar_init(ready0 + 8 * s, 4 * CTAS);        // one arrival per split warp
+            mbar_init(ready0 + 8 * s, (p.b_split ? 8 : 4) * CTAS);   // one arrival per split warp (A; and the weight when b_split)
             mbar_init(empty0 + 8 * s, 1);
         }
         for (int a = 0; a < acc_stages; ++a) {
@@ -349,11 +351,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         // A lands on this CTA's own barrier (its split warps wait for it), the weight halves on the leader's
                         mbar_expect_tx(fullA0 + 8 * s, (uint32_t)a_tile_bytes);
                         tma_load_2d(smem_u32(st), &tmA, kb * bk, m0, fullA0 + 8 * s);
-                        if (leader) mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(CTAS * 2 * b_tile_bytes));
-                        if (CTAS == 2) {
+                        if (p.b_split) {
+                            // raw fp32 weight box onto this CTA's OWN barrier: its weight-split warps wait for it
+                            mbar_expect_tx(fullB0 + 8 * s, (uint32_t)b_tile_bytes);
+                            tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fullB0 + 8 * s);
+                        } else if (CTAS == 2) {
+                            if (leader) mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(CTAS * 2 * b_tile_bytes));
                             tma_load_2d_pair(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fb);
                             tma_load_2d_pair(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * bk, n0, fb);
                         } else {
+                            mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(2 * b_tile_bytes));
                             tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fb);
                             tma_load_2d(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * bk, n0, fb);
                         }
@@ -397,7 +404,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1;
-                    wait_x(fullB0 + 8 * s, ph);
+                    if (!p.b_split) wait_x(fullB0 + 8 * s, ph);       // b_split: "ready" covers the weight tile too
                     if (p.terms == 3) wait_x(ready0 + 8 * s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
@@ -477,6 +484,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint8_t *row = smem + (size_t)s * stage_bytes + r * (bk * 4);
                     const uint32_t sw = bk == 32 ? swz : (uint32_t)((r >> 1) & 3);
                     uint32_t hi[32], lo[32];
+                    if (p.debug & 8) {                     // timing experiment: no A split work (TMEM ring holds garbage)
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(ready0 + 8 * s);
+                        continue;
+                    }
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
                         if (4 * c < bk) {
@@ -543,6 +555,45 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if (CTAS == 2) asm volatile("fence.proxy.async;" ::: "memory");
                     else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && tt == 0) p.dbg[it * 8 + 2] = clock64();
+                    __syncwarp();
+                    if (lane == 0) {
+                        if (CTAS == 2) mbar_arrive_cluster(L_ready0 + 8 * s);
+                        else mbar_arrive(ready0 + 8 * s);
+                    }
+                }
+            }
+        }
+    } else if (warp >= 10) {
+        // ---------------- warps 10..13: split the landed raw weight tile into hi / lo in shared memory (b_split) ----------------
+        // The weight stream from L2 was the larger half of the kernel's L2 -> SM traffic (hi + lo boxes: 32 of 64 KB per
+        // k-block at ~42 B/clk/SM); loading fp32 once and splitting here halves it.  Elementwise, so the swizzle is irrelevant;
+        // consecutive threads touch consecutive 16-byte cells (conflict-free).
+        if (p.terms == 3 && p.b_split) {
+            const int tt = threadIdx.x - 320;              // 0..127
+            const int cells = b_tile_bytes / 16;
+            uint32_t it = 0;
+            for (int t = tile0; t < num_tiles; t += tile_step) {
+                for (int kb = 0; kb < num_kb; ++kb, ++it) {
+                    const int s = it % stages;
+                    const uint32_t ph = (it / stages) & 1;
+                    mbar_wait(fullB0 + 8 * s, ph);
+                    float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * stage_bytes + b_off);
+                    float4 *lo = hi + cells;
+#pragma unroll 4
+                    for (int i = tt; i < cells; i += 128) {
+                        if (p.debug & 4) break;            // timing experiment: no weight split work
+                        const float4 v = hi[i];
+                        float4 h, l;
+                        uint32_t u;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
+                        hi[i] = h;
+                        lo[i] = l;
+                    }
+                    if (CTAS == 2) asm volatile("fence.proxy.async;" ::: "memory");
+                    else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                     __syncwarp();
                     if (lane == 0) {
                         if (CTAS == 2) mbar_arrive_cluster(L_ready0 + 8 * s);
@@ -678,20 +729,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 // hi = rn_tf32(x), lo = x - hi  (exact).  One pass over the layer weight per call.
 __global__ void k_split_tf32(const float *__restrict__ src, int64_t lds, float *__restrict__ hi, float *__restrict__ lo,
-                             int rows, int cols) {
+                             int rows, int cols, bool raw) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (int64_t)rows * cols) return;
     const int r = (int)(e / cols), c = (int)(e % cols);
     const float v = src[(int64_t)r * lds + c];
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    const float h = __uint_as_float(u);
+    const float h = raw ? v : __uint_as_float(u);
     hi[e] = h;
-    lo[e] = v - h;
+    if (lo != nullptr) lo[e] = v - h;
 }
 // Transposed variant for dgrad: out[c][r] from src[r][c].
 __global__ void k_transpose_split_tf32(const float *__restrict__ src, int64_t lds, float *__restrict__ hi,
-                                       float *__restrict__ lo, int rows, int cols) {
+                                       float *__restrict__ lo, int rows, int cols, bool raw) {
     __shared__ float tile[32][33];
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -705,7 +756,7 @@ __global__ void k_transpose_split_tf32(const float *__restrict__ src, int64_t ld
             const float v = tile[threadIdx.x][i];
             uint32_t u;
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-            const float h = __uint_as_float(u);
+            const float h = raw ? v : __uint_as_float(u);
             hi[(int64_t)c * rows + r] = h;
             if (lo != nullptr) lo[(int64_t)c * rows + r] = v - h;
         }
@@ -770,6 +821,18 @@ static int block_n_for(int precision, int64_t n) {
 
 }  // namespace tc
 
+// TF32X3 weight operands: pre-split hi / lo streamed by TMA (default), or raw fp32 split inside the GEMM by warps 10-13
+// (DCNR_GEMM_BSPLIT=1).  Measured on the 1 M x 256 x 256 layer: 0.81 ms pre-split, 0.88-0.91 ms split in-kernel, and 0.82 ms
+// with the in-kernel split's work skipped -- halving the weight stream from L2 buys nothing (L2 -> SM bandwidth is not the
+// limiter) and the extra shared-memory traffic of the split costs 8 %.
+bool gemm_tc_raw_weights() {
+    static const bool on = [] {
+        const char *e = getenv("DCNR_GEMM_BSPLIT");
+        return e != nullptr && atoi(e) != 0;
+    }();
+    return on;
+}
+
 int gemm_tc_n_tiles(int64_t n, int precision) {
     const int bn = tc::block_n_for(precision, n);
     return bn > 0 ? (int)(n / bn) : 1;
@@ -785,14 +848,15 @@ bool gemm_tc_supported(int precision, bool a_kmajor, bool b_kmajor, int64_t lda,
 }
 
 int launch_split_tf32(const float *src, int64_t lds, float *hi, float *lo, int32_t rows, int32_t cols, bool transpose,
-                      cudaStream_t stream) {
+                      cudaStream_t stream, bool raw) {
+    if (raw) lo = nullptr;
     if (rows <= 0 || cols <= 0) return DCNR_OK;
     if (transpose) {
         dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32)), block(32, 8);
-        tc::k_transpose_split_tf32<<<grid, block, 0, stream>>>(src, lds, hi, lo, rows, cols);
+        tc::k_transpose_split_tf32<<<grid, block, 0, stream>>>(src, lds, hi, lo, rows, cols, raw);
     } else {
         const int64_t total = (int64_t)rows * cols;
-        tc::k_split_tf32<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(src, lds, hi, lo, rows, cols);
+        tc::k_split_tf32<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(src, lds, hi, lo, rows, cols, raw);
     }
     DCNR_LAUNCHED();
     return DCNR_OK;
@@ -807,7 +871,7 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     DCNR_REQUIRE(gemm_tc_supported(precision, a_kmajor, b_kmajor, lda, ldb, ldc, m, n, k, split_k),
                  "shape not supported by the tcgen05 GEMM");
     const int terms = precision == DCNR_PREC_TF32X3 ? 3 : 1;
-    DCNR_REQUIRE(terms == 1 || B_lo != nullptr, "TF32X3 needs the pre-split weight (B_lo)");
+    // TF32X3: B_lo == NULL means B is the RAW fp32 weight and the kernel splits it (gemm_tc_raw_weights())
     DCNR_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)C | (uintptr_t)B_lo | (uintptr_t)dot_w) & 15) == 0,
                  "operands must be 16-byte aligned");
     DCNR_REQUIRE(C != nullptr || (dot_w != nullptr && dot_out != nullptr), "no output requested");
@@ -822,6 +886,7 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     p.terms = terms;
     p.a_tmem = (terms == 3 && atmem_enabled()) ? 1 : 0;
     p.a_col0 = 0;
+    p.b_split = (terms == 3 && B_lo == nullptr) ? 1 : 0;
     static const int forced_bk = [] {
         const char *e = getenv("DCNR_GEMM_BK");
         return e != nullptr ? atoi(e) : 0;
@@ -907,7 +972,7 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     if (epi.residual != nullptr) DCNR_TRY(make_map(&tmR, epi.residual, m, n, epi.ldr, 32, 32));
     else tmR = tmA;
     DCNR_TRY(make_map(&tmBhi, B, n, k, ldb, p.block_n / ctas, p.bk));
-    DCNR_TRY(make_map(&tmBlo, terms == 3 ? B_lo : B, n, k, ldb, p.block_n / ctas, p.bk));
+    DCNR_TRY(make_map(&tmBlo, (terms == 3 && B_lo != nullptr) ? B_lo : B, n, k, ldb, p.block_n / ctas, p.bk));
     p.num_m_tiles = (int32_t)ceil_div(m, BLOCK_M * ctas);
     const int64_t num_tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
     if (ctas == 2) {

@@ -61,20 +61,23 @@ int launch_gemm_simt(const float *A, int64_t lda, bool a_kmajor, const float *B,
 
 bool gemm_tc_supported(int precision, bool a_kmajor, bool b_kmajor, int64_t lda, int64_t ldb, int64_t ldc, int64_t m,
                        int64_t n, int64_t k, int split_k);
-// TF32X3: B is the tf32-rounded (hi) half of the weight and B_lo its exact remainder (launch_split_tf32)
+// TF32X3: B is the tf32-rounded (hi) half of the weight and B_lo its exact remainder (launch_split_tf32), or B is the raw
+// fp32 weight and B_lo NULL (the kernel splits the weight tiles itself)
 int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,
                    float *C, int64_t ldc, int64_t m, int64_t n, int64_t k, int split_k, const GemmEpilogue &epi,
                    cudaStream_t stream, const float *B_lo, const float *dot_w = nullptr, float *dot_out = nullptr);
 int gemm_tc_n_tiles(int64_t n, int precision);   // column tiles the tensor-core kernel uses for an output width n
 // hi = rn_tf32(src), lo = src - hi, dense [rows, cols] (or transposed: [cols, rows]); lo may be NULL when transposing
 int launch_split_tf32(const float *src, int64_t lds, float *hi, float *lo, int32_t rows, int32_t cols, bool transpose,
-                      cudaStream_t stream);
+                      cudaStream_t stream, bool raw = false);      // raw: plain (transposed) copy into `hi`, no `lo`
 // A pre-processed weight operand for the tensor-core path: `w` [n, k] row-major dense (ld = k).
 struct WeightOp {
-    const float *hi;   // tf32-rounded weight (TF32X3) or the raw weight (other precisions)
-    const float *lo;   // remainder (TF32X3 only), else NULL
+    const float *hi;   // tf32-rounded weight (TF32X3, pre-split form) or the raw weight (other precisions, and TF32X3 with `raw`)
+    const float *lo;   // remainder (TF32X3 pre-split form only), else NULL
     int64_t ld;
+    bool raw = false;  // TF32X3: `hi` is the raw fp32 weight, the GEMM splits it in shared memory (gemm_tc_raw_weights())
 };
+bool gemm_tc_raw_weights();
 // Optional fusion of the final row dot into the GEMM epilogue (tensor-core path only):
 // dot_out[tile][m] = sum over the tile's columns of epilogue(C)[m,n] * dot_w[n]; C itself is not stored.
 struct FusedDot {

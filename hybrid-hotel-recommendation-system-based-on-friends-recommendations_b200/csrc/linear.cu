@@ -9,7 +9,7 @@ bool gemm_any_uses_tc(int precision, int64_t lda, int64_t ldc, int64_t m, int64_
                       int64_t ldb) {
     if (precision == DCNR_PREC_BF16) precision = DCNR_PREC_TF32;
     if (precision == DCNR_PREC_TF32X3)
-        return wop != nullptr && wop->lo != nullptr && gemm_tc_supported(precision, true, true, lda, wop->ld, ldc, m, n, k, 1);
+        return wop != nullptr && (wop->lo != nullptr || wop->raw) && gemm_tc_supported(precision, true, true, lda, wop->ld, ldc, m, n, k, 1);
     if (precision == DCNR_PREC_TF32)
         return gemm_tc_supported(precision, true, true, lda, wop != nullptr ? wop->ld : ldb, ldc, m, n, k, 1);
     return false;
@@ -21,7 +21,7 @@ int gemm_any(int precision, const float *A, int64_t lda, bool a_kmajor, const fl
     if (precision == DCNR_PREC_BF16) precision = DCNR_PREC_TF32;     // no bf16 kernel yet: nearest tensor-core mode
     const float *dw = dot != nullptr ? dot->w : nullptr;
     float *dout = dot != nullptr ? dot->out : nullptr;
-    if (precision == DCNR_PREC_TF32X3 && wop != nullptr && wop->lo != nullptr &&
+    if (precision == DCNR_PREC_TF32X3 && wop != nullptr && (wop->lo != nullptr || wop->raw) &&
         gemm_tc_supported(precision, a_kmajor, true, lda, wop->ld, ldc, m, n, k, split_k))
         return launch_gemm_tc(precision, A, lda, a_kmajor, wop->hi, wop->ld, true, C, ldc, m, n, k, split_k, epi, stream,
                               wop->lo, dw, dout);
@@ -57,10 +57,12 @@ struct TempSplit {
             }
             pool_ready = true;
         }
+        const bool raw = precision == DCNR_PREC_TF32X3 && gemm_tc_raw_weights();
         DCNR_CUDA_CHECK(cudaMallocAsync(&buf, (size_t)n * 2 * sizeof(float), s));
-        DCNR_TRY(launch_split_tf32(w, ldw, buf, buf + n, rows, cols, transpose, s));
+        DCNR_TRY(launch_split_tf32(w, ldw, buf, buf + n, rows, cols, transpose, s, raw));
         op.hi = buf;
-        op.lo = precision == DCNR_PREC_TF32X3 ? buf + n : nullptr;
+        op.lo = (precision == DCNR_PREC_TF32X3 && !raw) ? buf + n : nullptr;
+        op.raw = raw;
         op.ld = transpose ? rows : cols;
         return DCNR_OK;
     }
