@@ -20,10 +20,10 @@ struct __align__(8) SmemSeg {
     const float *table;
     const int64_t *ids;
     int64_t rows;
-    int32_t id_stride, width;
+    int32_t id_stride, width, col0, pad_;
 };
 
-template <int NV>
+template <int NV, int R>
 __global__ void __launch_bounds__(kThreads)
 k_embed_cross_fwd(GatherArgs ga, const float *__restrict__ x_in, int64_t ldx_in, int64_t B, CrossArgs ca,
                   float *__restrict__ x0_out, int64_t ldx0, float *__restrict__ y_out, int64_t ldy,
@@ -49,6 +49,7 @@ k_embed_cross_fwd(GatherArgs ga, const float *__restrict__ x_in, int64_t ldx_in,
         sseg[tid].rows = ga.seg[tid].rows;
         sseg[tid].id_stride = ga.seg[tid].id_stride;
         sseg[tid].width = ga.seg[tid].width;
+        sseg[tid].col0 = ga.seg[tid].col0;
     }
     __syncthreads();
 
@@ -107,7 +108,6 @@ k_embed_cross_fwd(GatherArgs ga, const float *__restrict__ x_in, int64_t ldx_in,
     __syncthreads();
     // ids of the vector quads are fetched one row AHEAD, so a row costs one exposed memory round trip (the table
     // rows) instead of two dependent ones (id, then row)
-    int64_t idv[NV];
     auto load_ids = [&](int64_t r, int64_t (&dst)[NV]) {
 #pragma unroll
         for (int j = 0; j < NV; ++j) {
@@ -115,66 +115,331 @@ k_embed_cross_fwd(GatherArgs ga, const float *__restrict__ x_in, int64_t ldx_in,
             if (qseg[j] >= 0 && r < B) dst[j] = __ldg(sseg[qseg[j]].ids + r * sseg[qseg[j]].id_stride);
         }
     };
-    if (x_in == nullptr) load_ids(warp_first + ((tid >> 3) & 3), idv);
-    for (int64_t base = warp_first; base < B; base += stride) {
-        const int64_t row = base + ((tid >> 3) & 3);
-        const bool active = row < B;
-        float x[NE];
+    // R rows per 8-lane group per iteration (rows base + r * stride): every load of all R rows is issued before the first
+    // use, so a warp keeps R x 4 rows of gathers in flight (the kernel is latency-bound: bytes in flight per SM set the rate)
+    int64_t idv[R][NV];
+    if (x_in == nullptr) {
+#pragma unroll
+        for (int r = 0; r < R; ++r) load_ids(warp_first + ((tid >> 3) & 3) + r * stride, idv[r]);
+    }
+    for (int64_t base = warp_first; base < B; base += R * stride) {
+        int64_t row[R];
+        bool active[R];
+        float x[R][NE];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            row[r] = base + ((tid >> 3) & 3) + r * stride;
+            active[r] = row[r] < B;
+        }
         if (x_in != nullptr) {
 #pragma unroll
-            for (int k = 0; k < NE; ++k) {
-                int col = 32 * (k >> 2) + 4 * lane8 + (k & 3);
-                x[k] = (active && col < D) ? __ldg(x_in + row * ldx_in + col) : 0.f;
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int k = 0; k < NE; ++k) {
+                    int col = 32 * (k >> 2) + 4 * lane8 + (k & 3);
+                    x[r][k] = (active[r] && col < D) ? __ldg(x_in + row[r] * ldx_in + col) : 0.f;
+                }
             }
         } else {
-            int64_t idn[NV];
-            load_ids(row + stride, idn);
+            int64_t idn[R][NV];
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                if (qseg[j] >= 0) {
-                    float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (active) {
-                        const SmemSeg &s = sseg[qseg[j]];
-                        int64_t id = idv[j];
-                        if ((uint64_t)id >= (uint64_t)s.rows) {
-                            bad_id = true;
-                            id = 0;
-                        }
-                        v4 = ldg4(s.table + id * s.width + qoff[j]);
-                    }
-                    x[4 * j] = v4.x; x[4 * j + 1] = v4.y; x[4 * j + 2] = v4.z; x[4 * j + 3] = v4.w;
-                    continue;
-                }
+            for (int r = 0; r < R; ++r) load_ids(row[r] + R * stride, idn[r]);
 #pragma unroll
-                for (int e = 0; e < 4; ++e) {
-                    const int k = 4 * j + e;
-                    const int meta = smeta[lane8][k];
-                    const int kd = (meta & 0xff) - 2, of = meta >> 8;
-                    float v = 0.f;
-                    if (active) {
-                        if (kd >= 0) {
-                            const SmemSeg &s = sseg[kd];
-                            int64_t id = __ldg(s.ids + row * s.id_stride);
-                            if ((uint64_t)id >= (uint64_t)s.rows) {
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    if (qseg[j] >= 0) {
+                        float4 v4 = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (active[r]) {
+                            const SmemSeg &sg = sseg[qseg[j]];
+                            int64_t id = idv[r][j];
+                            if ((uint64_t)id >= (uint64_t)sg.rows) {
                                 bad_id = true;
                                 id = 0;
                             }
-                            v = __ldg(s.table + id * s.width + of);
-                        } else if (kd == -1) {
-                            v = __ldg(ga.num + row * ga.n_num + of);
+                            v4 = ldg4(sg.table + id * sg.width + qoff[j]);
                         }
+                        x[r][4 * j] = v4.x; x[r][4 * j + 1] = v4.y; x[r][4 * j + 2] = v4.z; x[r][4 * j + 3] = v4.w;
+                        continue;
                     }
-                    x[k] = v;
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        const int k = 4 * j + e;
+                        const int meta = smeta[lane8][k];
+                        const int kd = (meta & 0xff) - 2, of = meta >> 8;
+                        float v = 0.f;
+                        if (active[r]) {
+                            if (kd >= 0) {
+                                const SmemSeg &sg = sseg[kd];
+                                int64_t id = __ldg(sg.ids + row[r] * sg.id_stride);
+                                if ((uint64_t)id >= (uint64_t)sg.rows) {
+                                    bad_id = true;
+                                    id = 0;
+                                }
+                                v = __ldg(sg.table + id * sg.width + of);
+                            } else if (kd == -1) {
+                                v = __ldg(ga.num + row[r] * ga.n_num + of);
+                            }
+                        }
+                        x[r][k] = v;
+                    }
                 }
             }
 #pragma unroll
-            for (int j = 0; j < NV; ++j) idv[j] = idn[j];
+            for (int r = 0; r < R; ++r) {
+#pragma unroll
+                for (int j = 0; j < NV; ++j) idv[r][j] = idn[r][j];
+                if (x0_out != nullptr && active[r]) {
+                    if (x0_vec) {
+#pragma unroll
+                        for (int j = 0; j < NV; ++j)
+                            st4(x0_out + row[r] * ldx0 + 32 * j + 4 * lane8,
+                                make_float4(x[r][4 * j], x[r][4 * j + 1], x[r][4 * j + 2], x[r][4 * j + 3]));
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < NE; ++k) {
+                            int col = 32 * (k >> 2) + 4 * lane8 + (k & 3);
+                            if (col < ldx0 && col < DP) x0_out[row[r] * ldx0 + col] = x[r][k];
+                        }
+                    }
+                }
+            }
+        }
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            // cross layers: x <- x * (1 + x.w_l) + b_l
+            for (int l = 0; l < ca.L; ++l) {
+                const float *wl = sw + l * DP, *bl = sb + l * DP;
+                float p = 0.f;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    float4 w4 = *reinterpret_cast<const float4 *>(wl + 32 * j + 4 * lane8);
+                    p = fmaf(x[r][4 * j + 0], w4.x, p);
+                    p = fmaf(x[r][4 * j + 1], w4.y, p);
+                    p = fmaf(x[r][4 * j + 2], w4.z, p);
+                    p = fmaf(x[r][4 * j + 3], w4.w, p);
+                }
+                const float s = group8_sum(p);
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    float4 b4 = *reinterpret_cast<const float4 *>(bl + 32 * j + 4 * lane8);
+                    x[r][4 * j + 0] = fmaf(x[r][4 * j + 0], s, x[r][4 * j + 0]) + b4.x;
+                    x[r][4 * j + 1] = fmaf(x[r][4 * j + 1], s, x[r][4 * j + 1]) + b4.y;
+                    x[r][4 * j + 2] = fmaf(x[r][4 * j + 2], s, x[r][4 * j + 2]) + b4.z;
+                    x[r][4 * j + 3] = fmaf(x[r][4 * j + 3], s, x[r][4 * j + 3]) + b4.w;
+                }
+            }
+            if (y_out != nullptr && active[r]) {
+                if (y_vec) {
+#pragma unroll
+                    for (int j = 0; j < NV; ++j)
+                        st4(y_out + row[r] * ldy + 32 * j + 4 * lane8,
+                            make_float4(x[r][4 * j], x[r][4 * j + 1], x[r][4 * j + 2], x[r][4 * j + 3]));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NE; ++k) {
+                        int col = 32 * (k >> 2) + 4 * lane8 + (k & 3);
+                        if (col < D && col < ldy) y_out[row[r] * ldy + col] = x[r][k];
+                    }
+                }
+            }
+            if (logit_part != nullptr) {
+                float p = 0.f;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    float4 w4 = *reinterpret_cast<const float4 *>(swf + 32 * j + 4 * lane8);
+                    p = fmaf(x[r][4 * j + 0], w4.x, p);
+                    p = fmaf(x[r][4 * j + 1], w4.y, p);
+                    p = fmaf(x[r][4 * j + 2], w4.z, p);
+                    p = fmaf(x[r][4 * j + 3], w4.w, p);
+                }
+                const float s = group8_sum(p);
+                if (active[r] && lane8 == 0) logit_part[row[r]] = s;
+            }
+        }
+    }
+    if (bad_id && err_flag != nullptr) atomicExch(err_flag, 1);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Staged form of the gather (the default when the row layout allows it).  The element-by-element path
+// above spends ~250 of its ~350 warp instructions per 4 rows on the columns that are not 16-byte
+// aligned table quads (categorical rows of odd width, the numerics, the pad): the kernel was
+// issue-bound at ~50 % of HBM bandwidth.  Here a warp takes 32 consecutive rows per step:
+//   1. lane i loads the ids of row i (coalesced, bounds-checked once per id);
+//   2. the "mixed" columns [mix0, DP) of the 32 rows are assembled in a shared-memory tile with
+//      flat, coalesced loops (numerics: 32 x n_num contiguous floats; a categorical table: 32 x width
+//      elements, the row id fetched by shuffle) -- ~4 instructions per 32 elements;
+//   3. 8 passes of 4 rows: the aligned prefix segments (user / item rows) come straight from the
+//      tables as 128-bit loads (ids by shuffle), the rest as float4 reads of the tile; then exactly
+//      the register-resident cross layers / stores of the form above.
+// ------------------------------------------------------------------------------------------------
+constexpr int kMaxVecSeg = 4;
+
+template <int NV, int PF, int MB>
+__global__ void __launch_bounds__(kThreads, MB)
+k_embed_cross_fwd_staged(GatherArgs ga, int n_vec, int mix0, int64_t B, CrossArgs ca, float *__restrict__ x0_out,
+                         int64_t ldx0, float *__restrict__ y_out, int64_t ldy, const float *__restrict__ wf_cross,
+                         float *__restrict__ logit_part, int32_t *err_flag) {
+    constexpr int DP = NV * 32;
+    constexpr int NE = NV * 4;
+    constexpr unsigned kFull = 0xffffffffu;
+    extern __shared__ __align__(16) float smem[];
+    float *sw = smem;                    // [L][DP]
+    float *sb = sw + ca.L * DP;          // [L][DP]
+    float *swf = sb + ca.L * DP;         // [DP]
+    const int TW = DP - mix0, TS = TW + 4;          // tile row: the mixed columns, +4 floats so that rows spread over the banks
+    float *tiles = swf + DP;             // [warps][32][TS]
+    __shared__ SmemSeg sseg[2 + DCNR_MAX_CAT];
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < ca.L * DP; i += kThreads) {
+        int l = i / DP, c = i % DP;
+        sw[i] = c < ca.D ? ca.w[l][c] : 0.f;
+        sb[i] = c < ca.D ? ca.b[l][c] : 0.f;
+    }
+    for (int c = tid; c < DP; c += kThreads) swf[c] = (wf_cross != nullptr && c < ca.D) ? wf_cross[c] : 0.f;
+    for (int i = tid; i < (kThreads / 32) * 32 * TS; i += kThreads) tiles[i] = 0.f;     // pad columns stay zero
+    if (tid < ga.n_seg) {
+        sseg[tid].table = ga.seg[tid].table;
+        sseg[tid].ids = ga.seg[tid].ids;
+        sseg[tid].rows = ga.seg[tid].rows;
+        sseg[tid].id_stride = ga.seg[tid].id_stride;
+        sseg[tid].width = ga.seg[tid].width;
+        sseg[tid].col0 = ga.seg[tid].col0;
+    }
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31, lane8 = lane & 7, grp = lane >> 3;
+    float *tile = tiles + warp * 32 * TS;
+    // row-invariant source of each of this lane's column quads: an aligned table segment (index, offset) or the tile (-1, column)
+    int qseg[NV], qoff[NV];
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+        const int col = 32 * j + 4 * lane8;
+        qseg[j] = -1;
+        qoff[j] = col - mix0;
+        if (col < mix0) {
+            for (int sgi = 0; sgi < n_vec; ++sgi)
+                if (col >= sseg[sgi].col0 && col < sseg[sgi].col0 + sseg[sgi].width) {
+                    qseg[j] = sgi;
+                    qoff[j] = col - sseg[sgi].col0;
+                }
+        }
+    }
+    const bool x0_vec = x0_out != nullptr && ldx0 >= DP && (ldx0 & 3) == 0;
+    const bool y_vec = y_out != nullptr && ldy >= DP && (ldy & 3) == 0;
+    const int D = ga.D;
+    const int n_num = ga.n_num, num_c0 = ga.num_col0 - mix0;
+    const float inv_num = n_num > 0 ? 1.f / (float)n_num : 0.f;
+    bool bad_id = false;
+
+    const int64_t n_blocks = (B + 31) >> 5;
+    const int64_t blk_step = (int64_t)gridDim.x * (kThreads / 32);
+    constexpr int kMixPref = 2;          // ids of the first two narrow tables are fetched one step ahead as well
+    // ids of one 32-row step: lane i loads the ids of row 32 * blk + i (coalesced), bounds-checked here
+    auto load_ids = [&](int64_t blk, int (&v)[kMaxVecSeg], int (&c)[kMixPref]) {
+        const int64_t r = (blk << 5) + lane;
+        const bool have = blk < n_blocks && r < B;
+#pragma unroll
+        for (int sgi = 0; sgi < kMaxVecSeg; ++sgi) {
+            v[sgi] = 0;
+            if (sgi < n_vec && have) {
+                const int64_t id = __ldcs(sseg[sgi].ids + r * sseg[sgi].id_stride);
+                if ((uint64_t)id >= (uint64_t)sseg[sgi].rows) bad_id = true;
+                else v[sgi] = (int)id;
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kMixPref; ++m) {
+            c[m] = 0;
+            const int sgi = n_vec + m;
+            if (sgi < ga.n_seg && have) {
+                const int64_t id = __ldcs(sseg[sgi].ids + r * sseg[sgi].id_stride);
+                if ((uint64_t)id >= (uint64_t)sseg[sgi].rows) bad_id = true;
+                else c[m] = (int)id;
+            }
+        }
+    };
+    int vid[kMaxVecSeg], cpre[kMixPref];
+    const int64_t blk0 = (int64_t)blockIdx.x * (kThreads / 32) + warp;
+    load_ids(blk0, vid, cpre);
+    for (int64_t blk = blk0; blk < n_blocks; blk += blk_step) {
+        const int64_t base = blk << 5;
+        const int64_t myrow = base + lane;
+        const bool have = myrow < B;
+        // 2a. the remaining (narrow / unaligned) tables, element by element in flat order
+        for (int sgi = n_vec; sgi < ga.n_seg; ++sgi) {
+            const SmemSeg &sg = sseg[sgi];
+            int cid = 0;
+            if (sgi - n_vec < kMixPref) {
+                cid = sgi == n_vec ? cpre[0] : cpre[1];
+            } else if (have) {
+                const int64_t id = __ldcs(sg.ids + myrow * sg.id_stride);
+                if ((uint64_t)id >= (uint64_t)sg.rows) bad_id = true;
+                else cid = (int)id;
+            }
+            const int w = sg.width, c0 = sg.col0 - mix0;
+            const float inv_w = 1.f / (float)w;
+            for (int t = 0; t < w; ++t) {
+                const int idx = t * 32 + lane;
+                const int r = (int)(((float)idx + 0.5f) * inv_w);       // exact: idx <= 32 * w, w <= 256
+                const int c = idx - r * w;
+                const int rid = __shfl_sync(kFull, cid, r);
+                tile[r * TS + c0 + c] = __ldg(sg.table + (int64_t)rid * w + c);      // rows past B read row 0 (never stored)
+            }
+        }
+        // 2b. the numerics: 32 x n_num contiguous floats
+        if (n_num > 0) {
+            const float *np = ga.num + base * n_num;
+            const int64_t lim = (B - base) * n_num;
+            for (int t = 0; t < n_num; ++t) {
+                const int idx = t * 32 + lane;
+                const int r = (int)(((float)idx + 0.5f) * inv_num);
+                const int c = idx - r * n_num;
+                tile[r * TS + num_c0 + c] = idx < lim ? __ldcs(np + idx) : 0.f;
+            }
+        }
+        __syncwarp();
+        // ids of the next step now, so that they are in registers when this step's rows are done
+        int nvid[kMaxVecSeg], ncpre[kMixPref];
+        load_ids(blk + blk_step, nvid, ncpre);
+        // 3. four rows per pass, 8 lanes per row.  The table-row loads of PF passes are issued together (one exposed
+        //    memory round trip per PF passes instead of one per pass).
+#pragma unroll 1
+        for (int it0 = 0; it0 < 8; it0 += PF) {
+        float4 pre[PF][NV];
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int r = (it0 + u) * 4 + grp;
+            int rid[kMaxVecSeg];
+#pragma unroll
+            for (int sgi = 0; sgi < kMaxVecSeg; ++sgi) rid[sgi] = sgi < n_vec ? __shfl_sync(kFull, vid[sgi], r) : 0;
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                if (qseg[j] >= 0) {
+                    const SmemSeg &sg = sseg[qseg[j]];
+                    const int id = qseg[j] == 0 ? rid[0] : (qseg[j] == 1 ? rid[1] : (qseg[j] == 2 ? rid[2] : rid[3]));
+                    pre[u][j] = ldg4(sg.table + (int64_t)id * sg.width + qoff[j]);
+                }
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < PF; ++u) {
+            const int r = (it0 + u) * 4 + grp;
+            const int64_t row = base + r;
+            const bool active = row < B;
+            float x[NE];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const float4 v4 = qseg[j] >= 0 ? pre[u][j] : *reinterpret_cast<const float4 *>(tile + r * TS + qoff[j]);
+                x[4 * j] = v4.x; x[4 * j + 1] = v4.y; x[4 * j + 2] = v4.z; x[4 * j + 3] = v4.w;
+            }
             if (x0_out != nullptr && active) {
                 if (x0_vec) {
 #pragma unroll
                     for (int j = 0; j < NV; ++j)
-                        st4(x0_out + row * ldx0 + 32 * j + 4 * lane8,
-                            make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
+                        __stcs(reinterpret_cast<float4 *>(x0_out + row * ldx0 + 32 * j + 4 * lane8), make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
                 } else {
 #pragma unroll
                     for (int k = 0; k < NE; ++k) {
@@ -183,59 +448,64 @@ k_embed_cross_fwd(GatherArgs ga, const float *__restrict__ x_in, int64_t ldx_in,
                     }
                 }
             }
-        }
-        // cross layers: x <- x * (1 + x.w_l) + b_l
-        for (int l = 0; l < ca.L; ++l) {
-            const float *wl = sw + l * DP, *bl = sb + l * DP;
-            float p = 0.f;
+            for (int l = 0; l < ca.L; ++l) {
+                const float *wl = sw + l * DP, *bl = sb + l * DP;
+                float p = 0.f;
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                float4 w4 = *reinterpret_cast<const float4 *>(wl + 32 * j + 4 * lane8);
-                p = fmaf(x[4 * j + 0], w4.x, p);
-                p = fmaf(x[4 * j + 1], w4.y, p);
-                p = fmaf(x[4 * j + 2], w4.z, p);
-                p = fmaf(x[4 * j + 3], w4.w, p);
-            }
-            const float s = group8_sum(p);
+                for (int j = 0; j < NV; ++j) {
+                    float4 w4 = *reinterpret_cast<const float4 *>(wl + 32 * j + 4 * lane8);
+                    p = fmaf(x[4 * j + 0], w4.x, p);
+                    p = fmaf(x[4 * j + 1], w4.y, p);
+                    p = fmaf(x[4 * j + 2], w4.z, p);
+                    p = fmaf(x[4 * j + 3], w4.w, p);
+                }
+                const float sdot = group8_sum(p);
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                float4 b4 = *reinterpret_cast<const float4 *>(bl + 32 * j + 4 * lane8);
-                x[4 * j + 0] = fmaf(x[4 * j + 0], s, x[4 * j + 0]) + b4.x;
-                x[4 * j + 1] = fmaf(x[4 * j + 1], s, x[4 * j + 1]) + b4.y;
-                x[4 * j + 2] = fmaf(x[4 * j + 2], s, x[4 * j + 2]) + b4.z;
-                x[4 * j + 3] = fmaf(x[4 * j + 3], s, x[4 * j + 3]) + b4.w;
-            }
-        }
-        if (y_out != nullptr && active) {
-            if (y_vec) {
-#pragma unroll
-                for (int j = 0; j < NV; ++j)
-                    st4(y_out + row * ldy + 32 * j + 4 * lane8,
-                        make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
-            } else {
-#pragma unroll
-                for (int k = 0; k < NE; ++k) {
-                    int col = 32 * (k >> 2) + 4 * lane8 + (k & 3);
-                    if (col < D && col < ldy) y_out[row * ldy + col] = x[k];
+                for (int j = 0; j < NV; ++j) {
+                    float4 b4 = *reinterpret_cast<const float4 *>(bl + 32 * j + 4 * lane8);
+                    x[4 * j + 0] = fmaf(x[4 * j + 0], sdot, x[4 * j + 0]) + b4.x;
+                    x[4 * j + 1] = fmaf(x[4 * j + 1], sdot, x[4 * j + 1]) + b4.y;
+                    x[4 * j + 2] = fmaf(x[4 * j + 2], sdot, x[4 * j + 2]) + b4.z;
+                    x[4 * j + 3] = fmaf(x[4 * j + 3], sdot, x[4 * j + 3]) + b4.w;
                 }
             }
-        }
-        if (logit_part != nullptr) {
-            float p = 0.f;
+            if (y_out != nullptr && active) {
+                if (y_vec) {
 #pragma unroll
-            for (int j = 0; j < NV; ++j) {
-                float4 w4 = *reinterpret_cast<const float4 *>(swf + 32 * j + 4 * lane8);
-                p = fmaf(x[4 * j + 0], w4.x, p);
-                p = fmaf(x[4 * j + 1], w4.y, p);
-                p = fmaf(x[4 * j + 2], w4.z, p);
-                p = fmaf(x[4 * j + 3], w4.w, p);
+                    for (int j = 0; j < NV; ++j)
+                        __stcs(reinterpret_cast<float4 *>(y_out + row * ldy + 32 * j + 4 * lane8), make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NE; ++k) {
+                        int col = 32 * (k >> 2) + 4 * lane8 + (k & 3);
+                        if (col < D && col < ldy) y_out[row * ldy + col] = x[k];
+                    }
+                }
             }
-            const float s = group8_sum(p);
-            if (active && lane8 == 0) logit_part[row] = s;
+            if (logit_part != nullptr) {
+                float p = 0.f;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    float4 w4 = *reinterpret_cast<const float4 *>(swf + 32 * j + 4 * lane8);
+                    p = fmaf(x[4 * j + 0], w4.x, p);
+                    p = fmaf(x[4 * j + 1], w4.y, p);
+                    p = fmaf(x[4 * j + 2], w4.z, p);
+                    p = fmaf(x[4 * j + 3], w4.w, p);
+                }
+                const float sdot = group8_sum(p);
+                if (active && lane8 == 0) logit_part[row] = sdot;
+            }
         }
+        }
+        __syncwarp();       // the tile is rewritten by the next step
+#pragma unroll
+        for (int sgi = 0; sgi < kMaxVecSeg; ++sgi) vid[sgi] = nvid[sgi];
+#pragma unroll
+        for (int m = 0; m < kMixPref; ++m) cpre[m] = ncpre[m];
     }
     if (bad_id && err_flag != nullptr) atomicExch(err_flag, 1);
 }
+
 
 int make_gather_args(const dcnr_dims *dims, const dcnr_params *params, const dcnr_batch *batch, GatherArgs *out) {
     DCNR_REQUIRE(dims->n_cat >= 0 && dims->n_cat <= DCNR_MAX_CAT, "n_cat %d > %d", dims->n_cat, DCNR_MAX_CAT);
@@ -279,15 +549,102 @@ int launch_embed_cross_fwd(const GatherArgs *ga, const float *x_in, int64_t ldx_
     DCNR_REQUIRE(dim_pad % 32 == 0 && nv >= 1 && nv <= 8, "in_dim_pad %d unsupported (must be 32..256, multiple of 32)",
                  dim_pad);
     const size_t smem = (size_t)(2 * ca.L + 1) * dim_pad * sizeof(float);
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(B, kGroupsPerCta), (int64_t)sm_count() * 8);
-#define DCNR_CASE(NVV)                                                                                      \
-    case NVV:                                                                                               \
-        k_embed_cross_fwd<NVV><<<grid, kThreads, smem, stream>>>(*ga, x_in, ldx_in, B, ca, x0_out, ldx0,   \
-                                                                  y_out, ldy, wf_cross, logit_part, err_flag); \
+    // staged form (see k_embed_cross_fwd_staged): gather mode, a prefix of 16-byte aligned segments, the rest of the row
+    // (narrow tables, numerics, pad) no wider than 96 floats; DCNR_K1_STAGED=0 forces the element-wise form
+    static const bool staged_on = [] {
+        const char *e = getenv("DCNR_K1_STAGED");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    if (x_in == nullptr && staged_on && ga->n_seg > 0) {
+        int n_vec = 0, mix0 = 0;
+        bool ok = true;
+        for (int i = 0; i < ga->n_seg; ++i) {
+            const GatherSeg &sg = ga->seg[i];
+            ok = ok && sg.table != nullptr && sg.rows > 0 && sg.rows < (1ll << 31) && sg.width >= 1 && sg.width <= 256;
+            if (i == n_vec && n_vec < kMaxVecSeg && sg.col0 == mix0 && (sg.width & 3) == 0 && (sg.col0 & 3) == 0 &&
+                (reinterpret_cast<uintptr_t>(sg.table) & 15) == 0) {
+                ++n_vec;
+                mix0 = sg.col0 + sg.width;
+            }
+        }
+        const int tw = dim_pad - mix0;
+        ok = ok && tw >= 0 && tw <= 96 && ga->n_num <= 256 && (ga->n_num == 0 || ga->num != nullptr);
+        if (ok) {
+            const size_t smem_s = smem + (size_t)(kThreads / 32) * 32 * (tw + 4) * sizeof(float);
+            const unsigned grid_s = (unsigned)std::min<int64_t>(ceil_div(B, 32 * (kThreads / 32)), (int64_t)sm_count() * 8);
+            // Measured at 4 M rows (P0, us): one pass of row loads in flight at 64 registers (4 CTAs / SM) 463; 2 passes 500;
+            // 4 passes (130 registers) 548; 48 / 40 registers for 5 / 6 CTAs per SM 578 / 754 (spills); L2 evict_last on the
+            // table rows: no change.  DCNR_K1_PF selects the other builds for such experiments.
+            static const int forced_pf = [] {
+                const char *e = getenv("DCNR_K1_PF");
+                return e != nullptr ? atoi(e) : 0;
+            }();
+#define DCNR_LAUNCH_S(NVV, PFF) DCNR_LAUNCH_SM(NVV, PFF, 1)
+#define DCNR_LAUNCH_SM(NVV, PFF, MBB)                                                                                      \
+    do {                                                                                                                   \
+        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_embed_cross_fwd_staged<NVV, PFF, MBB>,                                      \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));                   \
+        k_embed_cross_fwd_staged<NVV, PFF, MBB><<<grid_s, kThreads, smem_s, stream>>>(*ga, n_vec, mix0, B, ca, x0_out, ldx0,    \
+                                                                                 y_out, ldy, wf_cross, logit_part,         \
+                                                                                 err_flag);                                \
+    } while (0)
+#define DCNR_CASE_S(NVV, PFF)                                                                                              \
+    case NVV:                                                                                                              \
+        DCNR_LAUNCH_S(NVV, PFF);                                                                                           \
+        break;
+            switch (nv) {
+                case 1:
+                case 2:
+                    if (nv == 1) DCNR_LAUNCH_SM(1, 1, 4);
+                    else if (forced_pf == 8) DCNR_LAUNCH_S(2, 8);
+                    else if (forced_pf == 4) DCNR_LAUNCH_S(2, 4);
+                    else if (forced_pf == 24) DCNR_LAUNCH_SM(2, 2, 4);
+                    else if (forced_pf == 23) DCNR_LAUNCH_SM(2, 2, 3);
+                    else if (forced_pf == 15) DCNR_LAUNCH_SM(2, 1, 5);
+                    else if (forced_pf == 16) DCNR_LAUNCH_SM(2, 1, 6);
+                    else DCNR_LAUNCH_SM(2, 1, 4);
+                    break;
+                DCNR_CASE_S(3, 2) DCNR_CASE_S(4, 2) DCNR_CASE_S(5, 1) DCNR_CASE_S(6, 1) DCNR_CASE_S(7, 1) DCNR_CASE_S(8, 1)
+            }
+#undef DCNR_LAUNCH_S
+#undef DCNR_LAUNCH_SM
+#undef DCNR_CASE_S
+            DCNR_LAUNCHED();
+            return DCNR_OK;
+        }
+    }
+    // rows per 8-lane group per iteration: narrow rows keep more gathers in flight (DCNR_K1_ROWS overrides: 1, 2 or 4)
+    static const int forced_rows = [] {
+        const char *e = getenv("DCNR_K1_ROWS");
+        return e != nullptr ? atoi(e) : 0;
+    }();
+    int rpi = 1;      // measured at 4 M rows (P0): 1 row 513 us, 2 rows 647 us, 4 rows 781 us -- the kernel is issue-bound
+    if (forced_rows == 1 || (forced_rows == 2 && nv <= 4) || (forced_rows == 4 && nv <= 2)) rpi = forced_rows;
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(B, kGroupsPerCta * rpi), (int64_t)sm_count() * 8);
+#define DCNR_LAUNCH(NVV, RR)                                                                                             \
+    k_embed_cross_fwd<NVV, RR><<<grid, kThreads, smem, stream>>>(*ga, x_in, ldx_in, B, ca, x0_out, ldx0, y_out, ldy,    \
+                                                                 wf_cross, logit_part, err_flag)
+#define DCNR_CASE_N(NVV)                                                                                                 \
+    case NVV:                                                                                                            \
+        if (rpi == 4) DCNR_LAUNCH(NVV, 4);                                                                               \
+        else if (rpi == 2) DCNR_LAUNCH(NVV, 2);                                                                          \
+        else DCNR_LAUNCH(NVV, 1);                                                                                        \
+        break;
+#define DCNR_CASE_M(NVV)                                                                                                 \
+    case NVV:                                                                                                            \
+        if (rpi == 2) DCNR_LAUNCH(NVV, 2);                                                                               \
+        else DCNR_LAUNCH(NVV, 1);                                                                                        \
+        break;
+#define DCNR_CASE(NVV)                                                                                                   \
+    case NVV:                                                                                                            \
+        DCNR_LAUNCH(NVV, 1);                                                                                             \
         break;
     switch (nv) {
-        DCNR_CASE(1) DCNR_CASE(2) DCNR_CASE(3) DCNR_CASE(4) DCNR_CASE(5) DCNR_CASE(6) DCNR_CASE(7) DCNR_CASE(8)
+        DCNR_CASE_N(1) DCNR_CASE_N(2) DCNR_CASE_M(3) DCNR_CASE_M(4) DCNR_CASE(5) DCNR_CASE(6) DCNR_CASE(7) DCNR_CASE(8)
     }
+#undef DCNR_CASE_N
+#undef DCNR_CASE_M
+#undef DCNR_LAUNCH
 #undef DCNR_CASE
     DCNR_LAUNCHED();
     return DCNR_OK;
