@@ -9,13 +9,13 @@ Everything computes through libdcnr_sm100a.so (include/dcnr.h); there is no CPU 
 """
 from . import _cabi
 from .knn import NearestNeighbors, merge_shards
-from .model import DCN_RecSys, CrossLayer, ResBlock
+from .model import DCN_RecSys, CrossLayer, ResBlock, CrossLayerV2, CrossNetworkV2
 from . import functional
 from . import serving
 from . import distributed
 from . import training
 
-__all__ = ["DCN_RecSys", "CrossLayer", "ResBlock", "NearestNeighbors", "merge_shards", "functional", "serving",
+__all__ = ["DCN_RecSys", "CrossLayer", "ResBlock", "CrossLayerV2", "CrossNetworkV2", "NearestNeighbors", "merge_shards", "functional", "serving",
            "distributed", "training", "library_path", "launch_count"]
 
 

@@ -84,6 +84,10 @@ _SIGS = {
                                c_int64, c_void_p]),
     "dcnr_linear_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int,
                                 c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p]),
+    "dcnr_cross_v2_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
+                                  c_int64, c_int32, c_int32, c_void_p]),
+    "dcnr_cross_v2_bwd_prep": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
+                                       c_void_p, c_int64, c_int, c_int64, c_int32, c_void_p]),
     "dcnr_linear_dgrad": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,
                                   c_int32, c_int32, c_int32, c_void_p]),
     "dcnr_linear_wgrad_scratch_bytes": (c_int64, [c_int64, c_int32, c_int32]),

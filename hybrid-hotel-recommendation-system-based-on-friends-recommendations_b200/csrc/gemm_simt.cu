@@ -114,7 +114,7 @@ k_sgemm(const float *__restrict__ A, int64_t lda, const float *__restrict__ B, i
         __syncthreads();
     }
 
-    // epilogue: v = acc*col_scale + bias + residual ; relu
+    // epilogue: v = (acc*col_scale + bias) [* hadamard] + residual ; relu
     float *Cz = C + (int64_t)blockIdx.z * M * ldc;
     const bool vecC = (ldc & 3) == 0 && ((uintptr_t)Cz & 15) == 0;
     const bool vecR = epi.residual != nullptr && (epi.ldr & 3) == 0 && ((uintptr_t)epi.residual & 15) == 0;
@@ -138,6 +138,11 @@ k_sgemm(const float *__restrict__ A, int64_t lda, const float *__restrict__ B, i
                         if (epi.col_scale != nullptr) v[j] *= __ldg(epi.col_scale + n + j);
                         if (epi.bias != nullptr) v[j] += __ldg(epi.bias + n + j);
                     }
+                }
+                if (epi.hadamard != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        if (n + j < N) v[j] *= __ldg(epi.hadamard + m * epi.ldh + n + j);
                 }
                 if (epi.residual != nullptr) {
                     if (full && vecR) {

@@ -615,7 +615,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
         uint8_t *slots = epi_slots + (size_t)ew * kEpiSlots * kEpiSlotBytes;
         const uint32_t rf0 = rfull0 + 8 * ew * kEpiSlots;
-        const bool has_res = p.epi.residual != nullptr, has_c = p.C != nullptr;
+        const bool has_res = p.epi.residual != nullptr, has_c = p.C != nullptr, has_had = p.epi.hadamard != nullptr;
         const int cpt = (p.block_n + 31) / 32;             // chunks per tile
         const uint32_t swz = (uint32_t)(lane & 7);
         auto issue_res_load = [&](uint32_t g) {            // lane 0: residual box of global chunk g into slot g % kEpiSlots
@@ -638,6 +638,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             if ((p.debug & 16) && blockIdx.x == 0 && tl < 8 && threadIdx.x == 192) p.dbg[512 + tl * 2] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int mw = m0 + quad * 32;                  // first row of this warp
+            const float *had_row = (has_had && (int64_t)mw + lane < p.M)
+                                       ? p.epi.hadamard + ((int64_t)mw + lane) * p.epi.ldh + n0 : nullptr;
             const uint32_t t_main = tmem_base + as * acc_stride + ((uint32_t)(quad * 32) << 16);
             float dot = 0.f;
             for (int c0 = 0; c0 < p.block_n; c0 += 32, ++g) {
@@ -673,6 +675,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     float4 v;
                     v.x = fmaf(__uint_as_float(r[4 * j]), s4.x, b4.x); v.y = fmaf(__uint_as_float(r[4 * j + 1]), s4.y, b4.y);
                     v.z = fmaf(__uint_as_float(r[4 * j + 2]), s4.z, b4.z); v.w = fmaf(__uint_as_float(r[4 * j + 3]), s4.w, b4.w);
+                    if (has_had) {                          // row-per-lane 128-byte segments straight from global memory
+                        const float4 h4 = had_row != nullptr ? ldg4(had_row + c0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                        v.x *= h4.x; v.y *= h4.y; v.z *= h4.z; v.w *= h4.w;
+                    }
                     if (has_res) {
                         const float4 q = *cell;
                         v.x += q.x; v.y += q.y; v.z += q.z; v.w += q.w;
@@ -877,6 +883,8 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     DCNR_REQUIRE(C != nullptr || (dot_w != nullptr && dot_out != nullptr), "no output requested");
     DCNR_REQUIRE(epi.residual == nullptr || ((epi.ldr & 3) == 0 && ((uintptr_t)epi.residual & 15) == 0),
                  "residual must be 16-byte aligned");
+    DCNR_REQUIRE(epi.hadamard == nullptr || ((epi.ldh & 3) == 0 && ((uintptr_t)epi.hadamard & 15) == 0),
+                 "hadamard operand must be 16-byte aligned");
     DCNR_REQUIRE((epi.bias == nullptr || ((uintptr_t)epi.bias & 15) == 0) &&
                      (epi.col_scale == nullptr || ((uintptr_t)epi.col_scale & 15) == 0),
                  "bias / col_scale must be 16-byte aligned");

@@ -49,6 +49,8 @@ struct GemmEpilogue {
     const float *residual;    // [m, ldr] or NULL
     int64_t ldr;
     int relu;
+    const float *hadamard = nullptr;   // [m, ldh] or NULL: v = (acc*col_scale + bias) * hadamard + residual (DCN-v2 cross layer)
+    int64_t ldh = 0;
 };
 // C[m,n] = sum_k A(m,k) * B(k,n) with
 //   a_kmajor: A(m,k) = A[m*lda + k]   else A(m,k) = A[k*lda + m]

@@ -156,3 +156,64 @@ extern "C" int dcnr_linear_wgrad(const float *dy, int64_t lddy, const float *x, 
     return launch_linear_wgrad(precision, dy, lddy, x, ldx, dw, lddw, db, m, n, k, k, reinterpret_cast<float *>(scratch),
                                as_stream(stream));
 }
+
+// ------------------------------------------------------------------------------------------------
+// DCN-v2 ("full-matrix") cross layer, the opt-in variant of SURVEY 8f-4 / the north_star sentence
+//     y = x0 * (x W^T + b) + x            (elementwise *, W [d, d], all rows padded to d = round_up(D, 32))
+// The reference's own CrossLayer is rank-1 (train.py:96-99) and stays the default; this variant has new parameters
+// (a [D, D] weight per layer), so it is checked against its own torch statement (oracle/cross_v2_oracle.py), not
+// against the reference.  Forward = ONE tcgen05 GEMM whose epilogue applies bias, the Hadamard product with x0 (row
+// segments read by the epilogue lanes) and the residual x (TMA-prefetched boxes).  Backward, for upstream g:
+//     gm = g * x0 ; dx0 += g * u (u = x W^T + b, recomputed by a plain GEMM) ; dx = gm W + g ; dW = gm^T x ; db = sum gm
+// i.e. this prep kernel plus the existing dgrad (residual = g) and wgrad entry points.
+// ------------------------------------------------------------------------------------------------
+namespace dcnr {
+__global__ void __launch_bounds__(256)
+k_cross_v2_bwd_prep(const float *__restrict__ g, int64_t ldg, const float *__restrict__ x0, int64_t ldx0,
+                    const float *__restrict__ u, int64_t ldu, float *__restrict__ gm, int64_t ldgm,
+                    float *__restrict__ dx0, int64_t lddx0, int accumulate, int64_t m, int d4) {
+    const int64_t total = m * d4;
+    for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = e / d4;
+        const int c = (int)(e - r * d4) * 4;
+        const float4 gv = ldg4(g + r * ldg + c), xv = ldg4(x0 + r * ldx0 + c), uv = ldg4(u + r * ldu + c);
+        st4(gm + r * ldgm + c, make_float4(gv.x * xv.x, gv.y * xv.y, gv.z * xv.z, gv.w * xv.w));
+        float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (accumulate) acc = *reinterpret_cast<const float4 *>(dx0 + r * lddx0 + c);
+        acc.x = fmaf(gv.x, uv.x, acc.x); acc.y = fmaf(gv.y, uv.y, acc.y);
+        acc.z = fmaf(gv.z, uv.z, acc.z); acc.w = fmaf(gv.w, uv.w, acc.w);
+        st4(dx0 + r * lddx0 + c, acc);
+    }
+}
+}  // namespace dcnr
+
+extern "C" int dcnr_cross_v2_fwd(const float *x0, int64_t ldx0, const float *x, int64_t ldx, const float *w, int64_t ldw,
+                                 const float *bias, float *y, int64_t ldy, int64_t m, int32_t d, int32_t precision,
+                                 dcnr_stream_t stream) {
+    DCNR_REQUIRE(x0 && x && w && y, "null argument");
+    DCNR_REQUIRE(d > 0 && ldx0 >= d && ldx >= d && ldw >= d && ldy >= d, "leading dimension too small");
+    DCNR_REQUIRE((ldx0 & 3) == 0 && ((uintptr_t)x0 & 15) == 0, "x0 must be 16-byte aligned with ld %% 4 == 0");
+    GemmEpilogue epi{nullptr, bias, x, ldx, 0};
+    epi.hadamard = x0;
+    epi.ldh = ldx0;
+    TempSplit ts;
+    if (precision != DCNR_PREC_FP32 && gemm_tc_supported(DCNR_PREC_TF32, true, true, ldx, d, ldy, m, d, d, 1))
+        DCNR_TRY(ts.make(precision, w, ldw, d, d, false, as_stream(stream)));
+    return gemm_any(precision, x, ldx, true, w, ldw, true, y, ldy, m, d, d, 1, epi, as_stream(stream), ts.get());
+}
+
+extern "C" int dcnr_cross_v2_bwd_prep(const float *g, int64_t ldg, const float *x0, int64_t ldx0, const float *u,
+                                      int64_t ldu, float *gm, int64_t ldgm, float *dx0, int64_t lddx0, int accumulate,
+                                      int64_t m, int32_t d, dcnr_stream_t stream) {
+    DCNR_REQUIRE(g && x0 && u && gm && dx0, "null argument");
+    DCNR_REQUIRE(d > 0 && (d & 3) == 0 && ((ldg | ldx0 | ldu | ldgm | lddx0) & 3) == 0, "d and leading dimensions must be multiples of 4");
+    DCNR_REQUIRE((((uintptr_t)g | (uintptr_t)x0 | (uintptr_t)u | (uintptr_t)gm | (uintptr_t)dx0) & 15) == 0,
+                 "operands must be 16-byte aligned");
+    if (m <= 0) return DCNR_OK;
+    const int64_t total = m * (d / 4);
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(total, 256), (int64_t)sm_count() * 16);
+    k_cross_v2_bwd_prep<<<grid, 256, 0, as_stream(stream)>>>(g, ldg, x0, ldx0, u, ldu, gm, ldgm, dx0, lddx0, accumulate, m,
+                                                            d / 4);
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}

@@ -75,6 +75,73 @@ def cross_network(x: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequ
     return _CrossFn.apply(x, len(weights), *weights, *biases)
 
 
+# ------------------------------------------------------------------------------------------ DCN-v2 cross (opt-in)
+def _pad_cols(t: torch.Tensor, width: int) -> torch.Tensor:
+    t = _f32c(t)
+    return t if t.shape[-1] == width else torch.nn.functional.pad(t, (0, width - t.shape[-1]))
+
+
+class _CrossV2Fn(Function):
+    """All layers of the full-matrix cross network on rows padded to a multiple of 32 floats:
+    x_{l+1} = x0 * (x_l W_l^T + b_l) + x_l.  Saves the layer inputs; recomputes u_l = x_l W_l^T + b_l in backward."""
+
+    @staticmethod
+    def forward(ctx, x0, n_layers, precision, *wb):
+        C.require_cuda(x0)
+        B, D = x0.shape
+        Dp = (D + 31) // 32 * 32
+        p = _prec(precision)
+        x0p = _pad_cols(x0, Dp)
+        ws = [torch.nn.functional.pad(_f32c(w), (0, Dp - D, 0, Dp - D)) for w in wb[:n_layers]]
+        bs = [_pad_cols(b, Dp) for b in wb[n_layers:]]
+        xs = [x0p]
+        for l in range(n_layers):
+            y = torch.empty_like(x0p)
+            C.check(C.lib().dcnr_cross_v2_fwd(C.ptr(x0p), Dp, C.ptr(xs[-1]), Dp, C.ptr(ws[l]), Dp, C.ptr(bs[l]), C.ptr(y), Dp,
+                                              B, Dp, p, C.stream()))
+            xs.append(y)
+        ctx.save_for_backward(*xs[:-1], *ws, *bs)
+        ctx.meta = (n_layers, D, Dp, p)
+        return xs[-1][:, :D].contiguous() if Dp != D else xs[-1]
+
+    @staticmethod
+    def backward(ctx, gy):
+        L, D, Dp, p = ctx.meta
+        xs, ws, bs = ctx.saved_tensors[:L], ctx.saved_tensors[L:2 * L], ctx.saved_tensors[2 * L:]
+        x0p = xs[0]
+        B = x0p.shape[0]
+        lib, st = C.lib(), C.stream()
+        g = _pad_cols(gy, Dp)
+        dx0 = torch.zeros_like(x0p)
+        gws, gbs = [None] * L, [None] * L
+        scratch = _scratch(lib.dcnr_linear_wgrad_scratch_bytes(B, Dp, Dp), x0p.device)
+        u, gm = torch.empty_like(x0p), torch.empty_like(x0p)
+        for l in reversed(range(L)):
+            # u = x_l W^T + b ; gm = g * x0 ; dx0 += g * u
+            C.check(lib.dcnr_linear_fwd(C.ptr(xs[l]), Dp, C.ptr(ws[l]), Dp, C.ptr(bs[l]), None, None, 0, 0, C.ptr(u), Dp, B, Dp,
+                                        Dp, p, st))
+            C.check(lib.dcnr_cross_v2_bwd_prep(C.ptr(g), Dp, C.ptr(x0p), Dp, C.ptr(u), Dp, C.ptr(gm), Dp, C.ptr(dx0), Dp, 1, B,
+                                               Dp, st))
+            gw = torch.empty((Dp, Dp), device=x0p.device, dtype=torch.float32)
+            gb = torch.empty(Dp, device=x0p.device, dtype=torch.float32)
+            C.check(lib.dcnr_linear_wgrad(C.ptr(gm), Dp, C.ptr(xs[l]), Dp, C.ptr(gw), Dp, C.ptr(gb), B, Dp, Dp, p,
+                                          C.ptr(scratch), scratch.numel(), st))
+            gws[l], gbs[l] = gw[:D, :D].contiguous(), gb[:D].contiguous()
+            g_next = torch.empty_like(x0p)       # dx_l = gm W + g
+            C.check(lib.dcnr_linear_dgrad(C.ptr(gm), Dp, C.ptr(ws[l]), Dp, C.ptr(g), Dp, C.ptr(g_next), Dp, B, Dp, Dp, p, st))
+            g = g_next
+        dx0 += g                                  # x_0 is also the first layer's input
+        gx0 = dx0[:, :D].contiguous() if Dp != D else dx0
+        return (gx0, None, None) + tuple(gws) + tuple(gbs)
+
+
+def cross_network_v2(x0: torch.Tensor, weights: Sequence[torch.Tensor], biases: Sequence[torch.Tensor],
+                     precision="tf32x3") -> torch.Tensor:
+    """DCN-v2 cross network (opt-in): x_{l+1} = x0 * (x_l W_l^T + b_l) + x_l with W_l [D, D].
+    Each layer is one tcgen05 GEMM with bias / Hadamard / residual in the epilogue (dcnr_cross_v2_fwd)."""
+    return _CrossV2Fn.apply(x0, len(weights), precision, *weights, *biases)
+
+
 # ------------------------------------------------------------------------------------------ linear
 def linear_forward_raw(x, w, bias=None, col_scale=None, residual=None, relu=False, precision="fp32"):
     C.require_cuda(x, w)

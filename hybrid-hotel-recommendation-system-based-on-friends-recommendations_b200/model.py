@@ -36,6 +36,35 @@ class CrossLayer(nn.Module):
         return F_.cross_network(x, [self.w.weight], [self.b])
 
 
+class CrossLayerV2(nn.Module):
+    """OPT-IN DCN-v2 cross layer y = x0 * (W x + b) + x with a full [D, D] weight (BASELINE.json north_star item 2,
+    SURVEY 8f-4).  Not in the reference (its CrossLayer above is rank-1) -- different parameters, own oracle
+    (oracle/cross_v2_oracle.py), never the default."""
+
+    def __init__(self, input_dim: int, precision: str = "tf32x3"):
+        super().__init__()
+        self.w = nn.Linear(input_dim, input_dim, bias=False)
+        self.b = nn.Parameter(torch.zeros(input_dim))
+        self.precision = precision
+
+    def forward(self, x0: torch.Tensor, x: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if x is not None and x is not x0:
+            raise ValueError("stand-alone CrossLayerV2 takes x == x0; stack layers with CrossNetworkV2")
+        return F_.cross_network_v2(x0, [self.w.weight], [self.b], self.precision)
+
+
+class CrossNetworkV2(nn.Module):
+    """n_layers CrossLayerV2 applied from x0 (x_{l+1} = x0 * (W_l x_l + b_l) + x_l), one fused GEMM per layer."""
+
+    def __init__(self, input_dim: int, n_layers: int, precision: str = "tf32x3"):
+        super().__init__()
+        self.layers = nn.ModuleList([CrossLayerV2(input_dim, precision) for _ in range(n_layers)])
+        self.precision = precision
+
+    def forward(self, x0: torch.Tensor) -> torch.Tensor:
+        return F_.cross_network_v2(x0, [l.w.weight for l in self.layers], [l.b for l in self.layers], self.precision)
+
+
 class ResBlock(nn.Module):
     """relu(BN2(L2(drop(relu(BN1(L1(x)))))) + x)   (train.py:102-122 / main.py:73-90)."""
 

@@ -206,6 +206,21 @@ int dcnr_linear_fwd(const float *x, int64_t ldx, const float *w, int64_t ldw, co
                     const float *col_scale, const float *residual, int64_t ldr, int relu, float *y, int64_t ldy,
                     int64_t m, int32_t n, int32_t k, int32_t precision, dcnr_stream_t stream);
 
+/* DCN-v2 ("full-matrix") cross layer -- OPT-IN variant (BASELINE.json north_star item 2), not the reference's
+ * rank-1 CrossLayer (train.py:96-99, served by dcnr_cross_fwd above):
+ *     y = x0 * (x W^T + bias) + x        elementwise *, x0 / x / y [m, d], W [d, d] (nn.Linear layout), bias [d] or NULL.
+ * One tcgen05 GEMM with bias, Hadamard and residual fused into the epilogue when d % 32 == 0 and precision != fp32
+ * (rows padded with zeros to d = round_up(D, 32), W zero-padded to [d, d]); the CUDA-core GEMM otherwise. */
+int dcnr_cross_v2_fwd(const float *x0, int64_t ldx0, const float *x, int64_t ldx, const float *w, int64_t ldw,
+                      const float *bias, float *y, int64_t ldy, int64_t m, int32_t d, int32_t precision,
+                      dcnr_stream_t stream);
+/* Elementwise part of its backward for upstream g = dL/dy and u = x W^T + bias (dcnr_linear_fwd):
+ *     gm = g * x0 ;  dx0 = (accumulate ? dx0 : 0) + g * u.
+ * The rest is dx = gm W + g (dcnr_linear_dgrad with residual g) and dW = gm^T x, db = sum gm (dcnr_linear_wgrad). */
+int dcnr_cross_v2_bwd_prep(const float *g, int64_t ldg, const float *x0, int64_t ldx0, const float *u, int64_t ldu,
+                           float *gm, int64_t ldgm, float *dx0, int64_t lddx0, int accumulate, int64_t m, int32_t d,
+                           dcnr_stream_t stream);
+
 /* dx = dy W (+ residual)   -- autograd of nn.Linear wrt its input.  dy [m,n], W [n,k], dx [m,k]. */
 int dcnr_linear_dgrad(const float *dy, int64_t lddy, const float *w, int64_t ldw, const float *residual,
                       int64_t ldr, float *dx, int64_t lddx, int64_t m, int32_t n, int32_t k, int32_t precision,

@@ -162,3 +162,36 @@ def test_mmr_oracle_matches_reference_rerank(name):
     z = np.load(os.path.join(os.path.dirname(__file__), "golden", f"mmr_{name}.npz"))
     got = mmr_oracle.mmr_rerank(z["E"], z["scores"], z["emb_idx"], float(z["lam"]), int(z["top_k"]))
     assert np.array_equal(got, z["order"])
+
+
+# ------------------------------------------------------------------------------------------------
+# opt-in DCN-v2 cross network: the two independent statements of the oracle agree (parity unpinned
+# against the reference, which has no such layer -- see oracle/cross_v2_oracle.py)
+# ------------------------------------------------------------------------------------------------
+def test_cross_v2_oracle_closed_form_matches_autograd():
+    from oracle import cross_v2_oracle as V2
+    g = torch.Generator().manual_seed(7)
+    B, D, L = 37, 57, 3
+    x0 = (torch.randn(B, D, generator=g, dtype=torch.float64) * 0.5).requires_grad_()
+    ws = [(torch.randn(D, D, generator=g, dtype=torch.float64) / D ** 0.5).requires_grad_() for _ in range(L)]
+    bs = [(torch.randn(D, generator=g, dtype=torch.float64) * 0.1).requires_grad_() for _ in range(L)]
+    gy = torch.randn(B, D, generator=g, dtype=torch.float64)
+    y = V2.cross_v2_forward_torch(x0, ws, bs)
+    y.backward(gy)
+    y_np, dx0, gws, gbs = V2.cross_v2_numpy(x0.detach().numpy(), [w.detach().numpy() for w in ws],
+                                            [b.detach().numpy() for b in bs], gy.numpy())
+    np.testing.assert_allclose(y_np, y.detach().numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(dx0, x0.grad.numpy(), rtol=1e-11, atol=1e-12)
+    for l in range(L):
+        np.testing.assert_allclose(gws[l], ws[l].grad.numpy(), rtol=1e-11, atol=1e-12)
+        np.testing.assert_allclose(gbs[l], bs[l].grad.numpy(), rtol=1e-11, atol=1e-12)
+
+
+def test_cross_v2_oracle_known_answer():
+    """Hand-computed: D = 2, one layer, W = [[1, 2], [3, 4]], b = [0.5, -1], x0 = [1, 2]:
+    u = W x0 + b = [5.5, 10], y = x0 * u + x0 = [6.5, 22]."""
+    from oracle import cross_v2_oracle as V2
+    x0 = torch.tensor([[1.0, 2.0]], dtype=torch.float64)
+    y = V2.cross_v2_forward_torch(x0, [torch.tensor([[1.0, 2.0], [3.0, 4.0]], dtype=torch.float64)],
+                                  [torch.tensor([0.5, -1.0], dtype=torch.float64)])
+    assert y.tolist() == [[6.5, 22.0]]
