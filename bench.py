@@ -321,6 +321,10 @@ def main():
             import kernel_probe
             result["kernels"] = {k: {kk: vv for kk, vv in v.items() if kk != "note"} for k, v in
                                  kernel_probe.probe(65_536, pk["hbm"]).items()}
+            torch.cuda.empty_cache()
+            result["kernels_4m_rows"] = {k: {kk: vv for kk, vv in v.items() if kk != "note"} for k, v in
+                                         kernel_probe.probe(1 << 22, pk["hbm"]).items()}
+            result["kernels_4m_rows"]["how"] = "the same operator calls at B = 4 194 304 rows (the bandwidth regime: every tensor > L2)"
             result["kernels"]["how"] = ("C-ABI operator calls at the configs[2] shape (B = 65536, tables 1M x 100K), CUDA events, "
                                         "algorithmic bytes per row from SURVEY.md 8d; hbm_frac = GB/s / measured copy bandwidth")
         if comm is not None:

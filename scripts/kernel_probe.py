@@ -55,6 +55,14 @@ def probe(B, hbm_peak):
     xc = torch.randn((B, D), device=dev, generator=g) * 0.1
     t = timed(lambda: F_.cross_network(xc, w, b))
     rec("K2_cross_fwd_standalone", t, 2 * D * 4, "x read + y write, unpadded rows (fused into K1 in the model: 0 extra bytes there)")
+    # opt-in DCN-v2 cross layer: one tcgen05 GEMM [B,64]x[64,64] with bias / Hadamard / residual in the epilogue
+    x0p = torch.randn((B, Dp), device=dev, generator=g) * 0.1
+    wv2 = torch.randn((Dp, Dp), device=dev, generator=g) / 8; bv2 = torch.zeros(Dp, device=dev); yv2 = torch.empty_like(x0p)
+    t = timed(lambda: C.check(C.lib().dcnr_cross_v2_fwd(C.ptr(x0p), Dp, C.ptr(x0p), Dp, C.ptr(wv2), Dp, C.ptr(bv2), C.ptr(yv2), Dp,
+                                                       B, Dp, C.PRECISIONS["tf32x3"], C.stream())))
+    rec("K2v2_cross_v2_layer_fwd", t, 3 * Dp * 4, "x0 read (Hadamard) + x read (GEMM operand; the residual box re-reads it through L2) + y write, "
+        "padded 64-float rows; 2*64*64 flops per row (tf32x3)")
+    del x0p, yv2
     H = 256
     z = torch.randn((B, H), device=dev, generator=g)
     mean = torch.empty(H, device=dev); rstd = torch.empty(H, device=dev)
