@@ -38,10 +38,14 @@ int sm_count() {
 // 32 columns x 8 slices per CTA: slice y adds its contiguous range of partial rows in ascending order in double,
 // then the 8 slice sums are added in slice order -- a fixed association, so the result does not depend on how the
 // producing grid was scheduled.  (One thread per column over ALL partials was a 20 us latency chain per call.)
-constexpr int kSumSlices = 8;
-__global__ void __launch_bounds__(32 * kSumSlices)
+// Slices per CTA = blockDim.x / 32: 8 for short partial lists, 32 from 64 partials on (a B = 65 536 step reduces 256 chunk
+// partials a dozen times: 32 slices make that one batch of 8 loads per thread instead of four dependent ones).
+constexpr int kSumSlices = 8, kSumSlicesMax = 32;
+static inline int sum_slices(int64_t n_partials) { return n_partials >= 64 ? kSumSlicesMax : kSumSlices; }
+__global__ void __launch_bounds__(32 * kSumSlicesMax)
 k_sum_partials(const float *__restrict__ partials, int64_t n_partials, int64_t ld, SegPtrs seg) {
-    __shared__ double sh[kSumSlices][33];
+    __shared__ double sh[kSumSlicesMax][33];
+    const int kSumSlices = blockDim.x >> 5;
     const int s = blockIdx.y;
     if (s >= seg.n || seg.out[s] == nullptr) return;                 // CTA-uniform
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -78,7 +82,7 @@ int launch_sum_partials(const float *partials, int64_t n_partials, int64_t ld, c
         if (seg.out[i] && seg.len[i] > maxlen) maxlen = seg.len[i];
     if (maxlen == 0) return DCNR_OK;
     dim3 grid((unsigned)ceil_div(maxlen, 32), (unsigned)seg.n);
-    k_sum_partials<<<grid, 32 * kSumSlices, 0, stream>>>(partials, n_partials, ld, seg);
+    k_sum_partials<<<grid, 32 * sum_slices(n_partials), 0, stream>>>(partials, n_partials, ld, seg);
     DCNR_LAUNCHED();
     return DCNR_OK;
 }
@@ -86,10 +90,11 @@ int launch_sum_partials(const float *partials, int64_t n_partials, int64_t ld, c
 // out[r, c] = sum over partial tables p of partials[p][r][c], same 32 x 8 scheme as k_sum_partials (fixed slices,
 // ascending order inside a slice, slices added in order).  A single chain over ~1 500 partial tables (tiny-table scatter
 // at B = 1 M) took 130 us.
-__global__ void __launch_bounds__(32 * kSumSlices)
+__global__ void __launch_bounds__(32 * kSumSlicesMax)
 k_sum_partials_2d(const float *__restrict__ partials, int64_t n_partials, int32_t rows, int32_t cols_pad, int32_t cols,
                   float *__restrict__ out, int64_t ldo) {
-    __shared__ double sh[kSumSlices][33];
+    __shared__ double sh[kSumSlicesMax][33];
+    const int kSumSlices = blockDim.x >> 5;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const int64_t e = (int64_t)blockIdx.x * 32 + tx;
     const int64_t total = (int64_t)rows * cols_pad;
@@ -123,7 +128,7 @@ k_sum_partials_2d(const float *__restrict__ partials, int64_t n_partials, int32_
 int launch_sum_partials_2d(const float *partials, int64_t n_partials, int32_t rows, int32_t cols_pad,
                            int32_t cols, float *out, int64_t ldo, cudaStream_t stream) {
     int64_t total = (int64_t)rows * cols_pad;
-    k_sum_partials_2d<<<(unsigned)ceil_div(total, 32), 32 * kSumSlices, 0, stream>>>(partials, n_partials, rows, cols_pad,
+    k_sum_partials_2d<<<(unsigned)ceil_div(total, 32), 32 * sum_slices(n_partials), 0, stream>>>(partials, n_partials, rows, cols_pad,
                                                                                    cols, out, ldo);
     DCNR_LAUNCHED();
     return DCNR_OK;
