@@ -226,6 +226,7 @@ struct Params {
     int32_t N_total, K, block_n, terms, stages, acc_cols, acc_stages, corr_sep, tmem_cols;
     int32_t bk;               // floats per k-block (32, or 16 with A in tensor memory: six finer pipeline stages)
     int32_t epi_slots;        // epilogue slots per warp (2 or 4)
+    int32_t epi_groups;       // 1: warps 6-9 drain the accumulator; 2: warps 10-13 as well (alternate 32-column chunks)
     int32_t a_tmem, a_col0;   // TF32X3: A hi / lo in a tensor-memory ring (64 columns per stage) starting at column a_col0
     int32_t b_split;          // TF32X3: the weight arrives as raw fp32 and warps 10-13 split it in shared memory (half the L2 stream)
     int32_t num_m_tiles, num_n_tiles;
@@ -236,7 +237,7 @@ struct Params {
     int64_t ldc;
     GemmEpilogue epi;
     const float *dot_w;       // optional fused row dot with the epilogue output: [N_total]
-    float *dot_out;           // [num_n_tiles][M] partial dots (summed by the caller)
+    float *dot_out;           // [num_n_tiles * epi_groups][M] partial dots (summed by the caller)
 };
 
 constexpr int kThreadsP = 448;                      // warp 0 TMA, warp 1 MMA, warps 2-5 A split, warps 6-9 epilogue, warps 10-13 weight split
@@ -276,9 +277,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int stages = p.stages, acc_stages = p.acc_stages;
     uint8_t *epi_slots = smem + (size_t)stages * stage_bytes;            // 1024-aligned (stage sizes are multiples of 1 KB)
     const int kEpiSlots = p.epi_slots;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_slots + 4 * kEpiSlots * kEpiSlotBytes);
-    // bars: fullA[stages], fullB[stages], ready[stages], empty[stages], tfull[acc_stages], tempty[acc_stages], rfull[4][kEpiSlots]
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * stages + 2 * acc_stages + 4 * kEpiSlotsMax);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_slots + 4 * p.epi_groups * kEpiSlots * kEpiSlotBytes);
+    // bars: fullA[stages], fullB[stages], ready[stages], empty[stages], tfull[acc_stages], tempty[acc_stages], rfull[8][kEpiSlots]
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * stages + 2 * acc_stages + 8 * kEpiSlotsMax);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t fullA0 = smem_u32(bars), fullB0 = smem_u32(bars + stages), ready0 = smem_u32(bars + 2 * stages),
@@ -301,9 +302,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
         for (int a = 0; a < acc_stages; ++a) {
             mbar_init(tfull0 + 8 * a, 1);
-            mbar_init(tempty0 + 8 * a, 4 * CTAS);       // one arrival per epilogue warp
+            mbar_init(tempty0 + 8 * a, 4 * CTAS * p.epi_groups);   // one arrival per epilogue warp
         }
-        for (int i = 0; i < 4 * kEpiSlots; ++i) mbar_init(rfull0 + 8 * i, 1);
+        for (int i = 0; i < 8 * kEpiSlots; ++i) mbar_init(rfull0 + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 1) {
@@ -563,7 +564,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
             }
         }
-    } else if (warp >= 10) {
+    } else if (warp >= 10 && p.epi_groups == 1) {
         // ---------------- warps 10..13: split the landed raw weight tile into hi / lo in shared memory (b_split) ----------------
         // The weight stream from L2 was the larger half of the kernel's L2 -> SM traffic (hi + lo boxes: 32 of 64 KB per
         // k-block at ~42 B/clk/SM); loading fp32 once and splitting here halves it.  Elementwise, so the swizzle is irrelevant;
@@ -602,8 +603,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
             }
         }
-    } else {
-        // ---------------- warps 6..9: epilogue (each CTA drains its own 128 accumulator rows) ----------------
+    } else if (warp < 10 || p.epi_groups == 2) {
+        // ---------------- warps 6..9 (and 10..13): epilogue (each CTA drains its own 128 accumulator rows) ----------------
         // TMEM gives each lane one accumulator ROW (32 columns per tcgen05.ld), so the arithmetic is done
         // row-per-thread; all global traffic is TMA.  A warp owns kEpiSlots shared-memory slots of
         // 32 rows x 32 columns (128B-swizzled, so a lane reads / writes its own 128-byte row without bank
@@ -611,18 +612,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // ahead (48 KB in flight per SM -- with register-staged loads the epilogue was latency-bound at
         // ~2.4 TB/s), the lane combines accumulator, scale, bias, residual, ReLU in place, and one lane
         // TMA-stores the slot to C (rows past M are clipped by the tensor map).
-        const int ew = warp - 6;
+        // With epi_groups == 2 the warps 10..13 join in: warp w and warp w + 4 share a TMEM lane quadrant and take
+        // alternate 32-column chunks of every tile (the K = 64 initial layer is epilogue-bound with four warps).
+        const int ew = warp - 6;                           // 0..7
+        const int eg = ew >> 2, ngroups = p.epi_groups;    // this warp's chunk phase
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
         uint8_t *slots = epi_slots + (size_t)ew * kEpiSlots * kEpiSlotBytes;
         const uint32_t rf0 = rfull0 + 8 * ew * kEpiSlots;
         const bool has_res = p.epi.residual != nullptr, has_c = p.C != nullptr, has_had = p.epi.hadamard != nullptr;
-        const int cpt = (p.block_n + 31) / 32;             // chunks per tile
+        const int cpt = (p.block_n + 31) / 32 / ngroups;   // chunks per tile for this warp (block_n / 32 is even when ngroups == 2)
         const uint32_t swz = (uint32_t)(lane & 7);
         auto issue_res_load = [&](uint32_t g) {            // lane 0: residual box of global chunk g into slot g % kEpiSlots
             const int t = tile0 + (int)(g / cpt) * tile_step;
             if (t >= num_tiles) return;
             const int m0 = (t / p.num_n_tiles) * (BLOCK_M * CTAS) + (int)rank * BLOCK_M + quad * 32;
-            const int n = (t % p.num_n_tiles) * p.block_n + (int)(g % cpt) * 32;
+            const int n = (t % p.num_n_tiles) * p.block_n + ((int)(g % cpt) * ngroups + eg) * 32;
             const uint32_t sl = g % kEpiSlots;
             mbar_expect_tx(rf0 + 8 * sl, (uint32_t)kEpiSlotBytes);
             tma_load_2d(smem_u32(slots + sl * kEpiSlotBytes), &tmR, n, m0, rf0 + 8 * sl);
@@ -642,7 +646,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                                        ? p.epi.hadamard + ((int64_t)mw + lane) * p.epi.ldh + n0 : nullptr;
             const uint32_t t_main = tmem_base + as * acc_stride + ((uint32_t)(quad * 32) << 16);
             float dot = 0.f;
-            for (int c0 = 0; c0 < p.block_n; c0 += 32, ++g) {
+            for (int c0 = 32 * eg; c0 < p.block_n; c0 += 32 * ngroups, ++g) {
                 const uint32_t sl = g % kEpiSlots;
                 uint8_t *row = slots + sl * kEpiSlotBytes + lane * 128;
                 const bool stamp = (p.debug & 16) && blockIdx.x == 0 && threadIdx.x == 192 && g >= 16 && g < 48;
@@ -716,7 +720,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 else mbar_arrive(tempty0 + 8 * as);
             }
             if (p.dot_w != nullptr && (int64_t)mw + lane < p.M)        // fused row dot: out[n_tile][m] = sum_n v[m,n] * w[n]
-                p.dot_out[(int64_t)n_tile * p.M + mw + lane] = dot;
+                p.dot_out[((int64_t)n_tile * ngroups + eg) * p.M + mw + lane] = dot;
         }
         if (lane == 0) bulk_wait_all();
     }
@@ -839,9 +843,24 @@ bool gemm_tc_raw_weights() {
     return on;
 }
 
-int gemm_tc_n_tiles(int64_t n, int precision) {
+// Epilogue warp groups: two (eight warps) for short reductions (k <= 64: the initial layer is epilogue-bound with four
+// warps -- 0.34 vs 0.43-0.54 ms per 1 M x 256 x 64), one otherwise (measured on the 256 x 256 layers: 0.83 vs 0.81 ms tf32x3,
+// 0.67 vs 0.62 ms tf32 -- the mainloop, not the epilogue, sets the pace there).  Also one when the tile has an odd number
+// of 32-column chunks or warps 10-13 split the weight (DCNR_GEMM_BSPLIT=1).  DCNR_GEMM_EPI_GROUPS=1|2 forces a choice.
+static int epi_groups_for(int block_n, int precision, int64_t k) {
+    static const int forced = [] {
+        const char *e = getenv("DCNR_GEMM_EPI_GROUPS");
+        return e != nullptr ? atoi(e) : 0;
+    }();
+    if (forced == 1 || block_n <= 0 || (block_n / 32) % 2 != 0) return 1;
+    if (precision == DCNR_PREC_TF32X3 && gemm_tc_raw_weights()) return 1;
+    if (forced == 2) return 2;
+    return k <= 64 ? 2 : 1;
+}
+
+int gemm_tc_n_tiles(int64_t n, int precision, int64_t k) {      // partial row dots a FusedDot produces: column tiles x epilogue groups
     const int bn = tc::block_n_for(precision, n);
-    return bn > 0 ? (int)(n / bn) : 1;
+    return bn > 0 ? (int)(n / bn) * epi_groups_for(bn, precision, k) : 1;
 }
 
 bool gemm_tc_supported(int precision, bool a_kmajor, bool b_kmajor, int64_t lda, int64_t ldb, int64_t ldc, int64_t m,
@@ -895,6 +914,7 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     p.a_tmem = (terms == 3 && atmem_enabled()) ? 1 : 0;
     p.a_col0 = 0;
     p.b_split = (terms == 3 && B_lo == nullptr) ? 1 : 0;
+    p.epi_groups = p.b_split ? 1 : epi_groups_for(p.block_n, precision, k);
     static const int forced_bk = [] {
         const char *e = getenv("DCNR_GEMM_BK");
         return e != nullptr ? atoi(e) : 0;
@@ -940,12 +960,14 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
         }();
         const int cap = p.a_tmem ? 256 / (2 * p.bk) : 6;
         auto stages_for = [&](int slots) {
-            const int budget = 227 * 1024 - 1024 - kBarBytes - 4 * slots * kEpiSlotBytes;
+            const int budget = 227 * 1024 - 1024 - kBarBytes - 4 * p.epi_groups * slots * kEpiSlotBytes;
             return std::max(1, std::min(cap, budget / stage_bytes));
         };
-        p.epi_slots = (forced_slots == 2 || forced_slots == 4) ? forced_slots : (stages_for(2) > stages_for(4) && p.a_tmem ? 2 : 4);
+        // eight epilogue warps take two slots each (the same 64 KB as four warps x four slots)
+        p.epi_slots = (forced_slots == 2 || forced_slots == 4) ? forced_slots
+                      : (p.epi_groups == 2 || (stages_for(2) > stages_for(4) && p.a_tmem) ? 2 : 4);
         p.stages = stages_for(p.epi_slots);
-        *smem_out = (size_t)p.stages * stage_bytes + 1024 + kBarBytes + 4 * p.epi_slots * kEpiSlotBytes;
+        *smem_out = (size_t)p.stages * stage_bytes + 1024 + kBarBytes + 4 * p.epi_groups * p.epi_slots * kEpiSlotBytes;
         // tensor memory: accumulator stage(s) first, then (A in TMEM) the operand ring, 64 columns (hi | lo) per stage
         const int ring_cols = p.a_tmem ? p.stages * 2 * p.bk : 0;
         p.corr_sep = (terms == 3 && 4 * p.acc_cols + ring_cols <= 512) ? 1 : 0;   // separate accumulator for the lo terms

@@ -68,7 +68,7 @@ bool gemm_tc_supported(int precision, bool a_kmajor, bool b_kmajor, int64_t lda,
 int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,
                    float *C, int64_t ldc, int64_t m, int64_t n, int64_t k, int split_k, const GemmEpilogue &epi,
                    cudaStream_t stream, const float *B_lo, const float *dot_w = nullptr, float *dot_out = nullptr);
-int gemm_tc_n_tiles(int64_t n, int precision);   // column tiles the tensor-core kernel uses for an output width n
+int gemm_tc_n_tiles(int64_t n, int precision, int64_t k);   // partial row dots per row a FusedDot gets for an [n, k] layer
 // hi = rn_tf32(src), lo = src - hi, dense [rows, cols] (or transposed: [cols, rows]); lo may be NULL when transposing
 int launch_split_tf32(const float *src, int64_t lds, float *hi, float *lo, int32_t rows, int32_t cols, bool transpose,
                       cudaStream_t stream, bool raw = false);      // raw: plain (transposed) copy into `hi`, no `lo`
@@ -84,7 +84,7 @@ bool gemm_tc_raw_weights();
 // dot_out[tile][m] = sum over the tile's columns of epilogue(C)[m,n] * dot_w[n]; C itself is not stored.
 struct FusedDot {
     const float *w;
-    float *out;       // [gemm_tc_n_tiles(n)][m]
+    float *out;       // [gemm_tc_n_tiles(n, precision, k)][m]
 };
 // precision dispatch (linear.cu).  wop == NULL -> B is used as is (CUDA-core path unless precision == TF32).
 int gemm_any(int precision, const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,

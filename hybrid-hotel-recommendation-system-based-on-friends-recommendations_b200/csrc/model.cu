@@ -214,7 +214,7 @@ extern "C" int dcnr_forward_eval(const dcnr_dims *dims, const dcnr_params *param
         auto run = [&](int idx, const float *A, int64_t lda, const float *W, int64_t ldw, const WeightOp &wop,
                        const GemmEpilogue &epi, float *out, int32_t K, bool *fused) -> int {
             *fused = false;
-            if (idx == last && gemm_tc_n_tiles(H, prec) <= 4 && gemm_any_uses_tc(prec, lda, H, rows, H, K, wo.get(wop), ldw)) {
+            if (idx == last && gemm_tc_n_tiles(H, prec, K) <= 4 && gemm_any_uses_tc(prec, lda, H, rows, H, K, wo.get(wop), ldw)) {
                 FusedDot fd{params->wf, w.dot_parts};
                 *fused = true;
                 return gemm_any(prec, A, lda, true, W, ldw, true, nullptr, H, rows, H, K, 1, epi, st, wo.get(wop), &fd);
@@ -234,7 +234,7 @@ extern "C" int dcnr_forward_eval(const dcnr_dims *dims, const dcnr_params *param
             std::swap(h, hn);
         }
         if (fused)
-            DCNR_TRY(launch_combine_logits(w.dot_parts, gemm_tc_n_tiles(H, prec), rows, w.logit_cross, params->bf, logits + r0, st));
+            DCNR_TRY(launch_combine_logits(w.dot_parts, gemm_tc_n_tiles(H, prec, H), rows, w.logit_cross, params->bf, logits + r0, st));
         else
             DCNR_TRY(launch_rowdot_fwd(h, H, params->wf, w.logit_cross, params->bf, logits + r0, rows, H, st));
     }
