@@ -63,6 +63,8 @@ _SIGS = {
     "dcnr_abi_version": (c_int, []),
     "dcnr_last_error_string": (c_char_p, []),
     "dcnr_launch_count": (c_int64, [c_int]),
+    "dcnr_gemm_timing_begin": (c_int, []),
+    "dcnr_gemm_timing_end": (c_int, [POINTER(c_double), POINTER(c_int64), POINTER(c_double)]),
     "dcnr_workspace_bytes": (c_int64, [POINTER(Dims), c_int64, c_int]),
     "dcnr_forward_eval": (c_int, [POINTER(Dims), POINTER(Params), POINTER(Batch), c_void_p, c_void_p, c_int64, c_void_p]),
     "dcnr_forward_train": (c_int, [POINTER(Dims), POINTER(Params), POINTER(Batch), c_uint64, c_void_p, c_void_p,
@@ -178,6 +180,17 @@ def require_cuda(*tensors):
 
 def launch_count(reset: bool = False) -> int:
     return int(lib().dcnr_launch_count(1 if reset else 0))
+
+
+def gemm_timing_begin() -> None:
+    check(lib().dcnr_gemm_timing_begin())
+
+
+def gemm_timing_end():
+    """(summed milliseconds, launches, algorithmic flops) of the GEMM launches since gemm_timing_begin()."""
+    ms, n, fl = ctypes.c_double(), ctypes.c_int64(), ctypes.c_double()
+    check(lib().dcnr_gemm_timing_end(ctypes.byref(ms), ctypes.byref(n), ctypes.byref(fl)))
+    return ms.value, n.value, fl.value
 
 
 def pad_dim(d: int) -> int:

@@ -90,6 +90,9 @@ struct SegPtrs {   // output vectors of one partial-sum finalize (NULL entries a
     int32_t n;
 };
 // out[i][c] = sum_p partials[p*ld + offset[i] + c], p ascending, accumulated in double.
+// event pair around a dense-layer GEMM launch when dcnr_gemm_timing_begin() is active (no-ops otherwise)
+void gemm_timer_before(cudaStream_t stream, double flops);
+void gemm_timer_after(cudaStream_t stream);
 int launch_sum_partials(const float *partials, int64_t n_partials, int64_t ld, const SegPtrs &seg,
                         cudaStream_t stream);
 // out[r*ldo + c] = sum_p partials[(p*rows + r)*cols_pad + c] for c < cols

@@ -178,6 +178,7 @@ int launch_gemm_simt(const float *A, int64_t lda, bool a_kmajor, const float *B,
     const int64_t k_per_split = round_up(ceil_div(std::max<int64_t>(k, 1), split_k), BK);
     dim3 grid((unsigned)ceil_div(m, BM), (unsigned)ceil_div(n, BN), (unsigned)split_k);
     DCNR_REQUIRE(grid.y <= 65535 && grid.z <= 65535, "gemm grid too large");
+    gemm_timer_before(stream, 2.0 * (double)m * (double)n * (double)k);
     if (a_kmajor && b_kmajor)
         k_sgemm<true, true><<<grid, 256, 0, stream>>>(A, lda, B, ldb, C, ldc, m, n, k, k_per_split, epi);
     else if (a_kmajor && !b_kmajor)
@@ -186,6 +187,7 @@ int launch_gemm_simt(const float *A, int64_t lda, bool a_kmajor, const float *B,
         k_sgemm<false, false><<<grid, 256, 0, stream>>>(A, lda, B, ldb, C, ldc, m, n, k, k_per_split, epi);
     else
         k_sgemm<false, true><<<grid, 256, 0, stream>>>(A, lda, B, ldb, C, ldc, m, n, k, k_per_split, epi);
+    gemm_timer_after(stream);
     DCNR_LAUNCHED();
     return DCNR_OK;
 }

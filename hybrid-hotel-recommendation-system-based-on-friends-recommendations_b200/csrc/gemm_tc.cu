@@ -1005,6 +1005,7 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     DCNR_TRY(make_map(&tmBlo, (terms == 3 && B_lo != nullptr) ? B_lo : B, n, k, ldb, p.block_n / ctas, p.bk));
     p.num_m_tiles = (int32_t)ceil_div(m, BLOCK_M * ctas);
     const int64_t num_tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
+    gemm_timer_before(stream, 2.0 * (double)m * (double)n * (double)k);
     if (ctas == 2) {
         cfg.gridDim = dim3(2 * (unsigned)std::min<int64_t>(num_tiles, max_pairs), 1, 1);
         DCNR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tc<2>, tmA, tmBhi, tmBlo, tmR, tmC, p));
@@ -1014,6 +1015,7 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
         const unsigned grid = (unsigned)std::min<int64_t>(num_tiles, sm_count());
         k_gemm_tc<1><<<grid, kThreadsP, smem, stream>>>(tmA, tmBhi, tmBlo, tmR, tmC, p);
     }
+    gemm_timer_after(stream);
     DCNR_LAUNCHED();
     if (debug_bits & 16) {              // timing experiment: dump the stamps of the first two launches
         static int dumps = 0;

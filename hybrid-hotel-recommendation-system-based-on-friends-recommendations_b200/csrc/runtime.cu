@@ -2,6 +2,8 @@
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
+#include <mutex>
+#include <vector>
 
 #include "common.cuh"
 
@@ -23,6 +25,39 @@ int cuda_fail(cudaError_t e, const char *what, const char *file, int line) {
 }
 
 void count_launch(int n) { g_launches += n; }
+
+// Optional device-side timing of the dense-layer GEMM launches (dcnr_gemm_timing_begin / _end): a CUDA event pair on the
+// launching stream around every GEMM launch, summed at _end.  bench.py uses it to report the dominant kernel's achieved
+// rate over the very steps it times.  Off by default: no events are created or recorded.
+namespace {
+struct GemmTimer {
+    std::mutex mu;
+    bool on = false;
+    std::vector<cudaEvent_t> pool;       // 2 events per launch, reused across sessions
+    size_t used = 0;
+    std::vector<double> flops;
+} g_timer;
+}  // namespace
+
+void gemm_timer_before(cudaStream_t stream, double flops) {
+    if (!g_timer.on) return;
+    std::lock_guard<std::mutex> lk(g_timer.mu);
+    if (!g_timer.on) return;
+    while (g_timer.pool.size() < g_timer.used + 2) {
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        g_timer.pool.push_back(e);
+    }
+    cudaEventRecord(g_timer.pool[g_timer.used], stream);
+    g_timer.flops.push_back(flops);
+    g_timer.used += 2;
+}
+void gemm_timer_after(cudaStream_t stream) {
+    if (!g_timer.on) return;
+    std::lock_guard<std::mutex> lk(g_timer.mu);
+    if (!g_timer.on || g_timer.used < 2) return;
+    cudaEventRecord(g_timer.pool[g_timer.used - 1], stream);
+}
 
 int sm_count() {
     static thread_local int cached = 0;
@@ -141,5 +176,32 @@ int dcnr_abi_version(void) { return DCNR_ABI_VERSION; }
 const char *dcnr_last_error_string(void) { return dcnr::g_err; }
 int64_t dcnr_launch_count(int reset) {
     return reset ? dcnr::g_launches.exchange(0) : dcnr::g_launches.load();
+}
+int dcnr_gemm_timing_begin(void) {
+    std::lock_guard<std::mutex> lk(dcnr::g_timer.mu);
+    dcnr::g_timer.used = 0;
+    dcnr::g_timer.flops.clear();
+    dcnr::g_timer.on = true;
+    return DCNR_OK;
+}
+int dcnr_gemm_timing_end(double *total_ms, int64_t *launches, double *total_flops) {
+    std::lock_guard<std::mutex> lk(dcnr::g_timer.mu);
+    dcnr::g_timer.on = false;
+    double ms = 0.0, fl = 0.0;
+    int64_t n = 0;
+    for (size_t i = 0; i + 1 < dcnr::g_timer.used; i += 2) {
+        DCNR_CUDA_CHECK(cudaEventSynchronize(dcnr::g_timer.pool[i + 1]));
+        float t = 0.f;
+        DCNR_CUDA_CHECK(cudaEventElapsedTime(&t, dcnr::g_timer.pool[i], dcnr::g_timer.pool[i + 1]));
+        ms += t;
+        fl += dcnr::g_timer.flops[i / 2];
+        ++n;
+    }
+    dcnr::g_timer.used = 0;
+    dcnr::g_timer.flops.clear();
+    if (total_ms) *total_ms = ms;
+    if (launches) *launches = n;
+    if (total_flops) *total_flops = fl;
+    return DCNR_OK;
 }
 }

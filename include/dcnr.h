@@ -56,6 +56,11 @@ const char *dcnr_last_error_string(void);
 /* Number of kernels this library has launched (process-wide) since the last reset
  * (bench.py's gpu_launches). */
 int64_t dcnr_launch_count(int reset);
+/* Device-side timing of the dense-layer GEMM launches (measurement aid, off by default): between _begin and _end every
+ * GEMM launch is bracketed by a CUDA event pair on its stream; _end waits for them and returns the summed duration, the
+ * number of launches and their algorithmic flops (2 m n k each).  bench.py reports roofline.achieved from it. */
+int dcnr_gemm_timing_begin(void);
+int dcnr_gemm_timing_end(double *total_ms, int64_t *launches, double *total_flops);
 
 /* ------------------------------------------------------------------------------------------
  * Model description: shapes of DCN_RecSys(n_users, n_items, cat_dims, n_num_features, params)
