@@ -11,6 +11,8 @@ from typing import Optional
 import numpy as np
 import torch
 
+from . import _cabi as C
+
 
 def rank_candidates(model, X_user, X_item, X_cat, X_num) -> np.ndarray:
     """scores for one request's candidates -- the body of main.py:320-324.
@@ -134,3 +136,147 @@ def expand_candidates(nn_model, item_embeddings: torch.Tensor, positive_rows, n_
         return np.empty((0, max(n_neighbors - 1, 0)), dtype=np.int64)
     _, ind = nn_model.kneighbors_tensor(item_embeddings[rows].to(torch.float32), n_neighbors)
     return ind[:, 1:].cpu().numpy()
+
+
+# ------------------------------------------------------------------------------------------------
+# Artifacts on disk (SURVEY 8b "Artifacts" row, 8f-4): the five files train.py:391-396 writes and
+# main.py:256-269 reads, unchanged.
+# ------------------------------------------------------------------------------------------------
+ARTIFACT_FILES = ("final_dcn_model.pth", "artifacts.gz", "item_embeddings.npy", "best_params.gz", "model_dims.gz")
+
+
+def save_ml_artifacts(artifacts_dir: str, model, artifacts: dict, best_params: dict, model_dims) -> None:
+    """What train.py:391-396 does after training: state_dict, the preprocessing dict
+    (user_id_mapping, item_id_mapping, scaler, cat_encoders, numerical_cols, categorical_cols; train.py:80-84),
+    the item-embedding matrix, the hyper-parameters and (n_users, n_items, cat_dims, n_num_features)."""
+    import os
+    import joblib
+    os.makedirs(artifacts_dir, exist_ok=True)
+    torch.save({k: v.detach().cpu() for k, v in model.state_dict().items()}, os.path.join(artifacts_dir, "final_dcn_model.pth"))
+    joblib.dump(artifacts, os.path.join(artifacts_dir, "artifacts.gz"))
+    np.save(os.path.join(artifacts_dir, "item_embeddings.npy"), model.item_embedding.weight.detach().cpu().numpy())
+    joblib.dump(best_params, os.path.join(artifacts_dir, "best_params.gz"))
+    joblib.dump(model_dims, os.path.join(artifacts_dir, "model_dims.gz"))
+
+
+def load_ml_artifacts(artifacts_dir: str = "artifacts", device="cuda", precision: Optional[str] = None) -> dict:
+    """main.py:256-272 on the GPU: returns the reference's ``ml_artifacts`` entries that belong to this path --
+    'device', 'artifacts', 'item_embeddings' (numpy, as the reference keeps it), 'final_model' (eval mode, on
+    ``device``), 'nn_model' (fitted ``NearestNeighbors(n_neighbors=16, metric='cosine', algorithm='brute')``) and
+    'reverse_item_map' -- plus 'item_embeddings_device' for the MMR / candidate-expansion calls.  The CSV frames
+    ('main_df', 'friendships_df') stay with the service's pandas code (out of scope)."""
+    import os
+    import joblib
+    from .knn import NearestNeighbors
+    from .model import DCN_RecSys
+    device = torch.device(device)
+    out = {"device": device}
+    out["artifacts"] = joblib.load(os.path.join(artifacts_dir, "artifacts.gz"))
+    model_dims = joblib.load(os.path.join(artifacts_dir, "model_dims.gz"))
+    best_params = joblib.load(os.path.join(artifacts_dir, "best_params.gz"))
+    out["item_embeddings"] = np.load(os.path.join(artifacts_dir, "item_embeddings.npy"))
+    n_users, n_items, cat_dims, n_num_features = model_dims
+    model = DCN_RecSys(n_users, n_items, cat_dims, n_num_features, best_params)
+    model.load_state_dict(torch.load(os.path.join(artifacts_dir, "final_dcn_model.pth"), map_location="cpu"))
+    if precision is not None:
+        model.precision = precision
+    model.to(device)
+    model.eval()
+    out["final_model"] = model
+    nn_model = NearestNeighbors(n_neighbors=16, metric="cosine", algorithm="brute")
+    nn_model.fit(out["item_embeddings"])
+    out["nn_model"] = nn_model
+    out["reverse_item_map"] = {v: k for k, v in out["artifacts"]["item_id_mapping"].items()}
+    out["item_embeddings_device"] = torch.from_numpy(out["item_embeddings"]).to(device)
+    return out
+
+
+# ------------------------------------------------------------------------------------------------
+# Feature prep for the ranking call on the device (main.py:215-230; SURVEY 8f-4)
+# ------------------------------------------------------------------------------------------------
+class RankingFeatures:
+    """Per-hotel ranking features resident on the GPU.
+
+    ``preprocess_for_ranking`` (main.py:215-230) rebuilds, per request and in pandas, the model inputs of the
+    candidate hotels: internal user id (unknown -> len(map) // 2), internal item ids (unknown -> 0), categorical
+    codes through ``cat_encoders`` (unknown -> 0) and the MinMax-scaled numerics.  Everything except the user id is a
+    function of the hotel row, so it is computed ONCE here for the de-duplicated hotel frame (first row per
+    ``item_id``, like ``drop_duplicates(subset=['item_id'])`` at main.py:314) with the same pandas / scikit-learn
+    calls, and kept as device tensors; a request is then an index gather."""
+
+    def __init__(self, artifacts: dict, hotels_df, device="cuda"):
+        import pandas as pd  # noqa: F401  (the frame is pandas, like the reference's main_df)
+        df = hotels_df.drop_duplicates(subset=["item_id"]).reset_index(drop=True)
+        self.artifacts = artifacts
+        self.device = torch.device(device)
+        self.row_of_item = {int(h): r for r, h in enumerate(df["item_id"].tolist())}
+        item_enc = df["item_id"].map(artifacts["item_id_mapping"]).fillna(0)
+        self.item_internal = torch.tensor(item_enc.values, dtype=torch.long, device=self.device)
+        cat = {}
+        for col, encoder in artifacts["cat_encoders"].items():
+            cat[col] = df[col].map(encoder).fillna(0).values
+        cat_arr = np.stack([cat[c] for c in artifacts["cat_encoders"]], axis=1) if cat else np.zeros((len(df), 0))
+        self.cat_codes = torch.tensor(cat_arr, dtype=torch.long, device=self.device)
+        num_scaled = artifacts["scaler"].transform(df[artifacts["numerical_cols"]])
+        self.num_scaled = torch.tensor(np.asarray(num_scaled), dtype=torch.float32, device=self.device)
+
+    def internal_user_id(self, user_id: int) -> int:
+        m = self.artifacts["user_id_mapping"]
+        return m.get(user_id, len(m) // 2)
+
+    def rows(self, hotel_ids) -> torch.Tensor:
+        """Feature-table rows of raw hotel ids (the order of ``hotel_ids`` is kept)."""
+        return torch.tensor([self.row_of_item[int(h)] for h in hotel_ids], dtype=torch.long, device=self.device)
+
+    def preprocess_for_ranking(self, hotel_ids, user_id: int):
+        """(X_collab_user, X_collab_item, X_cat, X_num) as CUDA tensors -- the tuple main.py:215-230 returns."""
+        r = self.rows(hotel_ids)
+        x_user = torch.full((r.numel(),), self.internal_user_id(user_id), dtype=torch.long, device=self.device)
+        return x_user, self.item_internal[r], self.cat_codes[r], self.num_scaled[r]
+
+
+class ItemFusedRanker:
+    """The ranking forward with the feature prep folded into the embedding gather.
+
+    The categorical embedding row and the numerics of a candidate depend only on its hotel row, so
+    ``cat_embeddings[i].weight[code_i(hotel)]`` and ``num(hotel)`` are pre-gathered into per-hotel tables and the
+    kernel's categorical segments are pointed at them: a request needs (user id, item id, hotel row) per candidate --
+    24 bytes instead of 76 -- and ``x0`` (hence every logit) is bit-identical to the explicit-feature call."""
+
+    def __init__(self, model, features: RankingFeatures):
+        if model.training:
+            raise RuntimeError("ItemFusedRanker serves an eval() model")
+        self.model, self.features = model, features
+        n_cat, n_num = features.cat_codes.shape[1], features.num_scaled.shape[1]
+        if n_cat + (1 if n_num else 0) > 8:
+            raise ValueError("too many categorical tables to fold the numerics in (DCNR_MAX_CAT = 8)")
+        with torch.no_grad():
+            self.tables = [model.cat_embeddings[i].weight.detach()[features.cat_codes[:, i]].contiguous() for i in range(n_cat)]
+            if n_num:
+                self.tables.append(features.num_scaled.contiguous())
+        self.n_rows = features.cat_codes.shape[0]
+
+    def score(self, user_internal: int, item_internal: torch.Tensor, hotel_rows: torch.Tensor) -> torch.Tensor:
+        m = self.model
+        dev = item_internal.device
+        B = item_internal.numel()
+        dims, ps = m._dims(), m._param_struct()
+        dims.n_cat, dims.n_num = len(self.tables), 0
+        for i, t in enumerate(self.tables):
+            dims.cat_rows[i], dims.cat_width[i] = self.n_rows, t.shape[1]
+            ps.cat_table[i] = C.ptr(t)
+        users = torch.full((B,), int(user_internal), dtype=torch.long, device=dev)
+        cat = hotel_rows.reshape(B, 1).expand(B, len(self.tables)).contiguous()
+        batch = C.Batch(C.ptr(users), C.ptr(item_internal.contiguous()), C.ptr(cat), None, B)
+        ws = torch.empty(C.lib().dcnr_workspace_bytes(dims, B, 0), dtype=torch.uint8, device=dev)
+        logits = torch.empty(B, dtype=torch.float32, device=dev)
+        C.check(C.lib().dcnr_forward_eval(dims, ps, batch, C.ptr(logits), C.ptr(ws), ws.numel(), C.stream()))
+        return logits
+
+    def rank(self, hotel_ids, user_id: int):
+        """main.py:319-325 for one request: scores of the candidate hotels, sorted descending with the reference's
+        stable python sort (``sort_scored``)."""
+        f = self.features
+        r = f.rows(hotel_ids)
+        scores = self.score(f.internal_user_id(user_id), f.item_internal[r], r).cpu().numpy()
+        return sort_scored(scores, list(hotel_ids))

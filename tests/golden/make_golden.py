@@ -172,6 +172,70 @@ def mmr_case(name, n_items, d, C, lam, top_k, seed, unmapped=()):
     print("mmr", name, "selected", len(chosen))
 
 
+def synth_hotels(n_hotels=40, seed=0):
+    """A tiny frame in the hackathon_augmented_data.csv schema + the preprocessing artifacts
+    train.py:40-84 would build from it (same calls: category codes, MinMaxScaler)."""
+    import pandas as pd
+    from sklearn.preprocessing import MinMaxScaler
+    rng = np.random.default_rng(seed)
+    cities = ["Kazan", "Moscow", "Sochi", "Ufa"]
+    types = ["hotel", "hostel", "apart"]
+    hotel_id = rng.permutation(np.arange(1000, 1000 + n_hotels))
+    rows = []
+    for h in hotel_id:
+        hr = np.random.default_rng(int(h))
+        base = dict(hotel_id=int(h), city=cities[int(h) % 4], hotel_type=types[int(h) % 3],
+                    price_rub=float(np.exp(hr.normal(8, 0.5))), stars=int(hr.integers(0, 6)),
+                    user_reviews_count=int(hr.integers(0, 500)),
+                    rating_location=float(hr.uniform(1, 10)), rating_cleanliness=float(hr.uniform(1, 10)),
+                    rating_food=float(hr.uniform(1, 10)), rating_service=float(hr.uniform(1, 10)))
+        for _ in range(int(hr.integers(1, 4))):           # several reviews per hotel, hotel attributes repeated
+            rows.append(dict(base, guest_id=int(rng.integers(1, 30)), rating_overall=float(rng.uniform(1, 10)),
+                             was_booked=int(rng.integers(0, 2))))
+    df = pd.DataFrame(rows)
+    df.rename(columns={"guest_id": "user_id", "hotel_id": "item_id"}, inplace=True)
+    # derived features exactly as main.py:244-250 / train.py:284-287
+    df["price_per_star"] = (df["price_rub"] / df["stars"]).replace([np.inf, -np.inf], 0).fillna(0)
+    df["cleanliness_vs_service"] = (df["rating_cleanliness"] / df["rating_service"]).replace([np.inf, -np.inf], 0).fillna(0)
+    df["location_premium"] = df["rating_overall"] - df["rating_location"]
+    categorical_cols = ["city", "hotel_type"]
+    numerical_cols = ["price_rub", "stars", "user_reviews_count", "rating_overall", "rating_location", "rating_cleanliness",
+                      "rating_food", "rating_service", "price_per_star", "cleanliness_vs_service", "location_premium"]
+    # the training frame misses the last 5 hotels, one city and a few users: the serving path must map those to 0 / mid id
+    train = df[~df["item_id"].isin(hotel_id[-5:]) & (df["city"] != "Ufa")]
+    user_map = {o: i for i, o in enumerate(train["user_id"].unique())}
+    item_map = {o: i for i, o in enumerate(train["item_id"].unique())}
+    cat_encoders = {}
+    for col in categorical_cols:
+        cats = train[col].astype("category").cat.categories
+        cat_encoders[col] = {c: i for i, c in enumerate(cats)}
+    scaler = MinMaxScaler().fit(train[numerical_cols])
+    artifacts = {"user_id_mapping": user_map, "item_id_mapping": item_map, "scaler": scaler, "cat_encoders": cat_encoders,
+                 "numerical_cols": numerical_cols, "categorical_cols": categorical_cols}
+    return df, artifacts
+
+
+def preprocess_case():
+    """Runs the reference's preprocess_for_ranking (main.py:215-230) on a de-duplicated candidate frame, as the
+    endpoint does (main.py:313-319), for a known and an unknown user."""
+    import joblib
+    df, artifacts = synth_hotels()
+    ref_main.ml_artifacts["artifacts"] = artifacts
+    out = {}
+    for tag, user_id, pick in (("known", int(df["user_id"].iloc[0]), slice(0, None, 2)), ("unknown", 987654, slice(1, None, 3))):
+        cand = list(dict.fromkeys(df["item_id"].tolist()))[pick]
+        items = df[df["item_id"].isin(cand)].drop_duplicates(subset=["item_id"])
+        xu, xi, xc, xn = ref_main.preprocess_for_ranking(items, user_id)
+        out[f"{tag}::user_id"] = np.int64(user_id)
+        out[f"{tag}::hotel_ids"] = items["item_id"].values.astype(np.int64)
+        out[f"{tag}::x_user"], out[f"{tag}::x_item"] = xu.numpy(), xi.numpy()
+        out[f"{tag}::x_cat"], out[f"{tag}::x_num"] = xc.numpy(), xn.numpy()
+    np.savez_compressed(os.path.join(HERE, "preprocess_ranking.npz"), **out)
+    # the frame is stored with joblib, not CSV: a text round trip moves some float64 values by an ulp
+    joblib.dump({"frame": df, "artifacts": artifacts}, os.path.join(HERE, "preprocess_ranking_inputs.gz"))
+    print("preprocess_ranking", {k: v.shape for k, v in out.items() if hasattr(v, "shape")})
+
+
 if __name__ == "__main__":
     P0 = dict(emb_dim=16, hidden_dim=256, n_cross_layers=3, n_res_blocks=2, dropout=0.0,
               lr=1e-3, batch_size=512)   # extra keys must be ignored (train.py:186-192)
@@ -191,3 +255,4 @@ if __name__ == "__main__":
     mmr_case("c300", 2000, 16, 300, 0.7, 20, 8)
     mmr_case("c40_unmapped", 500, 16, 40, 0.3, 20, 9, unmapped=(0, 5, 17))
     mmr_case("c12", 200, 64, 12, 0.5, 20, 10)
+    preprocess_case()

@@ -60,3 +60,53 @@ def test_expand_candidates_equals_per_hotel_queries():
         _, ind = ref.kneighbors(E[row].reshape(1, -1), n_neighbors=11)
         assert np.array_equal(got[r], ind[0][1:])
     assert set(got.reshape(-1)) == set(np.concatenate([ref.kneighbors(E[p].reshape(1, -1), n_neighbors=11)[1][0][1:] for p in positives]))
+
+
+# ------------------------------------------------------------------------------------------------
+# artifacts on disk + device feature prep (SURVEY 8b artifacts row, 8f-4)
+# ------------------------------------------------------------------------------------------------
+def _serving_fixture(tmp_path):
+    import joblib
+    import pandas as pd
+    blob = joblib.load(os.path.join(GOLDEN, "preprocess_ranking_inputs.gz"))
+    df, artifacts = blob["frame"], blob["artifacts"]
+    cat_dims = {c: len(e) for c, e in artifacts["cat_encoders"].items()}
+    dims = (len(artifacts["user_id_mapping"]), len(artifacts["item_id_mapping"]), cat_dims, len(artifacts["numerical_cols"]))
+    best = dict(emb_dim=16, hidden_dim=64, n_cross_layers=2, dropout=0.3, n_res_blocks=2)
+    torch.manual_seed(5)
+    model = dcnr_b200.DCN_RecSys(*dims, best)
+    with torch.no_grad():                       # non-trivial running statistics
+        for blk in model.res_blocks:
+            for bn in (blk.bn1, blk.bn2):
+                bn.running_mean.normal_(0, 0.3)
+                bn.running_var.uniform_(0.5, 1.5)
+    dcnr_b200.serving.save_ml_artifacts(str(tmp_path), model, artifacts, best, dims)
+    return df, artifacts, model
+
+
+@pytest.mark.gpu
+def test_load_ml_artifacts_round_trip_and_fused_item_tables(tmp_path):
+    df, artifacts, model_cpu = _serving_fixture(tmp_path)
+    ml = dcnr_b200.serving.load_ml_artifacts(str(tmp_path), device="cuda", precision="fp32")
+    model = ml["final_model"]
+    assert not model.training and next(model.parameters()).is_cuda
+    for k, v in model_cpu.state_dict().items():
+        assert torch.equal(model.state_dict()[k].cpu(), v), k
+    assert ml["reverse_item_map"] == {v: k for k, v in artifacts["item_id_mapping"].items()}
+    # the kNN object answers like main.py:300-302 expects (position 0 is the query item itself)
+    _, ind = ml["nn_model"].kneighbors(ml["item_embeddings"][3].reshape(1, -1), n_neighbors=6)
+    assert ind.dtype == np.int64 and ind.shape == (1, 6) and ind[0, 0] == 3
+
+    feats = dcnr_b200.serving.RankingFeatures(artifacts, df, device="cuda")
+    hotels = list(dict.fromkeys(df["item_id"].tolist()))
+    user_id = int(df["user_id"].iloc[0])
+    xu, xi, xc, xn = feats.preprocess_for_ranking(hotels, user_id)
+    with torch.no_grad():
+        ref_scores = model(xu, xi, xc, xn)
+    fused = dcnr_b200.serving.ItemFusedRanker(model, feats)
+    r = feats.rows(hotels)
+    got = fused.score(feats.internal_user_id(user_id), feats.item_internal[r], r)
+    assert torch.equal(got, ref_scores)                               # same x0 rows -> bit-identical logits
+    ranked = fused.rank(hotels, user_id)
+    assert [h for _, h in ranked] == [h for _, h in dcnr_b200.serving.sort_scored(ref_scores.cpu().numpy(), hotels)]
+    assert all(ranked[i][0] >= ranked[i + 1][0] for i in range(len(ranked) - 1))
