@@ -228,6 +228,8 @@ struct Params {
     int32_t epi_slots;        // epilogue slots per warp (2 or 4)
     int32_t epi_groups;       // 1: warps 6-9 drain the accumulator; 2: warps 10-13 as well (alternate 32-column chunks)
     int32_t a_tmem, a_col0;   // TF32X3: A hi / lo in a tensor-memory ring (64 columns per stage) starting at column a_col0
+    int32_t b_local;          // pairs with A in tensor memory: each CTA's weight boxes land on its OWN barrier (plain TMA, no
+                              // .cta_group::2 completion on the leader); its A-split warps wait for them before arriving on "ready"
     int32_t b_split;          // TF32X3: the weight arrives as raw fp32 and warps 10-13 split it in shared memory (half the L2 stream)
     int32_t num_m_tiles, num_n_tiles;
     long long *dbg;           // DCNR_GEMM_DEBUG bit 16: clock64 stamps of CTA 0's pipeline (first 64 k-blocks)
@@ -356,6 +358,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             // raw fp32 weight box onto this CTA's OWN barrier: its weight-split warps wait for it
                             mbar_expect_tx(fullB0 + 8 * s, (uint32_t)b_tile_bytes);
                             tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fullB0 + 8 * s);
+                        } else if (CTAS == 2 && p.b_local) {
+                            mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(2 * b_tile_bytes));
+                            tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fullB0 + 8 * s);
+                            tma_load_2d(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * bk, n0, fullB0 + 8 * s);
                         } else if (CTAS == 2) {
                             if (leader) mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(CTAS * 2 * b_tile_bytes));
                             tma_load_2d_pair(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fb);
@@ -405,7 +411,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1;
-                    if (!p.b_split) wait_x(fullB0 + 8 * s, ph);       // b_split: "ready" covers the weight tile too
+                    if (!p.b_split && !p.b_local) wait_x(fullB0 + 8 * s, ph);       // else "ready" covers the weight tile too
                     if (p.terms == 3) wait_x(ready0 + 8 * s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
@@ -519,6 +525,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) p.dbg[it * 8 + 2] = clock64();
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                    if (p.b_local) mbar_wait(fullB0 + 8 * s, ph);          // this CTA's weight boxes have landed too
                     __syncwarp();
                     if (lane == 0) {
                         if (CTAS == 2) mbar_arrive_cluster(L_ready0 + 8 * s);
@@ -914,6 +921,11 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     p.a_tmem = (terms == 3 && atmem_enabled()) ? 1 : 0;
     p.a_col0 = 0;
     p.b_split = (terms == 3 && B_lo == nullptr) ? 1 : 0;
+    static const int b_local_env = [] {
+        const char *e = getenv("DCNR_GEMM_BLOCAL");
+        return e != nullptr ? atoi(e) : 0;
+    }();
+    p.b_local = 0;
     p.epi_groups = p.b_split ? 1 : epi_groups_for(p.block_n, precision, k);
     static const int forced_bk = [] {
         const char *e = getenv("DCNR_GEMM_BK");
@@ -978,6 +990,7 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
         while (p.tmem_cols < p.a_col0 + ring_cols) p.tmem_cols <<= 1;
     };
     size_t smem = 0;
+    p.b_local = (ctas == 2 && p.a_tmem && !p.b_split && b_local_env) ? 1 : 0;
     if (ctas == 2) {
         plan(2, &smem);
         DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -993,6 +1006,7 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
             ctas = 1;
         }
     }
+    if (ctas != 2) p.b_local = 0;
     CUtensorMap tmA, tmBhi, tmBlo, tmR, tmC;
     DCNR_TRY(make_map(&tmA, A, m, k, lda, BLOCK_M, p.bk));
     // epilogue boxes: 32 rows x 32 columns of the residual / output (rows and columns past the matrix are
