@@ -507,6 +507,251 @@ k_embed_cross_fwd_staged(GatherArgs ga, int n_vec, int mix0, int64_t B, CrossArg
 }
 
 
+// ------------------------------------------------------------------------------------------------
+// cp.async-pipelined form of the staged gather (narrow rows; the default when it fits).  The staged
+// kernel above is latency-bound (ncu: long-scoreboard stalls, 4 CTAs / SM at 64 registers, and every
+// attempt to keep more row loads in flight per thread cost occupancy).  Here the loads need no
+// registers: a warp owns a ring of S shared-memory tiles of 32 FULL padded rows, and for step k + 1
+// it issues every byte of the 32 rows as cp.async (16-byte chunks for the aligned table rows, 4-byte
+// elements for narrow tables and the numerics, zero-fill past the batch) while step k is read back
+// from its tile, pushed through the register-resident cross layers and stored.  Ids are fetched one
+// step further ahead (plain loads, needed to form the cp.async addresses).
+// ------------------------------------------------------------------------------------------------
+constexpr int kPipeWarps = 4;
+
+__device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async4(uint32_t dst, const void *src, uint32_t src_bytes) {      // src_bytes 0 -> zero fill
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+template <int NV, int S>
+__global__ void __launch_bounds__(32 * kPipeWarps)
+k_embed_cross_fwd_pipe(GatherArgs ga, int n_vec, int64_t B, CrossArgs ca, float *__restrict__ x0_out, int64_t ldx0,
+                       float *__restrict__ y_out, int64_t ldy, const float *__restrict__ wf_cross,
+                       float *__restrict__ logit_part, int32_t *err_flag) {
+    constexpr int DP = NV * 32;
+    constexpr int NE = NV * 4;
+    constexpr int TS = DP + 4;           // tile row pitch in floats (+4: consecutive rows start 4 banks apart)
+    constexpr unsigned kFull = 0xffffffffu;
+    constexpr int kT = 32 * kPipeWarps;
+    constexpr int kMixPref = 2;
+    extern __shared__ __align__(16) float smem[];
+    float *sw = smem;                    // [L][DP]
+    float *sb = sw + ca.L * DP;          // [L][DP]
+    float *swf = sb + ca.L * DP;         // [DP]
+    float *tiles = swf + DP;             // [warps][S][32][TS]
+    __shared__ SmemSeg sseg[2 + DCNR_MAX_CAT];
+
+    const int tid = threadIdx.x;
+    for (int i = tid; i < ca.L * DP; i += kT) {
+        int l = i / DP, c = i % DP;
+        sw[i] = c < ca.D ? ca.w[l][c] : 0.f;
+        sb[i] = c < ca.D ? ca.b[l][c] : 0.f;
+    }
+    for (int c = tid; c < DP; c += kT) swf[c] = (wf_cross != nullptr && c < ca.D) ? wf_cross[c] : 0.f;
+    for (int i = tid; i < kPipeWarps * S * 32 * TS; i += kT) tiles[i] = 0.f;          // pad columns stay zero
+    if (tid < ga.n_seg) {
+        sseg[tid].table = ga.seg[tid].table;
+        sseg[tid].ids = ga.seg[tid].ids;
+        sseg[tid].rows = ga.seg[tid].rows;
+        sseg[tid].id_stride = ga.seg[tid].id_stride;
+        sseg[tid].width = ga.seg[tid].width;
+        sseg[tid].col0 = ga.seg[tid].col0;
+    }
+    __syncthreads();
+
+    const int warp = tid >> 5, lane = tid & 31, lane8 = lane & 7, grp = lane >> 3;
+    float *wtile = tiles + (size_t)warp * S * 32 * TS;
+    const uint32_t wtile_s = (uint32_t)__cvta_generic_to_shared(wtile);
+    const bool x0_vec = x0_out != nullptr && ldx0 >= DP && (ldx0 & 3) == 0;
+    const bool y_vec = y_out != nullptr && ldy >= DP && (ldy & 3) == 0;
+    const int D = ga.D;
+    const int n_num = ga.n_num, num_c0 = ga.num_col0;
+    const float inv_num = n_num > 0 ? 1.f / (float)n_num : 0.f;
+    bool bad_id = false;
+
+    const int64_t n_blocks = (B + 31) >> 5;
+    const int64_t blk_step = (int64_t)gridDim.x * kPipeWarps;
+    auto load_ids = [&](int64_t blk, int (&v)[kMaxVecSeg], int (&c)[kMixPref]) {
+        const int64_t r = (blk << 5) + lane;
+        const bool have = blk < n_blocks && r < B;
+#pragma unroll
+        for (int sgi = 0; sgi < kMaxVecSeg; ++sgi) {
+            v[sgi] = 0;
+            if (sgi < n_vec && have) {
+                const int64_t id = __ldcs(sseg[sgi].ids + r * sseg[sgi].id_stride);
+                if ((uint64_t)id >= (uint64_t)sseg[sgi].rows) bad_id = true;
+                else v[sgi] = (int)id;
+            }
+        }
+#pragma unroll
+        for (int m = 0; m < kMixPref; ++m) {
+            c[m] = 0;
+            const int sgi = n_vec + m;
+            if (sgi < ga.n_seg && have) {
+                const int64_t id = __ldcs(sseg[sgi].ids + r * sseg[sgi].id_stride);
+                if ((uint64_t)id >= (uint64_t)sseg[sgi].rows) bad_id = true;
+                else c[m] = (int)id;
+            }
+        }
+    };
+    // every byte of the 32 rows of step `blk` into ring slot `slot`, as cp.async (no registers held while in flight)
+    auto issue = [&](int64_t blk, int slot, const int (&v)[kMaxVecSeg], const int (&c)[kMixPref]) {
+        if (blk >= n_blocks) return;
+        const int64_t base = blk << 5;
+        const uint32_t t0 = wtile_s + (uint32_t)(slot * 32 * TS * 4);
+#pragma unroll
+        for (int sgi = 0; sgi < kMaxVecSeg; ++sgi) {
+            if (sgi < n_vec) {                               // aligned table rows: width / 4 chunks of 16 bytes per row
+                const SmemSeg &sg = sseg[sgi];
+                const int cpr = sg.width >> 2;
+                const float inv_c = 1.f / (float)cpr;
+                for (int t = 0; t < cpr; ++t) {
+                    const int idx = t * 32 + lane;
+                    const int r = (int)(((float)idx + 0.5f) * inv_c);
+                    const int part = idx - r * cpr;
+                    const int rid = __shfl_sync(kFull, v[sgi], r);
+                    cp_async16(t0 + (uint32_t)((r * TS + sg.col0 + 4 * part) * 4), sg.table + (int64_t)rid * sg.width + 4 * part);
+                }
+            }
+        }
+        for (int sgi = n_vec; sgi < ga.n_seg; ++sgi) {      // narrow / unaligned tables, element by element in flat order
+            const SmemSeg &sg = sseg[sgi];
+            int cid = 0;
+            if (sgi - n_vec < kMixPref) {
+                cid = sgi == n_vec ? c[0] : c[1];
+            } else if (base + lane < B) {
+                const int64_t id = __ldcs(sg.ids + (base + lane) * sg.id_stride);
+                if ((uint64_t)id >= (uint64_t)sg.rows) bad_id = true;
+                else cid = (int)id;
+            }
+            const int w = sg.width;
+            const float inv_w = 1.f / (float)w;
+            for (int t = 0; t < w; ++t) {
+                const int idx = t * 32 + lane;
+                const int r = (int)(((float)idx + 0.5f) * inv_w);       // exact: idx <= 32 * w, w <= 256
+                const int cc = idx - r * w;
+                const int rid = __shfl_sync(kFull, cid, r);
+                cp_async4(t0 + (uint32_t)((r * TS + sg.col0 + cc) * 4), sg.table + (int64_t)rid * w + cc, 4u);
+            }
+        }
+        if (n_num > 0) {                                     // numerics: 32 x n_num contiguous floats, zero past the batch
+            const float *np = ga.num + base * n_num;
+            const int64_t lim = (B - base) * n_num;
+            for (int t = 0; t < n_num; ++t) {
+                const int idx = t * 32 + lane;
+                const int r = (int)(((float)idx + 0.5f) * inv_num);
+                const int cc = idx - r * n_num;
+                const bool in = idx < lim;
+                cp_async4(t0 + (uint32_t)((r * TS + num_c0 + cc) * 4), in ? np + idx : ga.num, in ? 4u : 0u);
+            }
+        }
+    };
+
+    const int64_t blk0 = (int64_t)blockIdx.x * kPipeWarps + warp;
+    int vid[kMaxVecSeg], cpre[kMixPref];
+    // prologue: S - 1 steps in flight
+    load_ids(blk0, vid, cpre);
+#pragma unroll
+    for (int p = 0; p < S - 1; ++p) {
+        issue(blk0 + p * blk_step, p, vid, cpre);
+        cp_async_commit();
+        load_ids(blk0 + (p + 1) * blk_step, vid, cpre);
+    }
+    int k = 0;
+    for (int64_t blk = blk0; blk < n_blocks; blk += blk_step, ++k) {
+        // keep S - 1 steps ahead in flight: step k + S - 1 goes into the slot step k - 1 just released
+        issue(blk + (S - 1) * blk_step, (k + S - 1) % S, vid, cpre);
+        cp_async_commit();
+        load_ids(blk + (int64_t)S * blk_step, vid, cpre);        // its latency hides behind the compute below
+        cp_async_wait<S - 1>();                                  // step k has landed (this thread's copies) ...
+        __syncwarp();                                            // ... and every other lane's
+        const float *tile = wtile + (size_t)(k % S) * 32 * TS;
+        const int64_t base = blk << 5;
+#pragma unroll 2
+        for (int it = 0; it < 8; ++it) {
+            const int r = it * 4 + grp;
+            const int64_t row = base + r;
+            const bool active = row < B;
+            float x[NE];
+#pragma unroll
+            for (int j = 0; j < NV; ++j) {
+                const float4 v4 = *reinterpret_cast<const float4 *>(tile + r * TS + 32 * j + 4 * lane8);
+                x[4 * j] = v4.x; x[4 * j + 1] = v4.y; x[4 * j + 2] = v4.z; x[4 * j + 3] = v4.w;
+            }
+            if (x0_out != nullptr && active) {
+                if (x0_vec) {
+#pragma unroll
+                    for (int j = 0; j < NV; ++j)
+                        __stcs(reinterpret_cast<float4 *>(x0_out + row * ldx0 + 32 * j + 4 * lane8), make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < NE; ++kk) {
+                        int col = 32 * (kk >> 2) + 4 * lane8 + (kk & 3);
+                        if (col < ldx0 && col < DP) x0_out[row * ldx0 + col] = x[kk];
+                    }
+                }
+            }
+            for (int l = 0; l < ca.L; ++l) {
+                const float *wl = sw + l * DP, *bl = sb + l * DP;
+                float p = 0.f;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    float4 w4 = *reinterpret_cast<const float4 *>(wl + 32 * j + 4 * lane8);
+                    p = fmaf(x[4 * j + 0], w4.x, p);
+                    p = fmaf(x[4 * j + 1], w4.y, p);
+                    p = fmaf(x[4 * j + 2], w4.z, p);
+                    p = fmaf(x[4 * j + 3], w4.w, p);
+                }
+                const float sdot = group8_sum(p);
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    float4 b4 = *reinterpret_cast<const float4 *>(bl + 32 * j + 4 * lane8);
+                    x[4 * j + 0] = fmaf(x[4 * j + 0], sdot, x[4 * j + 0]) + b4.x;
+                    x[4 * j + 1] = fmaf(x[4 * j + 1], sdot, x[4 * j + 1]) + b4.y;
+                    x[4 * j + 2] = fmaf(x[4 * j + 2], sdot, x[4 * j + 2]) + b4.z;
+                    x[4 * j + 3] = fmaf(x[4 * j + 3], sdot, x[4 * j + 3]) + b4.w;
+                }
+            }
+            if (y_out != nullptr && active) {
+                if (y_vec) {
+#pragma unroll
+                    for (int j = 0; j < NV; ++j)
+                        __stcs(reinterpret_cast<float4 *>(y_out + row * ldy + 32 * j + 4 * lane8), make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]));
+                } else {
+#pragma unroll
+                    for (int kk = 0; kk < NE; ++kk) {
+                        int col = 32 * (kk >> 2) + 4 * lane8 + (kk & 3);
+                        if (col < D && col < ldy) y_out[row * ldy + col] = x[kk];
+                    }
+                }
+            }
+            if (logit_part != nullptr) {
+                float p = 0.f;
+#pragma unroll
+                for (int j = 0; j < NV; ++j) {
+                    float4 w4 = *reinterpret_cast<const float4 *>(swf + 32 * j + 4 * lane8);
+                    p = fmaf(x[4 * j + 0], w4.x, p);
+                    p = fmaf(x[4 * j + 1], w4.y, p);
+                    p = fmaf(x[4 * j + 2], w4.z, p);
+                    p = fmaf(x[4 * j + 3], w4.w, p);
+                }
+                const float sdot = group8_sum(p);
+                if (active && lane8 == 0) logit_part[row] = sdot;
+            }
+        }
+        __syncwarp();       // the slot is refilled by the next iteration's issue()
+    }
+    cp_async_wait<0>();
+    if (bad_id && err_flag != nullptr) atomicExch(err_flag, 1);
+}
+
+
 int make_gather_args(const dcnr_dims *dims, const dcnr_params *params, const dcnr_batch *batch, GatherArgs *out) {
     DCNR_REQUIRE(dims->n_cat >= 0 && dims->n_cat <= DCNR_MAX_CAT, "n_cat %d > %d", dims->n_cat, DCNR_MAX_CAT);
     DCNR_REQUIRE(batch->user_ids && batch->item_ids && (dims->n_cat == 0 || batch->cat_features) &&
@@ -569,6 +814,30 @@ int launch_embed_cross_fwd(const GatherArgs *ga, const float *x_in, int64_t ldx_
         }
         const int tw = dim_pad - mix0;
         ok = ok && tw >= 0 && tw <= 96 && ga->n_num <= 256 && (ga->n_num == 0 || ga->num != nullptr);
+        static const int pipe_stages = [] {          // DCNR_K1_PIPE=0 disables, 2 / 3 select the ring depth (default 2)
+            const char *e = getenv("DCNR_K1_PIPE");
+            return e != nullptr ? atoi(e) : 2;
+        }();
+        if (ok && nv <= 2 && pipe_stages >= 2) {
+            const int S = pipe_stages >= 3 ? 3 : 2;
+            const size_t smem_p = smem + (size_t)kPipeWarps * S * 32 * (dim_pad + 4) * sizeof(float);
+            const unsigned grid_p = (unsigned)std::min<int64_t>(ceil_div(B, 32 * kPipeWarps), (int64_t)sm_count() * 16);
+#define DCNR_LAUNCH_P(NVV, SS)                                                                                             \
+    do {                                                                                                                   \
+        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_embed_cross_fwd_pipe<NVV, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                             (int)smem_p));                                                                \
+        k_embed_cross_fwd_pipe<NVV, SS><<<grid_p, 32 * kPipeWarps, smem_p, stream>>>(*ga, n_vec, B, ca, x0_out, ldx0,      \
+                                                                                     y_out, ldy, wf_cross, logit_part,     \
+                                                                                     err_flag);                            \
+    } while (0)
+            if (nv == 1 && S == 2) DCNR_LAUNCH_P(1, 2);
+            else if (nv == 1) DCNR_LAUNCH_P(1, 3);
+            else if (S == 2) DCNR_LAUNCH_P(2, 2);
+            else DCNR_LAUNCH_P(2, 3);
+#undef DCNR_LAUNCH_P
+            DCNR_LAUNCHED();
+            return DCNR_OK;
+        }
         if (ok) {
             const size_t smem_s = smem + (size_t)(kThreads / 32) * 32 * (tw + 4) * sizeof(float);
             const unsigned grid_s = (unsigned)std::min<int64_t>(ceil_div(B, 32 * (kThreads / 32)), (int64_t)sm_count() * 8);

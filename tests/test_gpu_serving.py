@@ -9,6 +9,7 @@ import torch
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
+GOLDEN = GOLD
 
 
 @pytest.mark.parametrize("name", ["c300", "c40_unmapped", "c12"])
@@ -66,6 +67,7 @@ def test_expand_candidates_equals_per_hotel_queries():
 # artifacts on disk + device feature prep (SURVEY 8b artifacts row, 8f-4)
 # ------------------------------------------------------------------------------------------------
 def _serving_fixture(tmp_path):
+    import dcnr_b200
     import joblib
     import pandas as pd
     blob = joblib.load(os.path.join(GOLDEN, "preprocess_ranking_inputs.gz"))
@@ -86,6 +88,7 @@ def _serving_fixture(tmp_path):
 
 @pytest.mark.gpu
 def test_load_ml_artifacts_round_trip_and_fused_item_tables(tmp_path):
+    import dcnr_b200
     df, artifacts, model_cpu = _serving_fixture(tmp_path)
     ml = dcnr_b200.serving.load_ml_artifacts(str(tmp_path), device="cuda", precision="fp32")
     model = ml["final_model"]
