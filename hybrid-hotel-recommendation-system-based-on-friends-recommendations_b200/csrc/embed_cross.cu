@@ -517,7 +517,7 @@ k_embed_cross_fwd_staged(GatherArgs ga, int n_vec, int mix0, int64_t B, CrossArg
 // from its tile, pushed through the register-resident cross layers and stored.  Ids are fetched one
 // step further ahead (plain loads, needed to form the cp.async addresses).
 // ------------------------------------------------------------------------------------------------
-constexpr int kPipeWarps = 4;
+constexpr int kPipeWarps = 4;          // default warps per CTA (W below)
 
 __device__ __forceinline__ void cp_async16(uint32_t dst, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
@@ -529,8 +529,8 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-template <int NV, int S>
-__global__ void __launch_bounds__(32 * kPipeWarps)
+template <int NV, int S, int W, int RS>      // RS rows per step (32 or 16: half the tile, twice the warps per SM)
+__global__ void __launch_bounds__(32 * W)
 k_embed_cross_fwd_pipe(GatherArgs ga, int n_vec, int64_t B, CrossArgs ca, float *__restrict__ x0_out, int64_t ldx0,
                        float *__restrict__ y_out, int64_t ldy, const float *__restrict__ wf_cross,
                        float *__restrict__ logit_part, int32_t *err_flag) {
@@ -538,13 +538,13 @@ k_embed_cross_fwd_pipe(GatherArgs ga, int n_vec, int64_t B, CrossArgs ca, float 
     constexpr int NE = NV * 4;
     constexpr int TS = DP + 4;           // tile row pitch in floats (+4: consecutive rows start 4 banks apart)
     constexpr unsigned kFull = 0xffffffffu;
-    constexpr int kT = 32 * kPipeWarps;
+    constexpr int kT = 32 * W;
     constexpr int kMixPref = 2;
     extern __shared__ __align__(16) float smem[];
     float *sw = smem;                    // [L][DP]
     float *sb = sw + ca.L * DP;          // [L][DP]
     float *swf = sb + ca.L * DP;         // [DP]
-    float *tiles = swf + DP;             // [warps][S][32][TS]
+    float *tiles = swf + DP;             // [warps][S][RS][TS]
     __shared__ SmemSeg sseg[2 + DCNR_MAX_CAT];
 
     const int tid = threadIdx.x;
@@ -554,7 +554,7 @@ k_embed_cross_fwd_pipe(GatherArgs ga, int n_vec, int64_t B, CrossArgs ca, float 
         sb[i] = c < ca.D ? ca.b[l][c] : 0.f;
     }
     for (int c = tid; c < DP; c += kT) swf[c] = (wf_cross != nullptr && c < ca.D) ? wf_cross[c] : 0.f;
-    for (int i = tid; i < kPipeWarps * S * 32 * TS; i += kT) tiles[i] = 0.f;          // pad columns stay zero
+    for (int i = tid; i < W * S * RS * TS; i += kT) tiles[i] = 0.f;          // pad columns stay zero
     if (tid < ga.n_seg) {
         sseg[tid].table = ga.seg[tid].table;
         sseg[tid].ids = ga.seg[tid].ids;
@@ -566,7 +566,7 @@ k_embed_cross_fwd_pipe(GatherArgs ga, int n_vec, int64_t B, CrossArgs ca, float 
     __syncthreads();
 
     const int warp = tid >> 5, lane = tid & 31, lane8 = lane & 7, grp = lane >> 3;
-    float *wtile = tiles + (size_t)warp * S * 32 * TS;
+    float *wtile = tiles + (size_t)warp * S * RS * TS;
     const uint32_t wtile_s = (uint32_t)__cvta_generic_to_shared(wtile);
     const bool x0_vec = x0_out != nullptr && ldx0 >= DP && (ldx0 & 3) == 0;
     const bool y_vec = y_out != nullptr && ldy >= DP && (ldy & 3) == 0;
@@ -575,11 +575,11 @@ k_embed_cross_fwd_pipe(GatherArgs ga, int n_vec, int64_t B, CrossArgs ca, float 
     const float inv_num = n_num > 0 ? 1.f / (float)n_num : 0.f;
     bool bad_id = false;
 
-    const int64_t n_blocks = (B + 31) >> 5;
-    const int64_t blk_step = (int64_t)gridDim.x * kPipeWarps;
+    const int64_t n_blocks = (B + RS - 1) / RS;
+    const int64_t blk_step = (int64_t)gridDim.x * W;
     auto load_ids = [&](int64_t blk, int (&v)[kMaxVecSeg], int (&c)[kMixPref]) {
-        const int64_t r = (blk << 5) + lane;
-        const bool have = blk < n_blocks && r < B;
+        const int64_t r = blk * RS + lane;
+        const bool have = blk < n_blocks && r < B && lane < RS;
 #pragma unroll
         for (int sgi = 0; sgi < kMaxVecSeg; ++sgi) {
             v[sgi] = 0;
@@ -603,20 +603,21 @@ k_embed_cross_fwd_pipe(GatherArgs ga, int n_vec, int64_t B, CrossArgs ca, float 
     // every byte of the 32 rows of step `blk` into ring slot `slot`, as cp.async (no registers held while in flight)
     auto issue = [&](int64_t blk, int slot, const int (&v)[kMaxVecSeg], const int (&c)[kMixPref]) {
         if (blk >= n_blocks) return;
-        const int64_t base = blk << 5;
-        const uint32_t t0 = wtile_s + (uint32_t)(slot * 32 * TS * 4);
+        const int64_t base = blk * RS;
+        const uint32_t t0 = wtile_s + (uint32_t)(slot * RS * TS * 4);
 #pragma unroll
         for (int sgi = 0; sgi < kMaxVecSeg; ++sgi) {
             if (sgi < n_vec) {                               // aligned table rows: width / 4 chunks of 16 bytes per row
                 const SmemSeg &sg = sseg[sgi];
                 const int cpr = sg.width >> 2;
                 const float inv_c = 1.f / (float)cpr;
-                for (int t = 0; t < cpr; ++t) {
+                for (int t = 0; t * 32 < RS * cpr; ++t) {
                     const int idx = t * 32 + lane;
-                    const int r = (int)(((float)idx + 0.5f) * inv_c);
+                    const int r = min((int)(((float)idx + 0.5f) * inv_c), RS - 1);
                     const int part = idx - r * cpr;
                     const int rid = __shfl_sync(kFull, v[sgi], r);
-                    cp_async16(t0 + (uint32_t)((r * TS + sg.col0 + 4 * part) * 4), sg.table + (int64_t)rid * sg.width + 4 * part);
+                    if (idx < RS * cpr)
+                        cp_async16(t0 + (uint32_t)((r * TS + sg.col0 + 4 * part) * 4), sg.table + (int64_t)rid * sg.width + 4 * part);
                 }
             }
         }
@@ -625,35 +626,35 @@ k_embed_cross_fwd_pipe(GatherArgs ga, int n_vec, int64_t B, CrossArgs ca, float 
             int cid = 0;
             if (sgi - n_vec < kMixPref) {
                 cid = sgi == n_vec ? c[0] : c[1];
-            } else if (base + lane < B) {
+            } else if (base + lane < B && lane < RS) {
                 const int64_t id = __ldcs(sg.ids + (base + lane) * sg.id_stride);
                 if ((uint64_t)id >= (uint64_t)sg.rows) bad_id = true;
                 else cid = (int)id;
             }
             const int w = sg.width;
             const float inv_w = 1.f / (float)w;
-            for (int t = 0; t < w; ++t) {
+            for (int t = 0; t * 32 < RS * w; ++t) {
                 const int idx = t * 32 + lane;
-                const int r = (int)(((float)idx + 0.5f) * inv_w);       // exact: idx <= 32 * w, w <= 256
+                const int r = min((int)(((float)idx + 0.5f) * inv_w), RS - 1);       // exact: idx <= 32 * w, w <= 256
                 const int cc = idx - r * w;
                 const int rid = __shfl_sync(kFull, cid, r);
-                cp_async4(t0 + (uint32_t)((r * TS + sg.col0 + cc) * 4), sg.table + (int64_t)rid * w + cc, 4u);
+                if (idx < RS * w) cp_async4(t0 + (uint32_t)((r * TS + sg.col0 + cc) * 4), sg.table + (int64_t)rid * w + cc, 4u);
             }
         }
         if (n_num > 0) {                                     // numerics: 32 x n_num contiguous floats, zero past the batch
             const float *np = ga.num + base * n_num;
             const int64_t lim = (B - base) * n_num;
-            for (int t = 0; t < n_num; ++t) {
+            for (int t = 0; t * 32 < RS * n_num; ++t) {
                 const int idx = t * 32 + lane;
                 const int r = (int)(((float)idx + 0.5f) * inv_num);
                 const int cc = idx - r * n_num;
                 const bool in = idx < lim;
-                cp_async4(t0 + (uint32_t)((r * TS + num_c0 + cc) * 4), in ? np + idx : ga.num, in ? 4u : 0u);
+                if (idx < RS * n_num) cp_async4(t0 + (uint32_t)((r * TS + num_c0 + cc) * 4), in ? np + idx : ga.num, in ? 4u : 0u);
             }
         }
     };
 
-    const int64_t blk0 = (int64_t)blockIdx.x * kPipeWarps + warp;
+    const int64_t blk0 = (int64_t)blockIdx.x * W + warp;
     int vid[kMaxVecSeg], cpre[kMixPref];
     // prologue: S - 1 steps in flight
     load_ids(blk0, vid, cpre);
@@ -671,10 +672,10 @@ k_embed_cross_fwd_pipe(GatherArgs ga, int n_vec, int64_t B, CrossArgs ca, float 
         load_ids(blk + (int64_t)S * blk_step, vid, cpre);        // its latency hides behind the compute below
         cp_async_wait<S - 1>();                                  // step k has landed (this thread's copies) ...
         __syncwarp();                                            // ... and every other lane's
-        const float *tile = wtile + (size_t)(k % S) * 32 * TS;
-        const int64_t base = blk << 5;
+        const float *tile = wtile + (size_t)(k % S) * RS * TS;
+        const int64_t base = blk * RS;
 #pragma unroll 2
-        for (int it = 0; it < 8; ++it) {
+        for (int it = 0; it < RS / 4; ++it) {
             const int r = it * 4 + grp;
             const int64_t row = base + r;
             const bool active = row < B;
@@ -820,20 +821,38 @@ int launch_embed_cross_fwd(const GatherArgs *ga, const float *x_in, int64_t ldx_
         }();
         if (ok && nv <= 2 && pipe_stages >= 2) {
             const int S = pipe_stages >= 3 ? 3 : 2;
-            const size_t smem_p = smem + (size_t)kPipeWarps * S * 32 * (dim_pad + 4) * sizeof(float);
-            const unsigned grid_p = (unsigned)std::min<int64_t>(ceil_div(B, 32 * kPipeWarps), (int64_t)sm_count() * 16);
-#define DCNR_LAUNCH_P(NVV, SS)                                                                                             \
+            static const int pipe_warps = [] {       // DCNR_K1_PIPE_WARPS = 2 | 4 | 8 warps per CTA (experiments; default 4)
+                const char *e = getenv("DCNR_K1_PIPE_WARPS");
+                const int v = e != nullptr ? atoi(e) : kPipeWarps;
+                return (v == 2 || v == 8) ? v : kPipeWarps;
+            }();
+            // Measured per 4 M rows (P0; box-to-box spread is ~10 %): 32-row steps with 2 / 4 / 8 warps per CTA 405-470 / 414 /
+            // 510 us; 16-row steps (twice the warps per SM) 428 / 420 / 437 us; a ring of three tiles 516 us.
+            static const int pipe_rows = [] {        // DCNR_K1_PIPE_ROWS = 32 | 16 rows per step
+                const char *e = getenv("DCNR_K1_PIPE_ROWS");
+                return (e != nullptr && atoi(e) == 16) ? 16 : 32;
+            }();
+            const int W = S == 2 ? pipe_warps : kPipeWarps;
+            const int RS = (S == 2 && nv == 2) ? pipe_rows : 32;
+            const size_t smem_p = smem + (size_t)W * S * RS * (dim_pad + 4) * sizeof(float);
+            const unsigned grid_p = (unsigned)std::min<int64_t>(ceil_div(B, RS * W), (int64_t)sm_count() * 64 / W);
+#define DCNR_LAUNCH_P(NVV, SS, WW, RR)                                                                                     \
     do {                                                                                                                   \
-        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_embed_cross_fwd_pipe<NVV, SS>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                             (int)smem_p));                                                                \
-        k_embed_cross_fwd_pipe<NVV, SS><<<grid_p, 32 * kPipeWarps, smem_p, stream>>>(*ga, n_vec, B, ca, x0_out, ldx0,      \
+        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_embed_cross_fwd_pipe<NVV, SS, WW, RR>,                                      \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));                   \
+        k_embed_cross_fwd_pipe<NVV, SS, WW, RR><<<grid_p, 32 * WW, smem_p, stream>>>(*ga, n_vec, B, ca, x0_out, ldx0,      \
                                                                                      y_out, ldy, wf_cross, logit_part,     \
                                                                                      err_flag);                            \
     } while (0)
-            if (nv == 1 && S == 2) DCNR_LAUNCH_P(1, 2);
-            else if (nv == 1) DCNR_LAUNCH_P(1, 3);
-            else if (S == 2) DCNR_LAUNCH_P(2, 2);
-            else DCNR_LAUNCH_P(2, 3);
+            if (nv == 1 && S == 2) DCNR_LAUNCH_P(1, 2, 4, 32);
+            else if (nv == 1) DCNR_LAUNCH_P(1, 3, 4, 32);
+            else if (S == 3) DCNR_LAUNCH_P(2, 3, 4, 32);
+            else if (RS == 32 && W == 2) DCNR_LAUNCH_P(2, 2, 2, 32);
+            else if (RS == 32 && W == 8) DCNR_LAUNCH_P(2, 2, 8, 32);
+            else if (RS == 32) DCNR_LAUNCH_P(2, 2, 4, 32);
+            else if (W == 2) DCNR_LAUNCH_P(2, 2, 2, 16);
+            else if (W == 8) DCNR_LAUNCH_P(2, 2, 8, 16);
+            else DCNR_LAUNCH_P(2, 2, 4, 16);
 #undef DCNR_LAUNCH_P
             DCNR_LAUNCHED();
             return DCNR_OK;
