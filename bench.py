@@ -320,6 +320,10 @@ def main():
         if world > 1:
             comm = dcnr_b200.distributed.Communicator()
         result["train"] = bench_train(model, dev, world, rank, comm, barrier, max_over_ranks)
+        if world > 1:      # the same data-parallel step with 65 536 rows PER GPU: what the sync costs when every GPU has real work
+            tw = bench_train(model, dev, world, rank, comm, barrier, max_over_ranks, global_batch=65_536 * world, steps=5)
+            tw["scaling"] = "weak"
+            result["train_weak"] = tw
         del model
         torch.cuda.empty_cache()
         result["sharded"] = bench_sharded(dev, world, rank, comm, barrier, max_over_ranks, args.precision)
