@@ -97,6 +97,6 @@ int launch_sum_partials(const float *partials, int64_t n_partials, int64_t ld, c
                         cudaStream_t stream);
 // out[r*ldo + c] = sum_p partials[(p*rows + r)*cols_pad + c] for c < cols
 int launch_sum_partials_2d(const float *partials, int64_t n_partials, int32_t rows, int32_t cols_pad,
-                           int32_t cols, float *out, int64_t ldo, cudaStream_t stream);
+                           int32_t cols, float *out, int64_t ldo, cudaStream_t stream, int64_t pitch = 0);   // pitch 0: dense
 
 }  // namespace dcnr

@@ -127,6 +127,82 @@ k_scatter_window(const uint32_t *__restrict__ keys, const uint32_t *__restrict__
     }
 }
 
+// Widths <= 16 (the user / item tables of the P0 model): two windows per warp, lanes 0-15 and 16-31, so that every lane
+// carries a gradient column and a warp keeps 16 source rows in flight instead of 8 (the one-window form leaves half the
+// lanes idle).  A lane of a half holds two of its window's 32 sorted (key, val) pairs; everything else is the walk above.
+__global__ void __launch_bounds__(128)
+k_scatter_window16(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, int64_t B, int width,
+                   const float *__restrict__ dx0, int64_t lddx, ScatterTables tabs,
+                   float *__restrict__ carry, uint8_t *__restrict__ flags, int64_t n_windows) {
+    constexpr unsigned kFull = 0xffffffffu;
+    const int lane = threadIdx.x & 31, half = lane >> 4, hl = lane & 15;
+    const int64_t wpair = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (wpair * 2 >= n_windows) return;                           // warp-uniform
+    const int64_t w = wpair * 2 + half;
+    const bool wvalid = w < n_windows;
+    const int64_t p0 = w * kWin, p1 = wvalid ? min(B, p0 + kWin) : p0;
+    const int cnt = (int)(p1 - p0);
+    const bool has_left = wvalid && p0 > 0, has_right = wvalid && p1 < B;
+    const uint32_t k_lo = p0 + hl < p1 ? keys[p0 + hl] : 0u, k_hi = p0 + hl + 16 < p1 ? keys[p0 + hl + 16] : 0u;
+    const uint32_t v_lo = p0 + hl < p1 ? vals[p0 + hl] : 0u, v_hi = p0 + hl + 16 < p1 ? vals[p0 + hl + 16] : 0u;
+    uint32_t edge = 0u;
+    if (hl == 0 && has_left) edge = keys[p0 - 1];
+    if (hl == 1 && has_right) edge = keys[p1];
+    const uint32_t left_id = __shfl_sync(kFull, edge, 0, 16), right_id = __shfl_sync(kFull, edge, 1, 16);
+    const uint32_t first_key = __shfl_sync(kFull, k_lo, 0, 16);
+    const int col = hl;
+    const bool on = wvalid && col < width;
+    uint32_t cur = first_key;
+    float acc = 0.f;
+    bool first = true;
+    uint8_t fl = 0;
+#pragma unroll 1
+    for (int q0 = 0; q0 < kWin; q0 += 8) {                        // fixed trip count: both halves shuffle together
+        uint32_t id[8];
+        float x[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int pos = min(q0 + j, max(cnt - 1, 0));
+            const uint32_t ka = __shfl_sync(kFull, k_lo, pos & 15, 16), kb = __shfl_sync(kFull, k_hi, pos & 15, 16);
+            const uint32_t va = __shfl_sync(kFull, v_lo, pos & 15, 16), vb = __shfl_sync(kFull, v_hi, pos & 15, 16);
+            id[j] = pos < 16 ? ka : kb;
+            const uint32_t v = pos < 16 ? va : vb;
+            x[j] = (on && q0 + j < cnt) ? scatter_src(tabs, id[j], v, dx0, lddx, col) : 0.f;
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            if (q0 + j < cnt) {
+                if (id[j] != cur) {
+                    if (first && has_left && cur == left_id) {
+                        if (on) carry[(w * 2 + 0) * width + col] = acc;
+                        fl |= 1;
+                    } else if (on) {
+                        *scatter_dst(tabs, cur, width, col) = acc;
+                    }
+                    cur = id[j];
+                    acc = 0.f;
+                    first = false;
+                }
+                acc += x[j];
+            }
+        }
+    }
+    if (!wvalid) return;
+    const bool left_open = first && has_left && cur == left_id;
+    const bool right_open = has_right && cur == right_id;
+    if (left_open) {
+        if (on) carry[(w * 2 + 0) * width + col] = acc;
+        fl |= 1;
+        if (right_open) fl |= 2;
+    } else if (right_open) {
+        if (on) carry[(w * 2 + 1) * width + col] = acc;
+        fl |= 4;
+    } else if (on) {
+        *scatter_dst(tabs, cur, width, col) = acc;
+    }
+    if (col == 0) flags[w] = fl;
+}
+
 __global__ void __launch_bounds__(128)
 k_scatter_fixup(const uint32_t *__restrict__ keys, int64_t B, int width, ScatterTables tabs,
                 const float *__restrict__ carry, const uint8_t *__restrict__ flags, int64_t n_windows) {
@@ -198,6 +274,112 @@ static int small_subs_per_cta(int64_t n_rows, int32_t width) {
     return (int)std::min<int64_t>(kSmallThreads / width, kSmallSmemFloats / (n_rows * width));
 }
 static int64_t small_ctas(int64_t B, int subs) { return ceil_div(ceil_div(std::max<int64_t>(B, 1), kSubRows), subs); }
+
+// All tiny tables of a model in ONE pass over the batch (the P0 model has two: city and hotel_type, whose dx0 columns sit
+// in the same 64 bytes of every row): thread = (sub-chunk, column of one of the tables).  Same private-table scheme as
+// k_scatter_small; one partial block [sum of table sizes] per CTA.
+struct SmallTables {
+    const int64_t *ids[DCNR_MAX_CAT];
+    int32_t id_stride[DCNR_MAX_CAT], n_rows[DCNR_MAX_CAT], width[DCNR_MAX_CAT], col0[DCNR_MAX_CAT];
+    int32_t tab_off[DCNR_MAX_CAT], col_begin[DCNR_MAX_CAT + 1];
+    int32_t n, tsz_total, w_total;
+};
+
+__global__ void __launch_bounds__(kSmallThreads)
+k_scatter_small_multi(SmallTables st, int64_t B, const float *__restrict__ dx0, int64_t lddx, int subs_per_cta,
+                      float *__restrict__ partials) {
+    extern __shared__ __align__(16) float tab[];          // [subs_per_cta][tsz_total]
+    const int tsz = st.tsz_total;
+    for (int i = threadIdx.x; i < subs_per_cta * tsz; i += kSmallThreads) tab[i] = 0.f;
+    __syncthreads();
+    const int s = threadIdx.x / st.w_total, jj = threadIdx.x % st.w_total;
+    if (s < subs_per_cta) {
+        int t = 0;
+        while (t + 1 < st.n && jj >= st.col_begin[t + 1]) ++t;
+        const int j = jj - st.col_begin[t], width = st.width[t], n_rows = st.n_rows[t];
+        const int64_t *ids = st.ids[t];
+        const int64_t id_stride = st.id_stride[t];
+        const int col = st.col0[t] + j;
+        const int64_t b0 = ((int64_t)blockIdx.x * subs_per_cta + s) * kSubRows, b1 = min(B, b0 + kSubRows);
+        float *mine = tab + (size_t)s * tsz + st.tab_off[t] + j;
+        for (int64_t bb = b0; bb < b1; bb += 8) {                    // 8 (id, value) pairs in flight, added in batch order
+            int64_t id[8];
+            float v[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int64_t b = min(bb + q, b1 - 1);
+                id[q] = __ldg(ids + b * id_stride);
+                v[q] = __ldg(dx0 + b * lddx + col);
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                if (bb + q < b1) {
+                    const int64_t r = id[q] < 0 ? 0 : (id[q] >= n_rows ? n_rows - 1 : id[q]);   // dcnr_check_ids reports bad ids
+                    mine[r * width] += v[q];
+                }
+            }
+        }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < tsz; e += kSmallThreads) {
+        float acc = 0.f;
+        for (int q = 0; q < subs_per_cta; ++q) acc += tab[(size_t)q * tsz + e];
+        partials[(int64_t)blockIdx.x * tsz + e] = acc;
+    }
+}
+
+// true (and launched) when every categorical table with a gradient takes the tiny-table path and they fit one pass
+static bool try_scatter_small_multi(const dcnr_dims *dims, const dcnr_batch *batch, const float *dx0, int64_t lddx,
+                                    const dcnr_grads *grads, void *scratch, int64_t scratch_bytes, cudaStream_t stream, int *rc) {
+    static const bool enabled = [] {
+        const char *e = getenv("DCNR_SCATTER_MULTI");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    *rc = DCNR_OK;
+    const int64_t B = batch->batch;
+    if (!enabled || B <= 0) return false;
+    SmallTables st;
+    memset(&st, 0, sizeof(st));
+    int col = 2 * dims->emb_dim, n = 0;
+    float *out[DCNR_MAX_CAT];
+    for (int i = 0; i < dims->n_cat; ++i) {
+        if (grads->cat_table[i]) {
+            if (small_subs_per_cta(dims->cat_rows[i], dims->cat_width[i]) == 0) return false;
+            st.ids[n] = batch->cat_features + i;
+            st.id_stride[n] = dims->n_cat;
+            st.n_rows[n] = (int32_t)dims->cat_rows[i];
+            st.width[n] = dims->cat_width[i];
+            st.col0[n] = col;
+            st.tab_off[n] = st.tsz_total;
+            st.col_begin[n] = st.w_total;
+            st.tsz_total += st.n_rows[n] * st.width[n];
+            st.w_total += st.width[n];
+            out[n] = grads->cat_table[i];
+            ++n;
+        }
+        col += dims->cat_width[i];
+    }
+    st.n = n;
+    st.col_begin[n] = st.w_total;
+    if (n < 2 || st.w_total > 64 || st.tsz_total > kSmallMaxTable) return false;
+    const int subs = std::min(kSmallThreads / st.w_total, kSmallSmemFloats / st.tsz_total);
+    if (subs < 2) return false;
+    const int64_t ctas = small_ctas(B, subs);
+    if (scratch_bytes < ctas * st.tsz_total * 4) return false;
+    float *partials = reinterpret_cast<float *>(scratch);
+    const size_t smem = (size_t)subs * st.tsz_total * sizeof(float);
+    if (smem > 48 * 1024 &&
+        cudaFuncSetAttribute(k_scatter_small_multi, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    k_scatter_small_multi<<<(unsigned)ctas, kSmallThreads, smem, stream>>>(st, B, dx0, lddx, subs, partials);
+    DCNR_LAUNCHED();
+    for (int t = 0; t < n && *rc == DCNR_OK; ++t)
+        *rc = launch_sum_partials_2d(partials + st.tab_off[t], ctas, st.n_rows[t], st.width[t], st.width[t], out[t], st.width[t],
+                                     stream, st.tsz_total);
+    return true;
+}
 
 __global__ void k_pack_embed_grads(const int64_t *__restrict__ user_ids, const int64_t *__restrict__ item_ids,
                                    const float *__restrict__ dx0, int64_t lddx, int64_t B, int w2, int64_t *__restrict__ ids_out,
@@ -280,8 +462,16 @@ static int launch_scatter_sorted(const int64_t *ids0, int64_t stride0, int64_t r
     tabs.col0[0] = col0; tabs.col0[1] = two ? col1 : col0;
     tabs.tbit = tbit; tabs.B = B;
     const int64_t threads = n_windows * width;
-    k_scatter_window<<<(unsigned)ceil_div(n_windows, 4), 128, 0, stream>>>(kb.Current(), vb.Current(), n, width, dx0, lddx, tabs,
-                                                                         carry, flags, n_windows);
+    static const bool window16 = [] {               // DCNR_SCATTER_W16=0: the one-window-per-warp form for every width
+        const char *e = getenv("DCNR_SCATTER_W16");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    if (width <= 16 && window16)
+        k_scatter_window16<<<(unsigned)ceil_div(ceil_div(n_windows, 2), 4), 128, 0, stream>>>(kb.Current(), vb.Current(), n, width,
+                                                                                              dx0, lddx, tabs, carry, flags, n_windows);
+    else
+        k_scatter_window<<<(unsigned)ceil_div(n_windows, 4), 128, 0, stream>>>(kb.Current(), vb.Current(), n, width, dx0, lddx, tabs,
+                                                                             carry, flags, n_windows);
     DCNR_LAUNCHED();
     k_scatter_fixup<<<(unsigned)ceil_div(threads, 128), 128, 0, stream>>>(kb.Current(), n, width, tabs, carry, flags, n_windows);
     DCNR_LAUNCHED();
@@ -350,6 +540,8 @@ extern "C" int dcnr_embed_scatter_bwd(const dcnr_dims *dims, const dcnr_batch *b
     const int E = dims->emb_dim;
     DCNR_TRY(launch_embed_scatter_pair(batch->user_ids, 1, dims->n_users, grads->user_table, 0, batch->item_ids, 1, dims->n_items,
                                        grads->item_table, E, batch->batch, E, dx0, lddx, scratch, scratch_bytes, st));
+    int rc = DCNR_OK;
+    if (try_scatter_small_multi(dims, batch, dx0, lddx, grads, scratch, scratch_bytes, st, &rc)) return rc;
     int col = 2 * E;
     for (int i = 0; i < dims->n_cat; ++i) {
         if (grads->cat_table[i])

@@ -127,7 +127,7 @@ int launch_sum_partials(const float *partials, int64_t n_partials, int64_t ld, c
 // at B = 1 M) took 130 us.
 __global__ void __launch_bounds__(32 * kSumSlicesMax)
 k_sum_partials_2d(const float *__restrict__ partials, int64_t n_partials, int32_t rows, int32_t cols_pad, int32_t cols,
-                  float *__restrict__ out, int64_t ldo) {
+                  float *__restrict__ out, int64_t ldo, int64_t pitch) {       // pitch: floats between consecutive partial tables
     __shared__ double sh[kSumSlicesMax][33];
     const int kSumSlices = blockDim.x >> 5;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -141,11 +141,11 @@ k_sum_partials_2d(const float *__restrict__ partials, int64_t n_partials, int32_
         for (; p + 8 <= p1; p += 8) {
             float v[8];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = __ldg(partials + (p + j) * total + e);
+            for (int j = 0; j < 8; ++j) v[j] = __ldg(partials + (p + j) * pitch + e);
 #pragma unroll
             for (int j = 0; j < 8; ++j) acc += (double)v[j];
         }
-        for (; p < p1; ++p) acc += (double)__ldg(partials + p * total + e);
+        for (; p < p1; ++p) acc += (double)__ldg(partials + p * pitch + e);
     }
     sh[ty][tx] = acc;
     __syncthreads();
@@ -161,10 +161,11 @@ k_sum_partials_2d(const float *__restrict__ partials, int64_t n_partials, int32_
 }
 
 int launch_sum_partials_2d(const float *partials, int64_t n_partials, int32_t rows, int32_t cols_pad,
-                           int32_t cols, float *out, int64_t ldo, cudaStream_t stream) {
+                           int32_t cols, float *out, int64_t ldo, cudaStream_t stream, int64_t pitch) {
     int64_t total = (int64_t)rows * cols_pad;
+    if (pitch <= 0) pitch = total;
     k_sum_partials_2d<<<(unsigned)ceil_div(total, 32), 32 * sum_slices(n_partials), 0, stream>>>(partials, n_partials, rows, cols_pad,
-                                                                                   cols, out, ldo);
+                                                                                   cols, out, ldo, pitch);
     DCNR_LAUNCHED();
     return DCNR_OK;
 }
