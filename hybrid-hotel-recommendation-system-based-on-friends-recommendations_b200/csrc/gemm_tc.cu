@@ -228,6 +228,7 @@ struct Params {
     int32_t epi_slots;        // epilogue slots per warp (2 or 4)
     int32_t epi_groups;       // 1: warps 6-9 drain the accumulator; 2: warps 10-13 as well (alternate 32-column chunks)
     int32_t a_tmem, a_col0;   // TF32X3: A hi / lo in a tensor-memory ring (64 columns per stage) starting at column a_col0
+    int32_t one_arrive;       // A-in-TMEM split warps: one arrival per CTA on "ready" (named barrier among the four warps first)
     int32_t b_local;          // pairs with A in tensor memory: each CTA's weight boxes land on its OWN barrier (plain TMA, no
                               // .cta_group::2 completion on the leader); its A-split warps wait for them before arriving on "ready"
     int32_t b_split;          // TF32X3: the weight arrives as raw fp32 and warps 10-13 split it in shared memory (half the L2 stream)
@@ -299,7 +300,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int s = 0; s < stages; ++s) {
             mbar_init(fullA0 + 8 * s, 1);
             mbar_init(fullB0 + 8 * s, 1);
-            mbar_init(ready0 + 8 * s, (p.b_split ? 8 : 4) * CTAS);   // one arrival per split warp (A; and the weight when b_split)
+            mbar_init(ready0 + 8 * s, (p.one_arrive ? 1 : (p.b_split ? 8 : 4)) * CTAS);   // one arrival per split warp (A; and the weight when b_split)
             mbar_init(empty0 + 8 * s, 1);
         }
         for (int a = 0; a < acc_stages; ++a) {
@@ -526,10 +527,18 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) p.dbg[it * 8 + 2] = clock64();
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
                     if (p.b_local) mbar_wait(fullB0 + 8 * s, ph);          // this CTA's weight boxes have landed too
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (CTAS == 2) mbar_arrive_cluster(L_ready0 + 8 * s);
-                        else mbar_arrive(ready0 + 8 * s);
+                    if (p.one_arrive) {
+                        asm volatile("bar.sync 1, 128;" ::: "memory");       // the four split warps
+                        if (warp == 2 && lane == 0) {
+                            if (CTAS == 2) mbar_arrive_cluster(L_ready0 + 8 * s);
+                            else mbar_arrive(ready0 + 8 * s);
+                        }
+                    } else {
+                        __syncwarp();
+                        if (lane == 0) {
+                            if (CTAS == 2) mbar_arrive_cluster(L_ready0 + 8 * s);
+                            else mbar_arrive(ready0 + 8 * s);
+                        }
                     }
                 }
             }
@@ -926,6 +935,11 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
         return e != nullptr ? atoi(e) : 0;
     }();
     p.b_local = 0;
+    static const int one_arrive_env = [] {
+        const char *e = getenv("DCNR_GEMM_ONE_ARRIVE");
+        return e != nullptr ? atoi(e) : 0;
+    }();
+    p.one_arrive = (p.a_tmem && !p.b_split && one_arrive_env) ? 1 : 0;
     p.epi_groups = p.b_split ? 1 : epi_groups_for(p.block_n, precision, k);
     static const int forced_bk = [] {
         const char *e = getenv("DCNR_GEMM_BK");
