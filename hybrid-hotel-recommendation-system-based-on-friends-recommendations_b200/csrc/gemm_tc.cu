@@ -353,8 +353,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64) p.dbg[it * 8 + 0] = clock64();
                     if (p.terms == 3) {
                         // A lands on this CTA's own barrier (its split warps wait for it), the weight halves on the leader's
-                        mbar_expect_tx(fullA0 + 8 * s, (uint32_t)a_tile_bytes);
-                        tma_load_2d(smem_u32(st), &tmA, kb * bk, m0, fullA0 + 8 * s);
+                        if (!(p.debug & 32)) {                 // (bit 5: weight boxes first, then A -- issue-order experiment)
+                            mbar_expect_tx(fullA0 + 8 * s, (uint32_t)a_tile_bytes);
+                            tma_load_2d(smem_u32(st), &tmA, kb * bk, m0, fullA0 + 8 * s);
+                        }
                         if (p.b_split) {
                             // raw fp32 weight box onto this CTA's OWN barrier: its weight-split warps wait for it
                             mbar_expect_tx(fullB0 + 8 * s, (uint32_t)b_tile_bytes);
@@ -371,6 +373,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(2 * b_tile_bytes));
                             tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fb);
                             tma_load_2d(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * bk, n0, fb);
+                        }
+                        if (p.debug & 32) {
+                            mbar_expect_tx(fullA0 + 8 * s, (uint32_t)a_tile_bytes);
+                            tma_load_2d(smem_u32(st), &tmA, kb * bk, m0, fullA0 + 8 * s);
                         }
                     } else {
                         if (leader) mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(CTAS * (a_tile_bytes + b_tile_bytes)));
@@ -413,7 +419,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const int s = it % stages;
                     const uint32_t ph = (it / stages) & 1;
                     if (!p.b_split && !p.b_local) wait_x(fullB0 + 8 * s, ph);       // else "ready" covers the weight tile too
+                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && lane == 0) p.dbg[it * 8 + 5] = clock64();
                     if (p.terms == 3) wait_x(ready0 + 8 * s, ph);
+                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && lane == 0) p.dbg[it * 8 + 7] = clock64();
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
                     if (elect_one()) {
@@ -1055,8 +1063,9 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
             fprintf(stderr, "block_n %d stages %d a_tmem %d | it: TMA issue | +landed | +split loads/math | +st or fence | MMA start | issue done\n",
                     p.block_n, p.stages, p.a_tmem);
             for (int i = 8; i < 40; ++i)
-                fprintf(stderr, "%2d: %8lld  +%6lld  +%6lld  +%6lld  mma@%8lld  +%5lld\n", i, h[i * 8] - t0, h[i * 8 + 1] - h[i * 8],
-                        h[i * 8 + 6] - h[i * 8 + 1], h[i * 8 + 2] - h[i * 8 + 6], h[i * 8 + 3] - t0, h[i * 8 + 4] - h[i * 8 + 3]);
+                fprintf(stderr, "%2d: %8lld  +%6lld  +%6lld  +%6lld  mma@%8lld  +%5lld | weights seen @%8lld  A ready seen @%8lld\n", i,
+                        h[i * 8] - t0, h[i * 8 + 1] - h[i * 8], h[i * 8 + 6] - h[i * 8 + 1], h[i * 8 + 2] - h[i * 8 + 6], h[i * 8 + 3] - t0,
+                        h[i * 8 + 4] - h[i * 8 + 3], h[i * 8 + 5] - t0, h[i * 8 + 7] - t0);
             for (int t = 0; t < 8; ++t)
                 fprintf(stderr, "epilogue tile %d: start %8lld  took %6lld\n", t, h[512 + 2 * t] - t0, h[512 + 2 * t + 1] - h[512 + 2 * t]);
             fprintf(stderr, "epilogue chunk: start | slot wait | tmem ld | math+sts | fence | store/prefetch\n");
