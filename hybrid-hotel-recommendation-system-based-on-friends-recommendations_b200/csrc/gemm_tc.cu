@@ -59,6 +59,21 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (!ok && spins > (1u << 24)) __trap();
     }
 }
+// Non-suspending poll (mbarrier.test_wait): for the MMA-issuing warp, whose barriers are usually complete when it asks and
+// whose waits sit on the tensor pipe's critical path (try_wait may park the thread for a time slice).
+__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
+    uint32_t ok = 0;
+    for (uint32_t spins = 0; !ok; ++spins) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok && spins > (1u << 26)) __trap();
+    }
+}
 // mbarrier wait that synchronises with arrivals from the other CTA of a pair (remote arrive / multicast commit)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
@@ -259,8 +274,11 @@ constexpr int kBarBytes = 512;                      // mbarriers + the TMEM base
 // reads per CTA are halved.  The MMAs are issued by the leader CTA (cluster rank 0) only; barriers
 // that gate them (fullB, ready, tempty) live in the leader and are arrived on remotely by the peer;
 // barriers the leader releases (empty, tfull) are signalled in both CTAs by a multicast commit.
-template <int CTAS>
-__global__ void __launch_bounds__(kThreadsP, 1)
+// HAD: Hadamard operand in the epilogue (DCN-v2 cross layer).  EXTRA: warps 10-13 exist (second epilogue group for short
+// reductions, or the in-kernel weight split).  Both are compiled OUT of the dense 256 x 256 layers: as run-time branches they
+// cost the epilogue-bound tf32 form 15-40 % (0.62 -> 0.72 -> 0.94 ms) and the tf32x3 form 3 %.
+template <int CTAS, bool HAD, bool EXTRA>
+__global__ void __launch_bounds__(EXTRA ? kThreadsP : 320, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
           const __grid_constant__ CUtensorMap tmBlo, const __grid_constant__ CUtensorMap tmR,
           const __grid_constant__ CUtensorMap tmC, Params p) {
@@ -280,7 +298,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const int stages = p.stages, acc_stages = p.acc_stages;
     uint8_t *epi_slots = smem + (size_t)stages * stage_bytes;            // 1024-aligned (stage sizes are multiples of 1 KB)
     const int kEpiSlots = p.epi_slots;
-    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_slots + 4 * p.epi_groups * kEpiSlots * kEpiSlotBytes);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(epi_slots + 4 * (EXTRA ? p.epi_groups : 1) * kEpiSlots * kEpiSlotBytes);
     // bars: fullA[stages], fullB[stages], ready[stages], empty[stages], tfull[acc_stages], tempty[acc_stages], rfull[8][kEpiSlots]
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 4 * stages + 2 * acc_stages + 8 * kEpiSlotsMax);
 
@@ -300,12 +318,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int s = 0; s < stages; ++s) {
             mbar_init(fullA0 + 8 * s, 1);
             mbar_init(fullB0 + 8 * s, 1);
-            mbar_init(ready0 + 8 * s, (p.one_arrive ? 1 : (p.b_split ? 8 : 4)) * CTAS);   // one arrival per split warp (A; and the weight when b_split)
+            mbar_init(ready0 + 8 * s, (p.one_arrive ? 1 : ((EXTRA && p.b_split) ? 8 : 4)) * CTAS);   // one arrival per split warp (A; and the weight when b_split)
             mbar_init(empty0 + 8 * s, 1);
         }
         for (int a = 0; a < acc_stages; ++a) {
             mbar_init(tfull0 + 8 * a, 1);
-            mbar_init(tempty0 + 8 * a, 4 * CTAS * p.epi_groups);   // one arrival per epilogue warp
+            mbar_init(tempty0 + 8 * a, 4 * CTAS * (EXTRA ? p.epi_groups : 1));   // one arrival per epilogue warp
         }
         for (int i = 0; i < 8 * kEpiSlots; ++i) mbar_init(rfull0 + 8 * i, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -340,12 +358,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // ---------------- TMA producer (both CTAs of a pair) ----------------
         {
             uint32_t it = 0;
+            int rs = 0; uint32_t rph = 0;
             for (int t = tile0; t < num_tiles; t += tile_step) {
                 const int m0 = (t / p.num_n_tiles) * (BLOCK_M * CTAS) + (int)rank * BLOCK_M;
                 const int n0 = (t % p.num_n_tiles) * p.block_n + (int)rank * bn_cta;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1;
+                    const int s = rs;
+                    const uint32_t ph = rph;
+                    if (++rs == stages) { rs = 0; rph ^= 1u; }
                     wait_x(empty0 + 8 * s, ph ^ 1);
                     uint8_t *st = smem + (size_t)s * stage_bytes;
                     const uint32_t fb = L_fullB0 + 8 * s;
@@ -357,7 +377,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             mbar_expect_tx(fullA0 + 8 * s, (uint32_t)a_tile_bytes);
                             tma_load_2d(smem_u32(st), &tmA, kb * bk, m0, fullA0 + 8 * s);
                         }
-                        if (p.b_split) {
+                        if (EXTRA && p.b_split) {
                             // raw fp32 weight box onto this CTA's OWN barrier: its weight-split warps wait for it
                             mbar_expect_tx(fullB0 + 8 * s, (uint32_t)b_tile_bytes);
                             tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fullB0 + 8 * s);
@@ -410,17 +430,27 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 else umma_tf32_ts(d, a, b, idesc, acc);
             };
             uint32_t it = 0, tl = 0;
+            int rs = 0; uint32_t rph = 0;      // running stage index / phase bit (no runtime division on the issue path)
+            int ras = 0; uint32_t raph = 0;    // running accumulator stage / phase
             for (int t = tile0; t < num_tiles; t += tile_step, ++tl) {
-                const int as = tl % acc_stages;
-                wait_x(tempty0 + 8 * as, ((tl / acc_stages) & 1) ^ 1);        // epilogues drained this accumulator
+                const int as = ras;
+                const uint32_t aph = raph;
+                if (++ras == acc_stages) { ras = 0; raph ^= 1u; }
+                wait_x(tempty0 + 8 * as, aph ^ 1);        // epilogues drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_main = tmem_base + as * acc_stride, d_corr = d_main + corr_off;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1;
-                    if (!p.b_split && !p.b_local) wait_x(fullB0 + 8 * s, ph);       // else "ready" covers the weight tile too
+                    const int s = rs;
+                    const uint32_t ph = rph;
+                    if (++rs == stages) { rs = 0; rph ^= 1u; }
+                    if (CTAS == 1 && (p.debug & 64)) {            // experiment: non-suspending polls in the issuing warp
+                        if (!(EXTRA && p.b_split) && !p.b_local) mbar_wait_spin(fullB0 + 8 * s, ph);
+                        if (p.terms == 3) mbar_wait_spin(ready0 + 8 * s, ph);
+                    } else {
+                    if (!(EXTRA && p.b_split) && !p.b_local) wait_x(fullB0 + 8 * s, ph);       // else "ready" covers the weight tile too
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && lane == 0) p.dbg[it * 8 + 5] = clock64();
                     if (p.terms == 3) wait_x(ready0 + 8 * s, ph);
+                    }
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && lane == 0) p.dbg[it * 8 + 7] = clock64();
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
@@ -489,10 +519,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int r = quad * 32 + lane;
             const uint32_t swz = (uint32_t)(r & 7);
             uint32_t it = 0;
+            int rs = 0; uint32_t rph = 0;
             for (int t = tile0; t < num_tiles; t += tile_step) {
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1;
+                    const int s = rs;
+                    const uint32_t ph = rph;
+                    if (++rs == stages) { rs = 0; rph ^= 1u; }
                     mbar_wait(fullA0 + 8 * s, ph);
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) p.dbg[it * 8 + 1] = clock64();
                     // row pitch = the k-block width; chunk c of row r sits at c ^ (r & 7) (128-byte rows, SWIZZLE_128B) or at
@@ -553,10 +585,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         } else if (p.terms == 3) {
             const int tt = threadIdx.x - 64;               // 0..127
             uint32_t it = 0;
+            int rs = 0; uint32_t rph = 0;
             for (int t = tile0; t < num_tiles; t += tile_step) {
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1;
+                    const int s = rs;
+                    const uint32_t ph = rph;
+                    if (++rs == stages) { rs = 0; rph ^= 1u; }
                     mbar_wait(fullA0 + 8 * s, ph);
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && tt == 0) p.dbg[it * 8 + 1] = clock64();
                     float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * stage_bytes);
@@ -588,7 +622,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
             }
         }
-    } else if (warp >= 10 && p.epi_groups == 1) {
+    } else if (EXTRA && warp >= 10 && p.epi_groups == 1) {
         // ---------------- warps 10..13: split the landed raw weight tile into hi / lo in shared memory (b_split) ----------------
         // The weight stream from L2 was the larger half of the kernel's L2 -> SM traffic (hi + lo boxes: 32 of 64 KB per
         // k-block at ~42 B/clk/SM); loading fp32 once and splitting here halves it.  Elementwise, so the swizzle is irrelevant;
@@ -597,10 +631,12 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int tt = threadIdx.x - 320;              // 0..127
             const int cells = b_tile_bytes / 16;
             uint32_t it = 0;
+            int rs = 0; uint32_t rph = 0;
             for (int t = tile0; t < num_tiles; t += tile_step) {
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = it % stages;
-                    const uint32_t ph = (it / stages) & 1;
+                    const int s = rs;
+                    const uint32_t ph = rph;
+                    if (++rs == stages) { rs = 0; rph ^= 1u; }
                     mbar_wait(fullB0 + 8 * s, ph);
                     float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * stage_bytes + b_off);
                     float4 *lo = hi + cells;
@@ -627,7 +663,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
             }
         }
-    } else if (warp < 10 || p.epi_groups == 2) {
+    } else if (warp < 10 || (EXTRA && p.epi_groups == 2)) {
         // ---------------- warps 6..9 (and 10..13): epilogue (each CTA drains its own 128 accumulator rows) ----------------
         // TMEM gives each lane one accumulator ROW (32 columns per tcgen05.ld), so the arithmetic is done
         // row-per-thread; all global traffic is TMA.  A warp owns kEpiSlots shared-memory slots of
@@ -639,30 +675,43 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         // With epi_groups == 2 the warps 10..13 join in: warp w and warp w + 4 share a TMEM lane quadrant and take
         // alternate 32-column chunks of every tile (the K = 64 initial layer is epilogue-bound with four warps).
         const int ew = warp - 6;                           // 0..7
-        const int eg = ew >> 2, ngroups = p.epi_groups;    // this warp's chunk phase
+        const int eg = EXTRA ? (ew >> 2) : 0, ngroups = EXTRA ? p.epi_groups : 1;    // this warp's chunk phase
         const int quad = warp & 3;                         // TMEM lane quadrant this warp may access
         uint8_t *slots = epi_slots + (size_t)ew * kEpiSlots * kEpiSlotBytes;
         const uint32_t rf0 = rfull0 + 8 * ew * kEpiSlots;
-        const bool has_res = p.epi.residual != nullptr, has_c = p.C != nullptr, has_had = p.epi.hadamard != nullptr;
+        const bool has_res = p.epi.residual != nullptr, has_c = p.C != nullptr, has_had = HAD && p.epi.hadamard != nullptr;
         const int cpt = (p.block_n + 31) / 32 / ngroups;   // chunks per tile for this warp (block_n / 32 is even when ngroups == 2)
         const uint32_t swz = (uint32_t)(lane & 7);
-        auto issue_res_load = [&](uint32_t g) {            // lane 0: residual box of global chunk g into slot g % kEpiSlots
-            const int t = tile0 + (int)(g / cpt) * tile_step;
-            if (t >= num_tiles) return;
-            const int m0 = (t / p.num_n_tiles) * (BLOCK_M * CTAS) + (int)rank * BLOCK_M + quad * 32;
-            const int n = (t % p.num_n_tiles) * p.block_n + ((int)(g % cpt) * ngroups + eg) * 32;
-            const uint32_t sl = g % kEpiSlots;
-            mbar_expect_tx(rf0 + 8 * sl, (uint32_t)kEpiSlotBytes);
-            tma_load_2d(smem_u32(slots + sl * kEpiSlotBytes), &tmR, n, m0, rf0 + 8 * sl);
+        // residual prefetch cursor: boxes are requested in chunk order, so tile / chunk / slot advance incrementally
+        // (runtime divisions per chunk on the issuing lane were a measurable part of the epilogue)
+        int pl_t = tile0, pl_c = 0, pl_sl = 0;
+        int pl_m0 = (pl_t / p.num_n_tiles) * (BLOCK_M * CTAS) + (int)rank * BLOCK_M + quad * 32;
+        int pl_n0 = (pl_t % p.num_n_tiles) * p.block_n;
+        auto issue_res_load = [&]() {                      // lane 0: the next residual box into the next slot
+            if (pl_t < num_tiles) {
+                mbar_expect_tx(rf0 + 8 * pl_sl, (uint32_t)kEpiSlotBytes);
+                tma_load_2d(smem_u32(slots + pl_sl * kEpiSlotBytes), &tmR, pl_n0 + (pl_c * ngroups + eg) * 32, pl_m0, rf0 + 8 * pl_sl);
+            }
+            if (++pl_sl == kEpiSlots) pl_sl = 0;
+            if (++pl_c == cpt) {
+                pl_c = 0;
+                pl_t += tile_step;
+                pl_m0 = (pl_t / p.num_n_tiles) * (BLOCK_M * CTAS) + (int)rank * BLOCK_M + quad * 32;
+                pl_n0 = (pl_t % p.num_n_tiles) * p.block_n;
+            }
         };
         if (has_res && lane == 0)
-            for (uint32_t g = 0; g + 1 < (uint32_t)kEpiSlots; ++g) issue_res_load(g);
+            for (int q = 0; q + 1 < kEpiSlots; ++q) issue_res_load();
         uint32_t tl = 0, g = 0;
+        int ras = 0; uint32_t raph = 0;        // running accumulator stage / phase
+        int rsl = 0; uint32_t rsph = 0;        // running epilogue slot / phase
         for (int t = tile0; t < num_tiles; t += tile_step, ++tl) {
-            const int as = tl % acc_stages;
+            const int as = ras;
+            const uint32_t aph = raph;
+            if (++ras == acc_stages) { ras = 0; raph ^= 1u; }
             const int m0 = (t / p.num_n_tiles) * (BLOCK_M * CTAS) + (int)rank * BLOCK_M;
             const int n_tile = t % p.num_n_tiles, n0 = n_tile * p.block_n;
-            wait_x(tfull0 + 8 * as, (tl / acc_stages) & 1);
+            wait_x(tfull0 + 8 * as, aph);
             if ((p.debug & 16) && blockIdx.x == 0 && tl < 8 && threadIdx.x == 192) p.dbg[512 + tl * 2] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int mw = m0 + quad * 32;                  // first row of this warp
@@ -671,12 +720,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const uint32_t t_main = tmem_base + as * acc_stride + ((uint32_t)(quad * 32) << 16);
             float dot = 0.f;
             for (int c0 = 32 * eg; c0 < p.block_n; c0 += 32 * ngroups, ++g) {
-                const uint32_t sl = g % kEpiSlots;
+                const uint32_t sl = (uint32_t)rsl;
+                const uint32_t slph = rsph;
+                if (++rsl == kEpiSlots) { rsl = 0; rsph ^= 1u; }
                 uint8_t *row = slots + sl * kEpiSlotBytes + lane * 128;
                 const bool stamp = (p.debug & 16) && blockIdx.x == 0 && threadIdx.x == 192 && g >= 16 && g < 48;
                 if (stamp) p.dbg[600 + (g - 16) * 6 + 0] = clock64();
                 if (has_res) {
-                    mbar_wait(rf0 + 8 * sl, (g / kEpiSlots) & 1);
+                    mbar_wait(rf0 + 8 * sl, slph);
                 } else if (has_c) {                         // the store that last used this slot has finished reading it
                     if (lane == 0) {
                         if (kEpiSlots == 4) bulk_wait_read<3>();
@@ -703,7 +754,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     float4 v;
                     v.x = fmaf(__uint_as_float(r[4 * j]), s4.x, b4.x); v.y = fmaf(__uint_as_float(r[4 * j + 1]), s4.y, b4.y);
                     v.z = fmaf(__uint_as_float(r[4 * j + 2]), s4.z, b4.z); v.w = fmaf(__uint_as_float(r[4 * j + 3]), s4.w, b4.w);
-                    if (has_had) {                          // row-per-lane 128-byte segments straight from global memory
+                    if (HAD && has_had) {                   // row-per-lane 128-byte segments straight from global memory
                         const float4 h4 = had_row != nullptr ? ldg4(had_row + c0 + 4 * j) : make_float4(0.f, 0.f, 0.f, 0.f);
                         v.x *= h4.x; v.y *= h4.y; v.z *= h4.z; v.w *= h4.w;
                     }
@@ -731,7 +782,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                     if (has_res) {                          // refill the slot chunk g-1 used: its store must be done reading
                         if (has_c) bulk_wait_read<1>();
-                        issue_res_load(g + kEpiSlots - 1);
+                        issue_res_load();
                     }
                 }
                 if (stamp) p.dbg[600 + (g - 16) * 6 + 5] = clock64();
@@ -1011,19 +1062,28 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
         p.tmem_cols = 32;
         while (p.tmem_cols < p.a_col0 + ring_cols) p.tmem_cols <<= 1;
     };
+    // warps 10-13 exist only when they have a role (second epilogue group, in-kernel weight split): with 2-CTA pairs four
+    // idle warps per CTA measured 16 % slower (tf32, 1 M x 256 x 256: 0.72 vs 0.62 ms)
+    const unsigned threads = (p.b_split || p.epi_groups == 2) ? kThreadsP : 320u;
+    const bool had = epi.hadamard != nullptr, extra = threads == (unsigned)kThreadsP;
+    typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, Params);
+    const KernFn kern1 = had ? (extra ? k_gemm_tc<1, true, true> : k_gemm_tc<1, true, false>)
+                             : (extra ? k_gemm_tc<1, false, true> : k_gemm_tc<1, false, false>);
+    const KernFn kern2 = had ? (extra ? k_gemm_tc<2, true, true> : k_gemm_tc<2, true, false>)
+                             : (extra ? k_gemm_tc<2, false, true> : k_gemm_tc<2, false, false>);
     size_t smem = 0;
     p.b_local = (ctas == 2 && p.a_tmem && !p.b_split && b_local_env) ? 1 : 0;
     if (ctas == 2) {
         plan(2, &smem);
-        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tc<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DCNR_CUDA_CHECK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         cfg.gridDim = dim3(2 * (unsigned)sm_count(), 1, 1);
-        cfg.blockDim = dim3(kThreadsP, 1, 1);
+        cfg.blockDim = dim3(threads, 1, 1);
         cfg.dynamicSmemBytes = smem;
         cfg.stream = stream;
         attr[0].id = cudaLaunchAttributeClusterDimension;
         attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
         cfg.attrs = attr; cfg.numAttrs = 1;
-        if (cudaOccupancyMaxActiveClusters(&max_pairs, k_gemm_tc<2>, &cfg) != cudaSuccess || max_pairs < 1) {
+        if (cudaOccupancyMaxActiveClusters(&max_pairs, kern2, &cfg) != cudaSuccess || max_pairs < 1) {
             cudaGetLastError();
             ctas = 1;
         }
@@ -1044,12 +1104,12 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     gemm_timer_before(stream, 2.0 * (double)m * (double)n * (double)k);
     if (ctas == 2) {
         cfg.gridDim = dim3(2 * (unsigned)std::min<int64_t>(num_tiles, max_pairs), 1, 1);
-        DCNR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_gemm_tc<2>, tmA, tmBhi, tmBlo, tmR, tmC, p));
+        DCNR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kern2, tmA, tmBhi, tmBlo, tmR, tmC, p));
     } else {
         plan(1, &smem);
-        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_gemm_tc<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DCNR_CUDA_CHECK(cudaFuncSetAttribute(kern1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         const unsigned grid = (unsigned)std::min<int64_t>(num_tiles, sm_count());
-        k_gemm_tc<1><<<grid, kThreadsP, smem, stream>>>(tmA, tmBhi, tmBlo, tmR, tmC, p);
+        kern1<<<grid, threads, smem, stream>>>(tmA, tmBhi, tmBlo, tmR, tmC, p);
     }
     gemm_timer_after(stream);
     DCNR_LAUNCHED();
