@@ -243,6 +243,8 @@ struct Params {
     int32_t epi_slots;        // epilogue slots per warp (2 or 4)
     int32_t epi_groups;       // 1: warps 6-9 drain the accumulator; 2: warps 10-13 as well (alternate 32-column chunks)
     int32_t a_tmem, a_col0;   // TF32X3: A hi / lo in a tensor-memory ring (64 columns per stage) starting at column a_col0
+    int32_t fast;             // default TF32X3 form (1 CTA, A in TMEM, pre-split weights): the weight boxes complete on "ready" too (ONE
+                              // wait per k-block in the issuing warp) and the next k-block's barrier is probed between the MMAs
     int32_t one_arrive;       // A-in-TMEM split warps: one arrival per CTA on "ready" (named barrier among the four warps first)
     int32_t b_local;          // pairs with A in tensor memory: each CTA's weight boxes land on its OWN barrier (plain TMA, no
                               // .cta_group::2 completion on the leader); its A-split warps wait for them before arriving on "ready"
@@ -318,7 +320,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int s = 0; s < stages; ++s) {
             mbar_init(fullA0 + 8 * s, 1);
             mbar_init(fullB0 + 8 * s, 1);
-            mbar_init(ready0 + 8 * s, (p.one_arrive ? 1 : ((EXTRA && p.b_split) ? 8 : 4)) * CTAS);   // one arrival per split warp (A; and the weight when b_split)
+            mbar_init(ready0 + 8 * s, (p.one_arrive ? 1 : ((EXTRA && p.b_split) ? 8 : 4)) * CTAS + (p.fast ? 1 : 0));   // fast: + the producer's arrive.expect_tx   // one arrival per split warp (A; and the weight when b_split)
             mbar_init(empty0 + 8 * s, 1);
         }
         for (int a = 0; a < acc_stages; ++a) {
@@ -389,6 +391,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                             if (leader) mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(CTAS * 2 * b_tile_bytes));
                             tma_load_2d_pair(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fb);
                             tma_load_2d_pair(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * bk, n0, fb);
+                        } else if (p.fast) {                    // the weight boxes count on "ready" next to the split warps' arrivals
+                            mbar_expect_tx(ready0 + 8 * s, (uint32_t)(2 * b_tile_bytes));
+                            tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * bk, n0, ready0 + 8 * s);
+                            tma_load_2d(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * bk, n0, ready0 + 8 * s);
                         } else {
                             mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(2 * b_tile_bytes));
                             tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fb);
@@ -432,6 +438,63 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             uint32_t it = 0, tl = 0;
             int rs = 0; uint32_t rph = 0;      // running stage index / phase bit (no runtime division on the issue path)
             int ras = 0; uint32_t raph = 0;    // running accumulator stage / phase
+            if (CTAS == 1 && p.fast) {
+                // Default TF32X3 form.  The tensor pipe's queue is shallow: tcgen05.mma issue blocks on it, so whatever the issuing
+                // warp does between the last MMA of a k-block and the first of the next is dead time for the pipe (stamps: ~760 clk
+                // of a 1 530 clk k-block: two barrier waits of ~240 clk each although both had completed long before).  Here there
+                // is ONE barrier per k-block, and it is probed (non-blocking) for the NEXT k-block in the middle of this one's
+                // MMAs, when the issue is blocked on the queue anyway.
+                uint32_t pre_ok = 0;
+                for (int t = tile0; t < num_tiles; t += tile_step) {
+                    const int as = ras;
+                    const uint32_t aph = raph;
+                    if (++ras == acc_stages) { ras = 0; raph ^= 1u; }
+                    mbar_wait(tempty0 + 8 * as, aph ^ 1);        // epilogues drained this accumulator
+                    const uint32_t d_main = tmem_base + as * acc_stride, d_corr = d_main + corr_off;
+                    for (int kb = 0; kb < num_kb; ++kb) {
+                        const int s = rs;
+                        const uint32_t ph = rph;
+                        if (++rs == stages) { rs = 0; rph ^= 1u; }
+                        if (!pre_ok) mbar_wait(ready0 + 8 * s, ph);
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
+                        const uint32_t t_hi = tmem_base + (uint32_t)p.a_col0 + (uint32_t)(s * 2 * BLOCK_K), t_lo = t_hi + (uint32_t)BLOCK_K;
+                        const uint64_t db_hi = make_desc(a_hi + b_off), db_lo = make_desc(a_hi + b_off + b_tile_bytes);
+                        const uint32_t acc_main = p.corr_sep ? (uint32_t)(kb != 0) : 1u;
+                        if (elect_one()) {
+                            mma_ts(d_corr, t_lo, db_hi, kb != 0);
+                            mma_ts(d_corr, t_hi, db_lo, 1);
+                            mma_ts(d_main, t_hi, db_hi, acc_main);
+                            mma_ts(d_corr, t_lo + 8, db_hi + 2, 1);
+                            mma_ts(d_corr, t_hi + 8, db_lo + 2, 1);
+                            mma_ts(d_main, t_hi + 8, db_hi + 2, 1);
+                        }
+                        __syncwarp();
+                        {                                      // probe the next k-block's barrier while the queue drains
+                            uint32_t ok;
+                            asm volatile(
+                                "{\n\t.reg .pred p;\n\t"
+                                "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                                "selp.u32 %0, 1, 0, p;\n\t}"
+                                : "=r"(ok)
+                                : "r"(ready0 + 8 * rs), "r"(rph)
+                                : "memory");
+                            pre_ok = __shfl_sync(0xffffffffu, ok, 0);
+                        }
+                        if (elect_one()) {
+                            mma_ts(d_corr, t_lo + 16, db_hi + 4, 1);
+                            mma_ts(d_corr, t_hi + 16, db_lo + 4, 1);
+                            mma_ts(d_main, t_hi + 16, db_hi + 4, 1);
+                            mma_ts(d_corr, t_lo + 24, db_hi + 6, 1);
+                            mma_ts(d_corr, t_hi + 24, db_lo + 6, 1);
+                            mma_ts(d_main, t_hi + 24, db_hi + 6, 1);
+                            umma_commit(empty0 + 8 * s);
+                            if (kb == num_kb - 1) umma_commit(tfull0 + 8 * as);
+                        }
+                        __syncwarp();
+                    }
+                }
+            } else
             for (int t = tile0; t < num_tiles; t += tile_step, ++tl) {
                 const int as = ras;
                 const uint32_t aph = raph;
@@ -999,6 +1062,11 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
         return e != nullptr ? atoi(e) : 0;
     }();
     p.one_arrive = (p.a_tmem && !p.b_split && one_arrive_env) ? 1 : 0;
+    static const bool fast_env = [] {               // DCNR_GEMM_FAST=0: the generic issue loop (two barriers per k-block)
+        const char *e = getenv("DCNR_GEMM_FAST");
+        return e == nullptr || atoi(e) != 0;
+    }();
+    p.fast = 0;
     p.epi_groups = p.b_split ? 1 : epi_groups_for(p.block_n, precision, k);
     static const int forced_bk = [] {
         const char *e = getenv("DCNR_GEMM_BK");
@@ -1089,6 +1157,8 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
         }
     }
     if (ctas != 2) p.b_local = 0;
+    p.fast = (ctas == 1 && terms == 3 && p.a_tmem && !p.b_split && p.bk == BLOCK_K && !p.one_arrive && fast_env &&
+              (debug_bits & ~0) == 0) ? 1 : 0;      // any DCNR_GEMM_DEBUG experiment runs the generic loop
     CUtensorMap tmA, tmBhi, tmBlo, tmR, tmC;
     DCNR_TRY(make_map(&tmA, A, m, k, lda, BLOCK_M, p.bk));
     // epilogue boxes: 32 rows x 32 columns of the residual / output (rows and columns past the matrix are
