@@ -243,6 +243,9 @@ struct Params {
     int32_t epi_slots;        // epilogue slots per warp (2 or 4)
     int32_t epi_groups;       // 1: warps 6-9 drain the accumulator; 2: warps 10-13 as well (alternate 32-column chunks)
     int32_t a_tmem, a_col0;   // TF32X3: A hi / lo in a tensor-memory ring (64 columns per stage) starting at column a_col0
+    const float *A_raw;       // a_ldg: the A matrix itself (row pitch lda floats): the split warps read their rows with LDG
+    int64_t lda;
+    int32_t a_ldg;            // fast form only: A bypasses shared memory (no TMA box, no shared-memory read by the split warps)
     int32_t fast;             // default TF32X3 form (1 CTA, A in TMEM, pre-split weights): the weight boxes complete on "ready" too (ONE
                               // wait per k-block in the issuing warp) and the next k-block's barrier is probed between the MMAs
     int32_t one_arrive;       // A-in-TMEM split warps: one arrival per CTA on "ready" (named barrier among the four warps first)
@@ -375,7 +378,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     if ((p.debug & 16) && blockIdx.x == 0 && it < 64) p.dbg[it * 8 + 0] = clock64();
                     if (p.terms == 3) {
                         // A lands on this CTA's own barrier (its split warps wait for it), the weight halves on the leader's
-                        if (!(p.debug & 32)) {                 // (bit 5: weight boxes first, then A -- issue-order experiment)
+                        if (!(p.debug & 32) && !p.a_ldg) {     // (bit 5: weight boxes first, then A -- issue-order experiment)
                             mbar_expect_tx(fullA0 + 8 * s, (uint32_t)a_tile_bytes);
                             tma_load_2d(smem_u32(st), &tmA, kb * bk, m0, fullA0 + 8 * s);
                         }
@@ -573,7 +576,71 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         }
     } else if (warp < 6) {
         // ---------------- warps 2..5: split the landed A tile into hi / lo (TF32X3) ----------------
-        if (p.terms == 3 && p.a_tmem) {
+        if (CTAS == 1 && p.a_ldg) {
+            // A never touches shared memory: the thread that owns tile row r reads the 128 bytes of its row for a k-block
+            // straight from global memory (8 x LDG.128, one full line per lane), two k-blocks ahead in registers, splits
+            // them and writes hi / lo into the TMEM ring.  Shared-memory bandwidth is what bounds this kernel (TMA writes
+            // 48 KB + split reads 16 KB + MMA operand reads 48 KB + epilogue 32 KB per k-block against 128 B/clk); this
+            // removes the 16 KB TMA write and the 16 KB read of A.
+            const int quad = warp & 3;
+            const int r = quad * 32 + lane;
+            int rs = 0; uint32_t rph = 0;
+            // prefetch cursor (tile, k-block) runs two k-blocks ahead of the consume cursor
+            int pt = tile0, pkb = 0;
+            auto fetch = [&](float4 (&buf)[8]) {
+                if (pt < num_tiles) {
+                    const int64_t grow = (int64_t)(pt / p.num_n_tiles) * BLOCK_M + r;
+                    if (grow < p.M) {
+                        const float *src = p.A_raw + grow * p.lda + pkb * BLOCK_K;
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) buf[c] = ldg4(src + 4 * c);
+                    } else {
+#pragma unroll
+                        for (int c = 0; c < 8; ++c) buf[c] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    }
+                }
+                if (++pkb == num_kb) { pkb = 0; pt += tile_step; }
+            };
+            auto consume = [&](const float4 (&buf)[8]) {
+                const int s = rs;
+                const uint32_t ph = rph;
+                if (++rs == stages) { rs = 0; rph ^= 1u; }
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int c = 0; c < 8; ++c) {
+                    const float e[4] = {buf[c].x, buf[c].y, buf[c].z, buf[c].w};
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        uint32_t u;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(e[q]));
+                        hi[4 * c + q] = u;
+                        lo[4 * c + q] = __float_as_uint(e[q] - __uint_as_float(u));
+                    }
+                }
+                mbar_wait(empty0 + 8 * s, ph ^ 1);             // the MMAs that read ring slot s (one trip ago) are done
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t t_hi = tmem_base + (uint32_t)p.a_col0 + (uint32_t)(s * 2 * BLOCK_K) + ((uint32_t)(quad * 32) << 16);
+                tmem_st32(t_hi, hi);
+                tmem_st32(t_hi + 32u, lo);
+                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) mbar_arrive(ready0 + 8 * s);
+            };
+            float4 b0[8], b1[8];
+            fetch(b0);
+            fetch(b1);
+            int64_t total = 0;
+            for (int t = tile0; t < num_tiles; t += tile_step) total += num_kb;
+            for (int64_t i = 0; i < total; i += 2) {
+                consume(b0);
+                fetch(b0);
+                if (i + 1 < total) {
+                    consume(b1);
+                    fetch(b1);
+                }
+            }
+        } else if (p.terms == 3 && p.a_tmem) {
             // One thread per tile row: it reads its 128-byte row of the k-block from the swizzled TMA tile (chunk c of
             // row r sits at position c ^ (r & 7): conflict-free), splits it and writes hi / lo straight into the TMEM
             // operand ring (tcgen05.st: lane = row).  No hi / lo tiles in shared memory and no shared-memory operand
@@ -1159,6 +1226,13 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     if (ctas != 2) p.b_local = 0;
     p.fast = (ctas == 1 && terms == 3 && p.a_tmem && !p.b_split && p.bk == BLOCK_K && !p.one_arrive && fast_env &&
               (debug_bits & ~0) == 0) ? 1 : 0;      // any DCNR_GEMM_DEBUG experiment runs the generic loop
+    static const bool a_ldg_env = [] {              // DCNR_GEMM_ALDG=1: A straight from global memory in the split warps
+        const char *e = getenv("DCNR_GEMM_ALDG");
+        return e != nullptr && atoi(e) != 0;
+    }();
+    p.a_ldg = (p.fast && a_ldg_env) ? 1 : 0;
+    p.A_raw = A;
+    p.lda = lda;
     CUtensorMap tmA, tmBhi, tmBlo, tmR, tmC;
     DCNR_TRY(make_map(&tmA, A, m, k, lda, BLOCK_M, p.bk));
     // epilogue boxes: 32 rows x 32 columns of the residual / output (rows and columns past the matrix are
