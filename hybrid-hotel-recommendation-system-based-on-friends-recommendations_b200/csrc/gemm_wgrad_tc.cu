@@ -148,9 +148,12 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
 
     if (warp == 0) {
         // ---------------- TMA producer ----------------
+        int rs = 0; uint32_t rph = 0;                       // running stage / phase (no run-time division per k-block)
         for (int kb = 0; kb < num_kb; ++kb) {
-            const int s = kb % stages;
-            mbar_wait(empty0 + 8 * s, ((kb / stages) & 1) ^ 1);
+            const int s = rs;
+            const uint32_t ph = rph;
+            if (++rs == stages) { rs = 0; rph ^= 1u; }
+            mbar_wait(empty0 + 8 * s, ph ^ 1);
             uint8_t *st = smem + (size_t)s * stage_bytes;
             const int row = (int)(b0 + (int64_t)kb * BLOCK_K);           // rows past B are zero-filled: no contribution
             if (elect_one()) {
@@ -167,9 +170,12 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | (1u << 15) | (1u << 16) |
                                    ((uint32_t)(p.k_in >> 3) << 17) | ((uint32_t)(BLOCK_M >> 4) << 24);
             const uint32_t lbo = BLOCK_K * 128;                       // bytes between 32-float blocks
+            int rs = 0; uint32_t rph = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % stages;
-                mbar_wait((p.terms == 3 ? ready0 : full0) + 8 * s, (kb / stages) & 1);
+                const int s = rs;
+                const uint32_t ph = rph;
+                if (++rs == stages) { rs = 0; rph ^= 1u; }
+                mbar_wait((p.terms == 3 ? ready0 : full0) + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
                 if (elect_one()) {
@@ -200,9 +206,12 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const int tt = threadIdx.x - 64;                   // 0..127
         if (p.terms == 3) {
             const int n4 = (a_bytes + b_bytes) / 16;       // float4 of [A][B] (contiguous in the stage)
+            int rs = 0; uint32_t rph = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
-                const int s = kb % stages;
-                mbar_wait(full0 + 8 * s, (kb / stages) & 1);
+                const int s = rs;
+                const uint32_t ph = rph;
+                if (++rs == stages) { rs = 0; rph ^= 1u; }
+                mbar_wait(full0 + 8 * s, ph);
                 float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * stage_bytes);
                 float4 *lo = hi + n4;
                 for (int i = tt; i < n4; i += 128) {
