@@ -241,6 +241,8 @@ struct Params {
     int32_t N_total, K, block_n, terms, stages, acc_cols, acc_stages, corr_sep, tmem_cols;
     int32_t bk;               // floats per k-block (32, or 16 with A in tensor memory: six finer pipeline stages)
     int32_t epi_slots;        // epilogue slots per warp (2 or 4)
+    int32_t epi_depth;        // residual boxes requested this many chunks ahead (<= epi_slots - 1); the slot being refilled was
+                              // stored epi_slots - epi_depth chunks ago, so that many TMA stores may still be reading
     int32_t epi_groups;       // 1: warps 6-9 drain the accumulator; 2: warps 10-13 as well (alternate 32-column chunks)
     int32_t a_tmem, a_col0;   // TF32X3: A hi / lo in a tensor-memory ring (64 columns per stage) starting at column a_col0
     const float *A_raw;       // a_ldg: the A matrix itself (row pitch lda floats): the split warps read their rows with LDG
@@ -831,7 +833,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             }
         };
         if (has_res && lane == 0)
-            for (int q = 0; q + 1 < kEpiSlots; ++q) issue_res_load();
+            for (int q = 0; q < p.epi_depth; ++q) issue_res_load();
         uint32_t tl = 0, g = 0;
         int ras = 0; uint32_t raph = 0;        // running accumulator stage / phase
         int rsl = 0; uint32_t rsph = 0;        // running epilogue slot / phase
@@ -911,7 +913,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         bulk_commit();
                     }
                     if (has_res) {                          // refill the slot chunk g-1 used: its store must be done reading
-                        if (has_c) bulk_wait_read<1>();
+                        if (has_c) {
+                            if (kEpiSlots - p.epi_depth >= 2) bulk_wait_read<2>();
+                            else bulk_wait_read<1>();
+                        }
                         issue_res_load();
                     }
                 }
@@ -1187,6 +1192,11 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
         p.epi_slots = (forced_slots == 2 || forced_slots == 4) ? forced_slots
                       : (p.epi_groups == 2 || (stages_for(2) > stages_for(4) && p.a_tmem) ? 2 : 4);
         p.stages = stages_for(p.epi_slots);
+        static const int forced_depth = [] {
+            const char *e = getenv("DCNR_GEMM_EPI_DEPTH");
+            return e != nullptr ? atoi(e) : 0;
+        }();
+        p.epi_depth = (forced_depth >= 1 && forced_depth < p.epi_slots) ? forced_depth : p.epi_slots - 1;
         *smem_out = (size_t)p.stages * stage_bytes + 1024 + kBarBytes + 4 * p.epi_groups * p.epi_slots * kEpiSlotBytes;
         // tensor memory: accumulator stage(s) first, then (A in TMEM) the operand ring, 64 columns (hi | lo) per stage
         const int ring_cols = p.a_tmem ? p.stages * 2 * p.bk : 0;
