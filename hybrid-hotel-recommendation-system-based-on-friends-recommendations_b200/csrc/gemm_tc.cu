@@ -1235,7 +1235,7 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     }
     if (ctas != 2) p.b_local = 0;
     p.fast = (ctas == 1 && terms == 3 && p.a_tmem && !p.b_split && p.bk == BLOCK_K && !p.one_arrive && fast_env &&
-              (debug_bits & ~0) == 0) ? 1 : 0;      // any DCNR_GEMM_DEBUG experiment runs the generic loop
+              debug_bits == 0) ? 1 : 0;             // any DCNR_GEMM_DEBUG experiment runs the generic loop
     static const bool a_ldg_env = [] {              // DCNR_GEMM_ALDG=1: A straight from global memory in the split warps
         const char *e = getenv("DCNR_GEMM_ALDG");
         return e != nullptr && atoi(e) != 0;
