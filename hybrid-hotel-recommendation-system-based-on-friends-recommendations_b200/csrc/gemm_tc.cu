@@ -1200,7 +1200,12 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
         *smem_out = (size_t)p.stages * stage_bytes + 1024 + kBarBytes + 4 * p.epi_groups * p.epi_slots * kEpiSlotBytes;
         // tensor memory: accumulator stage(s) first, then (A in TMEM) the operand ring, 64 columns (hi | lo) per stage
         const int ring_cols = p.a_tmem ? p.stages * 2 * p.bk : 0;
-        p.corr_sep = (terms == 3 && 4 * p.acc_cols + ring_cols <= 512) ? 1 : 0;   // separate accumulator for the lo terms
+        // TF32X3: the lo.hi / hi.lo terms ALWAYS get their own accumulator.  The tensor core's fp32 accumulate truncates toward
+        // zero (profiles/r02_acc_probe.md: -0.8 eps per K = 8 step on same-sign sums), so every addition into the long-running
+        // main sum costs up to one ulp of that sum whatever the size of the addend; with the 2^-11-sized correction terms kept
+        // apart the main chain is k / 8 additions instead of 3 k / 8 and the measured rms error of a K = 256 layer drops from
+        // 38 eps to 13 eps (fp32 FMA chain: 6).  Room is made by single-buffering the accumulators when necessary.
+        p.corr_sep = (terms == 3 && 2 * p.acc_cols + ring_cols <= 512) ? 1 : 0;
         const int per_stage_cols = p.corr_sep ? 2 * p.acc_cols : p.acc_cols;
         p.acc_stages = 2 * per_stage_cols + ring_cols <= 512 ? 2 : 1;
         p.a_col0 = p.acc_stages * per_stage_cols;

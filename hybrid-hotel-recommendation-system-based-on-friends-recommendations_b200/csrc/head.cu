@@ -188,3 +188,26 @@ extern "C" int dcnr_check_ids(const dcnr_dims *dims, const dcnr_batch *batch, in
     }
     return DCNR_OK;
 }
+
+// out[j] = base[j] + sum_n v[n] * W[n * ldw + j]   (double accumulation, n ascending: deterministic).
+// Used for the initial layer's bias gradient: db0 = colsum(dz1 W1 + dy2) = colsum(dz1) W1 + colsum(dy2) by linearity, so the
+// batch sum never runs over GEMM outputs (whose tensor-core rounding errors do not average out over a cancelling sum).
+namespace dcnr {
+__global__ void __launch_bounds__(256)
+k_vecmat_add(const float *__restrict__ v, const float *__restrict__ W, int64_t ldw, int32_t n_rows, int32_t n_cols,
+             const float *__restrict__ base, float *__restrict__ out) {
+    const int j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_cols) return;
+    double acc = base != nullptr ? (double)base[j] : 0.0;
+    for (int n = 0; n < n_rows; ++n) acc += (double)__ldg(v + n) * (double)__ldg(W + (int64_t)n * ldw + j);
+    out[j] = (float)acc;
+}
+
+int launch_vecmat_add(const float *v, const float *W, int64_t ldw, int32_t n_rows, int32_t n_cols, const float *base,
+                      float *out, cudaStream_t stream) {
+    k_vecmat_add<<<(unsigned)ceil_div(n_cols, 256), 256, 0, stream>>>(v, W, ldw, n_rows, n_cols, base, out);
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}
+}  // namespace dcnr
+

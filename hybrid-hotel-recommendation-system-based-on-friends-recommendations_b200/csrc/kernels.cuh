@@ -144,6 +144,10 @@ int launch_combine_logits(const float *parts, int n_parts, int64_t m, const floa
 int launch_rowdot_bwd(const float *dlogit, const float *a, int64_t lda, const float *w, float *dh, int64_t lddh,
                       float *dw, float *dbf, int64_t m, int32_t n, float *scratch, cudaStream_t stream);
 
+// out[j] = base[j] + sum_n v[n] * W[n*ldw + j]  (base may be NULL)
+int launch_vecmat_add(const float *v, const float *W, int64_t ldw, int32_t n_rows, int32_t n_cols, const float *base,
+                      float *out, cudaStream_t stream);
+
 // ---- embedding backward (embed_bwd.cu) ----------------------------------------------------------
 int64_t scatter_scratch_bytes(int64_t B);
 int launch_embed_scatter_pair(const int64_t *ids0, int64_t stride0, int64_t rows0, float *grad0, int32_t col0,

@@ -86,7 +86,7 @@ struct TrainSaved {
 static bool dp_sparse_tables(const dcnr_dims *d) { return comm_world(d->comm) > 1 && d->dp_sparse_tables != 0; }
 
 struct BwdScratch {
-    float *ga, *gb, *gc, *dx0, *cross_partials, *wgrad, *bn, *wsplit;
+    float *ga, *gb, *gc, *dx0, *cross_partials, *wgrad, *bn, *wsplit, *vec_a, *vec_b;
     void *scatter;
     int64_t scatter_bytes;
     int64_t *pack_ids, *all_ids;       // [B][2] (user, item) of this rank / [world*B][2] of all ranks
@@ -102,6 +102,8 @@ struct BwdScratch {
                                        wgrad_scratch_floats(B, (int32_t)H, (int32_t)Dp)));
         bn = a.take<float>(bn_scratch_floats(B, (int32_t)H));
         wsplit = a.take<float>(WeightOps::floats(d));
+        vec_a = a.take<float>(H);
+        vec_b = a.take<float>(H);
         const int world = dp_sparse_tables(d) ? comm_world(d->comm) : 1;
         scatter_bytes = with_scatter ? scatter_scratch_bytes(2 * B * world) : 0;      // user + item share one sort
         scatter = a.take<char>(scatter_bytes);
@@ -326,8 +328,10 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
         GemmEpilogue none{nullptr, nullptr, nullptr, 0, 0};
         DCNR_TRY(gemm_any(prec, g2, H, true, params->res_w2[r], H, false, g3, H, B, H, H, 1, none, st, wt.get(wt.w2[r])));   // dd1
         // d1 = dropout(relu(BN1(z1))): dz1 in place in g3
+        // (block 0: colsum(dz1) is needed for the initial layer's bias gradient even when res_b1 itself is not wanted)
+        float *db1 = (r == 0 && grads->b0 != nullptr && grads->res_b1[r] == nullptr) ? w.vec_a : grads->res_b1[r];
         DCNR_TRY(launch_bn_act_bwd(g3, H, s.d1[r], H, s.z1[r], H, mean1, rstd1, params->res_g1[r], post, g3, H, nullptr,
-                                   0, grads->res_g1[r], grads->res_be1[r], grads->res_b1[r], B, H, w.bn, st, dims->comm));
+                                   0, grads->res_g1[r], grads->res_be1[r], db1, B, H, w.bn, st, dims->comm));
         if (grads->res_w1[r])
             DCNR_TRY(launch_linear_wgrad(prec, g3, H, s.h[r], H, grads->res_w1[r], H, nullptr, B, H, H, H, w.wgrad, st));
         GemmEpilogue idn{nullptr, nullptr, g, H, 0};                                                      // + dy2
@@ -335,8 +339,18 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
         std::swap(g, g2);
     }
     // initial_deep_layer: h0 = x0 W0^T + b0
-    if (grads->w0 || grads->b0)
-        DCNR_TRY(launch_linear_wgrad(prec, g, H, s.x0p, Dp, grads->w0, D, grads->b0, B, H, Dp, D, w.wgrad, st));
+    // db0 = colsum(g).  With ResBlocks g = dz1 W1 + dy2 (block 0), so by linearity db0 = colsum(dz1) W1 + colsum(dy2): the batch
+    // sum then runs over dy2 (elementwise products) instead of over GEMM outputs, whose tensor-core rounding errors are
+    // sign-correlated (truncating accumulate) and do not average out in this cancellation-heavy sum (it was the one gradient
+    // tensor above 2x the reference's own fp32 noise: 3.4e-5 vs 9e-6).  dy2 of block 0 is what `g2` holds after the last swap.
+    const bool b0_split = grads->b0 != nullptr && R > 0;
+    if (grads->w0 || (grads->b0 && !b0_split))
+        DCNR_TRY(launch_linear_wgrad(prec, g, H, s.x0p, Dp, grads->w0, D, b0_split ? nullptr : grads->b0, B, H, Dp, D, w.wgrad, st));
+    if (b0_split) {
+        const float *db1 = grads->res_b1[0] != nullptr ? grads->res_b1[0] : w.vec_a;
+        DCNR_TRY(launch_colsum(g2, H, B, H, w.vec_b, w.bn, st));
+        DCNR_TRY(launch_vecmat_add(db1, params->res_w1[0], H, H, H, w.vec_b, grads->b0, st));
+    }
     GemmEpilogue none{nullptr, nullptr, nullptr, 0, 0};
     DCNR_TRY(gemm_any(prec, g, H, true, s.w0p, Dp, false, w.dx0, Dp, B, Dp, H, 1, none, st, wt.get(wt.w0)));
     // cross network (recomputed from x0), accumulated onto dx0

@@ -76,7 +76,14 @@ def test_train_forward_backward_matches_reference_golden(name, precision):
     _, g64, _ = orc.forward_backward(st64, case["user_ids"], case["item_ids"], case["cat"], case["num"].double(),
                                      grad_logits=case["grad_logits"].double())
     _check_grads(got, g64)
-    _check_grads(got, case["grads"], tol=2e-4)      # and the reference's fp32 run, at its own noise level
+    # and the reference's own fp32 run: equal up to the sum of both sides' distance from the fp64 arbiter
+    scale = max(float(g.abs().max()) for g in g64.values())
+    for k, r32 in case["grads"].items():
+        r64 = g64[k].double()
+        if float(r64.abs().max()) < 1e-6 * scale:
+            continue
+        noise = orc.max_abs_normalised(r32.double(), r64)
+        assert orc.max_abs_normalised(got[k].detach().cpu().double().reshape(r32.shape), r32.double()) <= TOL + 2 * noise, k
     # running statistics and num_batches_tracked updated like nn.BatchNorm1d
     sd = m.state_dict()
     for k, ref in case["after"].items():
@@ -145,28 +152,29 @@ def _relu_patterns_gpu(m, u, i, c, x):
 
 
 @pytest.mark.parametrize("precision", PARITY_PRECISIONS)
-@pytest.mark.parametrize("zipf", [False, True])
-def test_large_batch_against_fp64_oracle(zipf, precision):
-    """B = 4096 (configs[0] size), P0: logits and every gradient against the float64 oracle.
+@pytest.mark.parametrize("zipf,B", [(False, 4096), (True, 4096), (True, 65536)])
+def test_large_batch_against_fp64_oracle(zipf, B, precision):
+    """B = 4096 (configs[0] size) and B = 65 536 (configs[2] size), P0: logits and every gradient against the float64
+    oracle.
 
     ReLU kinks are taken out of the problem instead of being masked: the BN biases
-    of the test state are nudged so that no ReLU input of this batch is within ~7e-4 of zero
+    of the test state are nudged so that no ReLU input of this batch is within ~1e-4 of zero
     (oracle.desensitize_relus); the on/off patterns of float64, of the reference's fp32 arithmetic
     and of our kernels are then asserted identical, so what is compared is arithmetic.
 
-    Criterion per gradient tensor: err(ours vs fp64) <= max(1e-5, F x err(reference fp32 arithmetic vs
-    fp64)), F = 2 for the CUDA-core fp32 path and F = 40 for tf32x3.  The reference's own fp32 noise
-    reaches ~1e-5 on cancellation-heavy reductions (bias gradients), so a flat 1e-5 would fail the
-    reference against itself; the tcgen05 3xTF32 path is parity-grade on logits (the same ~1e-6 as
-    the reference) but its gradients carry 4-35x the fp32 noise (2^-21 per product instead of 2^-24,
-    truncating tensor-core accumulation) -- measured table in DESIGN.md."""
+    Criterion per gradient tensor, the SAME for the CUDA-core fp32 path and the tcgen05 tf32x3 path:
+    err(ours vs fp64) <= max(1e-5, 2 x err(reference fp32 arithmetic vs fp64)).  The reference's own fp32
+    noise reaches ~1e-5 on cancellation-heavy reductions (bias gradients), so a flat 1e-5 would fail the
+    reference against itself.  (Round 1 needed a 40x allowance for tf32x3; round 2 found the cause -- the
+    tensor core's truncating accumulate, profiles/r02_acc_probe.md -- and removed it: lo terms in their own
+    accumulator, and the initial layer's bias gradient by linearity instead of a batch sum over GEMM outputs.)"""
     import dcnr_b200
     n_users, n_items, cat_dims, n_num = 20000, 5000, {"city": 100, "hotel_type": 6}, 11
     params = dict(emb_dim=16, hidden_dim=256, n_cross_layers=3, n_res_blocks=2, dropout=0.0)
     state = orc.make_state(n_users, n_items, cat_dims, n_num, params, seed=7, emb_scale=0.1, randomize_bn=True)
-    u, i, c, x, y = synth_inputs(n_users, n_items, cat_dims, n_num, 4096, seed=1234, zipf=zipf)
+    u, i, c, x, y = synth_inputs(n_users, n_items, cat_dims, n_num, B, seed=1234, zipf=zipf)
     state, margin = orc.desensitize_relus(state, u, i, c, x)
-    assert margin > 1e-4
+    assert margin > (1e-4 if B <= 4096 else 2e-5)
     m = dcnr_b200.DCN_RecSys(n_users, n_items, cat_dims, n_num, params, precision=precision)
     m.load_state_dict(state)
     m = m.cuda()
@@ -183,13 +191,13 @@ def test_large_batch_against_fp64_oracle(zipf, precision):
     for y64, y32, pat in zip(pre64, pre32, ours):
         assert torch.equal(pat, y64 > 0) and torch.equal(y32 > 0, y64 > 0)
     m.load_state_dict(state)                    # the pattern probe moved the running statistics
-    g = torch.randn(4096, generator=torch.Generator().manual_seed(5)) / 4096
+    g = torch.randn(B, generator=torch.Generator().manual_seed(5)) / B
     ref_logits, ref_grads, _ = orc.forward_backward(st64, u, i, c, x.double(), grad_logits=g.double())
     _, noise_grads, _ = orc.forward_backward(state, u, i, c, x, grad_logits=g)     # reference arithmetic, fp32
     out = m(u.cuda(), i.cuda(), c.cuda(), x.cuda())
     assert orc.max_abs_normalised(out.detach().cpu(), ref_logits) < TOL
     out.backward(gradient=g.cuda())
-    factor = 2.0 if precision == "fp32" else 40.0
+    factor = 2.0
     scale = max(float(v.abs().max()) for v in ref_grads.values())
     for k, p in m.named_parameters():
         r = ref_grads[k]
