@@ -13,7 +13,8 @@ import torch
 
 MAX_CAT, MAX_RES, MAX_CROSS, PAD = 8, 8, 8, 32
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_INDEX = 0, -1, -2, -3, -4
-PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "bf16": 3}
+PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "bf16": 3, "fp16x3": 4}
+ABI_VERSION = 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdcnr_sm100a.so")
@@ -24,7 +25,8 @@ class Dims(Structure):
                 ("n_cross", c_int32), ("n_res", c_int32), ("in_dim", c_int32), ("in_dim_pad", c_int32),
                 ("n_users", c_int64), ("n_items", c_int64), ("cat_rows", c_int64 * MAX_CAT),
                 ("cat_width", c_int32 * MAX_CAT), ("dropout_p", c_float), ("bn_eps", c_float),
-                ("bn_momentum", c_float), ("precision", c_int32), ("dp_sparse_tables", c_int32), ("dropout_step", c_void_p), ("comm", c_void_p)]
+                ("bn_momentum", c_float), ("precision", c_int32), ("dp_sparse_tables", c_int32), ("dropout_step", c_void_p),
+                ("eval_flags", c_void_p), ("comm", c_void_p)]
 
 
 def _ptr_fields(spec):
@@ -103,6 +105,10 @@ _SIGS = {
     "dcnr_bn_act_bwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p,
                                 c_float, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                                 c_int32, c_void_p, c_int64, c_void_p]),
+    "dcnr_tower_eval_supported": (c_int, [POINTER(Dims)]),
+    "dcnr_tower_eval_workspace_bytes": (c_int64, [POINTER(Dims)]),
+    "dcnr_tower_eval": (c_int, [POINTER(Dims), POINTER(Params), c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_int32,
+                                c_void_p, c_void_p, c_int64, c_void_p]),
     "dcnr_rowdot_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "dcnr_knn_normalize": (c_int, [c_void_p, c_void_p, c_int64, c_int32, c_void_p]),
     "dcnr_knn_scratch_bytes": (c_int64, [c_int64, c_int32, c_int32, c_int32]),
@@ -140,7 +146,7 @@ def lib():
         for name, (res, args) in _SIGS.items():
             fn = getattr(L, name)          # AttributeError here = header/library mismatch
             fn.restype, fn.argtypes = res, args
-        if L.dcnr_abi_version() != 2:
+        if L.dcnr_abi_version() != ABI_VERSION:
             raise RuntimeError("libdcnr_sm100a.so ABI version mismatch")
         _lib = L
     return _lib

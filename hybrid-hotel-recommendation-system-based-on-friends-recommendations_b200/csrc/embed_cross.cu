@@ -258,7 +258,7 @@ k_embed_cross_fwd(GatherArgs ga, const float *__restrict__ x_in, int64_t ldx_in,
             }
         }
     }
-    if (bad_id && err_flag != nullptr) atomicExch(err_flag, 1);
+    if (bad_id && err_flag != nullptr) atomicOr(err_flag, 1);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -503,7 +503,7 @@ k_embed_cross_fwd_staged(GatherArgs ga, int n_vec, int mix0, int64_t B, CrossArg
 #pragma unroll
         for (int m = 0; m < kMixPref; ++m) cpre[m] = ncpre[m];
     }
-    if (bad_id && err_flag != nullptr) atomicExch(err_flag, 1);
+    if (bad_id && err_flag != nullptr) atomicOr(err_flag, 1);
 }
 
 
@@ -749,7 +749,7 @@ k_embed_cross_fwd_pipe(GatherArgs ga, int n_vec, int64_t B, CrossArgs ca, float 
         __syncwarp();       // the slot is refilled by the next iteration's issue()
     }
     cp_async_wait<0>();
-    if (bad_id && err_flag != nullptr) atomicExch(err_flag, 1);
+    if (bad_id && err_flag != nullptr) atomicOr(err_flag, 1);
 }
 
 

@@ -104,6 +104,19 @@ int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const floa
                         int64_t lddw, float *db, int64_t m, int32_t n, int32_t k, int32_t k_valid, float *scratch,
                         cudaStream_t stream);
 
+// ---- fused eval tower (tower_eval.cu): initial layer + ResBlocks + deep half of the final dot in ONE persistent kernel ----
+bool tower_eval_supported(const dcnr_dims *d);                 // hidden 256, 1..4 ResBlocks, in_dim_pad <= 256
+int64_t tower_pack_bytes(const dcnr_dims *d);
+int launch_tower_prepare(const dcnr_dims *d, const dcnr_params *p, void *pack, int precision, cudaStream_t stream);
+int launch_tower_eval(const dcnr_dims *d, const float *x0, int64_t ldx0, const float *logit_cross, const float *bf,
+                      const void *pack, float *out, int64_t M, int32_t *flags, int precision, int single_cta,
+                      cudaStream_t stream);
+// dense-layer precision the GEMM kernels run for a requested mode: the fp16x3 / bf16 modes exist only in the fused eval
+// tower; everywhere else (training, unsupported shapes, operator-level calls) they run as tf32x3 / tf32
+static inline int gemm_precision(int precision) {
+    return precision == DCNR_PREC_FP16X3 ? DCNR_PREC_TF32X3 : (precision == DCNR_PREC_BF16 ? DCNR_PREC_TF32 : precision);
+}
+
 // ---- data-parallel communicator (comm.cu); `comm` is the opaque handle of dcnr_comm_create or NULL ----
 int comm_world(const void *comm);
 int comm_rank(const void *comm);

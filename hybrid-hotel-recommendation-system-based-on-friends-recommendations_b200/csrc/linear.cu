@@ -7,7 +7,7 @@ namespace dcnr {
 
 bool gemm_any_uses_tc(int precision, int64_t lda, int64_t ldc, int64_t m, int64_t n, int64_t k, const WeightOp *wop,
                       int64_t ldb) {
-    if (precision == DCNR_PREC_BF16) precision = DCNR_PREC_TF32;
+    precision = gemm_precision(precision);
     if (precision == DCNR_PREC_TF32X3)
         return wop != nullptr && (wop->lo != nullptr || wop->raw) && gemm_tc_supported(precision, true, true, lda, wop->ld, ldc, m, n, k, 1);
     if (precision == DCNR_PREC_TF32)
@@ -18,7 +18,7 @@ bool gemm_any_uses_tc(int precision, int64_t lda, int64_t ldc, int64_t m, int64_
 int gemm_any(int precision, const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,
              float *C, int64_t ldc, int64_t m, int64_t n, int64_t k, int split_k, const GemmEpilogue &epi,
              cudaStream_t stream, const WeightOp *wop, const FusedDot *dot) {
-    if (precision == DCNR_PREC_BF16) precision = DCNR_PREC_TF32;     // no bf16 kernel yet: nearest tensor-core mode
+    precision = gemm_precision(precision);       // fp16x3 / bf16 exist only in the fused eval tower
     const float *dw = dot != nullptr ? dot->w : nullptr;
     float *dout = dot != nullptr ? dot->out : nullptr;
     if (precision == DCNR_PREC_TF32X3 && wop != nullptr && (wop->lo != nullptr || wop->raw) &&
@@ -45,6 +45,7 @@ struct TempSplit {
     WeightOp op{nullptr, nullptr, 0};
     int make(int precision, const float *w, int64_t ldw, int32_t rows, int32_t cols, bool transpose, cudaStream_t s) {
         st = s;
+        precision = gemm_precision(precision);
         if (precision != DCNR_PREC_TF32X3 && !(transpose && precision != DCNR_PREC_FP32)) return DCNR_OK;
         const int64_t n = (int64_t)rows * cols;
         static thread_local bool pool_ready = false;
@@ -91,7 +92,7 @@ int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const floa
     const int splits = wgrad_splits(m, n, k);
     float *slabs = scratch;                                           // [splits][n][k]
     float *colsum_scratch = scratch + wgrad_scratch_floats(m, n, k) - bn_scratch_floats(m, n);
-    if (precision == DCNR_PREC_BF16) precision = DCNR_PREC_TF32;
+    precision = gemm_precision(precision);
     if (dw != nullptr && wgrad_tc_supported(precision, lddy, ldx, m, n, k)) {
         // tcgen05 path: MN-major operands straight from dy / x, one [n, k] partial per batch slab, slabs added in order
         DCNR_TRY(launch_wgrad_tc(precision, dy, lddy, x, ldx, slabs, m, n, k, stream));

@@ -32,7 +32,7 @@ struct WeightOps {
     }
     const WeightOp *get(const WeightOp &w) const { return on ? &w : nullptr; }
     int prepare(const dcnr_dims *d, const dcnr_params *p, const float *w0p, float *buf, bool transpose, cudaStream_t st) {
-        const int prec = d->precision == DCNR_PREC_BF16 ? DCNR_PREC_TF32 : d->precision;
+        const int prec = gemm_precision(d->precision);
         on = prec == DCNR_PREC_TF32X3 || (transpose && prec == DCNR_PREC_TF32);
         if (!on) return DCNR_OK;
         const bool raw = prec == DCNR_PREC_TF32X3 && gemm_tc_raw_weights();
@@ -120,11 +120,22 @@ struct BwdScratch {
 
 struct EvalWs {
     float *x0p, *w0p, *logit_cross, *ha, *hb, *ht, *fold, *wsplit, *dot_parts;   // fold: per block scale1, shift1, scale2, shift2
+    char *tower_pack;
+    // the fused tower (fp16x3 / bf16 on a supported shape) needs x0, the cross half of the logit and its weight pack only
+    static bool fused(const dcnr_dims *d) {
+        return (d->precision == DCNR_PREC_FP16X3 || d->precision == DCNR_PREC_BF16) && tower_eval_supported(d);
+    }
     void layout(const dcnr_dims *d, int64_t rows, Arena &a) {
         const int64_t H = d->hidden, Dp = d->in_dim_pad;
         x0p = a.take<float>(rows * Dp);
         w0p = a.take<float>(H * Dp);
         logit_cross = a.take<float>(rows);
+        tower_pack = nullptr;
+        if (fused(d)) {
+            tower_pack = a.take<char>(tower_pack_bytes(d));
+            ha = hb = ht = fold = wsplit = dot_parts = nullptr;
+            return;
+        }
         ha = a.take<float>(rows * H);
         hb = a.take<float>(rows * H);
         ht = a.take<float>(rows * H);
@@ -191,7 +202,23 @@ extern "C" int dcnr_forward_eval(const dcnr_dims *dims, const dcnr_params *param
         return DCNR_ERR_WORKSPACE;
     }
     cudaStream_t st = as_stream(stream);
-    const int H = dims->hidden, D = dims->in_dim, Dp = dims->in_dim_pad, prec = dims->precision;
+    const int H = dims->hidden, D = dims->in_dim, Dp = dims->in_dim_pad, prec = gemm_precision(dims->precision);
+    const CrossArgs ca = cross_args(dims, params);
+    if (EvalWs::fused(dims)) {
+        // gather + concat + cross network (K1), then ONE persistent kernel for the whole deep tower and the final dot
+        DCNR_TRY(launch_tower_prepare(dims, params, w.tower_pack, dims->precision, st));
+        for (int64_t r0 = 0; r0 < B; r0 += chunk) {
+            const int64_t rows = std::min(chunk, B - r0);
+            const dcnr_batch sb = slice_batch(dims, batch, r0, rows);
+            GatherArgs ga;
+            DCNR_TRY(make_gather_args(dims, params, &sb, &ga));
+            DCNR_TRY(launch_embed_cross_fwd(&ga, nullptr, 0, rows, ca, Dp, w.x0p, Dp, nullptr, 0, params->wf + H,
+                                            w.logit_cross, dims->eval_flags, st));
+            DCNR_TRY(launch_tower_eval(dims, w.x0p, Dp, w.logit_cross, params->bf, w.tower_pack, logits + r0, rows,
+                                       dims->eval_flags, dims->precision, 0, st));
+        }
+        return DCNR_OK;
+    }
     DCNR_TRY(launch_pad_rows(params->w0, D, w.w0p, Dp, H, D, Dp, st));
     for (int r = 0; r < dims->n_res; ++r) {
         float *f = w.fold + (int64_t)r * 4 * H;
@@ -202,14 +229,13 @@ extern "C" int dcnr_forward_eval(const dcnr_dims *dims, const dcnr_params *param
     }
     WeightOps wo;
     DCNR_TRY(wo.prepare(dims, params, w.w0p, w.wsplit, false, st));
-    const CrossArgs ca = cross_args(dims, params);
     for (int64_t r0 = 0; r0 < B; r0 += chunk) {
         const int64_t rows = std::min(chunk, B - r0);
         const dcnr_batch sb = slice_batch(dims, batch, r0, rows);
         GatherArgs ga;
         DCNR_TRY(make_gather_args(dims, params, &sb, &ga));
         DCNR_TRY(launch_embed_cross_fwd(&ga, nullptr, 0, rows, ca, Dp, w.x0p, Dp, nullptr, 0, params->wf + H,
-                                        w.logit_cross, nullptr, st));
+                                        w.logit_cross, dims->eval_flags, st));
         // The last GEMM of the tower never writes its output: the deep half of the final dot
         // (train.py:169-170) is taken in its epilogue when that GEMM runs on the tensor-core kernel.
         const int last = 2 * dims->n_res;                  // GEMM index: 0 = initial layer, 2r+1 / 2r+2 = block r
@@ -258,7 +284,7 @@ extern "C" int dcnr_forward_train(const dcnr_dims *dims, const dcnr_params *para
         return DCNR_ERR_WORKSPACE;
     }
     cudaStream_t st = as_stream(stream);
-    const int H = dims->hidden, D = dims->in_dim, Dp = dims->in_dim_pad, prec = dims->precision;
+    const int H = dims->hidden, D = dims->in_dim, Dp = dims->in_dim_pad, prec = gemm_precision(dims->precision);
     DCNR_TRY(launch_pad_rows(params->w0, D, s.w0p, Dp, H, D, Dp, st));
     WeightOps wo;
     DCNR_TRY(wo.prepare(dims, params, s.w0p, s.wsplit, false, st));
@@ -310,7 +336,7 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
         return DCNR_ERR_WORKSPACE;
     }
     cudaStream_t st = as_stream(stream);
-    const int H = dims->hidden, D = dims->in_dim, Dp = dims->in_dim_pad, R = dims->n_res, prec = dims->precision;
+    const int H = dims->hidden, D = dims->in_dim, Dp = dims->in_dim_pad, R = dims->n_res, prec = gemm_precision(dims->precision);
     const float post = dims->dropout_p > 0.f ? 1.f / (1.f - dims->dropout_p) : 1.f;
 
     WeightOps wt;      // transposed weights for the tensor-core dgrads
@@ -374,3 +400,28 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
     }
     return DCNR_OK;
 }
+
+extern "C" int dcnr_tower_eval_supported(const dcnr_dims *dims) { return dims != nullptr && check_dims(dims) == DCNR_OK && tower_eval_supported(dims) ? 1 : 0; }
+
+extern "C" int64_t dcnr_tower_eval_workspace_bytes(const dcnr_dims *dims) {
+    if (dims == nullptr || !tower_eval_supported(dims)) return -1;
+    return tower_pack_bytes(dims) + 256;
+}
+
+extern "C" int dcnr_tower_eval(const dcnr_dims *dims, const dcnr_params *params, const float *x0, int64_t ldx0,
+                               const float *logit_cross, float *logits, int64_t m, int32_t precision, int32_t options,
+                               int32_t *flags, void *workspace, int64_t workspace_bytes, dcnr_stream_t stream) {
+    DCNR_TRY(check_dims(dims));
+    DCNR_REQUIRE(params && x0 && logits && workspace, "null argument");
+    DCNR_REQUIRE(tower_eval_supported(dims), "the fused tower needs hidden_dim 256 and 1..4 ResBlocks");
+    Arena a(workspace, workspace_bytes);
+    char *pack = a.take<char>(tower_pack_bytes(dims));
+    if (!a.ok()) {
+        set_error("tower workspace too small (%lld < %lld)", (long long)workspace_bytes, (long long)a.used);
+        return DCNR_ERR_WORKSPACE;
+    }
+    cudaStream_t st = as_stream(stream);
+    DCNR_TRY(launch_tower_prepare(dims, params, pack, precision, st));
+    return launch_tower_eval(dims, x0, ldx0, logit_cross, params->bf, pack, logits, m, flags, precision, options & 1, st);
+}
+

@@ -143,9 +143,17 @@ class DCN_RecSys(nn.Module):
 
     ``params`` needs ``emb_dim``, ``hidden_dim``, ``n_cross_layers``, ``dropout`` and optionally
     ``n_res_blocks`` (default 2, train.py:134); other keys (lr, batch_size, ...) are ignored like in
-    the reference.  ``precision`` selects the dense-layer arithmetic: "fp32" (CUDA-core IEEE fp32,
-    the parity path), "tf32x3" (tcgen05 3-term split, parity-grade), "tf32" / "bf16" (tensor-core
-    fast paths with stated tolerances).
+    the reference.  ``precision`` selects the dense-layer arithmetic:
+
+    * ``"fp16x3"`` (default) -- parity-grade tensor-core mode.  eval(): the fused tower kernel (tcgen05 kind::f16 on a
+      3-term error-compensated fp16 split, activations resident in tensor memory; logits within 1e-5 of the reference);
+      train(): the tf32x3 kernels below.  Shapes the fused tower does not take (hidden_dim != 256, > 4 ResBlocks) run
+      tf32x3 in eval() too.  An eval batch whose activations leave the fp16 range is re-run on tf32x3 automatically.
+    * ``"tf32x3"`` -- tcgen05 kind::tf32 3-term split, one GEMM launch per layer; parity-grade: logits <= 1e-5, every
+      gradient tensor within max(1e-5, 2 x the reference's own fp32 noise) of the float64 oracle.
+    * ``"fp32"`` -- CUDA-core IEEE fp32 FMA GEMMs (strict, slow).
+    * ``"tf32"`` / ``"bf16"`` -- single-pass tensor-core modes with STATED tolerances, not parity (bf16: fused eval tower with
+      bf16 operands; training runs tf32).
     """
 
     def __init__(self, n_users: int, n_items: int, cat_dims: Dict[str, int], n_num_features: int,
@@ -174,8 +182,13 @@ class DCN_RecSys(nn.Module):
         self._shape = dict(emb_dim=emb_dim, n_num=n_num_features, hidden=hidden_dim, n_cross=n_cross_layers,
                            n_res=n_res_blocks, in_dim=input_dim, n_users=n_users, n_items=n_items,
                            cat_rows=list(cat_dims.values()), cat_width=widths, dropout=float(dropout))
-        self.precision = precision or os.environ.get("DCNR_PRECISION", "fp32")
-        self.check_ids = os.environ.get("DCNR_CHECK_IDS", "0") == "1"
+        self.precision = precision or os.environ.get("DCNR_PRECISION", "fp16x3")
+        self.check_ids = os.environ.get("DCNR_CHECK_IDS", "0") == "1"      # train(): bounds-check ids before every forward
+        # eval(): the kernels report out-of-range ids and fp16-range overflow in a device flag word that is read back after
+        # every forward (one 4-byte D2H).  A caller that batches many forwards (serving.RankingEngine) sets this to True and
+        # calls check_eval_flags() once at the end.
+        self.defer_eval_checks = False
+        self._eval_flags = None
         self._inject_drop_masks = None      # uint8 [n_res, B, H] keep-mask for parity tests
 
     # ---- C-ABI marshalling -----------------------------------------------------------------
@@ -320,11 +333,37 @@ class DCN_RecSys(nn.Module):
         else:
             # eval(): folded BatchNorm, no dropout, nothing saved.  The result carries no autograd
             # graph (the reference only calls eval() forwards under torch.no_grad()).
-            pstruct = self._param_struct()
-            ws = torch.empty(C.lib().dcnr_workspace_bytes(dims, B, 0), dtype=torch.uint8, device=user_ids.device)
-            logits = torch.empty(B, dtype=torch.float32, device=user_ids.device)
-            C.check(C.lib().dcnr_forward_eval(dims, pstruct, batch, C.ptr(logits), C.ptr(ws), ws.numel(), C.stream()))
+            logits = self._eval_call(dims, batch, B, user_ids.device)
+            if not self.defer_eval_checks and self.check_eval_flags():
+                # an activation left the fp16 range of the fused tower: same batch on the tf32x3 kernels (still the GPU)
+                dims.precision = C.PRECISIONS["tf32x3"]
+                logits = self._eval_call(dims, batch, B, user_ids.device)
+                if self.check_eval_flags():
+                    raise RuntimeError("unexpected range flag from the tf32x3 path")
         return logits.squeeze()       # [B]; 0-d when B == 1, like train.py:170
+
+    def _eval_call(self, dims, batch, B, dev):
+        if self._eval_flags is None or self._eval_flags.device != dev:
+            self._eval_flags = torch.zeros(1, dtype=torch.int32, device=dev)
+        dims.eval_flags = C.ptr(self._eval_flags)
+        pstruct = self._param_struct()
+        ws = torch.empty(C.lib().dcnr_workspace_bytes(dims, B, 0), dtype=torch.uint8, device=dev)
+        logits = torch.empty(B, dtype=torch.float32, device=dev)
+        C.check(C.lib().dcnr_forward_eval(dims, pstruct, batch, C.ptr(logits), C.ptr(ws), ws.numel(), C.stream()))
+        return logits
+
+    def check_eval_flags(self) -> bool:
+        """Read (and clear) the flag word of the eval() forwards since the last check.  Raises ``IndexError`` like
+        ``nn.Embedding`` if an id was out of range; returns True if a batch has to be re-run on the tf32x3 path because an
+        activation left the fp16 range of the fused tower.  Synchronises the current stream."""
+        if self._eval_flags is None:
+            return False
+        f = int(self._eval_flags.item())
+        if f:
+            self._eval_flags.zero_()
+        if f & 1:
+            raise IndexError("index out of range in self")
+        return bool(f & 2)
 
 
 class _NullCtx:

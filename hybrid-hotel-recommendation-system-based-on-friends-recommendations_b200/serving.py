@@ -65,6 +65,7 @@ class RankingEngine:
         if out is None:
             out = torch.empty(n, dtype=torch.float32, pin_memory=True)
         compute = torch.cuda.current_stream(self.dev)
+        deferred, self.model.defer_eval_checks = self.model.defer_eval_checks, True     # one flag read-back per score()
         for b in self.bufs:
             b["free"].record(compute)
         for i, r0 in enumerate(range(0, n, self.chunk_rows)):
@@ -83,6 +84,14 @@ class RankingEngine:
             out[r0:r1].copy_(logits.reshape(-1), non_blocking=True)
             b["free"].record(compute)
         compute.synchronize()
+        self.model.defer_eval_checks = deferred
+        if self.model.check_eval_flags():
+            # some chunk left the fp16 range of the fused tower: score everything again on the tf32x3 kernels
+            prec, self.model.precision = self.model.precision, "tf32x3"
+            try:
+                return self.score(user_ids, item_ids, cat, num, out)
+            finally:
+                self.model.precision = prec
         return out
 
 

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DCNR_ABI_VERSION 2
+#define DCNR_ABI_VERSION 3
 #define DCNR_MAX_CAT 8     /* categorical tables (reference uses 2: city, hotel_type; train.py:290) */
 #define DCNR_MAX_RES 8     /* ResBlocks          (search space 1..4; train.py:183) */
 #define DCNR_MAX_CROSS 8   /* CrossLayers        (search space 1..6; train.py:182) */
@@ -46,7 +46,12 @@ typedef enum dcnr_precision {
     DCNR_PREC_FP32 = 0,         /* CUDA-core FMA GEMMs, IEEE fp32 (parity path) */
     DCNR_PREC_TF32X3 = 1,       /* tcgen05 kind::tf32, 3-term error-compensated split, fp32 accumulate */
     DCNR_PREC_TF32 = 2,         /* tcgen05 kind::tf32 single pass (stated tolerance, not parity) */
-    DCNR_PREC_BF16 = 3          /* tcgen05 kind::f16 bf16 inputs, fp32 accumulate (stated tolerance) */
+    DCNR_PREC_BF16 = 3,         /* eval: fused tower on tcgen05 kind::f16 with bf16 operands, fp32 accumulate (stated
+                                 * tolerance, never the default); training and shapes the fused tower does not take run
+                                 * DCNR_PREC_TF32 */
+    DCNR_PREC_FP16X3 = 4        /* eval: fused tower on tcgen05 kind::f16 with a 3-term error-compensated fp16 split (hi.hi +
+                                 * lo.hi + hi.lo, fp32 accumulate) -- fp32 parity at twice the tf32x3 tensor rate; training and
+                                 * shapes the fused tower does not take run DCNR_PREC_TF32X3 */
 } dcnr_precision;
 
 typedef void *dcnr_stream_t;
@@ -81,6 +86,9 @@ typedef struct dcnr_dims {
     uint64_t *dropout_step;     /* optional DEVICE counter: its value is added to dropout_seed and every dcnr_forward_train
                                  * increments it, so a captured CUDA graph of the training step draws a fresh dropout mask
                                  * on every replay (NULL: the seed argument alone decides the mask) */
+    int32_t *eval_flags;        /* optional DEVICE int, OR-ed by dcnr_forward_eval (never cleared): bit 0 = an embedding id was out of
+                                 * range (the row was read as row 0; torch raises IndexError), bit 1 = an activation left the
+                                 * fp16 range of DCNR_PREC_FP16X3 (re-run the batch with DCNR_PREC_TF32X3).  NULL: not reported */
     void *comm;                 /* data-parallel group (dcnr_comm_create) or NULL.  When set, train-mode BatchNorm
                                  * statistics and the BatchNorm backward reductions cover the batches of ALL ranks, so an
                                  * N-rank step equals the reference's single-device step on the concatenated batch */
@@ -266,6 +274,19 @@ int dcnr_bn_act_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo, 
                     const float *mean, const float *rstd, const float *gamma, float post_scale, float *dz,
                     int64_t lddz, float *dy_out, int64_t lddy, float *dgamma, float *dbeta, float *dbias,
                     int64_t m, int32_t n, void *scratch, int64_t scratch_bytes, dcnr_stream_t stream);
+
+/* Fused eval-mode deep tower -- initial_deep_layer, every ResBlock with folded BatchNorm, and the deep half of the final
+ * dot in ONE persistent tcgen05 kernel; activations never leave the SM (train.py:161-170 in eval(), main.py:120-127):
+ *     logits[b] = wf[0:H] . tower(x0[b]) + logit_cross[b] + bf
+ * x0 [m, ldx0] is the padded output of dcnr_embed_concat_fwd (ldx0 >= in_dim_pad, pad columns zero); logit_cross [m] (the
+ * cross half, may be NULL).  precision: DCNR_PREC_FP16X3 or DCNR_PREC_BF16.  Needs hidden == 256, 1..4 ResBlocks
+ * (dcnr_tower_eval_supported).  workspace: dcnr_tower_eval_workspace_bytes().  flags: see dcnr_dims.eval_flags (may be NULL).
+ * options: bit 0 = single CTAs instead of 2-CTA pairs (measurement aid). */
+int dcnr_tower_eval_supported(const dcnr_dims *dims);
+int64_t dcnr_tower_eval_workspace_bytes(const dcnr_dims *dims);
+int dcnr_tower_eval(const dcnr_dims *dims, const dcnr_params *params, const float *x0, int64_t ldx0,
+                    const float *logit_cross, float *logits, int64_t m, int32_t precision, int32_t options, int32_t *flags,
+                    void *workspace, int64_t workspace_bytes, dcnr_stream_t stream);
 
 /* logit[b] = wf[0:H] . deep[b] + extra[b] + bf   -- the deep half of train.py:169-170 (the cross
  * half, wf[H:H+D] . cross[b], is produced by the fused gather+cross kernel into `extra`).

@@ -51,7 +51,7 @@ def _check_grads(got: dict, ref: dict, tol=TOL):
 PARITY_PRECISIONS = ["fp32", "tf32x3"]     # both must meet the 1e-5 contract
 
 
-@pytest.mark.parametrize("precision", PARITY_PRECISIONS)
+@pytest.mark.parametrize("precision", PARITY_PRECISIONS + ["fp16x3"])      # fp16x3: the fused eval tower where the shape allows
 @pytest.mark.parametrize("name", CASES)
 def test_eval_forward_matches_reference_golden(name, precision):
     case = load_model_case(name)
