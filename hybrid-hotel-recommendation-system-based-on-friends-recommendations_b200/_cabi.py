@@ -25,7 +25,7 @@ class Dims(Structure):
                 ("n_cross", c_int32), ("n_res", c_int32), ("in_dim", c_int32), ("in_dim_pad", c_int32),
                 ("n_users", c_int64), ("n_items", c_int64), ("cat_rows", c_int64 * MAX_CAT),
                 ("cat_width", c_int32 * MAX_CAT), ("dropout_p", c_float), ("bn_eps", c_float),
-                ("bn_momentum", c_float), ("precision", c_int32), ("dp_sparse_tables", c_int32), ("dropout_step", c_void_p),
+                ("bn_momentum", c_float), ("precision", c_int32), ("dp_sparse_tables", c_int32), ("dp_batch_cap", c_int64), ("dropout_step", c_void_p),
                 ("eval_flags", c_void_p), ("comm", c_void_p)]
 
 

@@ -149,15 +149,31 @@ extern "C" int dcnr_comm_alltoallv(void *comm, const void *send, const int64_t *
     Comm *c = static_cast<Comm *>(comm);
     DCNR_REQUIRE(c != nullptr && send_bytes_host && send_off_host && recv_bytes_host && recv_off_host, "bad argument");
     NcclApi *a = nccl();
+    DCNR_REQUIRE(a != nullptr, "no communicator");
     DCNR_NCCL_CHECK(a->GroupStart());
-    for (int p = 0; p < c->world; ++p) {
-        if (send_bytes_host[p] > 0)
-            DCNR_NCCL_CHECK(a->Send(static_cast<const char *>(send) + send_off_host[p], (size_t)send_bytes_host[p], ncclInt8, p,
-                                    c->comm, as_stream(stream)));
-        if (recv_bytes_host[p] > 0)
-            DCNR_NCCL_CHECK(a->Recv(static_cast<char *>(recv) + recv_off_host[p], (size_t)recv_bytes_host[p], ncclInt8, p, c->comm,
-                                    as_stream(stream)));
+    // an error inside the group must not leave it open: remember the first failure, stop queueing, ALWAYS call GroupEnd
+    int failed = ncclSuccess;
+    const char *what = "";
+    for (int p = 0; p < c->world && failed == ncclSuccess; ++p) {
+        if (send_bytes_host[p] > 0) {
+            failed = a->Send(static_cast<const char *>(send) + send_off_host[p], (size_t)send_bytes_host[p], ncclInt8, p, c->comm,
+                             as_stream(stream));
+            what = "ncclSend";
+        }
+        if (failed == ncclSuccess && recv_bytes_host[p] > 0) {
+            failed = a->Recv(static_cast<char *>(recv) + recv_off_host[p], (size_t)recv_bytes_host[p], ncclInt8, p, c->comm,
+                             as_stream(stream));
+            what = "ncclRecv";
+        }
     }
-    DCNR_NCCL_CHECK(a->GroupEnd());
+    const int ended = a->GroupEnd();
+    if (failed != ncclSuccess) {
+        set_error("NCCL: %s failed inside the all-to-all group: %s", what, a->GetErrorString(failed));
+        return DCNR_ERR_CUDA;
+    }
+    if (ended != ncclSuccess) {
+        set_error("NCCL: ncclGroupEnd failed: %s", a->GetErrorString(ended));
+        return DCNR_ERR_CUDA;
+    }
     return DCNR_OK;
 }

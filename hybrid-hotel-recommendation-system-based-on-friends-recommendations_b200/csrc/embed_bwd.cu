@@ -381,23 +381,26 @@ static bool try_scatter_small_multi(const dcnr_dims *dims, const dcnr_batch *bat
     return true;
 }
 
+// rows b >= B (up to cap) are padding: id 0 with an all-zero gradient row, which adds nothing to row 0's sum
 __global__ void k_pack_embed_grads(const int64_t *__restrict__ user_ids, const int64_t *__restrict__ item_ids,
-                                   const float *__restrict__ dx0, int64_t lddx, int64_t B, int w2, int64_t *__restrict__ ids_out,
-                                   float *__restrict__ rows_out) {
+                                   const float *__restrict__ dx0, int64_t lddx, int64_t B, int64_t cap, int w2,
+                                   int64_t *__restrict__ ids_out, float *__restrict__ rows_out) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (e >= B * w2) return;
+    if (e >= cap * w2) return;
     const int64_t b = e / w2;
     const int c = (int)(e % w2);
-    rows_out[e] = __ldg(dx0 + b * lddx + c);
-    if (c == 0) ids_out[2 * b] = user_ids[b];
-    if (c == 1) ids_out[2 * b + 1] = item_ids[b];
+    const bool real = b < B;
+    rows_out[e] = real ? __ldg(dx0 + b * lddx + c) : 0.f;
+    if (c == 0) ids_out[2 * b] = real ? user_ids[b] : 0;
+    if (c == 1) ids_out[2 * b + 1] = real ? item_ids[b] : 0;
 }
 
 int launch_pack_embed_grads(const int64_t *user_ids, const int64_t *item_ids, const float *dx0, int64_t lddx, int64_t B,
-                            int32_t emb_dim, int64_t *ids_out, float *rows_out, cudaStream_t stream) {
-    if (B <= 0) return DCNR_OK;
+                            int64_t cap, int32_t emb_dim, int64_t *ids_out, float *rows_out, cudaStream_t stream) {
+    if (cap <= 0) return DCNR_OK;
     const int w2 = 2 * emb_dim;
-    k_pack_embed_grads<<<(unsigned)ceil_div(B * w2, 256), 256, 0, stream>>>(user_ids, item_ids, dx0, lddx, B, w2, ids_out, rows_out);
+    k_pack_embed_grads<<<(unsigned)ceil_div(cap * w2, 256), 256, 0, stream>>>(user_ids, item_ids, dx0, lddx, B, cap, w2, ids_out,
+                                                                             rows_out);
     DCNR_LAUNCHED();
     return DCNR_OK;
 }

@@ -312,10 +312,15 @@ bool wgrad_tc_supported(int precision, int64_t lddy, int64_t ldx, int64_t m, int
     return m >= 1 && m <= 0x7fffff00LL;
 }
 
+// One slab per SM, but never more than kMaxSlabRows batch rows per slab: the tensor core's fp32 accumulate truncates
+// (profiles/r02_acc_probe.md), so the rounding error of a slab's partial product grows with the length of its accumulation
+// chain; 256 rows = 32 K-steps keeps a B = 65 536 weight gradient inside 2x the reference's own fp32 noise (896-row slabs
+// measured 1.4e-5 on initial_deep_layer.weight).  The slabs are summed in double, in slab order.
+constexpr int64_t kMaxSlabRows = 256;
 int wgrad_tc_slabs(int64_t m, int32_t n) {
     const int64_t m_tiles = n / wg::BLOCK_M;
     const int64_t want = std::max<int64_t>(1, (int64_t)sm_count() / m_tiles);
-    const int64_t rows = round_up(ceil_div(m, want), wg::BLOCK_K);
+    const int64_t rows = std::min<int64_t>(kMaxSlabRows, round_up(ceil_div(m, want), wg::BLOCK_K));
     return (int)ceil_div(m, rows);
 }
 
@@ -331,7 +336,7 @@ int launch_wgrad_tc(int precision, const float *dy, int64_t lddy, const float *x
     p.corr_sep = p.terms == 3 ? 1 : 0;
     p.tmem_cols = p.corr_sep ? 512 : 256;
     const int n_slabs = wgrad_tc_slabs(m, n);
-    p.rows_per_slab = round_up(ceil_div(m, n_slabs), BLOCK_K);
+    p.rows_per_slab = std::min<int64_t>(kMaxSlabRows, round_up(ceil_div(m, n_slabs), BLOCK_K));
     p.slabs = slabs;
     const int stage_bytes = (p.terms == 3 ? 2 : 1) * (BLOCK_M + k) * BLOCK_K * 4;
     p.stages = std::max(1, std::min(4, (220 * 1024) / stage_bytes));

@@ -109,7 +109,7 @@ bool tower_eval_supported(const dcnr_dims *d);                 // hidden 256, 1.
 int64_t tower_pack_bytes(const dcnr_dims *d);
 int launch_tower_prepare(const dcnr_dims *d, const dcnr_params *p, void *pack, int precision, cudaStream_t stream);
 int launch_tower_eval(const dcnr_dims *d, const float *x0, int64_t ldx0, const float *logit_cross, const float *bf,
-                      const void *pack, float *out, int64_t M, int32_t *flags, int precision, int single_cta,
+                      const void *pack, float *out, int64_t M, int32_t *flags, int precision, int options,
                       cudaStream_t stream);
 // dense-layer precision the GEMM kernels run for a requested mode: the fp16x3 / bf16 modes exist only in the fused eval
 // tower; everywhere else (training, unsupported shapes, operator-level calls) they run as tf32x3 / tf32
@@ -167,9 +167,10 @@ int launch_embed_scatter_pair(const int64_t *ids0, int64_t stride0, int64_t rows
                               const int64_t *ids1, int64_t stride1, int64_t rows1, float *grad1, int32_t col1, int64_t B,
                               int32_t width, const float *dx0, int64_t lddx, void *scratch, int64_t scratch_bytes,
                               cudaStream_t stream);
-// ids_out[b] = (user_ids[b], item_ids[b]); rows_out[b] = dx0[b, 0 : 2*emb_dim]  (the payload of the sparse gradient all-gather)
+// ids_out[b] = (user_ids[b], item_ids[b]); rows_out[b] = dx0[b, 0 : 2*emb_dim] for b < B, (0, 0) / zero rows up to cap
+// (the payload of the sparse gradient all-gather; cap = the largest local batch of any rank)
 int launch_pack_embed_grads(const int64_t *user_ids, const int64_t *item_ids, const float *dx0, int64_t lddx, int64_t B,
-                            int32_t emb_dim, int64_t *ids_out, float *rows_out, cudaStream_t stream);
+                            int64_t cap, int32_t emb_dim, int64_t *ids_out, float *rows_out, cudaStream_t stream);
 int launch_embed_scatter(const int64_t *ids, int64_t id_stride, int64_t B, int64_t n_rows, int32_t width,
                          const float *dx0, int64_t lddx, int32_t col0, float *grad_table, void *scratch,
                          int64_t scratch_bytes, cudaStream_t stream);

@@ -3,6 +3,8 @@
 //
 // Reference lines: DCN_RecSys.forward train.py:155-170 (main.py:114-127); training step
 // train.py:223-225; ranking call main.py:320-322.
+#include <cstdlib>
+
 #include "kernels.cuh"
 
 namespace dcnr {
@@ -86,7 +88,7 @@ struct TrainSaved {
 static bool dp_sparse_tables(const dcnr_dims *d) { return comm_world(d->comm) > 1 && d->dp_sparse_tables != 0; }
 
 struct BwdScratch {
-    float *ga, *gb, *gc, *dx0, *cross_partials, *wgrad, *bn, *wsplit, *vec_a, *vec_b;
+    float *ga, *gb, *gc, *dx0, *cross_partials, *wgrad, *bn, *wsplit, *vec_a, *vec_b, *w0_parts;
     void *scatter;
     int64_t scatter_bytes;
     int64_t *pack_ids, *all_ids;       // [B][2] (user, item) of this rank / [world*B][2] of all ranks
@@ -104,16 +106,18 @@ struct BwdScratch {
         wsplit = a.take<float>(WeightOps::floats(d));
         vec_a = a.take<float>(H);
         vec_b = a.take<float>(H);
+        w0_parts = a.take<float>(3 * H * Dp);
         const int world = dp_sparse_tables(d) ? comm_world(d->comm) : 1;
-        scatter_bytes = with_scatter ? scatter_scratch_bytes(2 * B * world) : 0;      // user + item share one sort
+        const int64_t cap = (world > 1 && d->dp_batch_cap > B) ? d->dp_batch_cap : B;    // rows per rank in the sparse exchange
+        scatter_bytes = with_scatter ? scatter_scratch_bytes(2 * cap * world) : 0;      // user + item share one sort
         scatter = a.take<char>(scatter_bytes);
         pack_ids = all_ids = nullptr;
         pack_rows = all_rows = nullptr;
         if (with_scatter && world > 1) {
-            pack_ids = a.take<int64_t>(B * 2);
-            all_ids = a.take<int64_t>(B * 2 * world);
-            pack_rows = a.take<float>(B * 2 * d->emb_dim);
-            all_rows = a.take<float>(B * 2 * d->emb_dim * world);
+            pack_ids = a.take<int64_t>(cap * 2);
+            all_ids = a.take<int64_t>(cap * 2 * world);
+            pack_rows = a.take<float>(cap * 2 * d->emb_dim);
+            all_rows = a.take<float>(cap * 2 * d->emb_dim * world);
         }
     }
 };
@@ -275,7 +279,9 @@ extern "C" int dcnr_forward_train(const dcnr_dims *dims, const dcnr_params *para
     DCNR_TRY(check_dims(dims));
     DCNR_REQUIRE(params && batch && logits && saved, "null argument");
     const int64_t B = batch->batch;
-    DCNR_REQUIRE(B >= 2 || dims->n_res == 0, "Expected more than 1 value per channel when training");
+    // (with a data-parallel group the statistics cover the GLOBAL batch, so a single local row is fine)
+    DCNR_REQUIRE(B >= 2 || dims->n_res == 0 || (B == 1 && comm_world(dims->comm) > 1),
+                 "Expected more than 1 value per channel when training");
     Arena a(saved, saved_bytes);
     TrainSaved s;
     s.layout(dims, B, a);
@@ -365,17 +371,26 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
         std::swap(g, g2);
     }
     // initial_deep_layer: h0 = x0 W0^T + b0
-    // db0 = colsum(g).  With ResBlocks g = dz1 W1 + dy2 (block 0), so by linearity db0 = colsum(dz1) W1 + colsum(dy2): the batch
-    // sum then runs over dy2 (elementwise products) instead of over GEMM outputs, whose tensor-core rounding errors are
-    // sign-correlated (truncating accumulate) and do not average out in this cancellation-heavy sum (it was the one gradient
-    // tensor above 2x the reference's own fp32 noise: 3.4e-5 vs 9e-6).  dy2 of block 0 is what `g2` holds after the last swap.
-    const bool b0_split = grads->b0 != nullptr && R > 0;
-    if (grads->w0 || (grads->b0 && !b0_split))
-        DCNR_TRY(launch_linear_wgrad(prec, g, H, s.x0p, Dp, grads->w0, D, b0_split ? nullptr : grads->b0, B, H, Dp, D, w.wgrad, st));
-    if (b0_split) {
-        const float *db1 = grads->res_b1[0] != nullptr ? grads->res_b1[0] : w.vec_a;
-        DCNR_TRY(launch_colsum(g2, H, B, H, w.vec_b, w.bn, st));
-        DCNR_TRY(launch_vecmat_add(db1, params->res_w1[0], H, H, H, w.vec_b, grads->b0, st));
+    // Gradients of the initial layer: db0 = colsum(g), dW0 = g^T x0.  With ResBlocks g = dz1 W1 + dy2 (block 0: dz1 is what `g3`
+    // holds, dy2 what `g2` holds after the last swap), so by linearity
+    //     db0 = colsum(dz1) W1 + colsum(dy2),        dW0 = W1^T (dz1^T x0) + dy2^T x0.
+    // Both batch sums then run over BatchNorm-backward outputs / elementwise products instead of over GEMM outputs.  The tensor
+    // core's accumulate truncates toward zero (profiles/r02_acc_probe.md), so a GEMM output carries a small error that is
+    // sign-correlated along the batch; every later BatchNorm backward removes its column mean, but nothing does for the
+    // initial layer, and a batch sum against the non-zero-mean columns of x0 (the [0, 1) numerics) or against 1 collects it:
+    // these were the two gradient tensors above 2x the reference's own fp32 noise (b0 3.4e-5 at B = 4096, W0 1.4e-5 at 65 536).
+    const bool l0_split = R > 0;
+    if (!l0_split) {
+        if (grads->w0 || grads->b0)
+            DCNR_TRY(launch_linear_wgrad(prec, g, H, s.x0p, Dp, grads->w0, D, grads->b0, B, H, Dp, D, w.wgrad, st));
+    } else {
+        if (grads->b0) {
+            const float *db1 = grads->res_b1[0] != nullptr ? grads->res_b1[0] : w.vec_a;
+            DCNR_TRY(launch_colsum(g2, H, B, H, w.vec_b, w.bn, st));
+            DCNR_TRY(launch_vecmat_add(db1, params->res_w1[0], H, H, H, w.vec_b, grads->b0, st));
+        }
+        if (grads->w0)      // EXPERIMENT: the initial layer's weight gradient on the CUDA-core fp32 GEMM
+            DCNR_TRY(launch_linear_wgrad(getenv("DCNR_W0_FP32") ? DCNR_PREC_FP32 : prec, g, H, s.x0p, Dp, grads->w0, D, nullptr, B, H, Dp, D, w.wgrad, st));
     }
     GemmEpilogue none{nullptr, nullptr, nullptr, 0, 0};
     DCNR_TRY(gemm_any(prec, g, H, true, s.w0p, Dp, false, w.dx0, Dp, B, Dp, H, 1, none, st, wt.get(wt.w0)));
@@ -386,12 +401,17 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
     if (want_tables && dp_sparse_tables(dims)) {
         // data parallel: user / item gradients from the global batch (rank-major = the concatenated batch order);
         // the tiny categorical tables stay local and are summed by the dense gradient all-reduce
+        // Every rank contributes `cap` rows (its own batch, zero-padded when shorter): equal NCCL counts on all ranks even for
+        // the ragged last batch of an epoch.  dp_batch_cap == 0 declares equal batch sizes.
         const int world = comm_world(dims->comm), E = dims->emb_dim;
-        DCNR_TRY(launch_pack_embed_grads(batch->user_ids, batch->item_ids, w.dx0, Dp, B, E, w.pack_ids, w.pack_rows, st));
-        DCNR_TRY(comm_allgather(dims->comm, w.pack_ids, w.all_ids, B * 2 * (int64_t)sizeof(int64_t), st));
-        DCNR_TRY(comm_allgather(dims->comm, w.pack_rows, w.all_rows, B * 2 * E * (int64_t)sizeof(float), st));
+        DCNR_REQUIRE(dims->dp_batch_cap == 0 || dims->dp_batch_cap >= B, "dp_batch_cap %lld < local batch %lld",
+                     (long long)dims->dp_batch_cap, (long long)B);
+        const int64_t cap = dims->dp_batch_cap > B ? dims->dp_batch_cap : B;
+        DCNR_TRY(launch_pack_embed_grads(batch->user_ids, batch->item_ids, w.dx0, Dp, B, cap, E, w.pack_ids, w.pack_rows, st));
+        DCNR_TRY(comm_allgather(dims->comm, w.pack_ids, w.all_ids, cap * 2 * (int64_t)sizeof(int64_t), st));
+        DCNR_TRY(comm_allgather(dims->comm, w.pack_rows, w.all_rows, cap * 2 * E * (int64_t)sizeof(float), st));
         DCNR_TRY(launch_embed_scatter_pair(w.all_ids, 2, dims->n_users, grads->user_table, 0, w.all_ids + 1, 2, dims->n_items,
-                                           grads->item_table, E, B * world, E, w.all_rows, 2 * E, w.scatter, w.scatter_bytes, st));
+                                           grads->item_table, E, cap * world, E, w.all_rows, 2 * E, w.scatter, w.scatter_bytes, st));
         dcnr_grads cat_only = *grads;
         cat_only.user_table = cat_only.item_table = nullptr;
         DCNR_TRY(dcnr_embed_scatter_bwd(dims, batch, w.dx0, Dp, &cat_only, w.scatter, w.scatter_bytes, stream));
@@ -422,6 +442,6 @@ extern "C" int dcnr_tower_eval(const dcnr_dims *dims, const dcnr_params *params,
     }
     cudaStream_t st = as_stream(stream);
     DCNR_TRY(launch_tower_prepare(dims, params, pack, precision, st));
-    return launch_tower_eval(dims, x0, ldx0, logit_cross, params->bf, pack, logits, m, flags, precision, options & 1, st);
+    return launch_tower_eval(dims, x0, ldx0, logit_cross, params->bf, pack, logits, m, flags, precision, options, st);
 }
 

@@ -46,7 +46,7 @@ constexpr int NSLOT = 6;
 constexpr int MAXL = 9;                // 1 + 2 * 4 ResBlocks
 constexpr int RES_BYTES = BM * H * 4;
 constexpr int kThreads = 384;
-constexpr int kNumBars = 2 * NSLOT + 2 + 8 + 1;
+constexpr int kNumBars = 2 * NSLOT + 2 + 8 + 1 + 8;
 constexpr int kSmemBytes = NSLOT * SLOT_BYTES + RES_BYTES + 2 * H * 4 + kNumBars * 8 + 16;
 constexpr float kRangeLimit = 60000.f;   // fp16 max is 65504
 
@@ -86,7 +86,7 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
     uint64_t *bars = reinterpret_cast<uint64_t *>(vecs + 2 * H);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kNumBars);
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * NSLOT, accfull0 = empty0 + 8 * NSLOT,
-                   aready0 = accfull0 + 16, accfree0 = aready0 + 64;
+                   aready0 = accfull0 + 16, accfree0 = aready0 + 64, xgo0 = accfree0 + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
@@ -104,6 +104,7 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
         mbar_init(accfull0 + 8, 1);
         for (int c = 0; c < 8; ++c) mbar_init(aready0 + 8 * c, 4 * CTAS);    // the four quadrant warps that own chunk c
         mbar_init(accfree0, 8 * CTAS);
+        for (int i = 0; i < 8; ++i) mbar_init(xgo0 + 8 * i, 1);             // producer -> loader: x0 slot i of this tile is free
         mbar_init_fence();
     }
     if (warp == 1) tmem_alloc<CTAS>(smem_u32(tmem_slot), 512);
@@ -113,9 +114,34 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    auto wait_x = [](uint32_t bar, uint32_t parity) {            // barriers signalled by the other CTA / multicast commits
-        if (CTAS == 2) mbar_wait_cluster(bar, parity);
-        else mbar_wait(bar, parity);
+    // Bounded wait.  A pipeline bug must not hang the GPU: after ~2^21 failed polls the waiter records who it is (flags[1] =
+    // warp | site << 8 | parity << 16 | block << 20, flags[2] = `info`; the caller may pass flags in pinned host memory so
+    // the record survives the trap) and traps.
+    int32_t *const dbg = p.flags;
+    auto wait_x = [dbg](uint32_t bar, uint32_t parity, int site, int info) {
+        uint32_t ok = 0;
+        for (uint32_t spins = 0; !ok; ++spins) {
+            if (CTAS == 2)
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            else
+                asm volatile(
+                    "{\n\t.reg .pred p;\n\t"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                    "selp.u32 %0, 1, 0, p;\n\t}"
+                    : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            if (!ok && spins > (1u << 21)) {
+                if (dbg != nullptr && (threadIdx.x & 31) == 0) {
+                    if (atomicCAS(dbg + 1, 0, (int)((threadIdx.x >> 5) | (site << 8) | (parity << 16) | (blockIdx.x << 20))) == 0)
+                        dbg[2] = info;
+                    __threadfence_system();
+                }
+                __trap();
+            }
+        }
     };
     const int L = p.L, n0 = p.K0 / 32;
     const int unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;      // a unit = one tile (CTAS = 1) or one tile pair
@@ -131,8 +157,16 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
             for (int l = 0; l < L; ++l) {
                 const int nslots = (l == 0 ? n0 : 8) * WSLOTS;
                 for (int s = 0; s < nslots; ++s) {
-                    if (l == 0 && (s % WSLOTS) == 0) r.next();   // the x0 slot of this K chunk (filled by the loader warps)
-                    wait_x(empty0 + 8 * r.s, r.ph ^ 1u);
+                    if (l == 0 && (s % WSLOTS) == 0) {
+                        // The x0 slot of this K chunk is filled by the loader warps, but the ring bookkeeping stays here: the loader
+                        // would otherwise wait for a slot a whole tile (11 ring revolutions) ahead, and a parity wait is only
+                        // meaningful at most one phase ahead.  The producer waits for the slot in sequence and hands it over.
+                        wait_x(empty0 + 8 * r.s, r.ph ^ 1u, 8, (u << 16) | (l << 8) | s);
+                        if (elect_one()) mbar_arrive(xgo0 + 8 * (s / WSLOTS));
+                        __syncwarp();
+                        r.next();
+                    }
+                    wait_x(empty0 + 8 * r.s, r.ph ^ 1u, 1, (u << 16) | (l << 8) | s);
                     if (elect_one()) {
                         const uint32_t dst = smem_u32(ring + r.s * SLOT_BYTES);
                         const int k = s * 16 * CTAS, row = l * 2 * H + (int)rank * (H / CTAS);
@@ -163,7 +197,7 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
                 for (int l = 0; l < L; ++l, ++g) {
                     const uint32_t d = tmem_base + (g & 1u) * 256u, a0 = tmem_base + ((g & 1u) ^ 1u) * 256u;
                     if (l == 1 && it > 0) {                      // every epilogue warp has drained the previous tile's last layer
-                        wait_x(accfree0, (it - 1u) & 1u);
+                        wait_x(accfree0, (it - 1u) & 1u, 2, (u << 16) | (l << 8));
                         tc_fence_after();
                     }
                     const int nchunks = l == 0 ? n0 : 8;
@@ -171,10 +205,10 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
                         int sx = 0;
                         if (l == 0) {                            // A = the x0 chunk in shared memory (hi | lo, 64-byte rows)
                             sx = r.s;
-                            wait_x(full0 + 8 * r.s, r.ph);
+                            wait_x(full0 + 8 * r.s, r.ph, 3, (u << 16) | (l << 8) | c);
                             r.next();
                         } else {                                 // A = chunk c of the previous layer's output in tensor memory
-                            wait_x(aready0 + 8 * c, hc & 1u);
+                            wait_x(aready0 + 8 * c, hc & 1u, 4, (u << 16) | (l << 8) | c);
                         }
                         tc_fence_after();
                         int sw = 0;
@@ -182,7 +216,7 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
                         for (int sp = 0; sp < 2; ++sp) {
                             if (CTAS == 1 || sp == 0) {
                                 sw = r.s;
-                                wait_x(full0 + 8 * r.s, r.ph);
+                                wait_x(full0 + 8 * r.s, r.ph, 5, (u << 16) | (l << 8) | (c << 1) | sp);
                                 tc_fence_after();
                                 r.next();
                             }
@@ -223,7 +257,8 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
         const int t2 = threadIdx.x - 64, rsub = t2 >> 3, c4 = t2 & 7;    // 8 lanes cover the 128 bytes of one row's K chunk
         Ring r;
         float mx = 0.f;
-        for (int u = unit0; u < num_units; u += unit_step) {
+        uint32_t nt = 0;                                         // tiles done by this CTA: xgo[i] completes once per tile
+        for (int u = unit0; u < num_units; u += unit_step, ++nt) {
             const int64_t m0 = ((int64_t)u * CTAS + rank) * BM;
             for (int i = 0; i < n0; ++i) {
                 float4 v[16];
@@ -233,7 +268,7 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
                     v[st] = row < p.M ? ldg4(p.x0 + row * p.ldx0 + 32 * i + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 const int sx = r.s;
-                wait_x(empty0 + 8 * r.s, r.ph ^ 1u);
+                wait_x(xgo0 + 8 * i, nt & 1u, 6, (u << 16) | i);
                 r.skip(1 + WSLOTS);
                 uint8_t *slot = ring + sx * SLOT_BYTES;
 #pragma unroll
@@ -287,7 +322,7 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
         for (int u = unit0; u < num_units; u += unit_step) {
             const int64_t m = ((int64_t)u * CTAS + rank) * BM + row;
             for (int l = 0; l < L; ++l, ++g) {
-                wait_x(accfull0 + 8 * (g & 1u), (g >> 1) & 1u);
+                wait_x(accfull0 + 8 * (g & 1u), (g >> 1) & 1u, 7, (u << 16) | (l << 8));
                 tc_fence_after();
                 // layer switch: everyone is done with the previous layer's vectors; publish this layer's, prefetch the next
                 asm volatile("bar.sync 1, 256;" ::: "memory");
@@ -516,7 +551,7 @@ int launch_tower_prepare(const dcnr_dims *d, const dcnr_params *p, void *pack, i
 }
 
 int launch_tower_eval(const dcnr_dims *d, const float *x0, int64_t ldx0, const float *logit_cross, const float *bf,
-                      const void *pack, float *out, int64_t M, int32_t *flags, int precision, int single_cta,
+                      const void *pack, float *out, int64_t M, int32_t *flags, int precision, int options,
                       cudaStream_t stream) {
     using namespace tw;
     DCNR_REQUIRE(tower_eval_supported(d), "model shape not supported by the fused tower");
@@ -539,6 +574,7 @@ int launch_tower_eval(const dcnr_dims *d, const float *x0, int64_t ldx0, const f
         if ((l & 1) == 0) p.resin_mask |= 1u << l;               // second layer of a block adds the block input
     }
     for (int l = 0; l + 1 < L; l += 2) p.resout_mask |= 1u << l;  // outputs that are the input of a following block
+    const int single_cta = options & 1, max_ctas = options >> 8;       // options >> 8: cap on the grid (tests: many tiles per CTA)
     const int ctas = (single_cta || p.num_tiles < 2) ? 1 : 2;
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) {
@@ -559,12 +595,14 @@ int launch_tower_eval(const dcnr_dims *d, const float *x0, int64_t ldx0, const f
             return DCNR_ERR_CUDA;
         }
     }
-    const int sms = sm_count();
+    const int sms = max_ctas > 0 ? std::min(max_ctas, sm_count()) : sm_count();
+    // algorithmic flops of the launch: initial layer on the UNPADDED input width, 2R hidden layers, deep half of the final dot
+    gemm_timer_before(stream, (double)M * (2.0 * d->in_dim * H + (double)(L - 1) * 2.0 * H * H + 2.0 * H));
     if (ctas == 2) {
         DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_tower_eval<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
         cudaLaunchConfig_t cfg = {};
         cudaLaunchAttribute attr[1];
-        const int pairs = (int)std::min<int64_t>(ceil_div(p.num_tiles, 2), sms / 2);
+        const int pairs = (int)std::min<int64_t>(ceil_div(p.num_tiles, 2), std::max(1, sms / 2));
         cfg.gridDim = dim3(2 * (unsigned)pairs, 1, 1);
         cfg.blockDim = dim3(kThreads, 1, 1);
         cfg.dynamicSmemBytes = kSmemBytes;
@@ -578,6 +616,7 @@ int launch_tower_eval(const dcnr_dims *d, const float *x0, int64_t ldx0, const f
         const unsigned grid = (unsigned)std::min<int64_t>(p.num_tiles, sms);
         k_tower_eval<1><<<grid, kThreads, kSmemBytes, stream>>>(tmW, p);
     }
+    gemm_timer_after(stream);
     DCNR_LAUNCHED();
     return DCNR_OK;
 }

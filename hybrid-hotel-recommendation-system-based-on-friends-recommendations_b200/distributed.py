@@ -104,9 +104,14 @@ class Communicator:
             self._h = None
 
 
-def attach(model, comm: Optional[Communicator]):
-    """Make ``model`` (a ``DCN_RecSys``) use global-batch BatchNorm statistics over ``comm`` in train()."""
+def attach(model, comm: Optional[Communicator], batch_capacity: Optional[int] = None):
+    """Make ``model`` (a ``DCN_RecSys``) use global-batch BatchNorm statistics over ``comm`` in train().
+
+    ``batch_capacity``: the largest LOCAL batch any rank will feed in one step.  With it the ranks may hold different
+    batch sizes (the ragged last batch of an epoch): the sparse table-gradient exchange pads every rank to the capacity.
+    ``None`` declares that all ranks always hold the same number of rows (a mismatch then shows up as an NCCL error)."""
     model._comm = comm
+    model._dp_batch_cap = int(batch_capacity) if batch_capacity else 0
     return model
 
 

@@ -211,6 +211,7 @@ class DCN_RecSys(nn.Module):
         d.comm = comm.handle if (comm is not None and comm.world > 1 and self.training) else None
         d.dp_sparse_tables = 1 if (d.comm and getattr(self, "dp_sparse_embedding_grads", True) and
                                    getattr(self, "_row_override", None) is None) else 0
+        d.dp_batch_cap = getattr(self, "_dp_batch_cap", 0) if d.dp_sparse_tables else 0
         rows = getattr(self, "_row_override", None)
         if rows is not None:                     # per-sample tables (row-sharded exchange): id = batch position
             d.n_users, d.n_items = rows[0].shape[0], rows[1].shape[0]
@@ -320,7 +321,7 @@ class DCN_RecSys(nn.Module):
             flag = torch.zeros(1, dtype=torch.int32, device=user_ids.device)
             C.check(C.lib().dcnr_check_ids(dims, batch, C.ptr(flag), C.stream()))
         if self.training:
-            if B == 1 and len(self.res_blocks) > 0:
+            if B == 1 and len(self.res_blocks) > 0 and dims.comm is None:
                 raise ValueError(f"Expected more than 1 value per channel when training, got input size "
                                  f"torch.Size([1, {self._shape['hidden']}])")
             params = self._ordered_params()
@@ -344,7 +345,7 @@ class DCN_RecSys(nn.Module):
 
     def _eval_call(self, dims, batch, B, dev):
         if self._eval_flags is None or self._eval_flags.device != dev:
-            self._eval_flags = torch.zeros(1, dtype=torch.int32, device=dev)
+            self._eval_flags = torch.zeros(4, dtype=torch.int32, device=dev)      # [0] flag bits, [1..2] diagnostics
         dims.eval_flags = C.ptr(self._eval_flags)
         pstruct = self._param_struct()
         ws = torch.empty(C.lib().dcnr_workspace_bytes(dims, B, 0), dtype=torch.uint8, device=dev)
@@ -358,7 +359,7 @@ class DCN_RecSys(nn.Module):
         activation left the fp16 range of the fused tower.  Synchronises the current stream."""
         if self._eval_flags is None:
             return False
-        f = int(self._eval_flags.item())
+        f = int(self._eval_flags[0].item())
         if f:
             self._eval_flags.zero_()
         if f & 1:

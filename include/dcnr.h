@@ -83,6 +83,10 @@ typedef struct dcnr_dims {
     int32_t dp_sparse_tables;   /* with comm: 1 = build the user / item table gradients from the all-gathered (id, gradient
                                  * row) pairs of ALL ranks (identical dense gradients on every rank, single-device summation
                                  * order, ~150 B per sample on the wire); 0 = local gradients, all-reduce them yourself */
+    int64_t dp_batch_cap;       /* with comm and dp_sparse_tables: the largest LOCAL batch of any rank in this step (equal on all
+                                 * ranks).  The (id, gradient row) all-gather moves dp_batch_cap rows per rank -- shorter local
+                                 * batches are padded with zero rows -- so ranks may hold different batch sizes (the short last
+                                 * batch of train.py:196's DataLoader).  0 = every rank has exactly `batch` rows */
     uint64_t *dropout_step;     /* optional DEVICE counter: its value is added to dropout_seed and every dcnr_forward_train
                                  * increments it, so a captured CUDA graph of the training step draws a fresh dropout mask
                                  * on every replay (NULL: the seed argument alone decides the mask) */
@@ -281,7 +285,9 @@ int dcnr_bn_act_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo, 
  * x0 [m, ldx0] is the padded output of dcnr_embed_concat_fwd (ldx0 >= in_dim_pad, pad columns zero); logit_cross [m] (the
  * cross half, may be NULL).  precision: DCNR_PREC_FP16X3 or DCNR_PREC_BF16.  Needs hidden == 256, 1..4 ResBlocks
  * (dcnr_tower_eval_supported).  workspace: dcnr_tower_eval_workspace_bytes().  flags: see dcnr_dims.eval_flags (may be NULL).
- * options: bit 0 = single CTAs instead of 2-CTA pairs (measurement aid). */
+ * options: bit 0 = single CTAs instead of 2-CTA pairs; bits 8.. = cap on the number of CTAs (0 = one per SM) -- measurement
+ * and test aids.  flags[1..2] receive a diagnostic record if a pipeline wait times out (the kernel then traps), so flags must
+ * point at >= 3 ints. */
 int dcnr_tower_eval_supported(const dcnr_dims *dims);
 int64_t dcnr_tower_eval_workspace_bytes(const dcnr_dims *dims);
 int dcnr_tower_eval(const dcnr_dims *dims, const dcnr_params *params, const float *x0, int64_t ldx0,

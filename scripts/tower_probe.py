@@ -23,7 +23,7 @@ def main():
     x0[:, :57] = torch.randn(rows, 57, device=dev) * 0.3
     cross = torch.randn(rows, device=dev)
     out = torch.empty(rows, device=dev)
-    flags = torch.zeros(1, dtype=torch.int32, device=dev)
+    flags = torch.zeros(4, dtype=torch.int32, device=dev)
     ws = torch.empty(C.lib().dcnr_tower_eval_workspace_bytes(dims), dtype=torch.uint8, device=dev)
     for prec in ("fp16x3", "bf16"):
         for options, tag in ((1, "single CTAs"), (0, "2-CTA pairs")):
@@ -32,7 +32,7 @@ def main():
                                                 options, C.ptr(flags), C.ptr(ws), ws.numel(), C.stream()))
             secs = bench.time_steps(run, 10, 3, lambda: None) / 10
             print(f"tower {prec:7s} {tag:12s} rows {rows}: {secs * 1e3:8.3f} ms  {rows / secs / 1e6:8.1f} M rows/s  "
-                  f"{FLOP_TOWER * rows / secs / 1e12:7.1f} TFLOP/s algorithmic  flags {int(flags.item())}", flush=True)
+                  f"{FLOP_TOWER * rows / secs / 1e12:7.1f} TFLOP/s algorithmic  flags {int(flags[0].item())}", flush=True)
     u, i, c, x = bench.synth_requests(max(1, rows // 500), 500, 1234, dev)
     for prec in ("fp16x3", "bf16", "tf32x3"):
         m.precision = prec

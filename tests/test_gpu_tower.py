@@ -39,12 +39,12 @@ def _tower_call(m, x0p, cross, precision, options):
     dims, ps = m._dims(), m._param_struct()
     B = x0p.shape[0]
     out = torch.full((B,), float("nan"), device="cuda")
-    flags = torch.zeros(1, dtype=torch.int32, device="cuda")
+    flags = torch.zeros(4, dtype=torch.int32, device="cuda")
     ws = torch.empty(C.lib().dcnr_tower_eval_workspace_bytes(dims), dtype=torch.uint8, device="cuda")
     C.check(C.lib().dcnr_tower_eval(dims, ps, C.ptr(x0p), x0p.shape[1], C.ptr(cross), C.ptr(out), B, C.PRECISIONS[precision],
                                     options, C.ptr(flags), C.ptr(ws), ws.numel(), C.stream()))
     torch.cuda.synchronize()
-    return out.cpu(), int(flags.item())
+    return out.cpu(), int(flags[0].item())
 
 
 def _oracle_deep(st, u, i, c, x):
@@ -69,6 +69,22 @@ def test_tower_operator_matches_oracle(B, options):
     got, flags = _tower_call(m, x0p.cuda(), cross.cuda(), "fp16x3", options)
     assert flags == 0
     assert orc.max_abs_normalised(got, deep + cross.double()) < TOL
+
+
+@pytest.mark.parametrize("options", [1 | (1 << 8), 0 | (2 << 8), 1 | (3 << 8), 0 | (6 << 8)],
+                         ids=["1_cta", "1_pair", "3_ctas", "3_pairs"])
+def test_tower_many_tiles_per_cta(options):
+    """Grid capped to 1..6 CTAs: every CTA walks many tiles (the tile-to-tile hand-over of the TMEM buffers and the ring)."""
+    params, st, nu, ni = _state()
+    B = 128 * 23 + 17
+    u, i, c, x, _ = synth_inputs(nu, ni, CAT, 11, B, seed=31)
+    _, deep, x0 = _oracle_deep(st, u, i, c, x)
+    m = _model(params, st, nu, ni, "fp16x3")
+    x0p = torch.zeros(B, m._dims().in_dim_pad)
+    x0p[:, : x0.shape[1]] = x0.float()
+    got, flags = _tower_call(m, x0p.cuda(), None, "fp16x3", options)
+    assert flags == 0
+    assert orc.max_abs_normalised(got, deep) < TOL
 
 
 @pytest.mark.parametrize("R,emb", [(1, 16), (4, 16), (2, 32), (3, 48)])
