@@ -3,13 +3,13 @@
 //
 // Reference lines: DCN_RecSys.forward train.py:155-170 (main.py:114-127); training step
 // train.py:223-225; ranking call main.py:320-322.
-#include <cstdlib>
-
 #include "kernels.cuh"
 
 namespace dcnr {
 
 constexpr int64_t kEvalChunkRows = 1 << 20;   // rows per pass of the eval forward (bounds the workspace)
+constexpr int64_t kEvalChunkRowsFused = 1 << 22;   // fused tower: only x0 (256 B / row) is staged, so a pass can be 4x longer
+                                                   // (fewer launch ramps and tile-wave tails: 55 tiles per SM per 2^20 rows)
 
 static int check_dims(const dcnr_dims *d) {
     DCNR_REQUIRE(d != nullptr, "null dims");
@@ -88,7 +88,7 @@ struct TrainSaved {
 static bool dp_sparse_tables(const dcnr_dims *d) { return comm_world(d->comm) > 1 && d->dp_sparse_tables != 0; }
 
 struct BwdScratch {
-    float *ga, *gb, *gc, *dx0, *cross_partials, *wgrad, *bn, *wsplit, *vec_a, *vec_b, *w0_parts;
+    float *ga, *gb, *gc, *dx0, *cross_partials, *wgrad, *bn, *wsplit, *vec_a, *vec_b;
     void *scatter;
     int64_t scatter_bytes;
     int64_t *pack_ids, *all_ids;       // [B][2] (user, item) of this rank / [world*B][2] of all ranks
@@ -106,7 +106,6 @@ struct BwdScratch {
         wsplit = a.take<float>(WeightOps::floats(d));
         vec_a = a.take<float>(H);
         vec_b = a.take<float>(H);
-        w0_parts = a.take<float>(3 * H * Dp);
         const int world = dp_sparse_tables(d) ? comm_world(d->comm) : 1;
         const int64_t cap = (world > 1 && d->dp_batch_cap > B) ? d->dp_batch_cap : B;    // rows per rank in the sparse exchange
         scatter_bytes = with_scatter ? scatter_scratch_bytes(2 * cap * world) : 0;      // user + item share one sort
@@ -149,6 +148,7 @@ struct EvalWs {
     }
 };
 
+
 static CrossArgs cross_args(const dcnr_dims *d, const dcnr_params *p) {
     CrossArgs ca;
     memset(&ca, 0, sizeof(ca));
@@ -177,7 +177,7 @@ extern "C" int64_t dcnr_workspace_bytes(const dcnr_dims *dims, int64_t batch, in
     Arena a(nullptr, 0);
     if (kind == 0) {
         EvalWs w;
-        w.layout(dims, std::min<int64_t>(std::max<int64_t>(batch, 1), kEvalChunkRows), a);
+        w.layout(dims, std::min<int64_t>(std::max<int64_t>(batch, 1), EvalWs::fused(dims) ? kEvalChunkRowsFused : kEvalChunkRows), a);
     } else if (kind == 1) {
         TrainSaved s;
         s.layout(dims, std::max<int64_t>(batch, 1), a);
@@ -197,7 +197,7 @@ extern "C" int dcnr_forward_eval(const dcnr_dims *dims, const dcnr_params *param
     DCNR_REQUIRE(params && batch && logits && workspace, "null argument");
     const int64_t B = batch->batch;
     if (B <= 0) return DCNR_OK;
-    const int64_t chunk = std::min<int64_t>(B, kEvalChunkRows);
+    const int64_t chunk = std::min<int64_t>(B, EvalWs::fused(dims) ? kEvalChunkRowsFused : kEvalChunkRows);
     Arena a(workspace, workspace_bytes);
     EvalWs w;
     w.layout(dims, chunk, a);
@@ -371,26 +371,20 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
         std::swap(g, g2);
     }
     // initial_deep_layer: h0 = x0 W0^T + b0
-    // Gradients of the initial layer: db0 = colsum(g), dW0 = g^T x0.  With ResBlocks g = dz1 W1 + dy2 (block 0: dz1 is what `g3`
-    // holds, dy2 what `g2` holds after the last swap), so by linearity
-    //     db0 = colsum(dz1) W1 + colsum(dy2),        dW0 = W1^T (dz1^T x0) + dy2^T x0.
-    // Both batch sums then run over BatchNorm-backward outputs / elementwise products instead of over GEMM outputs.  The tensor
-    // core's accumulate truncates toward zero (profiles/r02_acc_probe.md), so a GEMM output carries a small error that is
-    // sign-correlated along the batch; every later BatchNorm backward removes its column mean, but nothing does for the
-    // initial layer, and a batch sum against the non-zero-mean columns of x0 (the [0, 1) numerics) or against 1 collects it:
-    // these were the two gradient tensors above 2x the reference's own fp32 noise (b0 3.4e-5 at B = 4096, W0 1.4e-5 at 65 536).
-    const bool l0_split = R > 0;
-    if (!l0_split) {
-        if (grads->w0 || grads->b0)
-            DCNR_TRY(launch_linear_wgrad(prec, g, H, s.x0p, Dp, grads->w0, D, grads->b0, B, H, Dp, D, w.wgrad, st));
-    } else {
-        if (grads->b0) {
-            const float *db1 = grads->res_b1[0] != nullptr ? grads->res_b1[0] : w.vec_a;
-            DCNR_TRY(launch_colsum(g2, H, B, H, w.vec_b, w.bn, st));
-            DCNR_TRY(launch_vecmat_add(db1, params->res_w1[0], H, H, H, w.vec_b, grads->b0, st));
-        }
-        if (grads->w0)      // EXPERIMENT: the initial layer's weight gradient on the CUDA-core fp32 GEMM
-            DCNR_TRY(launch_linear_wgrad(getenv("DCNR_W0_FP32") ? DCNR_PREC_FP32 : prec, g, H, s.x0p, Dp, grads->w0, D, nullptr, B, H, Dp, D, w.wgrad, st));
+    // Bias gradient of the initial layer: db0 = colsum(g).  With ResBlocks g = dz1 W1 + dy2 (block 0: colsum(dz1) is the layer1
+    // bias gradient, dy2 what `g2` holds after the last swap), so by linearity db0 = colsum(dz1) W1 + colsum(dy2): the batch sum
+    // runs over dy2 (elementwise products) instead of over GEMM outputs.  The tensor core's accumulate truncates toward zero
+    // (profiles/r02_acc_probe.md), so a GEMM output carries a small error that is sign-correlated along the batch; a later
+    // BatchNorm backward removes its column mean, but nothing does for the initial layer, where this cancellation-heavy sum
+    // collected it (3.4e-5 against a reference fp32 noise of 9e-6 at B = 4096).  The same rewrite of dW0 was tried and measured
+    // WORSE (1.6e-5 vs 1.3e-5 at B = 65 536: the error there is the weight-gradient GEMM's own), so dW0 keeps the direct form.
+    const bool b0_split = grads->b0 != nullptr && R > 0;
+    if (grads->w0 || (grads->b0 && !b0_split))
+        DCNR_TRY(launch_linear_wgrad(prec, g, H, s.x0p, Dp, grads->w0, D, b0_split ? nullptr : grads->b0, B, H, Dp, D, w.wgrad, st));
+    if (b0_split) {
+        const float *db1 = grads->res_b1[0] != nullptr ? grads->res_b1[0] : w.vec_a;
+        DCNR_TRY(launch_colsum(g2, H, B, H, w.vec_b, w.bn, st));
+        DCNR_TRY(launch_vecmat_add(db1, params->res_w1[0], H, H, H, w.vec_b, grads->b0, st));
     }
     GemmEpilogue none{nullptr, nullptr, nullptr, 0, 0};
     DCNR_TRY(gemm_any(prec, g, H, true, s.w0p, Dp, false, w.dx0, Dp, B, Dp, H, 1, none, st, wt.get(wt.w0)));

@@ -22,8 +22,9 @@
 //   * The residual input of a block is kept as fp32 in shared memory (128 KB, [col/4][row] float4: conflict-free).
 //   * Weights stream from L2 through a 6-slot x 16 KB TMA ring (pre-split fp16 hi / lo, prepared once per call by
 //     k_tower_prep); the x0 tile enters the same ring as a shared-memory A operand (SS-form MMA) for the initial layer.
-//   * CTAS == 2: a CTA pair shares every weight tile (tcgen05.mma.cta_group::2, M = 256 over the pair): each CTA streams and
-//     holds HALF of the weight rows, halving the L2 -> shared-memory stream and the shared-memory operand reads per SM.
+//   * CTAS == 2 (opt-in, measured 8 % slower than single CTAs): a CTA pair shares every weight tile (tcgen05.mma.cta_group::2,
+//     M = 256 over the pair): each CTA streams and holds HALF of the weight rows, halving the L2 -> shared-memory stream and
+//     the shared-memory operand reads per SM.
 //
 // Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warps 2-3 x0 loader, warps 4-11 epilogue
 // (warp w and w + 4 share a TMEM lane quadrant and take alternate 32-column chunks).
@@ -574,8 +575,11 @@ int launch_tower_eval(const dcnr_dims *d, const float *x0, int64_t ldx0, const f
         if ((l & 1) == 0) p.resin_mask |= 1u << l;               // second layer of a block adds the block input
     }
     for (int l = 0; l + 1 < L; l += 2) p.resout_mask |= 1u << l;  // outputs that are the input of a following block
-    const int single_cta = options & 1, max_ctas = options >> 8;       // options >> 8: cap on the grid (tests: many tiles per CTA)
-    const int ctas = (single_cta || p.num_tiles < 2) ? 1 : 2;
+    // Single CTAs are the default: measured 689 M rows/s against 636 M rows/s for 2-CTA pairs (P0, 4 Mi rows) -- at one
+    // tile per SM the kernel is tensor-pipe bound, not shared-memory bound, and the pair form pays cluster-scope barrier
+    // latency on every operand hand-over.  options bit 0 selects pairs; options >> 8 caps the grid (tests: many tiles per CTA).
+    const int want_pairs = options & 1, max_ctas = options >> 8;
+    const int ctas = (want_pairs && p.num_tiles >= 2) ? 2 : 1;
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) {
         set_error("cuTensorMapEncodeTiled entry point not available");

@@ -4,7 +4,8 @@ At data-parallel batch sizes (8 192 - 32 768 rows per GPU) the ~100 kernels of a
 time to launch them from Python, so the step is captured once -- forward, loss, backward and the NCCL gradient
 exchange on the library's communicator -- and replayed.  Inputs live in static device tensors; dropout draws a
 fresh mask on every replay from a device-side step counter (``dcnr_dims.dropout_step``); gradients land in the
-parameters' ``.grad`` tensors (static across replays), so a stock ``torch.optim`` optimizer steps on them as usual.
+parameters' ``.grad`` tensors (static across replays, re-attached after every replay), so a stock ``torch.optim``
+optimizer loop -- ``zero_grad()`` with its default ``set_to_none=True`` included -- steps on them as usual.
 """
 from __future__ import annotations
 
@@ -47,6 +48,12 @@ class GraphedTrainStep:
         return loss
 
     def capture(self):
+        """Warm up on a side stream, then capture one step.  The warm-up steps are REAL train-mode steps on whatever the
+        static inputs hold, so everything they mutate besides the gradients -- BatchNorm running statistics,
+        ``num_batches_tracked``, the device dropout counter -- is snapshotted first and restored afterwards: capturing
+        leaves the model exactly as it found it (the reference's loop updates those once per batch, train.py:218-226)."""
+        snap = {n: b.detach().clone() for n, b in self.model.named_buffers()}
+        step0 = self.model._dropout_step.clone()
         cur = torch.cuda.current_stream()
         side = torch.cuda.Stream()
         side.wait_stream(cur)
@@ -62,6 +69,13 @@ class GraphedTrainStep:
         self.graph = torch.cuda.CUDAGraph()
         with torch.cuda.graph(self.graph):
             self.loss = self._step()
+        # the gradient tensors the graph writes on every replay; re-attached after each replay in case the training loop
+        # detached them (optimizer.zero_grad() defaults to set_to_none=True, train.py:222)
+        self._grads = [p.grad for p in self.params]
+        with torch.no_grad():
+            for n, b in self.model.named_buffers():
+                b.copy_(snap[n])
+            self.model._dropout_step.copy_(step0)
         return self
 
     def load(self, user_ids, item_ids, cat_features, num_features, labels):
@@ -79,4 +93,7 @@ class GraphedTrainStep:
         if self.graph is None:
             self.capture()
         self.graph.replay()
+        for p, g in zip(self.params, self._grads):
+            if p.grad is not g:
+                p.grad = g
         return self.loss

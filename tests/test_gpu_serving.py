@@ -113,3 +113,51 @@ def test_load_ml_artifacts_round_trip_and_fused_item_tables(tmp_path):
     ranked = fused.rank(hotels, user_id)
     assert [h for _, h in ranked] == [h for _, h in dcnr_b200.serving.sort_scored(ref_scores.cpu().numpy(), hotels)]
     assert all(ranked[i][0] >= ranked[i + 1][0] for i in range(len(ranked) - 1))
+
+
+def test_graphed_train_step_equals_eager_loop_with_stock_optimizer():
+    """training.GraphedTrainStep: N steps of the reference's loop (zero_grad -> forward -> BCE -> backward ->
+    optimizer.step, train.py:218-226) replayed from one CUDA graph leave the same parameters, BatchNorm buffers and
+    num_batches_tracked as the eager loop -- capture() itself must not move the running statistics, and zero_grad()'s
+    default set_to_none=True must not disconnect the optimizer from the graph's gradient buffers."""
+    import dcnr_b200
+    from oracle import dcnr_oracle as orc
+    from tests.helpers import synth_inputs
+    n_users, n_items, cat_dims, n_num = 3000, 900, {"city": 100, "hotel_type": 6}, 11
+    params = dict(emb_dim=16, hidden_dim=256, n_cross_layers=3, n_res_blocks=2, dropout=0.0)
+    state = orc.make_state(n_users, n_items, cat_dims, n_num, params, seed=4, emb_scale=0.1, randomize_bn=True)
+    B, steps = 2048, 4
+    batches = [tuple(t.cuda() for t in synth_inputs(n_users, n_items, cat_dims, n_num, B, seed=50 + s)) for s in range(steps)]
+
+    def fresh():
+        m = dcnr_b200.DCN_RecSys(n_users, n_items, cat_dims, n_num, params, precision="tf32x3")
+        m.load_state_dict(state)
+        return m.cuda().train()
+
+    eager = fresh()
+    opt = torch.optim.Adam(eager.parameters(), lr=1e-3)
+    for u, i, c, x, y in batches:
+        opt.zero_grad()
+        loss = torch.nn.BCEWithLogitsLoss()(eager(u, i, c, x), y)
+        loss.backward()
+        opt.step()
+
+    graphed = fresh()
+    opt_g = torch.optim.Adam(graphed.parameters(), lr=1e-3)
+    gs = dcnr_b200.training.GraphedTrainStep(graphed, B)
+    gs.load(*batches[0])
+    gs.capture()
+    for n, b in graphed.named_buffers():                      # capture left the model as it found it
+        assert torch.equal(b.cpu(), state[n]), n
+    for u, i, c, x, y in batches:
+        opt_g.zero_grad()                                     # set_to_none=True: detaches .grad
+        gs(u, i, c, x, y)
+        opt_g.step()
+    for (n, pe), (_, pg) in zip(eager.named_parameters(), graphed.named_parameters()):
+        assert torch.allclose(pe, pg, rtol=0, atol=2e-6 * float(pe.abs().max()) + 1e-9), n
+    for (n, be), (_, bg) in zip(eager.named_buffers(), graphed.named_buffers()):
+        if be.dtype.is_floating_point:
+            assert torch.allclose(be, bg, rtol=1e-6, atol=1e-7), n
+        else:
+            assert int(be) == int(bg) == steps, n
+

@@ -55,7 +55,7 @@ def _oracle_deep(st, u, i, c, x):
     return logits.reshape(-1), deep, parts["x0"]
 
 
-@pytest.mark.parametrize("options", [1, 0], ids=["single_cta", "cta_pairs"])
+@pytest.mark.parametrize("options", [0, 1], ids=["single_cta", "cta_pairs"])
 @pytest.mark.parametrize("B", [1, 127, 128, 129, 300, 4096, 37_001, 100_000])
 def test_tower_operator_matches_oracle(B, options):
     params, st, nu, ni = _state()
@@ -71,7 +71,7 @@ def test_tower_operator_matches_oracle(B, options):
     assert orc.max_abs_normalised(got, deep + cross.double()) < TOL
 
 
-@pytest.mark.parametrize("options", [1 | (1 << 8), 0 | (2 << 8), 1 | (3 << 8), 0 | (6 << 8)],
+@pytest.mark.parametrize("options", [0 | (1 << 8), 1 | (2 << 8), 0 | (3 << 8), 1 | (6 << 8)],
                          ids=["1_cta", "1_pair", "3_ctas", "3_pairs"])
 def test_tower_many_tiles_per_cta(options):
     """Grid capped to 1..6 CTAs: every CTA walks many tiles (the tile-to-tile hand-over of the TMEM buffers and the ring)."""
@@ -149,7 +149,7 @@ def test_fp16_range_overflow_falls_back_to_tf32x3():
     m = _model(params, st, nu, ni, "fp16x3")
     x0p = torch.zeros(B, m._dims().in_dim_pad)
     x0p[:, : x0.shape[1]] = x0.float()
-    _, flags = _tower_call(m, x0p.cuda(), None, "fp16x3", 0)
+    _, flags = _tower_call(m, x0p.cuda(), None, "fp16x3", 1)
     assert flags & 2
     with torch.no_grad():
         out = m(u.cuda(), i.cuda(), c.cuda(), x.cuda())
