@@ -87,13 +87,14 @@ _SIGS = {
                                c_void_p, c_int64, c_void_p, c_int64, POINTER(c_void_p), POINTER(c_void_p), c_void_p,
                                c_int64, c_void_p]),
     "dcnr_linear_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64, c_int,
-                                c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p]),
+                                c_void_p, c_int64, c_int64, c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
+    "dcnr_linear_workspace_bytes": (c_int64, [c_int32, c_int32, c_int32]),
     "dcnr_cross_v2_fwd": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_int64,
-                                  c_int64, c_int32, c_int32, c_void_p]),
+                                  c_int64, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
     "dcnr_cross_v2_bwd_prep": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64,
                                        c_void_p, c_int64, c_int, c_int64, c_int32, c_void_p]),
     "dcnr_linear_dgrad": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int64,
-                                  c_int32, c_int32, c_int32, c_void_p]),
+                                  c_int32, c_int32, c_int32, c_void_p, c_int64, c_void_p]),
     "dcnr_linear_wgrad_scratch_bytes": (c_int64, [c_int64, c_int32, c_int32]),
     "dcnr_linear_wgrad": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_int64, c_int32,
                                   c_int32, c_int32, c_void_p, c_int64, c_void_p]),

@@ -10,7 +10,6 @@
 //   3. a fix-up pass walks each window-crossing chain in window order.
 // No atomics, so the result is bit-reproducible.  The radix sort itself is CUB (library plumbing,
 // see DESIGN.md); steps 2-3 are the kernels below.
-#include <cub/device/device_radix_sort.cuh>
 
 #include "kernels.cuh"
 
@@ -331,13 +330,9 @@ k_scatter_small_multi(SmallTables st, int64_t B, const float *__restrict__ dx0, 
 // true (and launched) when every categorical table with a gradient takes the tiny-table path and they fit one pass
 static bool try_scatter_small_multi(const dcnr_dims *dims, const dcnr_batch *batch, const float *dx0, int64_t lddx,
                                     const dcnr_grads *grads, void *scratch, int64_t scratch_bytes, cudaStream_t stream, int *rc) {
-    static const bool enabled = [] {
-        const char *e = getenv("DCNR_SCATTER_MULTI");
-        return e == nullptr || atoi(e) != 0;
-    }();
     *rc = DCNR_OK;
     const int64_t B = batch->batch;
-    if (!enabled || B <= 0) return false;
+    if (B <= 0) return false;
     SmallTables st;
     memset(&st, 0, sizeof(st));
     int col = 2 * dims->emb_dim, n = 0;
@@ -411,20 +406,13 @@ static int sort_bits(int64_t n_rows) {
     return b;
 }
 
-static int64_t cub_temp_bytes(int64_t B) {
-    size_t bytes = 0;
-    cub::DoubleBuffer<uint32_t> k(nullptr, nullptr), v(nullptr, nullptr);
-    cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, v, (int)B, 0, 32, (cudaStream_t)0);
-    return (int64_t)round_up((int64_t)bytes + 256, 256);
-}
-
 int64_t scatter_scratch_bytes(int64_t B) {
     if (B <= 0) return 256;
     const int64_t n_windows = ceil_div(B, kWin);
     int64_t bytes = 4 * round_up(B * 4, 256);                       // keys/vals double buffers
     bytes += round_up(n_windows * 2 * 256 * 4, 256);                // carry, width <= 256
     bytes += round_up(n_windows, 256);                              // flags
-    bytes += cub_temp_bytes(B);
+    bytes += radix_sort_scratch_bytes(B);
     return bytes;      // (the tiny-table path's partial tables need <= 32 B per batch row: they reuse this space)
 }
 
@@ -451,32 +439,26 @@ static int launch_scatter_sorted(const int64_t *ids0, int64_t stride0, int64_t r
     uint32_t *v0 = ar.take<uint32_t>(n), *v1 = ar.take<uint32_t>(n);
     float *carry = ar.take<float>(n_windows * 2 * 256);
     uint8_t *flags = ar.take<uint8_t>(n_windows);
-    const int64_t temp_bytes = cub_temp_bytes(n);
-    void *temp = ar.take<char>(temp_bytes);
+    void *temp = ar.take<char>(radix_sort_scratch_bytes(n));
 
     k_scatter_prep<<<(unsigned)ceil_div(n, 256), 256, 0, stream>>>(ids0, stride0, rows0, ids1, stride1, rows1, B, tbit, k0, v0);
     DCNR_LAUNCHED();
-    cub::DoubleBuffer<uint32_t> kb(k0, k1), vb(v0, v1);
-    size_t tb = (size_t)temp_bytes;
-    DCNR_CUDA_CHECK(cub::DeviceRadixSort::SortPairs(temp, tb, kb, vb, (int)n, 0, two ? tbit + 1 : sort_bits(rows0), stream));
-    count_launch(3);
+    // stable LSD radix sort (radix_sort.cu, hand-written: 11-bit digits, two passes for the 21-bit keys of 1 M x 100 K tables)
+    uint32_t *ks = nullptr, *vs = nullptr;
+    DCNR_TRY(launch_radix_sort_pairs(k0, v0, k1, v1, n, two ? tbit + 1 : sort_bits(rows0), temp, &ks, &vs, stream));
     ScatterTables tabs;
     tabs.grad[0] = grad0; tabs.grad[1] = two ? grad1 : grad0;
     tabs.col0[0] = col0; tabs.col0[1] = two ? col1 : col0;
     tabs.tbit = tbit; tabs.B = B;
     const int64_t threads = n_windows * width;
-    static const bool window16 = [] {               // DCNR_SCATTER_W16=0: the one-window-per-warp form for every width
-        const char *e = getenv("DCNR_SCATTER_W16");
-        return e == nullptr || atoi(e) != 0;
-    }();
-    if (width <= 16 && window16)
-        k_scatter_window16<<<(unsigned)ceil_div(ceil_div(n_windows, 2), 4), 128, 0, stream>>>(kb.Current(), vb.Current(), n, width,
+    if (width <= 16)      // two sorted windows per warp (one window would leave half the lanes idle at width 16)
+        k_scatter_window16<<<(unsigned)ceil_div(ceil_div(n_windows, 2), 4), 128, 0, stream>>>(ks, vs, n, width,
                                                                                               dx0, lddx, tabs, carry, flags, n_windows);
     else
-        k_scatter_window<<<(unsigned)ceil_div(n_windows, 4), 128, 0, stream>>>(kb.Current(), vb.Current(), n, width, dx0, lddx, tabs,
+        k_scatter_window<<<(unsigned)ceil_div(n_windows, 4), 128, 0, stream>>>(ks, vs, n, width, dx0, lddx, tabs,
                                                                              carry, flags, n_windows);
     DCNR_LAUNCHED();
-    k_scatter_fixup<<<(unsigned)ceil_div(threads, 128), 128, 0, stream>>>(kb.Current(), n, width, tabs, carry, flags, n_windows);
+    k_scatter_fixup<<<(unsigned)ceil_div(threads, 128), 128, 0, stream>>>(ks, n, width, tabs, carry, flags, n_windows);
     DCNR_LAUNCHED();
     return DCNR_OK;
 }

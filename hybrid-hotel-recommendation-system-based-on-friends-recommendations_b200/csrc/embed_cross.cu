@@ -795,13 +795,12 @@ int launch_embed_cross_fwd(const GatherArgs *ga, const float *x_in, int64_t ldx_
     DCNR_REQUIRE(dim_pad % 32 == 0 && nv >= 1 && nv <= 8, "in_dim_pad %d unsupported (must be 32..256, multiple of 32)",
                  dim_pad);
     const size_t smem = (size_t)(2 * ca.L + 1) * dim_pad * sizeof(float);
-    // staged form (see k_embed_cross_fwd_staged): gather mode, a prefix of 16-byte aligned segments, the rest of the row
-    // (narrow tables, numerics, pad) no wider than 96 floats; DCNR_K1_STAGED=0 forces the element-wise form
-    static const bool staged_on = [] {
-        const char *e = getenv("DCNR_K1_STAGED");
-        return e == nullptr || atoi(e) != 0;
-    }();
-    if (x_in == nullptr && staged_on && ga->n_seg > 0) {
+    // Three forms, one per shape class (each measured the fastest for its class in round 1, profiles/r01_ncu_k1_*.md):
+    //   * narrow rows (in_dim_pad <= 64, the reference's default shape): k_embed_cross_fwd_pipe -- cp.async ring of two 32-row
+    //     tiles per warp, four warps per CTA;
+    //   * wider rows with a prefix of 16-byte aligned segments and a mixed tail of <= 96 floats: k_embed_cross_fwd_staged;
+    //   * everything else (cross-only calls on a given x, odd layouts): the element-wise k_embed_cross_fwd.
+    if (x_in == nullptr && ga->n_seg > 0) {
         int n_vec = 0, mix0 = 0;
         bool ok = true;
         for (int i = 0; i < ga->n_seg; ++i) {
@@ -815,44 +814,21 @@ int launch_embed_cross_fwd(const GatherArgs *ga, const float *x_in, int64_t ldx_
         }
         const int tw = dim_pad - mix0;
         ok = ok && tw >= 0 && tw <= 96 && ga->n_num <= 256 && (ga->n_num == 0 || ga->num != nullptr);
-        static const int pipe_stages = [] {          // DCNR_K1_PIPE=0 disables, 2 / 3 select the ring depth (default 2)
-            const char *e = getenv("DCNR_K1_PIPE");
-            return e != nullptr ? atoi(e) : 2;
-        }();
-        if (ok && nv <= 2 && pipe_stages >= 2) {
-            const int S = pipe_stages >= 3 ? 3 : 2;
-            static const int pipe_warps = [] {       // DCNR_K1_PIPE_WARPS = 2 | 4 | 8 warps per CTA (experiments; default 4)
-                const char *e = getenv("DCNR_K1_PIPE_WARPS");
-                const int v = e != nullptr ? atoi(e) : kPipeWarps;
-                return (v == 2 || v == 8) ? v : kPipeWarps;
-            }();
+        if (ok && nv <= 2) {
             // Measured per 4 M rows (P0; box-to-box spread is ~10 %): 32-row steps with 2 / 4 / 8 warps per CTA 405-470 / 414 /
             // 510 us; 16-row steps (twice the warps per SM) 428 / 420 / 437 us; a ring of three tiles 516 us.
-            static const int pipe_rows = [] {        // DCNR_K1_PIPE_ROWS = 32 | 16 rows per step
-                const char *e = getenv("DCNR_K1_PIPE_ROWS");
-                return (e != nullptr && atoi(e) == 16) ? 16 : 32;
-            }();
-            const int W = S == 2 ? pipe_warps : kPipeWarps;
-            const int RS = (S == 2 && nv == 2) ? pipe_rows : 32;
+            constexpr int S = 2, W = kPipeWarps, RS = 32;
             const size_t smem_p = smem + (size_t)W * S * RS * (dim_pad + 4) * sizeof(float);
             const unsigned grid_p = (unsigned)std::min<int64_t>(ceil_div(B, RS * W), (int64_t)sm_count() * 64 / W);
-#define DCNR_LAUNCH_P(NVV, SS, WW, RR)                                                                                     \
+#define DCNR_LAUNCH_P(NVV)                                                                                                 \
     do {                                                                                                                   \
-        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_embed_cross_fwd_pipe<NVV, SS, WW, RR>,                                      \
+        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_embed_cross_fwd_pipe<NVV, S, W, RS>,                                        \
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_p));                   \
-        k_embed_cross_fwd_pipe<NVV, SS, WW, RR><<<grid_p, 32 * WW, smem_p, stream>>>(*ga, n_vec, B, ca, x0_out, ldx0,      \
-                                                                                     y_out, ldy, wf_cross, logit_part,     \
-                                                                                     err_flag);                            \
+        k_embed_cross_fwd_pipe<NVV, S, W, RS><<<grid_p, 32 * W, smem_p, stream>>>(*ga, n_vec, B, ca, x0_out, ldx0, y_out,   \
+                                                                                  ldy, wf_cross, logit_part, err_flag);    \
     } while (0)
-            if (nv == 1 && S == 2) DCNR_LAUNCH_P(1, 2, 4, 32);
-            else if (nv == 1) DCNR_LAUNCH_P(1, 3, 4, 32);
-            else if (S == 3) DCNR_LAUNCH_P(2, 3, 4, 32);
-            else if (RS == 32 && W == 2) DCNR_LAUNCH_P(2, 2, 2, 32);
-            else if (RS == 32 && W == 8) DCNR_LAUNCH_P(2, 2, 8, 32);
-            else if (RS == 32) DCNR_LAUNCH_P(2, 2, 4, 32);
-            else if (W == 2) DCNR_LAUNCH_P(2, 2, 2, 16);
-            else if (W == 8) DCNR_LAUNCH_P(2, 2, 8, 16);
-            else DCNR_LAUNCH_P(2, 2, 4, 16);
+            if (nv == 1) DCNR_LAUNCH_P(1);
+            else DCNR_LAUNCH_P(2);
 #undef DCNR_LAUNCH_P
             DCNR_LAUNCHED();
             return DCNR_OK;
@@ -861,78 +837,34 @@ int launch_embed_cross_fwd(const GatherArgs *ga, const float *x_in, int64_t ldx_
             const size_t smem_s = smem + (size_t)(kThreads / 32) * 32 * (tw + 4) * sizeof(float);
             const unsigned grid_s = (unsigned)std::min<int64_t>(ceil_div(B, 32 * (kThreads / 32)), (int64_t)sm_count() * 8);
             // Measured at 4 M rows (P0, us): one pass of row loads in flight at 64 registers (4 CTAs / SM) 463; 2 passes 500;
-            // 4 passes (130 registers) 548; 48 / 40 registers for 5 / 6 CTAs per SM 578 / 754 (spills); L2 evict_last on the
-            // table rows: no change.  DCNR_K1_PF selects the other builds for such experiments.
-            static const int forced_pf = [] {
-                const char *e = getenv("DCNR_K1_PF");
-                return e != nullptr ? atoi(e) : 0;
-            }();
-#define DCNR_LAUNCH_S(NVV, PFF) DCNR_LAUNCH_SM(NVV, PFF, 1)
-#define DCNR_LAUNCH_SM(NVV, PFF, MBB)                                                                                      \
-    do {                                                                                                                   \
-        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_embed_cross_fwd_staged<NVV, PFF, MBB>,                                      \
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));                   \
-        k_embed_cross_fwd_staged<NVV, PFF, MBB><<<grid_s, kThreads, smem_s, stream>>>(*ga, n_vec, mix0, B, ca, x0_out, ldx0,    \
-                                                                                 y_out, ldy, wf_cross, logit_part,         \
-                                                                                 err_flag);                                \
-    } while (0)
+            // 4 passes (130 registers) 548; 48 / 40 registers for 5 / 6 CTAs per SM 578 / 754 (spills).
 #define DCNR_CASE_S(NVV, PFF)                                                                                              \
     case NVV:                                                                                                              \
-        DCNR_LAUNCH_S(NVV, PFF);                                                                                           \
+        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_embed_cross_fwd_staged<NVV, PFF, 1>,                                        \
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_s));                   \
+        k_embed_cross_fwd_staged<NVV, PFF, 1><<<grid_s, kThreads, smem_s, stream>>>(*ga, n_vec, mix0, B, ca, x0_out, ldx0, \
+                                                                                  y_out, ldy, wf_cross, logit_part,        \
+                                                                                  err_flag);                               \
         break;
             switch (nv) {
-                case 1:
-                case 2:
-                    if (nv == 1) DCNR_LAUNCH_SM(1, 1, 4);
-                    else if (forced_pf == 8) DCNR_LAUNCH_S(2, 8);
-                    else if (forced_pf == 4) DCNR_LAUNCH_S(2, 4);
-                    else if (forced_pf == 24) DCNR_LAUNCH_SM(2, 2, 4);
-                    else if (forced_pf == 23) DCNR_LAUNCH_SM(2, 2, 3);
-                    else if (forced_pf == 15) DCNR_LAUNCH_SM(2, 1, 5);
-                    else if (forced_pf == 16) DCNR_LAUNCH_SM(2, 1, 6);
-                    else DCNR_LAUNCH_SM(2, 1, 4);
-                    break;
                 DCNR_CASE_S(3, 2) DCNR_CASE_S(4, 2) DCNR_CASE_S(5, 1) DCNR_CASE_S(6, 1) DCNR_CASE_S(7, 1) DCNR_CASE_S(8, 1)
             }
-#undef DCNR_LAUNCH_S
-#undef DCNR_LAUNCH_SM
 #undef DCNR_CASE_S
             DCNR_LAUNCHED();
             return DCNR_OK;
         }
     }
-    // rows per 8-lane group per iteration: narrow rows keep more gathers in flight (DCNR_K1_ROWS overrides: 1, 2 or 4)
-    static const int forced_rows = [] {
-        const char *e = getenv("DCNR_K1_ROWS");
-        return e != nullptr ? atoi(e) : 0;
-    }();
-    int rpi = 1;      // measured at 4 M rows (P0): 1 row 513 us, 2 rows 647 us, 4 rows 781 us -- the kernel is issue-bound
-    if (forced_rows == 1 || (forced_rows == 2 && nv <= 4) || (forced_rows == 4 && nv <= 2)) rpi = forced_rows;
-    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(B, kGroupsPerCta * rpi), (int64_t)sm_count() * 8);
-#define DCNR_LAUNCH(NVV, RR)                                                                                             \
-    k_embed_cross_fwd<NVV, RR><<<grid, kThreads, smem, stream>>>(*ga, x_in, ldx_in, B, ca, x0_out, ldx0, y_out, ldy,    \
-                                                                 wf_cross, logit_part, err_flag)
-#define DCNR_CASE_N(NVV)                                                                                                 \
-    case NVV:                                                                                                            \
-        if (rpi == 4) DCNR_LAUNCH(NVV, 4);                                                                               \
-        else if (rpi == 2) DCNR_LAUNCH(NVV, 2);                                                                          \
-        else DCNR_LAUNCH(NVV, 1);                                                                                        \
-        break;
-#define DCNR_CASE_M(NVV)                                                                                                 \
-    case NVV:                                                                                                            \
-        if (rpi == 2) DCNR_LAUNCH(NVV, 2);                                                                               \
-        else DCNR_LAUNCH(NVV, 1);                                                                                        \
-        break;
+    // element-wise form, one row per 8-lane group per iteration (measured at 4 M rows, P0: 1 row 513 us, 2 rows 647 us, 4 rows
+    // 781 us -- the kernel is issue-bound)
+    const unsigned grid = (unsigned)std::min<int64_t>(ceil_div(B, kGroupsPerCta), (int64_t)sm_count() * 8);
 #define DCNR_CASE(NVV)                                                                                                   \
     case NVV:                                                                                                            \
-        DCNR_LAUNCH(NVV, 1);                                                                                             \
+        k_embed_cross_fwd<NVV, 1><<<grid, kThreads, smem, stream>>>(*ga, x_in, ldx_in, B, ca, x0_out, ldx0, y_out, ldy,  \
+                                                                    wf_cross, logit_part, err_flag);                     \
         break;
     switch (nv) {
-        DCNR_CASE_N(1) DCNR_CASE_N(2) DCNR_CASE_M(3) DCNR_CASE_M(4) DCNR_CASE(5) DCNR_CASE(6) DCNR_CASE(7) DCNR_CASE(8)
+        DCNR_CASE(1) DCNR_CASE(2) DCNR_CASE(3) DCNR_CASE(4) DCNR_CASE(5) DCNR_CASE(6) DCNR_CASE(7) DCNR_CASE(8)
     }
-#undef DCNR_CASE_N
-#undef DCNR_CASE_M
-#undef DCNR_LAUNCH
 #undef DCNR_CASE
     DCNR_LAUNCHED();
     return DCNR_OK;

@@ -59,21 +59,6 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (!ok && spins > (1u << 24)) __trap();
     }
 }
-// Non-suspending poll (mbarrier.test_wait): for the MMA-issuing warp, whose barriers are usually complete when it asks and
-// whose waits sit on the tensor pipe's critical path (try_wait may park the thread for a time slice).
-__device__ __forceinline__ void mbar_wait_spin(uint32_t bar, uint32_t parity) {
-    uint32_t ok = 0;
-    for (uint32_t spins = 0; !ok; ++spins) {
-        asm volatile(
-            "{\n\t.reg .pred p;\n\t"
-            "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-            "selp.u32 %0, 1, 0, p;\n\t}"
-            : "=r"(ok)
-            : "r"(bar), "r"(parity)
-            : "memory");
-        if (!ok && spins > (1u << 26)) __trap();
-    }
-}
 // mbarrier wait that synchronises with arrivals from the other CTA of a pair (remote arrive / multicast commit)
 __device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
     uint32_t ok = 0;
@@ -147,11 +132,6 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t a_desc, uint
         ::"r"(tmem_d), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap *tm, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-                 ::"l"(reinterpret_cast<uint64_t>(tm)), "r"(c0), "r"(c1)
-                 : "memory");
-}
 // A operand from tensor memory (rows = TMEM lanes, K = 8 consecutive 32-bit columns), B from shared memory
 __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc,
                                              uint32_t accumulate) {
@@ -159,15 +139,6 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
-        ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
-        : "memory");
-}
-__device__ __forceinline__ void umma_tf32_ts_pair(uint32_t tmem_d, uint32_t tmem_a, uint64_t b_desc, uint32_t idesc,
-                                                  uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
         ::"r"(tmem_d), "r"(tmem_a), "l"(b_desc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
@@ -203,25 +174,15 @@ __device__ __forceinline__ void umma_commit_pair(uint32_t bar) {
         ::"r"(bar)
         : "memory");
 }
-// K-major, SWIZZLE_128B canonical layout: 8-row groups 1024 B apart (SBO), LBO unused (1), version 1.
-// bk = floats per k-block row: 32 -> 128-byte rows, SWIZZLE_128B, 8-row groups 1024 B apart;
-//                               16 ->  64-byte rows, SWIZZLE_64B,  8-row groups  512 B apart
-__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, int bk = 32) {
+// K-major, SWIZZLE_128B canonical layout (128-byte rows): 8-row groups 1024 B apart (SBO), LBO unused (1), version 1.
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
     uint64_t d = 0;
     d |= (uint64_t)((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
     d |= (uint64_t)1 << 16;                             // leading byte offset (ignored for swizzled K-major)
-    d |= (uint64_t)((8 * bk * 4) >> 4) << 32;           // stride byte offset, bits [32,46)
+    d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset, bits [32,46)
     d |= (uint64_t)1 << 46;                             // descriptor version (Blackwell)
-    d |= (uint64_t)(bk == 32 ? 2 : 4) << 61;            // layout type SWIZZLE_128B / SWIZZLE_64B
+    d |= (uint64_t)2 << 61;                             // layout type SWIZZLE_128B
     return d;
-}
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[32], int o) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-        ::"r"(taddr), "r"(r[o]), "r"(r[o + 1]), "r"(r[o + 2]), "r"(r[o + 3]), "r"(r[o + 4]), "r"(r[o + 5]), "r"(r[o + 6]),
-          "r"(r[o + 7]), "r"(r[o + 8]), "r"(r[o + 9]), "r"(r[o + 10]), "r"(r[o + 11]), "r"(r[o + 12]), "r"(r[o + 13]),
-          "r"(r[o + 14]), "r"(r[o + 15])
-        : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
     asm volatile(
@@ -239,25 +200,12 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 struct Params {
     int64_t M;
     int32_t N_total, K, block_n, terms, stages, acc_cols, acc_stages, corr_sep, tmem_cols;
-    int32_t bk;               // floats per k-block (32, or 16 with A in tensor memory: six finer pipeline stages)
     int32_t epi_slots;        // epilogue slots per warp (2 or 4)
     int32_t epi_depth;        // residual boxes requested this many chunks ahead (<= epi_slots - 1); the slot being refilled was
                               // stored epi_slots - epi_depth chunks ago, so that many TMA stores may still be reading
     int32_t epi_groups;       // 1: warps 6-9 drain the accumulator; 2: warps 10-13 as well (alternate 32-column chunks)
-    int32_t a_tmem, a_col0;   // TF32X3: A hi / lo in a tensor-memory ring (64 columns per stage) starting at column a_col0
-    const float *A_raw;       // a_ldg: the A matrix itself (row pitch lda floats): the split warps read their rows with LDG
-    int64_t lda;
-    int32_t a_ldg;            // fast form only: A bypasses shared memory (no TMA box, no shared-memory read by the split warps)
-    int32_t fast;             // default TF32X3 form (1 CTA, A in TMEM, pre-split weights): the weight boxes complete on "ready" too (ONE
-                              // wait per k-block in the issuing warp) and the next k-block's barrier is probed between the MMAs
-    int32_t one_arrive;       // A-in-TMEM split warps: one arrival per CTA on "ready" (named barrier among the four warps first)
-    int32_t b_local;          // pairs with A in tensor memory: each CTA's weight boxes land on its OWN barrier (plain TMA, no
-                              // .cta_group::2 completion on the leader); its A-split warps wait for them before arriving on "ready"
-    int32_t b_split;          // TF32X3: the weight arrives as raw fp32 and warps 10-13 split it in shared memory (half the L2 stream)
+    int32_t a_col0;           // TF32X3: the A hi / lo ring in tensor memory (64 columns per stage) starts at this column
     int32_t num_m_tiles, num_n_tiles;
-    long long *dbg;           // DCNR_GEMM_DEBUG bit 16: clock64 stamps of CTA 0's pipeline (first 64 k-blocks)
-    int32_t debug;            // timing experiments only (DCNR_GEMM_DEBUG): bit0 skip the split arithmetic, bit1 hi.hi MMA only,
-                              // bit2 skip the in-kernel weight split, bit3 skip the A split (tensor-memory form)
     float *C;                 // may be NULL when only the fused row dot is wanted
     int64_t ldc;
     GemmEpilogue epi;
@@ -265,7 +213,7 @@ struct Params {
     float *dot_out;           // [num_n_tiles * epi_groups][M] partial dots (summed by the caller)
 };
 
-constexpr int kThreadsP = 448;                      // warp 0 TMA, warp 1 MMA, warps 2-5 A split, warps 6-9 epilogue, warps 10-13 weight split
+constexpr int kThreadsP = 448;                      // warp 0 TMA, warp 1 MMA, warps 2-5 A split, warps 6-9 epilogue, warps 10-13 second epilogue group
 constexpr int kEpiSlotBytes = 32 * 32 * 4;          // one epilogue slot: 32 rows x 32 fp32 columns, 128B-swizzled
 constexpr int kEpiSlotsMax = 4;                     // slots per epilogue warp: 4 (residual prefetch depth 3) or 2 (one more operand stage)
 constexpr int kBarBytes = 512;                      // mbarriers + the TMEM base slot
@@ -281,9 +229,11 @@ constexpr int kBarBytes = 512;                      // mbarriers + the TMEM base
 // reads per CTA are halved.  The MMAs are issued by the leader CTA (cluster rank 0) only; barriers
 // that gate them (fullB, ready, tempty) live in the leader and are arrived on remotely by the peer;
 // barriers the leader releases (empty, tfull) are signalled in both CTAs by a multicast commit.
+// TF32X3 always runs single CTAs with the A operand in tensor memory (the 2-CTA and all-shared-memory TF32X3 forms were
+// measured slower in round 1 and are gone: profiles/r01_gemm_pipeline_timing.md); CTAS = 2 serves single-pass TF32.
 // HAD: Hadamard operand in the epilogue (DCN-v2 cross layer).  EXTRA: warps 10-13 exist (second epilogue group for short
-// reductions, or the in-kernel weight split).  Both are compiled OUT of the dense 256 x 256 layers: as run-time branches they
-// cost the epilogue-bound tf32 form 15-40 % (0.62 -> 0.72 -> 0.94 ms) and the tf32x3 form 3 %.
+// reductions).  Both are compiled OUT of the dense 256 x 256 layers: as run-time branches they cost the epilogue-bound
+// tf32 form 15-40 % (0.62 -> 0.72 -> 0.94 ms) and the tf32x3 form 3 %.
 template <int CTAS, bool HAD, bool EXTRA>
 __global__ void __launch_bounds__(EXTRA ? kThreadsP : 320, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmBhi,
@@ -296,11 +246,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
     const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
     const int bn_cta = p.block_n / CTAS;                 // weight rows staged by this CTA
-    const int bk = p.bk;                                 // floats per k-block
+    constexpr int bk = BLOCK_K;                          // floats per k-block
     const int a_tile_bytes = BLOCK_M * bk * 4;
     const int b_tile_bytes = bn_cta * bk * 4;
-    // stage: [A (raw -> hi)][A lo][B hi][B lo] (TF32X3), [A][B hi][B lo] (TF32X3 with A in tensor memory), [A][B] (TF32)
-    const int b_off = (p.terms == 3 && !p.a_tmem) ? 2 * a_tile_bytes : a_tile_bytes;
+    // stage: [A][B hi][B lo] (TF32X3: the raw A tile, split into tensor memory by warps 2-5), [A][B] (TF32)
+    const int b_off = a_tile_bytes;
     const int stage_bytes = b_off + (p.terms == 3 ? 2 : 1) * b_tile_bytes;
     const int stages = p.stages, acc_stages = p.acc_stages;
     uint8_t *epi_slots = smem + (size_t)stages * stage_bytes;            // 1024-aligned (stage sizes are multiples of 1 KB)
@@ -315,8 +265,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                    tempty0 = smem_u32(bars + 4 * stages + acc_stages),
                    rfull0 = smem_u32(bars + 4 * stages + 2 * acc_stages);
     // the same barriers in the leader CTA, as shared::cluster addresses (identity for CTAS == 1)
-    const uint32_t L_fullB0 = CTAS == 2 ? mapa(fullB0, 0) : fullB0, L_ready0 = CTAS == 2 ? mapa(ready0, 0) : ready0,
-                   L_tempty0 = CTAS == 2 ? mapa(tempty0, 0) : tempty0;
+    const uint32_t L_fullB0 = CTAS == 2 ? mapa(fullB0, 0) : fullB0, L_tempty0 = CTAS == 2 ? mapa(tempty0, 0) : tempty0;
     const int num_kb = p.K / bk;
     const int num_tiles = p.num_m_tiles * p.num_n_tiles;
     const int tile0 = blockIdx.x / CTAS, tile_step = gridDim.x / CTAS;
@@ -325,7 +274,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
         for (int s = 0; s < stages; ++s) {
             mbar_init(fullA0 + 8 * s, 1);
             mbar_init(fullB0 + 8 * s, 1);
-            mbar_init(ready0 + 8 * s, (p.one_arrive ? 1 : ((EXTRA && p.b_split) ? 8 : 4)) * CTAS + (p.fast ? 1 : 0));   // fast: + the producer's arrive.expect_tx   // one arrival per split warp (A; and the weight when b_split)
+            mbar_init(ready0 + 8 * s, 4 + 1);         // TF32X3: one arrival per A-split warp + the producer's arrive.expect_tx (weights)
             mbar_init(empty0 + 8 * s, 1);
         }
         for (int a = 0; a < acc_stages; ++a) {
@@ -377,38 +326,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     uint8_t *st = smem + (size_t)s * stage_bytes;
                     const uint32_t fb = L_fullB0 + 8 * s;
                     if (elect_one()) {
-                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64) p.dbg[it * 8 + 0] = clock64();
                     if (p.terms == 3) {
-                        // A lands on this CTA's own barrier (its split warps wait for it), the weight halves on the leader's
-                        if (!(p.debug & 32) && !p.a_ldg) {     // (bit 5: weight boxes first, then A -- issue-order experiment)
-                            mbar_expect_tx(fullA0 + 8 * s, (uint32_t)a_tile_bytes);
-                            tma_load_2d(smem_u32(st), &tmA, kb * bk, m0, fullA0 + 8 * s);
-                        }
-                        if (EXTRA && p.b_split) {
-                            // raw fp32 weight box onto this CTA's OWN barrier: its weight-split warps wait for it
-                            mbar_expect_tx(fullB0 + 8 * s, (uint32_t)b_tile_bytes);
-                            tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fullB0 + 8 * s);
-                        } else if (CTAS == 2 && p.b_local) {
-                            mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(2 * b_tile_bytes));
-                            tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fullB0 + 8 * s);
-                            tma_load_2d(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * bk, n0, fullB0 + 8 * s);
-                        } else if (CTAS == 2) {
-                            if (leader) mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(CTAS * 2 * b_tile_bytes));
-                            tma_load_2d_pair(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fb);
-                            tma_load_2d_pair(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * bk, n0, fb);
-                        } else if (p.fast) {                    // the weight boxes count on "ready" next to the split warps' arrivals
-                            mbar_expect_tx(ready0 + 8 * s, (uint32_t)(2 * b_tile_bytes));
-                            tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * bk, n0, ready0 + 8 * s);
-                            tma_load_2d(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * bk, n0, ready0 + 8 * s);
-                        } else {
-                            mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(2 * b_tile_bytes));
-                            tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * bk, n0, fb);
-                            tma_load_2d(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * bk, n0, fb);
-                        }
-                        if (p.debug & 32) {
-                            mbar_expect_tx(fullA0 + 8 * s, (uint32_t)a_tile_bytes);
-                            tma_load_2d(smem_u32(st), &tmA, kb * bk, m0, fullA0 + 8 * s);
-                        }
+                        // TF32X3 (single CTAs): A lands on its own barrier (the split warps wait for it); the pre-split weight
+                        // boxes count on "ready" next to the split warps' arrivals, so the issuing warp has ONE wait per k-block
+                        mbar_expect_tx(fullA0 + 8 * s, (uint32_t)a_tile_bytes);
+                        tma_load_2d(smem_u32(st), &tmA, kb * bk, m0, fullA0 + 8 * s);
+                        mbar_expect_tx(ready0 + 8 * s, (uint32_t)(2 * b_tile_bytes));
+                        tma_load_2d(smem_u32(st + b_off), &tmBhi, kb * bk, n0, ready0 + 8 * s);
+                        tma_load_2d(smem_u32(st + b_off + b_tile_bytes), &tmBlo, kb * bk, n0, ready0 + 8 * s);
                     } else {
                         if (leader) mbar_expect_tx(fullB0 + 8 * s, (uint32_t)(CTAS * (a_tile_bytes + b_tile_bytes)));
                         if (CTAS == 2) {
@@ -436,14 +361,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 if (CTAS == 2) umma_tf32_pair(d, a, b, idesc, acc);
                 else umma_tf32(d, a, b, idesc, acc);
             };
-            auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t acc) {
-                if (CTAS == 2) umma_tf32_ts_pair(d, a, b, idesc, acc);
-                else umma_tf32_ts(d, a, b, idesc, acc);
-            };
+            auto mma_ts = [&](uint32_t d, uint32_t a, uint64_t b, uint32_t acc) { umma_tf32_ts(d, a, b, idesc, acc); };
             uint32_t it = 0, tl = 0;
             int rs = 0; uint32_t rph = 0;      // running stage index / phase bit (no runtime division on the issue path)
             int ras = 0; uint32_t raph = 0;    // running accumulator stage / phase
-            if (CTAS == 1 && p.fast) {
+            if (p.terms == 3) {
                 // Default TF32X3 form.  The tensor pipe's queue is shallow: tcgen05.mma issue blocks on it, so whatever the issuing
                 // warp does between the last MMA of a k-block and the first of the next is dead time for the pipe (stamps: ~760 clk
                 // of a 1 530 clk k-block: two barrier waits of ~240 clk each although both had completed long before).  Here there
@@ -501,148 +423,41 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 }
             } else
             for (int t = tile0; t < num_tiles; t += tile_step, ++tl) {
+                // single-pass TF32: A and B from shared memory (single CTAs or 2-CTA pairs)
                 const int as = ras;
                 const uint32_t aph = raph;
                 if (++ras == acc_stages) { ras = 0; raph ^= 1u; }
                 wait_x(tempty0 + 8 * as, aph ^ 1);        // epilogues drained this accumulator
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t d_main = tmem_base + as * acc_stride, d_corr = d_main + corr_off;
+                const uint32_t d_main = tmem_base + as * acc_stride;
                 for (int kb = 0; kb < num_kb; ++kb, ++it) {
                     const int s = rs;
                     const uint32_t ph = rph;
                     if (++rs == stages) { rs = 0; rph ^= 1u; }
-                    if (CTAS == 1 && (p.debug & 64)) {            // experiment: non-suspending polls in the issuing warp
-                        if (!(EXTRA && p.b_split) && !p.b_local) mbar_wait_spin(fullB0 + 8 * s, ph);
-                        if (p.terms == 3) mbar_wait_spin(ready0 + 8 * s, ph);
-                    } else {
-                    if (!(EXTRA && p.b_split) && !p.b_local) wait_x(fullB0 + 8 * s, ph);       // else "ready" covers the weight tile too
-                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && lane == 0) p.dbg[it * 8 + 5] = clock64();
-                    if (p.terms == 3) wait_x(ready0 + 8 * s, ph);
-                    }
-                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && lane == 0) p.dbg[it * 8 + 7] = clock64();
+                    wait_x(fullB0 + 8 * s, ph);
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_hi = smem_u32(smem + (size_t)s * stage_bytes);
                     if (elect_one()) {
-                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64) p.dbg[it * 8 + 3] = clock64();
-                    if (p.terms == 3 && p.a_tmem) {
-                        // A hi / lo of this k-block sit in the TMEM ring slot the split warps just filled
-                        const uint32_t t_hi = tmem_base + (uint32_t)p.a_col0 + (uint32_t)(s * 2 * bk), t_lo = t_hi + (uint32_t)bk;
-                        const uint64_t db_hi = make_desc(a_hi + b_off, bk), db_lo = make_desc(a_hi + b_off + b_tile_bytes, bk);
-#pragma unroll 4
-                        for (int k = 0; k < bk / UMMA_K; ++k) {
-                            const uint64_t o = (uint64_t)(k * UMMA_K * 4 >> 4);
-                            const uint32_t tk = k * UMMA_K;
-                            if (p.debug & 2) {
-                                mma_ts(d_main, t_hi + tk, db_hi + o, (uint32_t)((kb | k) != 0));
-                                continue;
-                            }
-                            mma_ts(d_corr, t_lo + tk, db_hi + o, (kb | k) != 0);
-                            mma_ts(d_corr, t_hi + tk, db_lo + o, 1);
-                            mma_ts(d_main, t_hi + tk, db_hi + o, p.corr_sep ? (uint32_t)((kb | k) != 0) : 1u);
-                        }
-                    } else if (p.terms == 3) {
-                        const uint64_t da_hi = make_desc(a_hi), da_lo = make_desc(a_hi + a_tile_bytes);
-                        const uint64_t db_hi = make_desc(a_hi + 2 * a_tile_bytes), db_lo = make_desc(a_hi + 2 * a_tile_bytes + b_tile_bytes);
-#pragma unroll
-                        for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
-                            const uint64_t o = (uint64_t)(k * UMMA_K * 4 >> 4);
-                            if (p.debug & 2) {
-                                mma(d_main, da_hi + o, db_hi + o, (uint32_t)((kb | k) != 0));
-                                continue;
-                            }
-                            // lo terms first; with a separate accumulator (corr_sep) the long-running main sum
-                            // sees a third of the additions (the tensor core's fp32 accumulate truncates)
-                            mma(d_corr, da_lo + o, db_hi + o, (kb | k) != 0);
-                            mma(d_corr, da_hi + o, db_lo + o, 1);
-                            mma(d_main, da_hi + o, db_hi + o, p.corr_sep ? (uint32_t)((kb | k) != 0) : 1u);
-                        }
-                    } else {
                         const uint64_t da = make_desc(a_hi), db = make_desc(a_hi + a_tile_bytes);
 #pragma unroll
                         for (int k = 0; k < BLOCK_K / UMMA_K; ++k) {
                             const uint64_t o = (uint64_t)(k * UMMA_K * 4 >> 4);
                             mma(d_main, da + o, db + o, (kb | k) != 0);
                         }
-                    }
-                    if (CTAS == 2) umma_commit_pair(empty0 + 8 * s);
-                    else umma_commit(empty0 + 8 * s);
-                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64) p.dbg[it * 8 + 4] = clock64();
-                    if (kb == num_kb - 1) {                // same elected lane: the commit covers every MMA of this tile
-                        if (CTAS == 2) umma_commit_pair(tfull0 + 8 * as);
-                        else umma_commit(tfull0 + 8 * as);
-                    }
+                        if (CTAS == 2) umma_commit_pair(empty0 + 8 * s);
+                        else umma_commit(empty0 + 8 * s);
+                        if (kb == num_kb - 1) {                // same elected lane: the commit covers every MMA of this tile
+                            if (CTAS == 2) umma_commit_pair(tfull0 + 8 * as);
+                            else umma_commit(tfull0 + 8 * as);
+                        }
                     }
                     __syncwarp();
                 }
             }
         }
     } else if (warp < 6) {
-        // ---------------- warps 2..5: split the landed A tile into hi / lo (TF32X3) ----------------
-        if (CTAS == 1 && p.a_ldg) {
-            // A never touches shared memory: the thread that owns tile row r reads the 128 bytes of its row for a k-block
-            // straight from global memory (8 x LDG.128, one full line per lane), two k-blocks ahead in registers, splits
-            // them and writes hi / lo into the TMEM ring.  Shared-memory bandwidth is what bounds this kernel (TMA writes
-            // 48 KB + split reads 16 KB + MMA operand reads 48 KB + epilogue 32 KB per k-block against 128 B/clk); this
-            // removes the 16 KB TMA write and the 16 KB read of A.
-            const int quad = warp & 3;
-            const int r = quad * 32 + lane;
-            int rs = 0; uint32_t rph = 0;
-            // prefetch cursor (tile, k-block) runs two k-blocks ahead of the consume cursor
-            int pt = tile0, pkb = 0;
-            auto fetch = [&](float4 (&buf)[8]) {
-                if (pt < num_tiles) {
-                    const int64_t grow = (int64_t)(pt / p.num_n_tiles) * BLOCK_M + r;
-                    if (grow < p.M) {
-                        const float *src = p.A_raw + grow * p.lda + pkb * BLOCK_K;
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) buf[c] = ldg4(src + 4 * c);
-                    } else {
-#pragma unroll
-                        for (int c = 0; c < 8; ++c) buf[c] = make_float4(0.f, 0.f, 0.f, 0.f);
-                    }
-                }
-                if (++pkb == num_kb) { pkb = 0; pt += tile_step; }
-            };
-            auto consume = [&](const float4 (&buf)[8]) {
-                const int s = rs;
-                const uint32_t ph = rph;
-                if (++rs == stages) { rs = 0; rph ^= 1u; }
-                uint32_t hi[32], lo[32];
-#pragma unroll
-                for (int c = 0; c < 8; ++c) {
-                    const float e[4] = {buf[c].x, buf[c].y, buf[c].z, buf[c].w};
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        uint32_t u;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(e[q]));
-                        hi[4 * c + q] = u;
-                        lo[4 * c + q] = __float_as_uint(e[q] - __uint_as_float(u));
-                    }
-                }
-                mbar_wait(empty0 + 8 * s, ph ^ 1);             // the MMAs that read ring slot s (one trip ago) are done
-                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-                const uint32_t t_hi = tmem_base + (uint32_t)p.a_col0 + (uint32_t)(s * 2 * BLOCK_K) + ((uint32_t)(quad * 32) << 16);
-                tmem_st32(t_hi, hi);
-                tmem_st32(t_hi + 32u, lo);
-                asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                __syncwarp();
-                if (lane == 0) mbar_arrive(ready0 + 8 * s);
-            };
-            float4 b0[8], b1[8];
-            fetch(b0);
-            fetch(b1);
-            int64_t total = 0;
-            for (int t = tile0; t < num_tiles; t += tile_step) total += num_kb;
-            for (int64_t i = 0; i < total; i += 2) {
-                consume(b0);
-                fetch(b0);
-                if (i + 1 < total) {
-                    consume(b1);
-                    fetch(b1);
-                }
-            }
-        } else if (p.terms == 3 && p.a_tmem) {
+        // ---------------- warps 2..5: split the landed A tile into hi / lo in tensor memory (TF32X3) ----------------
+        if (p.terms == 3) {
             // One thread per tile row: it reads its 128-byte row of the k-block from the swizzled TMA tile (chunk c of
             // row r sits at position c ^ (r & 7): conflict-free), splits it and writes hi / lo straight into the TMEM
             // operand ring (tcgen05.st: lane = row).  No hi / lo tiles in shared memory and no shared-memory operand
@@ -658,140 +473,27 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     const uint32_t ph = rph;
                     if (++rs == stages) { rs = 0; rph ^= 1u; }
                     mbar_wait(fullA0 + 8 * s, ph);
-                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) p.dbg[it * 8 + 1] = clock64();
-                    // row pitch = the k-block width; chunk c of row r sits at c ^ (r & 7) (128-byte rows, SWIZZLE_128B) or at
-                    // c ^ ((r >> 1) & 3) (64-byte rows, SWIZZLE_64B): conflict-free either way
                     const uint8_t *row = smem + (size_t)s * stage_bytes + r * (bk * 4);
-                    const uint32_t sw = bk == 32 ? swz : (uint32_t)((r >> 1) & 3);
                     uint32_t hi[32], lo[32];
-                    if (p.debug & 8) {                     // timing experiment: no A split work (TMEM ring holds garbage)
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(ready0 + 8 * s);
-                        continue;
-                    }
 #pragma unroll
                     for (int c = 0; c < 8; ++c) {
-                        if (4 * c < bk) {
-                            const float4 v = *reinterpret_cast<const float4 *>(row + (((uint32_t)c ^ sw) << 4));
-                            const float e[4] = {v.x, v.y, v.z, v.w};
+                        const float4 v = *reinterpret_cast<const float4 *>(row + (((uint32_t)c ^ swz) << 4));
+                        const float e[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                uint32_t u;
-                                asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(e[q]));
-                                hi[4 * c + q] = u;
-                                lo[4 * c + q] = __float_as_uint(e[q] - __uint_as_float(u));
-                            }
-                        } else {
-#pragma unroll
-                            for (int q = 0; q < 4; ++q) hi[4 * c + q] = lo[4 * c + q] = 0u;
+                        for (int q = 0; q < 4; ++q) {
+                            uint32_t u;
+                            asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(e[q]));
+                            hi[4 * c + q] = u;
+                            lo[4 * c + q] = __float_as_uint(e[q] - __uint_as_float(u));
                         }
                     }
                     const uint32_t t_hi = tmem_base + (uint32_t)p.a_col0 + (uint32_t)(s * 2 * bk) + ((uint32_t)(quad * 32) << 16);
-                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) p.dbg[it * 8 + 6] = clock64();
-                    if (bk == 32) {
-                        tmem_st32(t_hi, hi);
-                        tmem_st32(t_hi + 32u, lo);
-                    } else {
-                        tmem_st16(t_hi, hi, 0);
-                        tmem_st16(t_hi + 16u, lo, 0);
-                    }
+                    tmem_st32(t_hi, hi);
+                    tmem_st32(t_hi + 32u, lo);
                     asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
-                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && threadIdx.x == 64) p.dbg[it * 8 + 2] = clock64();
                     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
-                    if (p.b_local) mbar_wait(fullB0 + 8 * s, ph);          // this CTA's weight boxes have landed too
-                    if (p.one_arrive) {
-                        asm volatile("bar.sync 1, 128;" ::: "memory");       // the four split warps
-                        if (warp == 2 && lane == 0) {
-                            if (CTAS == 2) mbar_arrive_cluster(L_ready0 + 8 * s);
-                            else mbar_arrive(ready0 + 8 * s);
-                        }
-                    } else {
-                        __syncwarp();
-                        if (lane == 0) {
-                            if (CTAS == 2) mbar_arrive_cluster(L_ready0 + 8 * s);
-                            else mbar_arrive(ready0 + 8 * s);
-                        }
-                    }
-                }
-            }
-        } else if (p.terms == 3) {
-            const int tt = threadIdx.x - 64;               // 0..127
-            uint32_t it = 0;
-            int rs = 0; uint32_t rph = 0;
-            for (int t = tile0; t < num_tiles; t += tile_step) {
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = rs;
-                    const uint32_t ph = rph;
-                    if (++rs == stages) { rs = 0; rph ^= 1u; }
-                    mbar_wait(fullA0 + 8 * s, ph);
-                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && tt == 0) p.dbg[it * 8 + 1] = clock64();
-                    float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * stage_bytes);
-                    float4 *lo = hi + a_tile_bytes / 16;
-#pragma unroll
-                    for (int i = 0; i < a_tile_bytes / 16 / 128; ++i) {
-                        if (p.debug & 1) break;
-                        const float4 v = hi[tt + 128 * i];
-                        float4 h, l;
-                        uint32_t u;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
-                        hi[tt + 128 * i] = h;
-                        lo[tt + 128 * i] = l;
-                    }
-                    // every lane publishes its writes to the async proxy, then one lane per warp arrives
-                    // (128 remote arrivals per k-block from the peer CTA were a measurable part of the hop)
-                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && tt == 0) p.dbg[it * 8 + 6] = clock64();
-                    if (CTAS == 2) asm volatile("fence.proxy.async;" ::: "memory");
-                    else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    if ((p.debug & 16) && blockIdx.x == 0 && it < 64 && tt == 0) p.dbg[it * 8 + 2] = clock64();
                     __syncwarp();
-                    if (lane == 0) {
-                        if (CTAS == 2) mbar_arrive_cluster(L_ready0 + 8 * s);
-                        else mbar_arrive(ready0 + 8 * s);
-                    }
-                }
-            }
-        }
-    } else if (EXTRA && warp >= 10 && p.epi_groups == 1) {
-        // ---------------- warps 10..13: split the landed raw weight tile into hi / lo in shared memory (b_split) ----------------
-        // The weight stream from L2 was the larger half of the kernel's L2 -> SM traffic (hi + lo boxes: 32 of 64 KB per
-        // k-block at ~42 B/clk/SM); loading fp32 once and splitting here halves it.  Elementwise, so the swizzle is irrelevant;
-        // consecutive threads touch consecutive 16-byte cells (conflict-free).
-        if (p.terms == 3 && p.b_split) {
-            const int tt = threadIdx.x - 320;              // 0..127
-            const int cells = b_tile_bytes / 16;
-            uint32_t it = 0;
-            int rs = 0; uint32_t rph = 0;
-            for (int t = tile0; t < num_tiles; t += tile_step) {
-                for (int kb = 0; kb < num_kb; ++kb, ++it) {
-                    const int s = rs;
-                    const uint32_t ph = rph;
-                    if (++rs == stages) { rs = 0; rph ^= 1u; }
-                    mbar_wait(fullB0 + 8 * s, ph);
-                    float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * stage_bytes + b_off);
-                    float4 *lo = hi + cells;
-#pragma unroll 4
-                    for (int i = tt; i < cells; i += 128) {
-                        if (p.debug & 4) break;            // timing experiment: no weight split work
-                        const float4 v = hi[i];
-                        float4 h, l;
-                        uint32_t u;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.y)); h.y = __uint_as_float(u); l.y = v.y - h.y;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.z)); h.z = __uint_as_float(u); l.z = v.z - h.z;
-                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.w)); h.w = __uint_as_float(u); l.w = v.w - h.w;
-                        hi[i] = h;
-                        lo[i] = l;
-                    }
-                    if (CTAS == 2) asm volatile("fence.proxy.async;" ::: "memory");
-                    else asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-                    __syncwarp();
-                    if (lane == 0) {
-                        if (CTAS == 2) mbar_arrive_cluster(L_ready0 + 8 * s);
-                        else mbar_arrive(ready0 + 8 * s);
-                    }
+                    if (lane == 0) mbar_arrive(ready0 + 8 * s);
                 }
             }
         }
@@ -844,7 +546,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
             const int m0 = (t / p.num_n_tiles) * (BLOCK_M * CTAS) + (int)rank * BLOCK_M;
             const int n_tile = t % p.num_n_tiles, n0 = n_tile * p.block_n;
             wait_x(tfull0 + 8 * as, aph);
-            if ((p.debug & 16) && blockIdx.x == 0 && tl < 8 && threadIdx.x == 192) p.dbg[512 + tl * 2] = clock64();
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const int mw = m0 + quad * 32;                  // first row of this warp
             const float *had_row = (has_had && (int64_t)mw + lane < p.M)
@@ -856,8 +557,6 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                 const uint32_t slph = rsph;
                 if (++rsl == kEpiSlots) { rsl = 0; rsph ^= 1u; }
                 uint8_t *row = slots + sl * kEpiSlotBytes + lane * 128;
-                const bool stamp = (p.debug & 16) && blockIdx.x == 0 && threadIdx.x == 192 && g >= 16 && g < 48;
-                if (stamp) p.dbg[600 + (g - 16) * 6 + 0] = clock64();
                 if (has_res) {
                     mbar_wait(rf0 + 8 * sl, slph);
                 } else if (has_c) {                         // the store that last used this slot has finished reading it
@@ -867,10 +566,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                     __syncwarp();
                 }
-                if (stamp) p.dbg[600 + (g - 16) * 6 + 1] = clock64();
                 uint32_t r[32];
                 tmem_ld32(t_main + (uint32_t)c0, r);
-                if (stamp) p.dbg[600 + (g - 16) * 6 + 2] = clock64();
                 if (p.corr_sep) {
                     uint32_t r2[32];
                     tmem_ld32(t_main + corr_off + (uint32_t)c0, r2);
@@ -903,10 +600,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                     }
                     if (has_c) *cell = v;
                 }
-                if (stamp) p.dbg[600 + (g - 16) * 6 + 3] = clock64();
                 if (has_c) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                 __syncwarp();
-                if (stamp) p.dbg[600 + (g - 16) * 6 + 4] = clock64();
                 if (lane == 0) {
                     if (has_c) {
                         tma_store_2d(&tmC, smem_u32(slots + sl * kEpiSlotBytes), n0 + c0, mw);
@@ -920,9 +615,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
                         issue_res_load();
                     }
                 }
-                if (stamp) p.dbg[600 + (g - 16) * 6 + 5] = clock64();
             }
-            if ((p.debug & 16) && blockIdx.x == 0 && tl < 8 && threadIdx.x == 192) p.dbg[512 + tl * 2 + 1] = clock64();
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) {                                // one arrival per epilogue warp frees the accumulator stage
@@ -949,20 +642,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUten
 
 // hi = rn_tf32(x), lo = x - hi  (exact).  One pass over the layer weight per call.
 __global__ void k_split_tf32(const float *__restrict__ src, int64_t lds, float *__restrict__ hi, float *__restrict__ lo,
-                             int rows, int cols, bool raw) {
+                             int rows, int cols) {
     const int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (e >= (int64_t)rows * cols) return;
     const int r = (int)(e / cols), c = (int)(e % cols);
     const float v = src[(int64_t)r * lds + c];
     uint32_t u;
     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-    const float h = raw ? v : __uint_as_float(u);
+    const float h = __uint_as_float(u);
     hi[e] = h;
     if (lo != nullptr) lo[e] = v - h;
 }
 // Transposed variant for dgrad: out[c][r] from src[r][c].
 __global__ void k_transpose_split_tf32(const float *__restrict__ src, int64_t lds, float *__restrict__ hi,
-                                       float *__restrict__ lo, int rows, int cols, bool raw) {
+                                       float *__restrict__ lo, int rows, int cols) {
     __shared__ float tile[32][33];
     const int c0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
     for (int i = threadIdx.y; i < 32; i += blockDim.y) {
@@ -976,7 +669,7 @@ __global__ void k_transpose_split_tf32(const float *__restrict__ src, int64_t ld
             const float v = tile[threadIdx.x][i];
             uint32_t u;
             asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
-            const float h = raw ? v : __uint_as_float(u);
+            const float h = __uint_as_float(u);
             hi[(int64_t)c * rows + r] = h;
             if (lo != nullptr) lo[(int64_t)c * rows + r] = v - h;
         }
@@ -1000,7 +693,7 @@ static EncodeTiledFn encode_fn() {
 }
 
 static int make_map(CUtensorMap *tm, const float *base, int64_t rows, int64_t cols, int64_t ld, int box_rows,
-                    int box_cols = BLOCK_K) {       // box_cols 32 -> SWIZZLE_128B, 16 -> SWIZZLE_64B
+                    int box_cols = BLOCK_K) {       // 32-float (128-byte) box rows, SWIZZLE_128B
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) {
         set_error("cuTensorMapEncodeTiled entry point not available");
@@ -1011,7 +704,7 @@ static int make_map(CUtensorMap *tm, const float *base, int64_t rows, int64_t co
     cuuint32_t box[2] = {(cuuint32_t)box_cols, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, box_cols == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): rows %lld cols %lld ld %lld", (int)r, (long long)rows,
@@ -1026,51 +719,24 @@ static int pick_block_n(int64_t n, int cap = 256) {
         if (n % bn == 0) return bn;
     return 0;
 }
-// TF32X3 takes the A operand from tensor memory (128-column tiles, single CTAs): measured 0.79 ms per 1 M x 256 x 256
-// layer against 0.89 ms for the all-shared-memory 2-CTA form, which DCNR_GEMM_ATMEM=0 selects.
-static bool atmem_enabled() {
-    static const bool on = [] {
-        const char *e = getenv("DCNR_GEMM_ATMEM");
-        return e == nullptr || atoi(e) != 0;
-    }();
-    return on;
-}
-static int block_n_for(int precision, int64_t n) {
-    return pick_block_n(n, (precision == DCNR_PREC_TF32X3 && atmem_enabled()) ? 128 : 256);
-}
+// TF32X3 takes the A operand from tensor memory: 128-column tiles (2 x 128 accumulator columns + the operand ring), single
+// CTAs.  Single-pass TF32 runs 256-column tiles on 2-CTA pairs.
+static int block_n_for(int precision, int64_t n) { return pick_block_n(n, precision == DCNR_PREC_TF32X3 ? 128 : 256); }
 
 }  // namespace tc
-
-// TF32X3 weight operands: pre-split hi / lo streamed by TMA (default), or raw fp32 split inside the GEMM by warps 10-13
-// (DCNR_GEMM_BSPLIT=1).  Measured on the 1 M x 256 x 256 layer: 0.81 ms pre-split, 0.88-0.91 ms split in-kernel, and 0.82 ms
-// with the in-kernel split's work skipped -- halving the weight stream from L2 buys nothing (L2 -> SM bandwidth is not the
-// limiter) and the extra shared-memory traffic of the split costs 8 %.
-bool gemm_tc_raw_weights() {
-    static const bool on = [] {
-        const char *e = getenv("DCNR_GEMM_BSPLIT");
-        return e != nullptr && atoi(e) != 0;
-    }();
-    return on;
-}
 
 // Epilogue warp groups: two (eight warps) for short reductions (k <= 64: the initial layer is epilogue-bound with four
 // warps -- 0.34 vs 0.43-0.54 ms per 1 M x 256 x 64), one otherwise (measured on the 256 x 256 layers: 0.83 vs 0.81 ms tf32x3,
 // 0.67 vs 0.62 ms tf32 -- the mainloop, not the epilogue, sets the pace there).  Also one when the tile has an odd number
-// of 32-column chunks or warps 10-13 split the weight (DCNR_GEMM_BSPLIT=1).  DCNR_GEMM_EPI_GROUPS=1|2 forces a choice.
-static int epi_groups_for(int block_n, int precision, int64_t k) {
-    static const int forced = [] {
-        const char *e = getenv("DCNR_GEMM_EPI_GROUPS");
-        return e != nullptr ? atoi(e) : 0;
-    }();
-    if (forced == 1 || block_n <= 0 || (block_n / 32) % 2 != 0) return 1;
-    if (precision == DCNR_PREC_TF32X3 && gemm_tc_raw_weights()) return 1;
-    if (forced == 2) return 2;
+// of 32-column chunks.
+static int epi_groups_for(int block_n, int64_t k) {
+    if (block_n <= 0 || (block_n / 32) % 2 != 0) return 1;
     return k <= 64 ? 2 : 1;
 }
 
 int gemm_tc_n_tiles(int64_t n, int precision, int64_t k) {      // partial row dots a FusedDot produces: column tiles x epilogue groups
     const int bn = tc::block_n_for(precision, n);
-    return bn > 0 ? (int)(n / bn) * epi_groups_for(bn, precision, k) : 1;
+    return bn > 0 ? (int)(n / bn) * epi_groups_for(bn, k) : 1;
 }
 
 bool gemm_tc_supported(int precision, bool a_kmajor, bool b_kmajor, int64_t lda, int64_t ldb, int64_t ldc, int64_t m,
@@ -1083,15 +749,14 @@ bool gemm_tc_supported(int precision, bool a_kmajor, bool b_kmajor, int64_t lda,
 }
 
 int launch_split_tf32(const float *src, int64_t lds, float *hi, float *lo, int32_t rows, int32_t cols, bool transpose,
-                      cudaStream_t stream, bool raw) {
-    if (raw) lo = nullptr;
+                      cudaStream_t stream) {
     if (rows <= 0 || cols <= 0) return DCNR_OK;
     if (transpose) {
         dim3 grid((unsigned)ceil_div(cols, 32), (unsigned)ceil_div(rows, 32)), block(32, 8);
-        tc::k_transpose_split_tf32<<<grid, block, 0, stream>>>(src, lds, hi, lo, rows, cols, raw);
+        tc::k_transpose_split_tf32<<<grid, block, 0, stream>>>(src, lds, hi, lo, rows, cols);
     } else {
         const int64_t total = (int64_t)rows * cols;
-        tc::k_split_tf32<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(src, lds, hi, lo, rows, cols, raw);
+        tc::k_split_tf32<<<(unsigned)ceil_div(total, 256), 256, 0, stream>>>(src, lds, hi, lo, rows, cols);
     }
     DCNR_LAUNCHED();
     return DCNR_OK;
@@ -1106,7 +771,7 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     DCNR_REQUIRE(gemm_tc_supported(precision, a_kmajor, b_kmajor, lda, ldb, ldc, m, n, k, split_k),
                  "shape not supported by the tcgen05 GEMM");
     const int terms = precision == DCNR_PREC_TF32X3 ? 3 : 1;
-    // TF32X3: B_lo == NULL means B is the RAW fp32 weight and the kernel splits it (gemm_tc_raw_weights())
+    DCNR_REQUIRE(terms == 1 || B_lo != nullptr, "TF32X3 needs the pre-split weight (launch_split_tf32)");
     DCNR_REQUIRE((((uintptr_t)A | (uintptr_t)B | (uintptr_t)C | (uintptr_t)B_lo | (uintptr_t)dot_w) & 15) == 0,
                  "operands must be 16-byte aligned");
     DCNR_REQUIRE(C != nullptr || (dot_w != nullptr && dot_out != nullptr), "no output requested");
@@ -1117,89 +782,38 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     DCNR_REQUIRE((epi.bias == nullptr || ((uintptr_t)epi.bias & 15) == 0) &&
                      (epi.col_scale == nullptr || ((uintptr_t)epi.col_scale & 15) == 0),
                  "bias / col_scale must be 16-byte aligned");
-    Params p;
+    Params p{};
     p.M = m; p.N_total = (int32_t)n; p.K = (int32_t)k;
     p.block_n = block_n_for(precision, n);
     p.terms = terms;
-    p.a_tmem = (terms == 3 && atmem_enabled()) ? 1 : 0;
-    p.a_col0 = 0;
-    p.b_split = (terms == 3 && B_lo == nullptr) ? 1 : 0;
-    static const int b_local_env = [] {
-        const char *e = getenv("DCNR_GEMM_BLOCAL");
-        return e != nullptr ? atoi(e) : 0;
-    }();
-    p.b_local = 0;
-    static const int one_arrive_env = [] {
-        const char *e = getenv("DCNR_GEMM_ONE_ARRIVE");
-        return e != nullptr ? atoi(e) : 0;
-    }();
-    p.one_arrive = (p.a_tmem && !p.b_split && one_arrive_env) ? 1 : 0;
-    static const bool fast_env = [] {               // DCNR_GEMM_FAST=0: the generic issue loop (two barriers per k-block)
-        const char *e = getenv("DCNR_GEMM_FAST");
-        return e == nullptr || atoi(e) != 0;
-    }();
-    p.fast = 0;
-    p.epi_groups = p.b_split ? 1 : epi_groups_for(p.block_n, precision, k);
-    static const int forced_bk = [] {
-        const char *e = getenv("DCNR_GEMM_BK");
-        return e != nullptr ? atoi(e) : 0;
-    }();
-    // 64-byte k-blocks (DCNR_GEMM_BK=16: six pipeline stages instead of three) are implemented and parity-clean but measured
-    // slower (1.15 vs 0.79 ms): the weight boxes become 64-byte rows and their TMA loads, not the A path, set the pace
-    p.bk = (p.a_tmem && forced_bk == 16) ? 16 : BLOCK_K;
+    p.epi_groups = epi_groups_for(p.block_n, k);
     p.C = C; p.ldc = ldc; p.epi = epi;
     p.dot_w = dot_w; p.dot_out = dot_out;
-    static const int debug_bits = [] {
-        const char *e = getenv("DCNR_GEMM_DEBUG");
-        return e != nullptr ? atoi(e) : 0;
-    }();
-    p.debug = debug_bits;
-    p.dbg = nullptr;
-    static long long *dbg_buf = nullptr;
-    if (debug_bits & 16) {
-        if (dbg_buf == nullptr) cudaMalloc(&dbg_buf, 1024 * sizeof(long long));
-        cudaMemsetAsync(dbg_buf, 0, 1024 * sizeof(long long), stream);
-        p.dbg = dbg_buf;
-    }
     p.acc_cols = 32;
     while (p.acc_cols < p.block_n) p.acc_cols <<= 1;
     p.num_n_tiles = (int32_t)(n / p.block_n);
 
-    // CTA pairs (2-CTA MMA) whenever the tile splits evenly and a pair has work; DCNR_GEMM_CTAS=1 forces single CTAs
-    static const int forced_ctas = [] {
-        const char *e = getenv("DCNR_GEMM_CTAS");
-        return e != nullptr ? atoi(e) : 0;
-    }();
-    int ctas = m > BLOCK_M ? 2 : 1;
-    if (forced_ctas == 1 || (p.a_tmem && forced_ctas != 2)) ctas = 1;     // A-in-TMEM: pairs measured slower (1.06 vs 0.79 ms)
+    // TF32X3: single CTAs (A in tensor memory); single-pass TF32: 2-CTA pairs whenever a pair has work
+    int ctas = (terms == 1 && m > BLOCK_M) ? 2 : 1;
     int max_pairs = 0;
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute attr[1];
     auto plan = [&](int c, size_t *smem_out) {
-        const int b_bytes = (p.block_n / c) * p.bk * 4;
-        const int stage_bytes = ((terms == 3 && !p.a_tmem) ? 2 : 1) * BLOCK_M * p.bk * 4 + (terms == 3 ? 2 : 1) * b_bytes;
+        const int b_bytes = (p.block_n / c) * BLOCK_K * 4;
+        const int stage_bytes = BLOCK_M * BLOCK_K * 4 + (terms == 3 ? 2 : 1) * b_bytes;
         // four epilogue slots per warp (residual prefetch depth 3) unless two slots buy another operand stage
-        static const int forced_slots = [] {
-            const char *e = getenv("DCNR_GEMM_EPI_SLOTS");
-            return e != nullptr ? atoi(e) : 0;
-        }();
-        const int cap = p.a_tmem ? 256 / (2 * p.bk) : 6;
+        const int cap = terms == 3 ? 256 / (2 * BLOCK_K) : 6;
         auto stages_for = [&](int slots) {
             const int budget = 227 * 1024 - 1024 - kBarBytes - 4 * p.epi_groups * slots * kEpiSlotBytes;
             return std::max(1, std::min(cap, budget / stage_bytes));
         };
         // eight epilogue warps take two slots each (the same 64 KB as four warps x four slots)
-        p.epi_slots = (forced_slots == 2 || forced_slots == 4) ? forced_slots
-                      : (p.epi_groups == 2 || (stages_for(2) > stages_for(4) && p.a_tmem) ? 2 : 4);
+        p.epi_slots = (p.epi_groups == 2 || (stages_for(2) > stages_for(4) && terms == 3)) ? 2 : 4;
         p.stages = stages_for(p.epi_slots);
-        static const int forced_depth = [] {
-            const char *e = getenv("DCNR_GEMM_EPI_DEPTH");
-            return e != nullptr ? atoi(e) : 0;
-        }();
-        p.epi_depth = (forced_depth >= 1 && forced_depth < p.epi_slots) ? forced_depth : p.epi_slots - 1;
+        p.epi_depth = p.epi_slots - 1;
         *smem_out = (size_t)p.stages * stage_bytes + 1024 + kBarBytes + 4 * p.epi_groups * p.epi_slots * kEpiSlotBytes;
-        // tensor memory: accumulator stage(s) first, then (A in TMEM) the operand ring, 64 columns (hi | lo) per stage
-        const int ring_cols = p.a_tmem ? p.stages * 2 * p.bk : 0;
+        // tensor memory: accumulator stage(s) first, then (TF32X3) the operand ring, 64 columns (hi | lo) per stage
+        const int ring_cols = terms == 3 ? p.stages * 2 * BLOCK_K : 0;
         // TF32X3: the lo.hi / hi.lo terms ALWAYS get their own accumulator.  The tensor core's fp32 accumulate truncates toward
         // zero (profiles/r02_acc_probe.md: -0.8 eps per K = 8 step on same-sign sums), so every addition into the long-running
         // main sum costs up to one ulp of that sum whatever the size of the addend; with the 2^-11-sized correction terms kept
@@ -1212,9 +826,9 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
         p.tmem_cols = 32;
         while (p.tmem_cols < p.a_col0 + ring_cols) p.tmem_cols <<= 1;
     };
-    // warps 10-13 exist only when they have a role (second epilogue group, in-kernel weight split): with 2-CTA pairs four
-    // idle warps per CTA measured 16 % slower (tf32, 1 M x 256 x 256: 0.72 vs 0.62 ms)
-    const unsigned threads = (p.b_split || p.epi_groups == 2) ? kThreadsP : 320u;
+    // warps 10-13 exist only when they have a role (second epilogue group): with 2-CTA pairs four idle warps per CTA
+    // measured 16 % slower (tf32, 1 M x 256 x 256: 0.72 vs 0.62 ms)
+    const unsigned threads = p.epi_groups == 2 ? kThreadsP : 320u;
     const bool had = epi.hadamard != nullptr, extra = threads == (unsigned)kThreadsP;
     typedef void (*KernFn)(const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, const CUtensorMap, Params);
     const KernFn kern1 = had ? (extra ? k_gemm_tc<1, true, true> : k_gemm_tc<1, true, false>)
@@ -1222,7 +836,6 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     const KernFn kern2 = had ? (extra ? k_gemm_tc<2, true, true> : k_gemm_tc<2, true, false>)
                              : (extra ? k_gemm_tc<2, false, true> : k_gemm_tc<2, false, false>);
     size_t smem = 0;
-    p.b_local = (ctas == 2 && p.a_tmem && !p.b_split && b_local_env) ? 1 : 0;
     if (ctas == 2) {
         plan(2, &smem);
         DCNR_CUDA_CHECK(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1238,26 +851,16 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
             ctas = 1;
         }
     }
-    if (ctas != 2) p.b_local = 0;
-    p.fast = (ctas == 1 && terms == 3 && p.a_tmem && !p.b_split && p.bk == BLOCK_K && !p.one_arrive && fast_env &&
-              debug_bits == 0) ? 1 : 0;             // any DCNR_GEMM_DEBUG experiment runs the generic loop
-    static const bool a_ldg_env = [] {              // DCNR_GEMM_ALDG=1: A straight from global memory in the split warps
-        const char *e = getenv("DCNR_GEMM_ALDG");
-        return e != nullptr && atoi(e) != 0;
-    }();
-    p.a_ldg = (p.fast && a_ldg_env) ? 1 : 0;
-    p.A_raw = A;
-    p.lda = lda;
     CUtensorMap tmA, tmBhi, tmBlo, tmR, tmC;
-    DCNR_TRY(make_map(&tmA, A, m, k, lda, BLOCK_M, p.bk));
+    DCNR_TRY(make_map(&tmA, A, m, k, lda, BLOCK_M));
     // epilogue boxes: 32 rows x 32 columns of the residual / output (rows and columns past the matrix are
     // zero-filled on load and clipped on store)
     if (C != nullptr) DCNR_TRY(make_map(&tmC, C, m, n, ldc, 32, 32));
     else tmC = tmA;                                  // never dereferenced
     if (epi.residual != nullptr) DCNR_TRY(make_map(&tmR, epi.residual, m, n, epi.ldr, 32, 32));
     else tmR = tmA;
-    DCNR_TRY(make_map(&tmBhi, B, n, k, ldb, p.block_n / ctas, p.bk));
-    DCNR_TRY(make_map(&tmBlo, (terms == 3 && B_lo != nullptr) ? B_lo : B, n, k, ldb, p.block_n / ctas, p.bk));
+    DCNR_TRY(make_map(&tmBhi, B, n, k, ldb, p.block_n / ctas));
+    DCNR_TRY(make_map(&tmBlo, terms == 3 ? B_lo : B, n, k, ldb, p.block_n / ctas));
     p.num_m_tiles = (int32_t)ceil_div(m, BLOCK_M * ctas);
     const int64_t num_tiles = (int64_t)p.num_m_tiles * p.num_n_tiles;
     gemm_timer_before(stream, 2.0 * (double)m * (double)n * (double)k);
@@ -1272,29 +875,6 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     }
     gemm_timer_after(stream);
     DCNR_LAUNCHED();
-    if (debug_bits & 16) {              // timing experiment: dump the stamps of the first two launches
-        static int dumps = 0;
-        if (dumps++ < 2) {
-            long long h[1024];
-            cudaStreamSynchronize(stream);
-            cudaMemcpy(h, dbg_buf, sizeof(h), cudaMemcpyDeviceToHost);
-            const long long t0 = h[0];
-            fprintf(stderr, "block_n %d stages %d a_tmem %d | it: TMA issue | +landed | +split loads/math | +st or fence | MMA start | issue done\n",
-                    p.block_n, p.stages, p.a_tmem);
-            for (int i = 8; i < 40; ++i)
-                fprintf(stderr, "%2d: %8lld  +%6lld  +%6lld  +%6lld  mma@%8lld  +%5lld | weights seen @%8lld  A ready seen @%8lld\n", i,
-                        h[i * 8] - t0, h[i * 8 + 1] - h[i * 8], h[i * 8 + 6] - h[i * 8 + 1], h[i * 8 + 2] - h[i * 8 + 6], h[i * 8 + 3] - t0,
-                        h[i * 8 + 4] - h[i * 8 + 3], h[i * 8 + 5] - t0, h[i * 8 + 7] - t0);
-            for (int t = 0; t < 8; ++t)
-                fprintf(stderr, "epilogue tile %d: start %8lld  took %6lld\n", t, h[512 + 2 * t] - t0, h[512 + 2 * t + 1] - h[512 + 2 * t]);
-            fprintf(stderr, "epilogue chunk: start | slot wait | tmem ld | math+sts | fence | store/prefetch\n");
-            for (int c = 0; c < 32; ++c) {
-                const long long *e = h + 600 + c * 6;
-                fprintf(stderr, "%2d: %8lld  +%5lld +%5lld +%5lld +%5lld +%5lld\n", c + 16, e[0] - t0, e[1] - e[0], e[2] - e[1], e[3] - e[2],
-                        e[4] - e[3], e[5] - e[4]);
-            }
-        }
-    }
     return DCNR_OK;
 }
 

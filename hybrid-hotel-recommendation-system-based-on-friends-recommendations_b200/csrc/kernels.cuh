@@ -63,23 +63,20 @@ int launch_gemm_simt(const float *A, int64_t lda, bool a_kmajor, const float *B,
 
 bool gemm_tc_supported(int precision, bool a_kmajor, bool b_kmajor, int64_t lda, int64_t ldb, int64_t ldc, int64_t m,
                        int64_t n, int64_t k, int split_k);
-// TF32X3: B is the tf32-rounded (hi) half of the weight and B_lo its exact remainder (launch_split_tf32), or B is the raw
-// fp32 weight and B_lo NULL (the kernel splits the weight tiles itself)
+// TF32X3: B is the tf32-rounded (hi) half of the weight and B_lo its exact remainder (launch_split_tf32)
 int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, const float *B, int64_t ldb, bool b_kmajor,
                    float *C, int64_t ldc, int64_t m, int64_t n, int64_t k, int split_k, const GemmEpilogue &epi,
                    cudaStream_t stream, const float *B_lo, const float *dot_w = nullptr, float *dot_out = nullptr);
 int gemm_tc_n_tiles(int64_t n, int precision, int64_t k);   // partial row dots per row a FusedDot gets for an [n, k] layer
 // hi = rn_tf32(src), lo = src - hi, dense [rows, cols] (or transposed: [cols, rows]); lo may be NULL when transposing
 int launch_split_tf32(const float *src, int64_t lds, float *hi, float *lo, int32_t rows, int32_t cols, bool transpose,
-                      cudaStream_t stream, bool raw = false);      // raw: plain (transposed) copy into `hi`, no `lo`
+                      cudaStream_t stream);
 // A pre-processed weight operand for the tensor-core path: `w` [n, k] row-major dense (ld = k).
 struct WeightOp {
-    const float *hi;   // tf32-rounded weight (TF32X3, pre-split form) or the raw weight (other precisions, and TF32X3 with `raw`)
-    const float *lo;   // remainder (TF32X3 pre-split form only), else NULL
+    const float *hi;   // tf32-rounded weight (TF32X3) or the (transposed) weight itself (TF32)
+    const float *lo;   // exact remainder (TF32X3), else NULL
     int64_t ld;
-    bool raw = false;  // TF32X3: `hi` is the raw fp32 weight, the GEMM splits it in shared memory (gemm_tc_raw_weights())
 };
-bool gemm_tc_raw_weights();
 // Optional fusion of the final row dot into the GEMM epilogue (tensor-core path only):
 // dot_out[tile][m] = sum over the tile's columns of epilogue(C)[m,n] * dot_w[n]; C itself is not stored.
 struct FusedDot {
@@ -160,6 +157,11 @@ int launch_rowdot_bwd(const float *dlogit, const float *a, int64_t lda, const fl
 // out[j] = base[j] + sum_n v[n] * W[n*ldw + j]  (base may be NULL)
 int launch_vecmat_add(const float *v, const float *W, int64_t ldw, int32_t n_rows, int32_t n_cols, const float *base,
                       float *out, cudaStream_t stream);
+
+// ---- stable radix sort of (key, value) pairs (radix_sort.cu) ----------------------------------------------------
+int64_t radix_sort_scratch_bytes(int64_t n);
+int launch_radix_sort_pairs(uint32_t *k0, uint32_t *v0, uint32_t *k1, uint32_t *v1, int64_t n, int end_bit, void *scratch,
+                            uint32_t **k_out, uint32_t **v_out, cudaStream_t stream);
 
 // ---- embedding backward (embed_bwd.cu) ----------------------------------------------------------
 int64_t scatter_scratch_bytes(int64_t B);

@@ -9,7 +9,7 @@ bool gemm_any_uses_tc(int precision, int64_t lda, int64_t ldc, int64_t m, int64_
                       int64_t ldb) {
     precision = gemm_precision(precision);
     if (precision == DCNR_PREC_TF32X3)
-        return wop != nullptr && (wop->lo != nullptr || wop->raw) && gemm_tc_supported(precision, true, true, lda, wop->ld, ldc, m, n, k, 1);
+        return wop != nullptr && wop->lo != nullptr && gemm_tc_supported(precision, true, true, lda, wop->ld, ldc, m, n, k, 1);
     if (precision == DCNR_PREC_TF32)
         return gemm_tc_supported(precision, true, true, lda, wop != nullptr ? wop->ld : ldb, ldc, m, n, k, 1);
     return false;
@@ -21,7 +21,7 @@ int gemm_any(int precision, const float *A, int64_t lda, bool a_kmajor, const fl
     precision = gemm_precision(precision);       // fp16x3 / bf16 exist only in the fused eval tower
     const float *dw = dot != nullptr ? dot->w : nullptr;
     float *dout = dot != nullptr ? dot->out : nullptr;
-    if (precision == DCNR_PREC_TF32X3 && wop != nullptr && (wop->lo != nullptr || wop->raw) &&
+    if (precision == DCNR_PREC_TF32X3 && wop != nullptr && wop->lo != nullptr &&
         gemm_tc_supported(precision, a_kmajor, true, lda, wop->ld, ldc, m, n, k, split_k))
         return launch_gemm_tc(precision, A, lda, a_kmajor, wop->hi, wop->ld, true, C, ldc, m, n, k, split_k, epi, stream,
                               wop->lo, dw, dout);
@@ -37,40 +37,34 @@ int gemm_any(int precision, const float *A, int64_t lda, bool a_kmajor, const fl
     return launch_gemm_simt(A, lda, a_kmajor, B, ldb, b_kmajor, C, ldc, m, n, k, split_k, epi, stream);
 }
 
-// Stream-ordered temporary for the operator-level entry points (the whole-model calls carve the
-// split weights out of their workspaces instead).
+// Tensor-core operand form of one weight for the operator-level entry points, built in the CALLER's workspace
+// (dcnr_linear_workspace_bytes): hi / lo tf32 split for TF32X3, the transpose for the dgrads.  (The whole-model calls carve
+// the same operands out of their own workspaces.)
 struct TempSplit {
-    float *buf = nullptr;
-    cudaStream_t st;
     WeightOp op{nullptr, nullptr, 0};
-    int make(int precision, const float *w, int64_t ldw, int32_t rows, int32_t cols, bool transpose, cudaStream_t s) {
-        st = s;
+    bool made = false;
+    static int64_t bytes(int precision, int32_t rows, int32_t cols) {
+        return gemm_precision(precision) == DCNR_PREC_FP32 ? 0 : round_up((int64_t)rows * cols * 2 * (int64_t)sizeof(float), 256);
+    }
+    int make(int precision, const float *w, int64_t ldw, int32_t rows, int32_t cols, bool transpose, void *workspace,
+             int64_t workspace_bytes, cudaStream_t s) {
         precision = gemm_precision(precision);
         if (precision != DCNR_PREC_TF32X3 && !(transpose && precision != DCNR_PREC_FP32)) return DCNR_OK;
         const int64_t n = (int64_t)rows * cols;
-        static thread_local bool pool_ready = false;
-        if (!pool_ready) {       // keep freed blocks cached in the stream-ordered pool instead of returning them at every sync
-            int dev = 0;
-            cudaMemPool_t pool;
-            if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-                uint64_t keep = 1ull << 28;
-                cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-            }
-            pool_ready = true;
+        if (workspace == nullptr || workspace_bytes < bytes(precision, rows, cols)) {
+            set_error("linear workspace too small (%lld < %lld): size it with dcnr_linear_workspace_bytes", (long long)workspace_bytes,
+                      (long long)bytes(precision, rows, cols));
+            return DCNR_ERR_WORKSPACE;
         }
-        const bool raw = precision == DCNR_PREC_TF32X3 && gemm_tc_raw_weights();
-        DCNR_CUDA_CHECK(cudaMallocAsync(&buf, (size_t)n * 2 * sizeof(float), s));
-        DCNR_TRY(launch_split_tf32(w, ldw, buf, buf + n, rows, cols, transpose, s, raw));
+        float *buf = reinterpret_cast<float *>(workspace);
+        DCNR_TRY(launch_split_tf32(w, ldw, buf, buf + n, rows, cols, transpose, s));
         op.hi = buf;
-        op.lo = (precision == DCNR_PREC_TF32X3 && !raw) ? buf + n : nullptr;
-        op.raw = raw;
+        op.lo = precision == DCNR_PREC_TF32X3 ? buf + n : nullptr;
         op.ld = transpose ? rows : cols;
+        made = true;
         return DCNR_OK;
     }
-    const WeightOp *get() const { return buf != nullptr ? &op : nullptr; }
-    ~TempSplit() {
-        if (buf != nullptr) cudaFreeAsync(buf, st);
-    }
+    const WeightOp *get() const { return made ? &op : nullptr; }
 };
 
 int wgrad_splits(int64_t m, int32_t n, int32_t k) {
@@ -114,21 +108,26 @@ int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const floa
 
 using namespace dcnr;
 
+extern "C" int64_t dcnr_linear_workspace_bytes(int32_t n, int32_t k, int32_t precision) {
+    return TempSplit::bytes(precision, n, k);
+}
+
 extern "C" int dcnr_linear_fwd(const float *x, int64_t ldx, const float *w, int64_t ldw, const float *bias,
                                const float *col_scale, const float *residual, int64_t ldr, int relu, float *y,
-                               int64_t ldy, int64_t m, int32_t n, int32_t k, int32_t precision, dcnr_stream_t stream) {
+                               int64_t ldy, int64_t m, int32_t n, int32_t k, int32_t precision, void *workspace,
+                               int64_t workspace_bytes, dcnr_stream_t stream) {
     DCNR_REQUIRE(x && w && y, "null argument");
     DCNR_REQUIRE(ldx >= k && ldw >= k && ldy >= n && (residual == nullptr || ldr >= n), "leading dimension too small");
     GemmEpilogue epi{col_scale, bias, residual, ldr, relu};
     TempSplit ts;
     if (precision != DCNR_PREC_FP32 && gemm_tc_supported(DCNR_PREC_TF32, true, true, ldx, k, ldy, m, n, k, 1))
-        DCNR_TRY(ts.make(precision, w, ldw, n, k, false, as_stream(stream)));
+        DCNR_TRY(ts.make(precision, w, ldw, n, k, false, workspace, workspace_bytes, as_stream(stream)));
     return gemm_any(precision, x, ldx, true, w, ldw, true, y, ldy, m, n, k, 1, epi, as_stream(stream), ts.get());
 }
 
 extern "C" int dcnr_linear_dgrad(const float *dy, int64_t lddy, const float *w, int64_t ldw, const float *residual,
                                  int64_t ldr, float *dx, int64_t lddx, int64_t m, int32_t n, int32_t k,
-                                 int32_t precision, dcnr_stream_t stream) {
+                                 int32_t precision, void *workspace, int64_t workspace_bytes, dcnr_stream_t stream) {
     DCNR_REQUIRE(dy && w && dx, "null argument");
     DCNR_REQUIRE(lddy >= n && ldw >= k && lddx >= k && (residual == nullptr || ldr >= k), "leading dimension too small");
     GemmEpilogue epi{nullptr, nullptr, residual, ldr, 0};
@@ -136,7 +135,7 @@ extern "C" int dcnr_linear_dgrad(const float *dy, int64_t lddy, const float *w, 
     // The tensor-core kernel takes K-major operands only, so it is fed W^T (one small transpose per call).
     TempSplit ts;
     if (precision != DCNR_PREC_FP32 && gemm_tc_supported(DCNR_PREC_TF32, true, true, lddy, n, lddx, m, k, n, 1))
-        DCNR_TRY(ts.make(precision, w, ldw, n, k, true, as_stream(stream)));
+        DCNR_TRY(ts.make(precision, w, ldw, n, k, true, workspace, workspace_bytes, as_stream(stream)));
     return gemm_any(precision, dy, lddy, true, w, ldw, false, dx, lddx, m, k, n, 1, epi, as_stream(stream), ts.get());
 }
 
@@ -190,7 +189,7 @@ k_cross_v2_bwd_prep(const float *__restrict__ g, int64_t ldg, const float *__res
 
 extern "C" int dcnr_cross_v2_fwd(const float *x0, int64_t ldx0, const float *x, int64_t ldx, const float *w, int64_t ldw,
                                  const float *bias, float *y, int64_t ldy, int64_t m, int32_t d, int32_t precision,
-                                 dcnr_stream_t stream) {
+                                 void *workspace, int64_t workspace_bytes, dcnr_stream_t stream) {
     DCNR_REQUIRE(x0 && x && w && y, "null argument");
     DCNR_REQUIRE(d > 0 && ldx0 >= d && ldx >= d && ldw >= d && ldy >= d, "leading dimension too small");
     DCNR_REQUIRE((ldx0 & 3) == 0 && ((uintptr_t)x0 & 15) == 0, "x0 must be 16-byte aligned with ld %% 4 == 0");
@@ -199,7 +198,7 @@ extern "C" int dcnr_cross_v2_fwd(const float *x0, int64_t ldx0, const float *x, 
     epi.ldh = ldx0;
     TempSplit ts;
     if (precision != DCNR_PREC_FP32 && gemm_tc_supported(DCNR_PREC_TF32, true, true, ldx, d, ldy, m, d, d, 1))
-        DCNR_TRY(ts.make(precision, w, ldw, d, d, false, as_stream(stream)));
+        DCNR_TRY(ts.make(precision, w, ldw, d, d, false, workspace, workspace_bytes, as_stream(stream)));
     return gemm_any(precision, x, ldx, true, w, ldw, true, y, ldy, m, d, d, 1, epi, as_stream(stream), ts.get());
 }
 

@@ -37,16 +37,14 @@ struct WeightOps {
         const int prec = gemm_precision(d->precision);
         on = prec == DCNR_PREC_TF32X3 || (transpose && prec == DCNR_PREC_TF32);
         if (!on) return DCNR_OK;
-        const bool raw = prec == DCNR_PREC_TF32X3 && gemm_tc_raw_weights();
-        const bool lo = prec == DCNR_PREC_TF32X3 && !raw;
+        const bool lo = prec == DCNR_PREC_TF32X3;
         const int H = d->hidden, Dp = d->in_dim_pad;
         auto one = [&](WeightOp &op, const float *w, int64_t ldw, int rows, int cols) -> int {
             const int64_t n = (int64_t)rows * cols;
             op.hi = buf;
             op.lo = lo ? buf + n : nullptr;
             op.ld = transpose ? rows : cols;
-            op.raw = raw;
-            DCNR_TRY(launch_split_tf32(w, ldw, buf, lo ? buf + n : nullptr, rows, cols, transpose, st, raw));
+            DCNR_TRY(launch_split_tf32(w, ldw, buf, lo ? buf + n : nullptr, rows, cols, transpose, st));
             buf += 2 * n;
             return DCNR_OK;
         };

@@ -659,8 +659,7 @@ extern "C" int dcnr_knn_topk(const float *catalog_hat, int64_t n, int32_t d, con
 
     if (p.stream) {
         // single cooperative launch (scan + bound exchange + merge) whenever the grid can be co-resident
-        static const bool no_fuse = getenv("DCNR_KNN_NO_FUSE") != nullptr;
-        if (!no_fuse && p.qt == 1) {         // (8-query tiles: the separate sampled pre-pass measured faster, 0.53 vs 0.65 ms)
+        if (p.qt == 1) {         // (8-query tiles: the separate sampled pre-pass measured faster, 0.53 vs 0.65 ms)
             FusedOut fo{probes, dist_out, idx_out, idx_base};
             bool fused_ok = false;
             DCNR_TRY(launch_stream_any(d, catalog_hat, n, queries_hat, n_queries, k, p, p.slices, p.groups_per_slice, 1, nullptr,

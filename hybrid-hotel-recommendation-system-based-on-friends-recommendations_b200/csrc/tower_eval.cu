@@ -16,9 +16,10 @@
 //     beyond the fp16 range sets bit 1 of *flags (the caller re-runs the batch on the tf32x3 path).  terms == 1 is the bf16
 //     mode (stated tolerance, not parity): hi only, bf16 operands, no range limit.
 //   * Tensor memory (512 columns) = two 256-column buffers.  Layer l accumulates into buffer l & 1 while its A operand is
-//     read from buffer (l - 1) & 1: the epilogue of layer l - 1 converts the accumulator IN PLACE, 32 columns at a time,
-//     into the fp16 hi / lo operand of layer l (32 fp32 columns -> 16 columns of packed hi pairs + 16 of lo pairs), so the
-//     MMAs of layer l start on K-chunk c as soon as chunk c of layer l - 1 is converted (TS-form MMA: A from tensor memory).
+//     read from buffer (l - 1) & 1: the epilogue of layer l - 1 converts the accumulator IN PLACE, 16 columns at a time,
+//     into the fp16 hi / lo operand of layer l (16 fp32 columns -> 8 columns of packed hi pairs + 8 of lo pairs = one K = 16
+//     MMA step), so the MMAs of layer l start on K-step s as soon as group s of layer l - 1 is converted (TS-form MMA: A
+//     from tensor memory).
 //   * The residual input of a block is kept as fp32 in shared memory (128 KB, [col/4][row] float4: conflict-free).
 //   * Weights stream from L2 through a 6-slot x 16 KB TMA ring (pre-split fp16 hi / lo, prepared once per call by
 //     k_tower_prep); the x0 tile enters the same ring as a shared-memory A operand (SS-form MMA) for the initial layer.
@@ -26,8 +27,10 @@
 //     M = 256 over the pair): each CTA streams and holds HALF of the weight rows, halving the L2 -> shared-memory stream and
 //     the shared-memory operand reads per SM.
 //
-// Warp roles (384 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warps 2-3 x0 loader, warps 4-11 epilogue
-// (warp w and w + 4 share a TMEM lane quadrant and take alternate 32-column chunks).
+// Warp roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warps 2-3 x0 loader, warps 4-19 epilogue
+// (the four warps w, w + 4, w + 8, w + 12 share a TMEM lane quadrant and take every fourth 16-column group).  Sixteen epilogue
+// warps because the epilogue is latency-bound: with eight (round-2 first version, ncu: tensor pipe 56 % active) a layer's
+// conversion took ~8 500 clk against 6 144 clk of MMAs and set the pace of the whole kernel.
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -46,8 +49,9 @@ constexpr int SLOT_BYTES = 16384;
 constexpr int NSLOT = 6;
 constexpr int MAXL = 9;                // 1 + 2 * 4 ResBlocks
 constexpr int RES_BYTES = BM * H * 4;
-constexpr int kThreads = 384;
-constexpr int kNumBars = 2 * NSLOT + 2 + 8 + 1 + 8;
+constexpr int kThreads = 640;
+constexpr int kEpiThreads = 512;       // warps 4..19
+constexpr int kNumBars = 2 * NSLOT + 2 + 16 + 1 + 8;
 constexpr int kSmemBytes = NSLOT * SLOT_BYTES + RES_BYTES + 2 * H * 4 + kNumBars * 8 + 16;
 constexpr float kRangeLimit = 60000.f;   // fp16 max is 65504
 
@@ -87,7 +91,7 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
     uint64_t *bars = reinterpret_cast<uint64_t *>(vecs + 2 * H);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kNumBars);
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * NSLOT, accfull0 = empty0 + 8 * NSLOT,
-                   aready0 = accfull0 + 16, accfree0 = aready0 + 64, xgo0 = accfree0 + 8;
+                   aready0 = accfull0 + 16, accfree0 = aready0 + 128, xgo0 = accfree0 + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
@@ -103,8 +107,8 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
         }
         mbar_init(accfull0, 1);
         mbar_init(accfull0 + 8, 1);
-        for (int c = 0; c < 8; ++c) mbar_init(aready0 + 8 * c, 4 * CTAS);    // the four quadrant warps that own chunk c
-        mbar_init(accfree0, 8 * CTAS);
+        for (int c = 0; c < 16; ++c) mbar_init(aready0 + 8 * c, 4 * CTAS);   // the four quadrant warps that own 16-column group c
+        mbar_init(accfree0, 16 * CTAS);
         for (int i = 0; i < 8; ++i) mbar_init(xgo0 + 8 * i, 1);             // producer -> loader: x0 slot i of this tile is free
         mbar_init_fence();
     }
@@ -201,50 +205,62 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
                         wait_x(accfree0, (it - 1u) & 1u, 2, (u << 16) | (l << 8));
                         tc_fence_after();
                     }
-                    const int nchunks = l == 0 ? n0 : 8;
-                    for (int c = 0; c < nchunks; ++c) {
-                        int sx = 0;
-                        if (l == 0) {                            // A = the x0 chunk in shared memory (hi | lo, 64-byte rows)
-                            sx = r.s;
+                    if (l == 0) {
+                        // A = the x0 tile in shared memory (SS form): per 32-wide K chunk one x0 slot (hi | lo, 64-byte rows)
+                        for (int c = 0; c < n0; ++c) {
+                            const int sx = r.s;
                             wait_x(full0 + 8 * r.s, r.ph, 3, (u << 16) | (l << 8) | c);
                             r.next();
-                        } else {                                 // A = chunk c of the previous layer's output in tensor memory
-                            wait_x(aready0 + 8 * c, hc & 1u, 4, (u << 16) | (l << 8) | c);
-                        }
-                        tc_fence_after();
-                        int sw = 0;
+                            tc_fence_after();
+                            int sw = 0;
 #pragma unroll
-                        for (int sp = 0; sp < 2; ++sp) {
-                            if (CTAS == 1 || sp == 0) {
-                                sw = r.s;
-                                wait_x(full0 + 8 * r.s, r.ph, 5, (u << 16) | (l << 8) | (c << 1) | sp);
-                                tc_fence_after();
-                                r.next();
-                            }
-                            const uint32_t wb = smem_u32(ring + sw * SLOT_BYTES) + (CTAS == 2 ? sp * 32 : 0);
-                            const bool last_of_slot = CTAS == 1 || sp == 1;
-                            if (elect_one()) {
-                                const uint64_t db_hi = smem_desc_kmajor(wb, WROW), db_lo = smem_desc_kmajor(wb + SLOT_BYTES / 2, WROW);
-                                const uint32_t acc = (uint32_t)((c | sp) != 0);
-                                if (l == 0) {
+                            for (int sp = 0; sp < 2; ++sp) {
+                                if (CTAS == 1 || sp == 0) {
+                                    sw = r.s;
+                                    wait_x(full0 + 8 * r.s, r.ph, 5, (u << 16) | (l << 8) | (c << 1) | sp);
+                                    tc_fence_after();
+                                    r.next();
+                                }
+                                const uint32_t wb = smem_u32(ring + sw * SLOT_BYTES) + (CTAS == 2 ? sp * 32 : 0);
+                                if (elect_one()) {
+                                    const uint64_t db_hi = smem_desc_kmajor(wb, WROW), db_lo = smem_desc_kmajor(wb + SLOT_BYTES / 2, WROW);
                                     const uint32_t xb = smem_u32(ring + sx * SLOT_BYTES) + sp * 32;
                                     const uint64_t da_hi = smem_desc_kmajor(xb, 64), da_lo = smem_desc_kmajor(xb + SLOT_BYTES / 2, 64);
-                                    mma_f16_ss<CTAS>(d, da_hi, db_hi, idesc, acc);
+                                    mma_f16_ss<CTAS>(d, da_hi, db_hi, idesc, (uint32_t)((c | sp) != 0));
                                     if (three) {
                                         mma_f16_ss<CTAS>(d, da_lo, db_hi, idesc, 1u);
                                         mma_f16_ss<CTAS>(d, da_hi, db_lo, idesc, 1u);
                                     }
-                                } else {
-                                    const uint32_t ta_hi = a0 + (uint32_t)(32 * c + 8 * sp), ta_lo = ta_hi + 16u;
-                                    mma_f16_ts<CTAS>(d, ta_hi, db_hi, idesc, acc);
-                                    if (three) {
-                                        mma_f16_ts<CTAS>(d, ta_lo, db_hi, idesc, 1u);
-                                        mma_f16_ts<CTAS>(d, ta_hi, db_lo, idesc, 1u);
-                                    }
+                                    if (CTAS == 1 || sp == 1) mma_commit<CTAS>(empty0 + 8 * sw);
+                                    if (sp == 1) mma_commit<CTAS>(empty0 + 8 * sx);
+                                    if (c == n0 - 1 && sp == 1) mma_commit<CTAS>(accfull0 + 8 * (g & 1u));
                                 }
-                                if (last_of_slot) mma_commit<CTAS>(empty0 + 8 * sw);
-                                if (l == 0 && sp == 1) mma_commit<CTAS>(empty0 + 8 * sx);
-                                if (c == nchunks - 1 && sp == 1) mma_commit<CTAS>(accfull0 + 8 * (g & 1u));
+                                __syncwarp();
+                            }
+                        }
+                    } else {
+                        // A = the previous layer's output in tensor memory (TS form), one K = 16 step per converted 16-column group
+                        int sw = 0;
+                        for (int ks = 0; ks < 16; ++ks) {
+                            wait_x(aready0 + 8 * ks, hc & 1u, 4, (u << 16) | (l << 8) | ks);
+                            tc_fence_after();
+                            if (CTAS == 1 || (ks & 1) == 0) {
+                                sw = r.s;
+                                wait_x(full0 + 8 * r.s, r.ph, 5, (u << 16) | (l << 8) | ks);
+                                tc_fence_after();
+                                r.next();
+                            }
+                            const uint32_t wb = smem_u32(ring + sw * SLOT_BYTES) + (CTAS == 2 ? (ks & 1) * 32 : 0);
+                            if (elect_one()) {
+                                const uint64_t db_hi = smem_desc_kmajor(wb, WROW), db_lo = smem_desc_kmajor(wb + SLOT_BYTES / 2, WROW);
+                                const uint32_t ta_hi = a0 + (uint32_t)(16 * ks), ta_lo = ta_hi + 8u;
+                                mma_f16_ts<CTAS>(d, ta_hi, db_hi, idesc, (uint32_t)(ks != 0));
+                                if (three) {
+                                    mma_f16_ts<CTAS>(d, ta_lo, db_hi, idesc, 1u);
+                                    mma_f16_ts<CTAS>(d, ta_hi, db_lo, idesc, 1u);
+                                }
+                                if (CTAS == 1 || (ks & 1) == 1) mma_commit<CTAS>(empty0 + 8 * sw);
+                                if (ks == 15) mma_commit<CTAS>(accfull0 + 8 * (g & 1u));
                             }
                             __syncwarp();
                         }
@@ -308,15 +324,15 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
         }
         if (!p.bf16 && mx > kRangeLimit && p.flags != nullptr) atomicOr(p.flags, 2);
     } else {
-        // ---------------- epilogue warps 4..11: thread = one tile row, 32 accumulator columns at a time ----------------
+        // ---------------- epilogue warps 4..19: thread = one tile row, 16 accumulator columns (one K = 16 step) at a time ----------------
         const int ew = warp - 4, grp = ew >> 2, quad = warp & 3;
         const int row = quad * 32 + lane, et = threadIdx.x - 128;
         const uint32_t lane_addr = (uint32_t)(quad * 32) << 16;
         float4 *res4 = reinterpret_cast<float4 *>(res);
-        float wreg[4];                                           // wfs of this group's chunks: column 32 c + lane
+        float wreg[4];                                           // wfs of this warp's groups: column 16 (grp + 4 cc) + (lane & 15)
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) wreg[cc] = __ldg(p.vec + (int64_t)L * 2 * H + 32 * (2 * cc + grp) + lane);
-        float pre_s = __ldg(p.vec + et), pre_h = __ldg(p.vec + H + et);
+        for (int cc = 0; cc < 4; ++cc) wreg[cc] = __ldg(p.vec + (int64_t)L * 2 * H + 16 * (grp + 4 * cc) + (lane & 15));
+        float pre = __ldg(p.vec + et);                           // [scale | shift] of the next layer to drain, one float per thread
         const float bias_f = p.bf != nullptr ? __ldg(p.bf) : 0.f;
         uint32_t g = 0;
         float mx = 0.f;
@@ -326,28 +342,23 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
                 wait_x(accfull0 + 8 * (g & 1u), (g >> 1) & 1u, 7, (u << 16) | (l << 8));
                 tc_fence_after();
                 // layer switch: everyone is done with the previous layer's vectors; publish this layer's, prefetch the next
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                vecs[et] = pre_s;
-                vecs[H + et] = pre_h;
-                asm volatile("bar.sync 1, 256;" ::: "memory");
-                {
-                    const int nl = l + 1 == L ? 0 : l + 1;
-                    pre_s = __ldg(p.vec + (int64_t)nl * 2 * H + et);
-                    pre_h = __ldg(p.vec + (int64_t)nl * 2 * H + H + et);
-                }
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                vecs[et] = pre;
+                asm volatile("bar.sync 1, 512;" ::: "memory");
+                pre = __ldg(p.vec + (int64_t)(l + 1 == L ? 0 : l + 1) * 2 * H + et);
                 const bool relu = (p.relu_mask >> l) & 1u, res_in = (p.resin_mask >> l) & 1u, res_out = (p.resout_mask >> l) & 1u;
                 const bool last = l + 1 == L;
                 const uint32_t tbuf = tmem_base + (g & 1u) * 256u + lane_addr;
                 float dot = 0.f;
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
-                    const int c = 2 * cc + grp;
-                    uint32_t v[32];
-                    tmem_ld32(tbuf + 32u * c, v);
-                    float y[32];
-                    const float4 *sv = reinterpret_cast<const float4 *>(vecs + 32 * c), *hv = reinterpret_cast<const float4 *>(vecs + H + 32 * c);
+                    const int ks = grp + 4 * cc;                 // 16-column group = K step of the next layer
+                    uint32_t v[16];
+                    tmem_ld16(tbuf + 16u * ks, v);
+                    float y[16];
+                    const float4 *sv = reinterpret_cast<const float4 *>(vecs + 16 * ks), *hv = reinterpret_cast<const float4 *>(vecs + H + 16 * ks);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
+                    for (int q = 0; q < 4; ++q) {
                         const float4 s4 = sv[q], h4 = hv[q];
                         y[4 * q] = fmaf(__uint_as_float(v[4 * q]), s4.x, h4.x);
                         y[4 * q + 1] = fmaf(__uint_as_float(v[4 * q + 1]), s4.y, h4.y);
@@ -356,62 +367,63 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
                     }
                     if (res_in) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 r4 = res4[(8 * c + q) * BM + row];
+                        for (int q = 0; q < 4; ++q) {
+                            const float4 r4 = res4[(4 * ks + q) * BM + row];
                             y[4 * q] += r4.x; y[4 * q + 1] += r4.y; y[4 * q + 2] += r4.z; y[4 * q + 3] += r4.w;
                         }
                     }
                     if (relu) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) y[j] = fmaxf(y[j], 0.f);
+                        for (int j = 0; j < 16; ++j) y[j] = fmaxf(y[j], 0.f);
                     }
                     if (res_out) {
 #pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            res4[(8 * c + q) * BM + row] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
+                        for (int q = 0; q < 4; ++q)
+                            res4[(4 * ks + q) * BM + row] = make_float4(y[4 * q], y[4 * q + 1], y[4 * q + 2], y[4 * q + 3]);
                     }
                     if (!last) {
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, fabsf(y[j]));
-                        uint32_t o[32];
+                        for (int j = 0; j < 16; ++j) mx = fmaxf(mx, fabsf(y[j]));
+                        uint32_t o[16];                          // columns 0..7: packed hi pairs, 8..15: packed lo pairs
                         if (p.bf16) {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
+                            for (int j = 0; j < 8; ++j) {
                                 const __nv_bfloat162 h2 = __floats2bfloat162_rn(y[2 * j], y[2 * j + 1]);
                                 o[j] = *reinterpret_cast<const uint32_t *>(&h2);
-                                o[16 + j] = 0u;
+                                o[8 + j] = 0u;
                             }
                         } else {
 #pragma unroll
-                            for (int j = 0; j < 16; ++j) {
+                            for (int j = 0; j < 8; ++j) {
                                 const __half2 h2 = __floats2half2_rn(y[2 * j], y[2 * j + 1]);
                                 const float2 b2 = __half22float2(h2);
                                 const __half2 l2 = __floats2half2_rn(y[2 * j] - b2.x, y[2 * j + 1] - b2.y);
                                 o[j] = *reinterpret_cast<const uint32_t *>(&h2);
-                                o[16 + j] = *reinterpret_cast<const uint32_t *>(&l2);
+                                o[8 + j] = *reinterpret_cast<const uint32_t *>(&l2);
                             }
                         }
-                        tmem_st32(tbuf + 32u * c, o);
+                        tmem_st16(tbuf + 16u * ks, o);
                         tmem_st_wait();
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) {
-                            if (CTAS == 2) mbar_arrive_cluster(L_aready0 + 8 * c);
-                            else mbar_arrive(aready0 + 8 * c);
+                            if (CTAS == 2) mbar_arrive_cluster(L_aready0 + 8 * ks);
+                            else mbar_arrive(aready0 + 8 * ks);
                         }
                     } else {
                         const float wv = cc == 0 ? wreg[0] : (cc == 1 ? wreg[1] : (cc == 2 ? wreg[2] : wreg[3]));
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) dot = fmaf(y[j], __shfl_sync(0xffffffffu, wv, j), dot);
+                        for (int j = 0; j < 16; ++j) dot = fmaf(y[j], __shfl_sync(0xffffffffu, wv, j), dot);
                     }
                 }
                 if (last) {
-                    // group 1 hands its half of the row dot to group 0 through a residual cell it has already consumed
-                    if (grp == 1) res[(8 * BM + row) * 4] = dot;
-                    asm volatile("bar.sync 3, 256;" ::: "memory");
+                    // groups 1..3 hand their part of the row dot to group 0 through a residual cell they have already consumed
+                    // (the first float4 of their first 16-column group)
+                    if (grp != 0) res[(4 * grp * BM + row) * 4] = dot;
+                    asm volatile("bar.sync 3, 512;" ::: "memory");
                     if (grp == 0 && m < p.M) {
                         const float cross = p.logit_cross != nullptr ? __ldg(p.logit_cross + m) : 0.f;
-                        p.out[m] = dot + res[(8 * BM + row) * 4] + cross + bias_f;
+                        p.out[m] = ((dot + res[(4 * BM + row) * 4]) + (res[(8 * BM + row) * 4] + res[(12 * BM + row) * 4])) + cross + bias_f;
                     }
                     tc_fence_before();
                     __syncwarp();

@@ -95,10 +95,11 @@ class _CrossV2Fn(Function):
         ws = [torch.nn.functional.pad(_f32c(w), (0, Dp - D, 0, Dp - D)) for w in wb[:n_layers]]
         bs = [_pad_cols(b, Dp) for b in wb[n_layers:]]
         xs = [x0p]
+        lws = _scratch(C.lib().dcnr_linear_workspace_bytes(Dp, Dp, p), x0p.device)
         for l in range(n_layers):
             y = torch.empty_like(x0p)
             C.check(C.lib().dcnr_cross_v2_fwd(C.ptr(x0p), Dp, C.ptr(xs[-1]), Dp, C.ptr(ws[l]), Dp, C.ptr(bs[l]), C.ptr(y), Dp,
-                                              B, Dp, p, C.stream()))
+                                              B, Dp, p, C.ptr(lws), lws.numel(), C.stream()))
             xs.append(y)
         ctx.save_for_backward(*xs[:-1], *ws, *bs)
         ctx.meta = (n_layers, D, Dp, p)
@@ -115,11 +116,12 @@ class _CrossV2Fn(Function):
         dx0 = torch.zeros_like(x0p)
         gws, gbs = [None] * L, [None] * L
         scratch = _scratch(lib.dcnr_linear_wgrad_scratch_bytes(B, Dp, Dp), x0p.device)
+        lws = _scratch(lib.dcnr_linear_workspace_bytes(Dp, Dp, p), x0p.device)
         u, gm = torch.empty_like(x0p), torch.empty_like(x0p)
         for l in reversed(range(L)):
             # u = x_l W^T + b ; gm = g * x0 ; dx0 += g * u
             C.check(lib.dcnr_linear_fwd(C.ptr(xs[l]), Dp, C.ptr(ws[l]), Dp, C.ptr(bs[l]), None, None, 0, 0, C.ptr(u), Dp, B, Dp,
-                                        Dp, p, st))
+                                        Dp, p, C.ptr(lws), lws.numel(), st))
             C.check(lib.dcnr_cross_v2_bwd_prep(C.ptr(g), Dp, C.ptr(x0p), Dp, C.ptr(u), Dp, C.ptr(gm), Dp, C.ptr(dx0), Dp, 1, B,
                                                Dp, st))
             gw = torch.empty((Dp, Dp), device=x0p.device, dtype=torch.float32)
@@ -128,7 +130,8 @@ class _CrossV2Fn(Function):
                                           C.ptr(scratch), scratch.numel(), st))
             gws[l], gbs[l] = gw[:D, :D].contiguous(), gb[:D].contiguous()
             g_next = torch.empty_like(x0p)       # dx_l = gm W + g
-            C.check(lib.dcnr_linear_dgrad(C.ptr(gm), Dp, C.ptr(ws[l]), Dp, C.ptr(g), Dp, C.ptr(g_next), Dp, B, Dp, Dp, p, st))
+            C.check(lib.dcnr_linear_dgrad(C.ptr(gm), Dp, C.ptr(ws[l]), Dp, C.ptr(g), Dp, C.ptr(g_next), Dp, B, Dp, Dp, p,
+                                          C.ptr(lws), lws.numel(), st))
             g = g_next
         dx0 += g                                  # x_0 is also the first layer's input
         gx0 = dx0[:, :D].contiguous() if Dp != D else dx0
@@ -150,8 +153,9 @@ def linear_forward_raw(x, w, bias=None, col_scale=None, residual=None, relu=Fals
     n = w.shape[0]
     y = torch.empty((m, n), device=x.device, dtype=torch.float32)
     residual = None if residual is None else _f32c(residual)
+    lws = _scratch(C.lib().dcnr_linear_workspace_bytes(n, k, _prec(precision)), x.device)
     C.check(C.lib().dcnr_linear_fwd(C.ptr(x), k, C.ptr(w), k, C.ptr(bias), C.ptr(col_scale), C.ptr(residual), n,
-                                    1 if relu else 0, C.ptr(y), n, m, n, k, _prec(precision), C.stream()))
+                                    1 if relu else 0, C.ptr(y), n, m, n, k, _prec(precision), C.ptr(lws), lws.numel(), C.stream()))
     return y
 
 
@@ -174,7 +178,9 @@ class _LinearFn(Function):
         gx = gw = gb = None
         if ctx.needs_input_grad[0]:
             gx = torch.empty_like(x)
-            C.check(C.lib().dcnr_linear_dgrad(C.ptr(gy), n, C.ptr(w), k, None, 0, C.ptr(gx), k, m, n, k, p, C.stream()))
+            lws = _scratch(C.lib().dcnr_linear_workspace_bytes(n, k, p), x.device)
+            C.check(C.lib().dcnr_linear_dgrad(C.ptr(gy), n, C.ptr(w), k, None, 0, C.ptr(gx), k, m, n, k, p, C.ptr(lws), lws.numel(),
+                                              C.stream()))
         if ctx.needs_input_grad[1] or (ctx.has_bias and ctx.needs_input_grad[2]):
             gw = torch.empty_like(w)
             gb = torch.empty(n, device=x.device, dtype=torch.float32) if ctx.has_bias else None

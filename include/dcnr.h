@@ -221,7 +221,11 @@ int dcnr_cross_bwd(const float *x, int64_t ldx, int64_t batch, int32_t dim, int3
  *   v = acc * col_scale[n] ; v += bias[n] ; v += residual[m,n] ; v = max(v, 0) if relu. */
 int dcnr_linear_fwd(const float *x, int64_t ldx, const float *w, int64_t ldw, const float *bias,
                     const float *col_scale, const float *residual, int64_t ldr, int relu, float *y, int64_t ldy,
-                    int64_t m, int32_t n, int32_t k, int32_t precision, dcnr_stream_t stream);
+                    int64_t m, int32_t n, int32_t k, int32_t precision, void *workspace, int64_t workspace_bytes,
+                    dcnr_stream_t stream);
+/* Workspace of dcnr_linear_fwd / dcnr_linear_dgrad / dcnr_cross_v2_fwd for an [n, k] weight: room for its tensor-core
+ * operand form (tf32 hi / lo split, transposed for the dgrad).  0 for DCNR_PREC_FP32 (workspace may then be NULL). */
+int64_t dcnr_linear_workspace_bytes(int32_t n, int32_t k, int32_t precision);
 
 /* DCN-v2 ("full-matrix") cross layer -- OPT-IN variant (BASELINE.json north_star item 2), not the reference's
  * rank-1 CrossLayer (train.py:96-99, served by dcnr_cross_fwd above):
@@ -230,7 +234,7 @@ int dcnr_linear_fwd(const float *x, int64_t ldx, const float *w, int64_t ldw, co
  * (rows padded with zeros to d = round_up(D, 32), W zero-padded to [d, d]); the CUDA-core GEMM otherwise. */
 int dcnr_cross_v2_fwd(const float *x0, int64_t ldx0, const float *x, int64_t ldx, const float *w, int64_t ldw,
                       const float *bias, float *y, int64_t ldy, int64_t m, int32_t d, int32_t precision,
-                      dcnr_stream_t stream);
+                      void *workspace, int64_t workspace_bytes, dcnr_stream_t stream);
 /* Elementwise part of its backward for upstream g = dL/dy and u = x W^T + bias (dcnr_linear_fwd):
  *     gm = g * x0 ;  dx0 = (accumulate ? dx0 : 0) + g * u.
  * The rest is dx = gm W + g (dcnr_linear_dgrad with residual g) and dW = gm^T x, db = sum gm (dcnr_linear_wgrad). */
@@ -241,7 +245,7 @@ int dcnr_cross_v2_bwd_prep(const float *g, int64_t ldg, const float *x0, int64_t
 /* dx = dy W (+ residual)   -- autograd of nn.Linear wrt its input.  dy [m,n], W [n,k], dx [m,k]. */
 int dcnr_linear_dgrad(const float *dy, int64_t lddy, const float *w, int64_t ldw, const float *residual,
                       int64_t ldr, float *dx, int64_t lddx, int64_t m, int32_t n, int32_t k, int32_t precision,
-                      dcnr_stream_t stream);
+                      void *workspace, int64_t workspace_bytes, dcnr_stream_t stream);
 
 /* dW = dy^T x, db = column sums of dy  -- autograd of nn.Linear wrt weight and bias.
  * dw [n, lddw] (only the first k columns are written), db [n] (may be NULL).

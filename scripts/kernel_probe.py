@@ -58,8 +58,9 @@ def probe(B, hbm_peak):
     # opt-in DCN-v2 cross layer: one tcgen05 GEMM [B,64]x[64,64] with bias / Hadamard / residual in the epilogue
     x0p = torch.randn((B, Dp), device=dev, generator=g) * 0.1
     wv2 = torch.randn((Dp, Dp), device=dev, generator=g) / 8; bv2 = torch.zeros(Dp, device=dev); yv2 = torch.empty_like(x0p)
+    lws = torch.empty(max(1, C.lib().dcnr_linear_workspace_bytes(Dp, Dp, C.PRECISIONS["tf32x3"])), dtype=torch.uint8, device=dev)
     t = timed(lambda: C.check(C.lib().dcnr_cross_v2_fwd(C.ptr(x0p), Dp, C.ptr(x0p), Dp, C.ptr(wv2), Dp, C.ptr(bv2), C.ptr(yv2), Dp,
-                                                       B, Dp, C.PRECISIONS["tf32x3"], C.stream())))
+                                                       B, Dp, C.PRECISIONS["tf32x3"], C.ptr(lws), lws.numel(), C.stream())))
     rec("K2v2_cross_v2_layer_fwd", t, 3 * Dp * 4, "x0 read (Hadamard) + x read (GEMM operand; the residual box re-reads it through L2) + y write, "
         "padded 64-float rows; 2*64*64 flops per row (tf32x3)")
     del x0p, yv2
