@@ -334,7 +334,7 @@ def main():
                             10, 3, lambda: None)
         k_flops = M * (2.0 * dims.in_dim * H + 4 * 2.0 * H * H + 2.0 * H)
         del x0, tout
-        kname = f"k_tower_eval<1> (fused tower, tcgen05 kind::f16, {args.precision})"
+        kname = f"k_tower_eval (fused tower, tcgen05 kind::f16, {args.precision})"
         what = ("one fused-tower launch per 1 Mi-row chunk (initial layer + four 256x256 layers + final dot, activations in TMEM); "
                 "algorithmic flops = rows x (2*57*256 + 4*2*256*256 + 2*256)")
         iso_how = f"dcnr_tower_eval on {M} resident rows alone, 10 launches after 3 warm-ups (includes the weight-pack kernel)"

@@ -102,6 +102,34 @@ k_radix_scan_sums(uint32_t *__restrict__ sums, int64_t n_chunks) {
     }
 }
 
+// small inputs (total <= 64 Ki counts): the whole exclusive scan in ONE CTA, and the chunk bases it makes redundant zeroed
+__global__ void __launch_bounds__(1024)
+k_radix_scan_single(uint32_t *__restrict__ counts, int64_t total, uint32_t *__restrict__ sums, int64_t n_chunks) {
+    const int64_t per = (total + 1023) / 1024;
+    const int64_t i0 = min(total, threadIdx.x * per), i1 = min(total, i0 + per);
+    uint32_t s = 0;
+    for (int64_t i = i0; i < i1; ++i) s += counts[i];
+    // inclusive scan of the 1024 partial sums: warp scans + one pass over the 32 warp totals
+    uint32_t incl = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+        if ((threadIdx.x & 31) >= o) incl += t;
+    }
+    __shared__ uint32_t wtot[32];
+    if ((threadIdx.x & 31) == 31) wtot[threadIdx.x >> 5] = incl;
+    __syncthreads();
+    uint32_t woff = 0;
+    for (int w = 0; w < (int)(threadIdx.x >> 5); ++w) woff += wtot[w];
+    uint32_t run = woff + incl - s;
+    for (int64_t i = i0; i < i1; ++i) {
+        const uint32_t v = counts[i];
+        counts[i] = run;
+        run += v;
+    }
+    for (int64_t c = threadIdx.x; c < n_chunks; c += 1024) sums[c] = 0u;
+}
+
 __global__ void __launch_bounds__(kThreads)
 k_radix_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ vals, uint32_t *__restrict__ keys_out,
                 uint32_t *__restrict__ vals_out, int64_t n, int shift, int radix, int64_t n_tiles,
@@ -221,13 +249,14 @@ int launch_radix_sort_pairs(uint32_t *k0, uint32_t *v0, uint32_t *k1, uint32_t *
         const int64_t total = (int64_t)radix * n_tiles, n_chunks = ceil_div(total, kThreads * 8);
         k_radix_hist<<<(unsigned)n_tiles, kThreads, radix * 4, stream>>>(*k_out, n, shift, radix, n_tiles, counts);
         DCNR_LAUNCHED();
-        k_radix_scan_local<<<(unsigned)n_chunks, kThreads, 0, stream>>>(counts, total, sums);
-        DCNR_LAUNCHED();
-        if (n_chunks > 1) {
-            k_radix_scan_sums<<<1, 1024, 0, stream>>>(sums, n_chunks);
+        if (total <= 65536) {
+            k_radix_scan_single<<<1, 1024, 0, stream>>>(counts, total, sums, n_chunks);
             DCNR_LAUNCHED();
         } else {
-            DCNR_CUDA_CHECK(cudaMemsetAsync(sums, 0, 4, stream));
+            k_radix_scan_local<<<(unsigned)n_chunks, kThreads, 0, stream>>>(counts, total, sums);
+            DCNR_LAUNCHED();
+            k_radix_scan_sums<<<1, 1024, 0, stream>>>(sums, n_chunks);
+            DCNR_LAUNCHED();
         }
         uint32_t *ko = *k_out == k0 ? k1 : k0, *vo = *v_out == v0 ? v1 : v0;
         k_radix_scatter<<<(unsigned)n_tiles, kThreads, 0, stream>>>(*k_out, *v_out, ko, vo, n, shift, radix, n_tiles,

@@ -21,16 +21,15 @@
 //     MMA step), so the MMAs of layer l start on K-step s as soon as group s of layer l - 1 is converted (TS-form MMA: A
 //     from tensor memory).
 //   * The residual input of a block is kept as fp32 in shared memory (128 KB, [col/4][row] float4: conflict-free).
-//   * Weights stream from L2 through a 6-slot x 16 KB TMA ring (pre-split fp16 hi / lo, prepared once per call by
-//     k_tower_prep); the x0 tile enters the same ring as a shared-memory A operand (SS-form MMA) for the initial layer.
-//   * CTAS == 2 (opt-in, measured 8 % slower than single CTAs): a CTA pair shares every weight tile (tcgen05.mma.cta_group::2,
-//     M = 256 over the pair): each CTA streams and holds HALF of the weight rows, halving the L2 -> shared-memory stream and
-//     the shared-memory operand reads per SM.
+//   * Weights stream from L2 through a 3-slot x 32 KB TMA ring (pre-split fp16 hi / lo, prepared once per call by
+//     k_tower_prep; one slot = the [256 x 32] hi | lo tile of a K = 32 step); the x0 tile enters the same ring as a
+//     shared-memory A operand (SS-form MMA) for the initial layer.
+//   * Single CTAs, one per SM.  A 2-CTA form (tcgen05.mma.cta_group::2 sharing every weight tile between two SMs) was built
+//     and measured first: 636 M rows/s against 689 M rows/s for single CTAs (P0, 4 Mi rows) -- at one tile per SM the kernel is
+//     not shared-memory bound, and the pair pays cluster-scope barrier latency on every operand hand-over -- so it was removed.
 //
-// Warp roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer (leader CTA), warps 2-3 x0 loader, warps 4-19 epilogue
-// (the four warps w, w + 4, w + 8, w + 12 share a TMEM lane quadrant and take every fourth 16-column group).  Sixteen epilogue
-// warps because the epilogue is latency-bound: with eight (round-2 first version, ncu: tensor pipe 56 % active) a layer's
-// conversion took ~8 500 clk against 6 144 clk of MMAs and set the pace of the whole kernel.
+// Warp roles (640 threads): warp 0 TMA producer, warp 1 MMA issuer, warps 2-3 x0 loader, warps 4-19 epilogue (the four warps
+// w, w + 4, w + 8, w + 12 share a TMEM lane quadrant and take every fourth 16-column group).
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -45,13 +44,12 @@ using namespace ptx;
 
 constexpr int H = 256;                 // hidden width this kernel is built for (accumulator = 256 TMEM columns)
 constexpr int BM = 128;                // rows per CTA tile
-constexpr int SLOT_BYTES = 16384;
-constexpr int NSLOT = 6;
+constexpr int SLOT_BYTES = 32768;      // one ring slot: the [256 x 32] hi | lo weight tile of a K = 32 step (or an x0 chunk)
+constexpr int NSLOT = 3;
 constexpr int MAXL = 9;                // 1 + 2 * 4 ResBlocks
 constexpr int RES_BYTES = BM * H * 4;
 constexpr int kThreads = 640;
-constexpr int kEpiThreads = 512;       // warps 4..19
-constexpr int kNumBars = 2 * NSLOT + 2 + 16 + 1 + 8;
+constexpr int kNumBars = 2 * NSLOT + 2 + 8 + 1 + 8;
 constexpr int kSmemBytes = NSLOT * SLOT_BYTES + RES_BYTES + 2 * H * 4 + kNumBars * 8 + 16;
 constexpr float kRangeLimit = 60000.f;   // fp16 max is 65504
 
@@ -68,7 +66,7 @@ struct Params {
     uint32_t relu_mask, resin_mask, resout_mask;      // bit l: layer l applies ReLU / adds the saved residual / saves its output
 };
 
-struct Ring {                 // running slot / phase of the shared 6-slot ring (every role walks the same sequence)
+struct Ring {                 // running slot / phase of the shared ring (every role walks the same sequence)
     int s = 0;
     uint32_t ph = 0;
     __device__ __forceinline__ void next() {
@@ -81,7 +79,6 @@ struct Ring {                 // running slot / phase of the shared 6-slot ring 
     }
 };
 
-template <int CTAS>
 __global__ void __launch_bounds__(kThreads, 1)
 k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -91,31 +88,25 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
     uint64_t *bars = reinterpret_cast<uint64_t *>(vecs + 2 * H);
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + kNumBars);
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * NSLOT, accfull0 = empty0 + 8 * NSLOT,
-                   aready0 = accfull0 + 16, accfree0 = aready0 + 128, xgo0 = accfree0 + 8;
+                   aready0 = accfull0 + 16, accfree0 = aready0 + 64, xgo0 = accfree0 + 8;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t rank = CTAS == 2 ? cluster_ctarank() : 0u;
-    const bool leader = rank == 0;
-    // barriers the leader's MMA warp waits on, as shared::cluster addresses of the LEADER's copies
-    const uint32_t L_full0 = CTAS == 2 ? mapa(full0, 0) : full0, L_aready0 = CTAS == 2 ? mapa(aready0, 0) : aready0,
-                   L_accfree0 = CTAS == 2 ? mapa(accfree0, 0) : accfree0;
 
     if ((smem_u32(smem) & 1023u) != 0) __trap();                 // swizzled operand tiles need the 1024-byte alignment
     if (threadIdx.x == 0) {
         for (int i = 0; i < NSLOT; ++i) {
-            mbar_init(full0 + 8 * i, CTAS);                      // producer / loader of each CTA
+            mbar_init(full0 + 8 * i, 1);                         // producer's arrive.expect_tx / the loader's arrive
             mbar_init(empty0 + 8 * i, 1);                        // tcgen05.commit
         }
         mbar_init(accfull0, 1);
         mbar_init(accfull0 + 8, 1);
-        for (int c = 0; c < 16; ++c) mbar_init(aready0 + 8 * c, 4 * CTAS);   // the four quadrant warps that own 16-column group c
-        mbar_init(accfree0, 16 * CTAS);
+        for (int c = 0; c < 8; ++c) mbar_init(aready0 + 8 * c, 8);           // the eight warps that convert 32-column chunk c
+        mbar_init(accfree0, 16);
         for (int i = 0; i < 8; ++i) mbar_init(xgo0 + 8 * i, 1);             // producer -> loader: x0 slot i of this tile is free
         mbar_init_fence();
     }
-    if (warp == 1) tmem_alloc<CTAS>(smem_u32(tmem_slot), 512);
+    if (warp == 1) tmem_alloc<1>(smem_u32(tmem_slot), 512);
     tc_fence_before();
     __syncthreads();
-    if (CTAS == 2) cluster_sync();                               // the peer's barriers exist before anyone signals them
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
@@ -126,18 +117,11 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
     auto wait_x = [dbg](uint32_t bar, uint32_t parity, int site, int info) {
         uint32_t ok = 0;
         for (uint32_t spins = 0; !ok; ++spins) {
-            if (CTAS == 2)
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-                    "selp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-            else
-                asm volatile(
-                    "{\n\t.reg .pred p;\n\t"
-                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                    "selp.u32 %0, 1, 0, p;\n\t}"
-                    : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+            asm volatile(
+                "{\n\t.reg .pred p;\n\t"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                "selp.u32 %0, 1, 0, p;\n\t}"
+                : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
             if (!ok && spins > (1u << 21)) {
                 if (dbg != nullptr && (threadIdx.x & 31) == 0) {
                     if (atomicCAS(dbg + 1, 0, (int)((threadIdx.x >> 5) | (site << 8) | (parity << 16) | (blockIdx.x << 20))) == 0)
@@ -149,42 +133,30 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
         }
     };
     const int L = p.L, n0 = p.K0 / 32;
-    const int unit0 = blockIdx.x / CTAS, unit_step = gridDim.x / CTAS;      // a unit = one tile (CTAS = 1) or one tile pair
-    const int num_units = (p.num_tiles + CTAS - 1) / CTAS;
-    constexpr int WROW = 32 * CTAS;                              // bytes of one weight row inside a slot (= its swizzle span)
-    constexpr int WSLOTS = 2 / CTAS;                             // weight slots per 32-wide K chunk
 
     if (warp == 0) {
-        // ---------------- TMA producer: this CTA's rows of every weight tile, in layer / K order ----------------
+        // ---------------- TMA producer: the weight tile of every K = 32 step, in layer / K order ----------------
         Ring r;
         const uint32_t tx_bytes = (uint32_t)((p.terms == 3 ? 2 : 1) * (SLOT_BYTES / 2));
-        for (int u = unit0; u < num_units; u += unit_step) {
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
             for (int l = 0; l < L; ++l) {
-                const int nslots = (l == 0 ? n0 : 8) * WSLOTS;
-                for (int s = 0; s < nslots; ++s) {
-                    if (l == 0 && (s % WSLOTS) == 0) {
+                const int nchunks = l == 0 ? n0 : 8;
+                for (int c = 0; c < nchunks; ++c) {
+                    if (l == 0) {
                         // The x0 slot of this K chunk is filled by the loader warps, but the ring bookkeeping stays here: the loader
-                        // would otherwise wait for a slot a whole tile (11 ring revolutions) ahead, and a parity wait is only
+                        // would otherwise wait for a slot a whole tile (many ring revolutions) ahead, and a parity wait is only
                         // meaningful at most one phase ahead.  The producer waits for the slot in sequence and hands it over.
-                        wait_x(empty0 + 8 * r.s, r.ph ^ 1u, 8, (u << 16) | (l << 8) | s);
-                        if (elect_one()) mbar_arrive(xgo0 + 8 * (s / WSLOTS));
+                        wait_x(empty0 + 8 * r.s, r.ph ^ 1u, 8, (t << 16) | (l << 8) | c);
+                        if (elect_one()) mbar_arrive(xgo0 + 8 * c);
                         __syncwarp();
                         r.next();
                     }
-                    wait_x(empty0 + 8 * r.s, r.ph ^ 1u, 1, (u << 16) | (l << 8) | s);
+                    wait_x(empty0 + 8 * r.s, r.ph ^ 1u, 1, (t << 16) | (l << 8) | c);
                     if (elect_one()) {
                         const uint32_t dst = smem_u32(ring + r.s * SLOT_BYTES);
-                        const int k = s * 16 * CTAS, row = l * 2 * H + (int)rank * (H / CTAS);
-                        if (CTAS == 2) {
-                            if (leader) mbar_expect_tx(full0 + 8 * r.s, 2u * tx_bytes);
-                            else mbar_arrive_cluster(L_full0 + 8 * r.s);
-                            tma_load_2d_pair(dst, &tmW, k, row, L_full0 + 8 * r.s);
-                            if (p.terms == 3) tma_load_2d_pair(dst + SLOT_BYTES / 2, &tmW, k, row + H, L_full0 + 8 * r.s);
-                        } else {
-                            mbar_expect_tx(full0 + 8 * r.s, tx_bytes);
-                            tma_load_2d(dst, &tmW, k, row, full0 + 8 * r.s);
-                            if (p.terms == 3) tma_load_2d(dst + SLOT_BYTES / 2, &tmW, k, row + H, full0 + 8 * r.s);
-                        }
+                        mbar_expect_tx(full0 + 8 * r.s, tx_bytes);
+                        tma_load_2d(dst, &tmW, 32 * c, l * 2 * H, full0 + 8 * r.s);
+                        if (p.terms == 3) tma_load_2d(dst + SLOT_BYTES / 2, &tmW, 32 * c, l * 2 * H + H, full0 + 8 * r.s);
                     }
                     __syncwarp();
                     r.next();
@@ -192,81 +164,69 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
             }
         }
     } else if (warp == 1) {
-        // ---------------- MMA issuer (leader CTA; all lanes loop, one elected lane issues) ----------------
-        if (leader) {
-            const uint32_t idesc = idesc_f16(p.bf16 ? 1 : 0, BM * CTAS, H);
-            const bool three = p.terms == 3;
-            Ring r;
-            uint32_t g = 0, hc = 0, it = 0;
-            for (int u = unit0; u < num_units; u += unit_step, ++it) {
-                for (int l = 0; l < L; ++l, ++g) {
-                    const uint32_t d = tmem_base + (g & 1u) * 256u, a0 = tmem_base + ((g & 1u) ^ 1u) * 256u;
-                    if (l == 1 && it > 0) {                      // every epilogue warp has drained the previous tile's last layer
-                        wait_x(accfree0, (it - 1u) & 1u, 2, (u << 16) | (l << 8));
-                        tc_fence_after();
-                    }
-                    if (l == 0) {
-                        // A = the x0 tile in shared memory (SS form): per 32-wide K chunk one x0 slot (hi | lo, 64-byte rows)
-                        for (int c = 0; c < n0; ++c) {
-                            const int sx = r.s;
-                            wait_x(full0 + 8 * r.s, r.ph, 3, (u << 16) | (l << 8) | c);
-                            r.next();
-                            tc_fence_after();
-                            int sw = 0;
-#pragma unroll
-                            for (int sp = 0; sp < 2; ++sp) {
-                                if (CTAS == 1 || sp == 0) {
-                                    sw = r.s;
-                                    wait_x(full0 + 8 * r.s, r.ph, 5, (u << 16) | (l << 8) | (c << 1) | sp);
-                                    tc_fence_after();
-                                    r.next();
-                                }
-                                const uint32_t wb = smem_u32(ring + sw * SLOT_BYTES) + (CTAS == 2 ? sp * 32 : 0);
-                                if (elect_one()) {
-                                    const uint64_t db_hi = smem_desc_kmajor(wb, WROW), db_lo = smem_desc_kmajor(wb + SLOT_BYTES / 2, WROW);
-                                    const uint32_t xb = smem_u32(ring + sx * SLOT_BYTES) + sp * 32;
-                                    const uint64_t da_hi = smem_desc_kmajor(xb, 64), da_lo = smem_desc_kmajor(xb + SLOT_BYTES / 2, 64);
-                                    mma_f16_ss<CTAS>(d, da_hi, db_hi, idesc, (uint32_t)((c | sp) != 0));
-                                    if (three) {
-                                        mma_f16_ss<CTAS>(d, da_lo, db_hi, idesc, 1u);
-                                        mma_f16_ss<CTAS>(d, da_hi, db_lo, idesc, 1u);
-                                    }
-                                    if (CTAS == 1 || sp == 1) mma_commit<CTAS>(empty0 + 8 * sw);
-                                    if (sp == 1) mma_commit<CTAS>(empty0 + 8 * sx);
-                                    if (c == n0 - 1 && sp == 1) mma_commit<CTAS>(accfull0 + 8 * (g & 1u));
-                                }
-                                __syncwarp();
-                            }
-                        }
-                    } else {
-                        // A = the previous layer's output in tensor memory (TS form), one K = 16 step per converted 16-column group
-                        int sw = 0;
-                        for (int ks = 0; ks < 16; ++ks) {
-                            wait_x(aready0 + 8 * ks, hc & 1u, 4, (u << 16) | (l << 8) | ks);
-                            tc_fence_after();
-                            if (CTAS == 1 || (ks & 1) == 0) {
-                                sw = r.s;
-                                wait_x(full0 + 8 * r.s, r.ph, 5, (u << 16) | (l << 8) | ks);
-                                tc_fence_after();
-                                r.next();
-                            }
-                            const uint32_t wb = smem_u32(ring + sw * SLOT_BYTES) + (CTAS == 2 ? (ks & 1) * 32 : 0);
-                            if (elect_one()) {
-                                const uint64_t db_hi = smem_desc_kmajor(wb, WROW), db_lo = smem_desc_kmajor(wb + SLOT_BYTES / 2, WROW);
-                                const uint32_t ta_hi = a0 + (uint32_t)(16 * ks), ta_lo = ta_hi + 8u;
-                                mma_f16_ts<CTAS>(d, ta_hi, db_hi, idesc, (uint32_t)(ks != 0));
-                                if (three) {
-                                    mma_f16_ts<CTAS>(d, ta_lo, db_hi, idesc, 1u);
-                                    mma_f16_ts<CTAS>(d, ta_hi, db_lo, idesc, 1u);
-                                }
-                                if (CTAS == 1 || (ks & 1) == 1) mma_commit<CTAS>(empty0 + 8 * sw);
-                                if (ks == 15) mma_commit<CTAS>(accfull0 + 8 * (g & 1u));
-                            }
-                            __syncwarp();
-                        }
-                    }
-                    if (l > 0) ++hc;
+        // ---------------- MMA issuer (all lanes loop, one elected lane issues) ----------------
+        // One ring slot = one K = 32 step = two K = 16 MMA groups, and the converted operand is signalled per 32 columns, so the
+        // issuing warp has two barriers per six MMAs (768 clk of tensor work).  Measured history of this loop (P0, 4 Mi rows):
+        // one barrier pair per K = 16 group 6.1-6.4 ms (the loop cost ~520 clk per group against 384 clk of MMAs and bounded the
+        // kernel); per K = 32 group 5.6 ms; probing the next chunk's barriers between the MMA groups (mbarrier.test_wait) 5.7 ms,
+        // no gain; two N = 128 passes per layer (to overlap the first conversion with the second pass) 6.7 ms -- twice the
+        // barrier traffic again.
+        const uint32_t idesc = idesc_f16(p.bf16 ? 1 : 0, BM, H);
+        const bool three = p.terms == 3;
+        Ring r;
+        uint32_t g = 0, hc = 0, it = 0;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++it) {
+            for (int l = 0; l < L; ++l, ++g) {
+                const uint32_t d = tmem_base + (g & 1u) * 256u, a0 = tmem_base + ((g & 1u) ^ 1u) * 256u;
+                if (l == 1 && it > 0) {                      // every epilogue warp has drained the previous tile's last layer
+                    wait_x(accfree0, (it - 1u) & 1u, 2, (t << 16) | (l << 8));
+                    tc_fence_after();
                 }
+                const int nchunks = l == 0 ? n0 : 8;
+                for (int c = 0; c < nchunks; ++c) {
+                    int sx = 0;
+                    if (l == 0) {                            // A = the x0 chunk in shared memory (hi | lo, 64-byte rows): SS form
+                        sx = r.s;
+                        wait_x(full0 + 8 * r.s, r.ph, 3, (t << 16) | (l << 8) | c);
+                        r.next();
+                    } else {                                 // A = chunk c of the previous layer's output in tensor memory: TS form
+                        wait_x(aready0 + 8 * c, hc & 1u, 4, (t << 16) | (l << 8) | c);
+                    }
+                    const int sw = r.s;
+                    wait_x(full0 + 8 * r.s, r.ph, 5, (t << 16) | (l << 8) | c);
+                    r.next();
+                    tc_fence_after();
+                    const uint32_t wb = smem_u32(ring + sw * SLOT_BYTES), xb = smem_u32(ring + sx * SLOT_BYTES);
+#pragma unroll
+                    for (int sp = 0; sp < 2; ++sp) {
+                        if (elect_one()) {
+                            const uint64_t db_hi = smem_desc_kmajor(wb + sp * 32, 64), db_lo = smem_desc_kmajor(wb + SLOT_BYTES / 2 + sp * 32, 64);
+                            const uint32_t acc = (uint32_t)((c | sp) != 0);
+                            if (l == 0) {
+                                const uint64_t da_hi = smem_desc_kmajor(xb + sp * 32, 64), da_lo = smem_desc_kmajor(xb + 8192 + sp * 32, 64);
+                                mma_f16_ss<1>(d, da_hi, db_hi, idesc, acc);
+                                if (three) {
+                                    mma_f16_ss<1>(d, da_lo, db_hi, idesc, 1u);
+                                    mma_f16_ss<1>(d, da_hi, db_lo, idesc, 1u);
+                                }
+                            } else {
+                                const uint32_t ta_hi = a0 + (uint32_t)(32 * c + 16 * sp), ta_lo = ta_hi + 8u;
+                                mma_f16_ts<1>(d, ta_hi, db_hi, idesc, acc);
+                                if (three) {
+                                    mma_f16_ts<1>(d, ta_lo, db_hi, idesc, 1u);
+                                    mma_f16_ts<1>(d, ta_hi, db_lo, idesc, 1u);
+                                }
+                            }
+                            if (sp == 1) {
+                                mma_commit<1>(empty0 + 8 * sw);
+                                if (l == 0) mma_commit<1>(empty0 + 8 * sx);
+                                if (c == nchunks - 1) mma_commit<1>(accfull0 + 8 * (g & 1u));
+                            }
+                        }
+                        __syncwarp();
+                    }
+                }
+                if (l > 0) ++hc;
             }
         }
     } else if (warp < 4) {
@@ -275,8 +235,8 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
         Ring r;
         float mx = 0.f;
         uint32_t nt = 0;                                         // tiles done by this CTA: xgo[i] completes once per tile
-        for (int u = unit0; u < num_units; u += unit_step, ++nt) {
-            const int64_t m0 = ((int64_t)u * CTAS + rank) * BM;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x, ++nt) {
+            const int64_t m0 = (int64_t)t * BM;
             for (int i = 0; i < n0; ++i) {
                 float4 v[16];
 #pragma unroll
@@ -285,8 +245,8 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
                     v[st] = row < p.M ? ldg4(p.x0 + row * p.ldx0 + 32 * i + 4 * c4) : make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 const int sx = r.s;
-                wait_x(xgo0 + 8 * i, nt & 1u, 6, (u << 16) | i);
-                r.skip(1 + WSLOTS);
+                wait_x(xgo0 + 8 * i, nt & 1u, 6, (t << 16) | i);
+                r.skip(2);
                 uint8_t *slot = ring + sx * SLOT_BYTES;
 #pragma unroll
                 for (int st = 0; st < 16; ++st) {
@@ -310,17 +270,13 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
                         lo.y = *reinterpret_cast<const uint32_t *>(&l23);
                     }
                     *reinterpret_cast<uint2 *>(slot + off) = hi;
-                    *reinterpret_cast<uint2 *>(slot + SLOT_BYTES / 2 + off) = lo;
+                    *reinterpret_cast<uint2 *>(slot + 8192 + off) = lo;
                 }
-                if (CTAS == 2) asm volatile("fence.proxy.async;" ::: "memory");      // the leader's MMA reads this CTA's tile too
-                else fence_proxy_async_smem();
+                fence_proxy_async_smem();
                 asm volatile("bar.sync 2, 64;" ::: "memory");
-                if (t2 == 0) {
-                    if (CTAS == 2) mbar_arrive_cluster(L_full0 + 8 * sx);
-                    else mbar_arrive(full0 + 8 * sx);
-                }
+                if (t2 == 0) mbar_arrive(full0 + 8 * sx);
             }
-            r.skip((L - 1) * 8 * WSLOTS);
+            r.skip((L - 1) * 8);
         }
         if (!p.bf16 && mx > kRangeLimit && p.flags != nullptr) atomicOr(p.flags, 2);
     } else {
@@ -336,10 +292,10 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
         const float bias_f = p.bf != nullptr ? __ldg(p.bf) : 0.f;
         uint32_t g = 0;
         float mx = 0.f;
-        for (int u = unit0; u < num_units; u += unit_step) {
-            const int64_t m = ((int64_t)u * CTAS + rank) * BM + row;
+        for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+            const int64_t m = (int64_t)t * BM + row;
             for (int l = 0; l < L; ++l, ++g) {
-                wait_x(accfull0 + 8 * (g & 1u), (g >> 1) & 1u, 7, (u << 16) | (l << 8));
+                wait_x(accfull0 + 8 * (g & 1u), (g >> 1) & 1u, 7, (t << 16) | (l << 8));
                 tc_fence_after();
                 // layer switch: everyone is done with the previous layer's vectors; publish this layer's, prefetch the next
                 asm volatile("bar.sync 1, 512;" ::: "memory");
@@ -353,6 +309,7 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
 #pragma unroll 1
                 for (int cc = 0; cc < 4; ++cc) {
                     const int ks = grp + 4 * cc;                 // 16-column group = K step of the next layer
+
                     uint32_t v[16];
                     tmem_ld16(tbuf + 16u * ks, v);
                     float y[16];
@@ -406,10 +363,7 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
                         tmem_st_wait();
                         tc_fence_before();
                         __syncwarp();
-                        if (lane == 0) {
-                            if (CTAS == 2) mbar_arrive_cluster(L_aready0 + 8 * ks);
-                            else mbar_arrive(aready0 + 8 * ks);
-                        }
+                        if (lane == 0) mbar_arrive(aready0 + 8 * (ks >> 1));
                     } else {
                         const float wv = cc == 0 ? wreg[0] : (cc == 1 ? wreg[1] : (cc == 2 ? wreg[2] : wreg[3]));
 #pragma unroll
@@ -427,10 +381,7 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
                     }
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) {
-                        if (CTAS == 2) mbar_arrive_cluster(L_accfree0);
-                        else mbar_arrive(accfree0);
-                    }
+                    if (lane == 0) mbar_arrive(accfree0);
                 }
             }
         }
@@ -438,8 +389,7 @@ k_tower_eval(const __grid_constant__ CUtensorMap tmW, Params p) {
     }
     tc_fence_before();
     __syncthreads();
-    if (CTAS == 2) cluster_sync();                               // no CTA leaves while its pair may still use its memory / barriers
-    if (warp == 1) tmem_dealloc<CTAS>(tmem_base, 512);
+    if (warp == 1) tmem_dealloc<1>(tmem_base, 512);
 }
 
 // ---- weight / vector preparation: one CTA per layer ------------------------------------------------------------------------
@@ -587,11 +537,7 @@ int launch_tower_eval(const dcnr_dims *d, const float *x0, int64_t ldx0, const f
         if ((l & 1) == 0) p.resin_mask |= 1u << l;               // second layer of a block adds the block input
     }
     for (int l = 0; l + 1 < L; l += 2) p.resout_mask |= 1u << l;  // outputs that are the input of a following block
-    // Single CTAs are the default: measured 689 M rows/s against 636 M rows/s for 2-CTA pairs (P0, 4 Mi rows) -- at one
-    // tile per SM the kernel is tensor-pipe bound, not shared-memory bound, and the pair form pays cluster-scope barrier
-    // latency on every operand hand-over.  options bit 0 selects pairs; options >> 8 caps the grid (tests: many tiles per CTA).
-    const int want_pairs = options & 1, max_ctas = options >> 8;
-    const int ctas = (want_pairs && p.num_tiles >= 2) ? 2 : 1;
+    const int max_ctas = options >> 8;           // options >> 8 caps the grid (tests: many tiles per CTA)
     EncodeTiledFn fn = encode_fn();
     if (fn == nullptr) {
         set_error("cuTensorMapEncodeTiled entry point not available");
@@ -601,10 +547,10 @@ int launch_tower_eval(const dcnr_dims *d, const float *x0, int64_t ldx0, const f
     {
         cuuint64_t dims[2] = {(cuuint64_t)H, (cuuint64_t)L * 2 * H};
         cuuint64_t strides[1] = {(cuuint64_t)H * 2};
-        cuuint32_t box[2] = {(cuuint32_t)(16 * ctas), (cuuint32_t)(H / ctas)};
+        cuuint32_t box[2] = {32, (cuuint32_t)H};             // one K = 32 step of all 256 weight rows: 64-byte rows, SWIZZLE_64B
         cuuint32_t estr[2] = {1, 1};
         CUresult r = fn(&tmW, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, const_cast<void *>(pack), dims, strides, box, estr,
-                        CU_TENSOR_MAP_INTERLEAVE_NONE, ctas == 2 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
                         CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
         if (r != CUDA_SUCCESS) {
             set_error("cuTensorMapEncodeTiled failed (%d) for the tower weights", (int)r);
@@ -614,24 +560,9 @@ int launch_tower_eval(const dcnr_dims *d, const float *x0, int64_t ldx0, const f
     const int sms = max_ctas > 0 ? std::min(max_ctas, sm_count()) : sm_count();
     // algorithmic flops of the launch: initial layer on the UNPADDED input width, 2R hidden layers, deep half of the final dot
     gemm_timer_before(stream, (double)M * (2.0 * d->in_dim * H + (double)(L - 1) * 2.0 * H * H + 2.0 * H));
-    if (ctas == 2) {
-        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_tower_eval<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        cudaLaunchConfig_t cfg = {};
-        cudaLaunchAttribute attr[1];
-        const int pairs = (int)std::min<int64_t>(ceil_div(p.num_tiles, 2), std::max(1, sms / 2));
-        cfg.gridDim = dim3(2 * (unsigned)pairs, 1, 1);
-        cfg.blockDim = dim3(kThreads, 1, 1);
-        cfg.dynamicSmemBytes = kSmemBytes;
-        cfg.stream = stream;
-        attr[0].id = cudaLaunchAttributeClusterDimension;
-        attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-        cfg.attrs = attr; cfg.numAttrs = 1;
-        DCNR_CUDA_CHECK(cudaLaunchKernelEx(&cfg, k_tower_eval<2>, tmW, p));
-    } else {
-        DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_tower_eval<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-        const unsigned grid = (unsigned)std::min<int64_t>(p.num_tiles, sms);
-        k_tower_eval<1><<<grid, kThreads, kSmemBytes, stream>>>(tmW, p);
-    }
+    DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_tower_eval, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    const unsigned grid = (unsigned)std::min<int64_t>(p.num_tiles, sms);
+    k_tower_eval<<<grid, kThreads, kSmemBytes, stream>>>(tmW, p);
     gemm_timer_after(stream);
     DCNR_LAUNCHED();
     return DCNR_OK;

@@ -289,7 +289,7 @@ int dcnr_bn_act_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo, 
  * x0 [m, ldx0] is the padded output of dcnr_embed_concat_fwd (ldx0 >= in_dim_pad, pad columns zero); logit_cross [m] (the
  * cross half, may be NULL).  precision: DCNR_PREC_FP16X3 or DCNR_PREC_BF16.  Needs hidden == 256, 1..4 ResBlocks
  * (dcnr_tower_eval_supported).  workspace: dcnr_tower_eval_workspace_bytes().  flags: see dcnr_dims.eval_flags (may be NULL).
- * options: bit 0 = 2-CTA pairs (tcgen05 cta_group::2) instead of single CTAs; bits 8.. = cap on the number of CTAs (0 = one per SM) -- measurement
+ * options: bits 8.. = cap on the number of CTAs (0 = one per SM) -- measurement
  * and test aids.  flags[1..2] receive a diagnostic record if a pipeline wait times out (the kernel then traps), so flags must
  * point at >= 3 ints. */
 int dcnr_tower_eval_supported(const dcnr_dims *dims);

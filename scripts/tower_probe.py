@@ -26,7 +26,7 @@ def main():
     flags = torch.zeros(4, dtype=torch.int32, device=dev)
     ws = torch.empty(C.lib().dcnr_tower_eval_workspace_bytes(dims), dtype=torch.uint8, device=dev)
     for prec in ("fp16x3", "bf16"):
-        for options, tag in ((0, "single CTAs"), (1, "2-CTA pairs")):
+        for options, tag in ((0, "one CTA per SM"),):
             def run():
                 C.check(C.lib().dcnr_tower_eval(dims, ps, C.ptr(x0), x0.shape[1], C.ptr(cross), C.ptr(out), rows, C.PRECISIONS[prec],
                                                 options, C.ptr(flags), C.ptr(ws), ws.numel(), C.stream()))

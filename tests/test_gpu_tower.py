@@ -3,7 +3,7 @@
 Checker: the float64 oracle's deep tower (oracle/dcnr_oracle.forward(..., return_parts=True): initial layer, ResBlocks
 with running-statistics BatchNorm, deep half of the final dot -- main.py:83-90,120-127 in eval()).  Contract: fp16x3
 logits within 1e-5 (max-abs-normalised) like every parity mode; bf16 is a stated-tolerance mode and the test states it.
-Covered: single CTAs and 2-CTA pairs, ragged row counts (1, 127, 128, 129, ...), many tiles per CTA (tile-to-tile
+Covered: ragged row counts (1, 127, 128, 129, ...), many tiles per CTA (tile-to-tile
 pipelining), 1 / 2 / 4 ResBlocks, a 96-wide padded input (three K chunks in the initial layer), the whole-model eval
 call, the out-of-range-id flag and the fp16-range fallback.
 """
@@ -55,9 +55,8 @@ def _oracle_deep(st, u, i, c, x):
     return logits.reshape(-1), deep, parts["x0"]
 
 
-@pytest.mark.parametrize("options", [0, 1], ids=["single_cta", "cta_pairs"])
 @pytest.mark.parametrize("B", [1, 127, 128, 129, 300, 4096, 37_001, 100_000])
-def test_tower_operator_matches_oracle(B, options):
+def test_tower_operator_matches_oracle(B, options=0):
     params, st, nu, ni = _state()
     u, i, c, x, _ = synth_inputs(nu, ni, CAT, 11, B, seed=5 + B)
     _, deep, x0 = _oracle_deep(st, u, i, c, x)
@@ -71,8 +70,7 @@ def test_tower_operator_matches_oracle(B, options):
     assert orc.max_abs_normalised(got, deep + cross.double()) < TOL
 
 
-@pytest.mark.parametrize("options", [0 | (1 << 8), 1 | (2 << 8), 0 | (3 << 8), 1 | (6 << 8)],
-                         ids=["1_cta", "1_pair", "3_ctas", "3_pairs"])
+@pytest.mark.parametrize("options", [1 << 8, 2 << 8, 3 << 8, 7 << 8], ids=["1_cta", "2_ctas", "3_ctas", "7_ctas"])
 def test_tower_many_tiles_per_cta(options):
     """Grid capped to 1..6 CTAs: every CTA walks many tiles (the tile-to-tile hand-over of the TMEM buffers and the ring)."""
     params, st, nu, ni = _state()
@@ -98,7 +96,7 @@ def test_tower_depths_and_input_widths(R, emb):
     Dp = m._dims().in_dim_pad
     x0p = torch.zeros(B, Dp)
     x0p[:, : x0.shape[1]] = x0.float()
-    for options in (0, 1):
+    for options in (0, 5 << 8):
         got, flags = _tower_call(m, x0p.cuda(), None, "fp16x3", options)
         assert flags == 0
         assert orc.max_abs_normalised(got, deep) < TOL, (R, emb, options)
@@ -149,7 +147,7 @@ def test_fp16_range_overflow_falls_back_to_tf32x3():
     m = _model(params, st, nu, ni, "fp16x3")
     x0p = torch.zeros(B, m._dims().in_dim_pad)
     x0p[:, : x0.shape[1]] = x0.float()
-    _, flags = _tower_call(m, x0p.cuda(), None, "fp16x3", 1)
+    _, flags = _tower_call(m, x0p.cuda(), None, "fp16x3", 0)
     assert flags & 2
     with torch.no_grad():
         out = m(u.cuda(), i.cuda(), c.cuda(), x.cuda())
