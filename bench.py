@@ -577,6 +577,9 @@ def bench_train(model, dev, world, rank, comm, barrier, max_over_ranks, global_b
                        "BatchNorm and the all-gather of (id, gradient row) pairs that builds the table gradients "
                        "(optimizer excluded)",
            "gpu_launches_per_step": per_step}
+    if comm is not None and world > 1:
+        out["syncbn_exchange"] = ("one peer-to-peer kernel per BatchNorm exchange (CUDA IPC over NVLink)" if comm.uses_peer_memory
+                                  else "NCCL all-gather per BatchNorm exchange")
     if single is not None:
         out["single_device"] = single
     return out

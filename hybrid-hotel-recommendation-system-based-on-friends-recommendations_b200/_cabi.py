@@ -122,6 +122,8 @@ _SIGS = {
     "dcnr_comm_create": (c_int, [c_void_p, c_int32, c_int32, POINTER(c_void_p)]),
     "dcnr_comm_destroy": (c_int, [c_void_p]),
     "dcnr_comm_info": (c_int, [c_void_p, POINTER(c_int32), POINTER(c_int32)]),
+    "dcnr_comm_uses_peer_memory": (c_int, [c_void_p]),
+    "dcnr_comm_set_peer_memory": (c_int, [c_void_p, c_int32]),
     "dcnr_comm_allreduce_f32": (c_int, [c_void_p, c_void_p, c_int64, c_void_p]),
     "dcnr_comm_allgather": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p]),
     "dcnr_comm_alltoallv": (c_int, [c_void_p, c_void_p, POINTER(c_int64), POINTER(c_int64), c_void_p, POINTER(c_int64),

@@ -9,6 +9,7 @@
 // walking rows.  Every reduction is chunk-local in a fixed order, written as one partial row per
 // chunk and finalised in chunk order, so results are bit-reproducible run to run.
 #include "kernels.cuh"
+#include "p2p.cuh"
 
 namespace dcnr {
 
@@ -141,6 +142,64 @@ __global__ void k_bn_stats_finalize(const double *__restrict__ gmean, const doub
     }
 }
 
+// SyncBN forward over peer memory: ONE CTA folds this rank's groups, exchanges (mean | M2 | count) with every rank through the
+// NVLink-mapped staging slots, folds the ranks in rank order (identical on every rank) and emits mean / rstd / running
+// statistics -- the pack kernel, the NCCL all-gather and the fold kernel of the NCCL path in a single launch.
+__global__ void __launch_bounds__(256)
+k_bn_stats_finalize_sync(const P2pView *__restrict__ views, int rank, int world, const double *__restrict__ gmean,
+                         const double *__restrict__ gm2, const double *__restrict__ gcnt, int64_t groups, int n, float eps,
+                         float momentum, float *__restrict__ mean_out, float *__restrict__ rstd_out, float *running_mean,
+                         float *running_var, int64_t *nbt) {
+    const P2pExchange x(views, rank, world);
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        Moments acc{0.0, 0.0, 0.0};
+        for (int64_t k = 0; k < groups; ++k) merge_moments(acc, Moments{gcnt[k], gmean[k * n + c], gm2[k * n + c]});
+        for (int r = 0; r < world; ++r) {
+            double *dst = x.send_slot(r);
+            dst[c] = acc.mean;
+            dst[n + c] = acc.m2;
+            if (c == 0) dst[2 * n] = acc.n;
+        }
+    }
+    x.publish_and_wait();
+    for (int c = threadIdx.x; c < n; c += blockDim.x) {
+        Moments acc{0.0, 0.0, 0.0};
+        for (int r = 0; r < world; ++r) {
+            const volatile double *src = x.recv_slot(r);
+            merge_moments(acc, Moments{src[2 * n], src[c], src[n + c]});
+        }
+        const double m = acc.n;
+        const double var_b = acc.m2 / m;
+        mean_out[c] = (float)acc.mean;
+        rstd_out[c] = (float)(1.0 / sqrt(var_b + (double)eps));
+        if (running_mean != nullptr) {
+            const double var_u = m > 1.0 ? acc.m2 / (m - 1.0) : var_b;
+            running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * acc.mean);
+            running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * var_u);
+        }
+    }
+    if (threadIdx.x == 0 && nbt != nullptr) *nbt += 1;
+    x.finish();
+}
+
+// SyncBN backward over peer memory: exchange (sum dy | sum dy*xhat | rows), add the ranks in rank order, leave the global sums
+// and 1 / global rows in `sums` for k_bn_bwd_apply -- pack + all-gather + unpack in one launch.
+__global__ void __launch_bounds__(256)
+k_bn_bwd_sync(const P2pView *__restrict__ views, int rank, int world, float *__restrict__ sums, int n2, double rows) {
+    const P2pExchange x(views, rank, world);
+    for (int c = threadIdx.x; c <= n2; c += blockDim.x) {
+        const double v = c < n2 ? (double)sums[c] : rows;
+        for (int r = 0; r < world; ++r) x.send_slot(r)[c] = v;
+    }
+    x.publish_and_wait();
+    for (int c = threadIdx.x; c <= n2; c += blockDim.x) {
+        double acc = 0.0;
+        for (int r = 0; r < world; ++r) acc += x.recv_slot(r)[c];
+        sums[c] = c < n2 ? (float)acc : (float)(1.0 / acc);      // sums[n2] = 1 / global batch rows
+    }
+    x.finish();
+}
+
 // SyncBN backward: pack this rank's (sum dy | sum dy*xhat | rows) as doubles; after the all-gather, add the ranks in
 // rank order and leave the global sums and 1 / global rows for k_bn_bwd_apply.
 __global__ void k_bn_bwd_pack(const float *__restrict__ sums, int n2, double rows, double *__restrict__ pack) {
@@ -187,11 +246,17 @@ int launch_bn_stats(const float *z, int64_t ldz, int64_t m, int32_t n, float eps
     const int world = comm_world(comm);
     if (world > 1) {
         DCNR_REQUIRE(world <= kMaxWorld, "data-parallel group larger than %d ranks", kMaxWorld);
+        if (const P2pView *views = comm_p2p_views(comm); views != nullptr && 2 * n + 2 <= kP2pCap) {
+            k_bn_stats_finalize_sync<<<1, 256, 0, stream>>>(views, comm_rank(comm), world, gmean, gm2, gcnt, groups, n, eps, momentum,
+                                                           mean, rstd, running_mean, running_var, nbt);
+            DCNR_LAUNCHED();
+            return DCNR_OK;
+        }
         double *mine = gcnt + groups, *all = mine + (2 * n + 2);              // exchange buffers (see bn_scratch_floats)
         k_bn_stats_finalize<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(gmean, gm2, gcnt, groups, n, 1, n, eps, momentum,
                                                                           nullptr, nullptr, nullptr, nullptr, nullptr, mine);
         DCNR_LAUNCHED();
-        DCNR_TRY(comm_allgather(comm, mine, all, (2 * (int64_t)n + 2) * 8, stream));
+        DCNR_TRY(comm_allgather_f64(comm, mine, all, 2 * n + 2, stream));
         k_bn_stats_finalize<<<(unsigned)ceil_div(n, 128), 128, 0, stream>>>(all, all + n, all + 2 * n, world, 2 * n + 2,
                                                                           2 * n + 2, n, eps, momentum, mean, rstd,
                                                                           running_mean, running_var, nbt, nullptr);
@@ -386,13 +451,19 @@ int launch_bn_act_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo
     const int world = comm_world(comm);
     if (world > 1) {            // dgamma / dbeta stay this rank's sums (they are all-reduced with the other gradients)
         DCNR_REQUIRE(world <= kMaxWorld, "data-parallel group larger than %d ranks", kMaxWorld);
+        const P2pView *views = comm_p2p_views(comm);
         double *mine = reinterpret_cast<double *>(scratch + bn_scratch_floats(m, n) - 2 * (int64_t)(kMaxWorld + 1) * (2 * (int64_t)n + 2));
         double *all = mine + (2 * n + 2);
-        k_bn_bwd_pack<<<(unsigned)ceil_div(2 * n + 1, 128), 128, 0, stream>>>(sums, 2 * n, (double)m, mine);
-        DCNR_LAUNCHED();
-        DCNR_TRY(comm_allgather(comm, mine, all, (2 * (int64_t)n + 2) * 8, stream));
-        k_bn_bwd_unpack<<<(unsigned)ceil_div(2 * n + 1, 128), 128, 0, stream>>>(all, world, 2 * n, sums);
-        DCNR_LAUNCHED();
+        if (views != nullptr && 2 * n + 2 <= kP2pCap) {
+            k_bn_bwd_sync<<<1, 256, 0, stream>>>(views, comm_rank(comm), world, sums, 2 * n, (double)m);
+            DCNR_LAUNCHED();
+        } else {
+            k_bn_bwd_pack<<<(unsigned)ceil_div(2 * n + 1, 128), 128, 0, stream>>>(sums, 2 * n, (double)m, mine);
+            DCNR_LAUNCHED();
+            DCNR_TRY(comm_allgather_f64(comm, mine, all, 2 * n + 2, stream));
+            k_bn_bwd_unpack<<<(unsigned)ceil_div(2 * n + 1, 128), 128, 0, stream>>>(all, world, 2 * n, sums);
+            DCNR_LAUNCHED();
+        }
     }
     smem = (size_t)cm.ty_n * n * sizeof(float);
     if (smem > 48 * 1024)

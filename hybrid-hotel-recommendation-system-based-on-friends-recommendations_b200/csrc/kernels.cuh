@@ -118,6 +118,8 @@ static inline int gemm_precision(int precision) {
 int comm_world(const void *comm);
 int comm_rank(const void *comm);
 int comm_allgather(const void *comm, const void *send, void *recv, int64_t bytes_per_rank, cudaStream_t stream);
+// recv[r * n + i] = rank r's send[i]: the small SyncBN exchanges (one peer-memory kernel over NVLink when available, else NCCL)
+int comm_allgather_f64(const void *comm, const double *send, double *recv, int n, cudaStream_t stream);
 constexpr int kMaxWorld = 64;
 
 // ---- batch norm / elementwise (bn.cu) -------------------------------------------------------

@@ -66,6 +66,17 @@ class Communicator:
     def handle(self):
         return self._h
 
+    @property
+    def uses_peer_memory(self) -> bool:
+        """True when the small BatchNorm exchanges run as peer-to-peer kernels over NVLink instead of NCCL all-gathers."""
+        from . import _cabi as C
+        return bool(C.lib().dcnr_comm_uses_peer_memory(self._h))
+
+    def set_peer_memory(self, enable: bool) -> None:
+        """Park (False) or restore (True) the peer-memory exchanges; same value on every rank, between steps."""
+        from . import _cabi as C
+        C.check(C.lib().dcnr_comm_set_peer_memory(self._h, int(bool(enable))))
+
     def allreduce_(self, t: torch.Tensor) -> torch.Tensor:
         from . import _cabi as C
         assert t.is_cuda and t.dtype == torch.float32 and t.is_contiguous()

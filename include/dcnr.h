@@ -349,6 +349,12 @@ int dcnr_comm_unique_id(uint8_t *id_host /* [128] */);
 int dcnr_comm_create(const uint8_t *id_host, int32_t rank, int32_t world, void **comm_out);
 int dcnr_comm_destroy(void *comm);
 int dcnr_comm_info(const void *comm, int32_t *rank, int32_t *world);
+/* 1 when the ranks of `comm` mapped each other's memory (CUDA IPC over NVLink) at creation: the small BatchNorm exchanges of a
+ * training step then run as one peer-to-peer kernel each instead of an NCCL all-gather. */
+int dcnr_comm_uses_peer_memory(const void *comm);
+/* enable = 0 parks the peer-memory path (the exchanges go through NCCL), 1 restores it when the mapping exists.  Must be called
+ * with the same value on every rank, between steps.  Both paths fold the ranks in rank order in float64: identical results. */
+int dcnr_comm_set_peer_memory(void *comm, int32_t enable);
 /* In-place sum over the ranks (gradient all-reduce after dcnr_backward). */
 int dcnr_comm_allreduce_f32(void *comm, float *buf, int64_t count, dcnr_stream_t stream);
 /* recv[r*bytes_per_rank ..] = rank r's send buffer (sparse embedding-gradient segments, top-k lists). */

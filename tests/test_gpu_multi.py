@@ -47,6 +47,7 @@ def _worker(rank, world, port, ret):
     out = {}
     try:
         comm = D.Communicator()
+        out["syncbn_over_peer_memory"] = comm.uses_peer_memory
         state = orc.make_state(N_USERS, N_ITEMS, CAT, N_NUM, P, seed=3, emb_scale=0.1, randomize_bn=True)
         B = 4096
         u, i, c, x, gl = _batch(B, 11)
@@ -81,6 +82,18 @@ def _worker(rank, world, port, ret):
             out[f"dp_{prec}_worst"] = max(errs, key=errs.get)
             if prec == "fp32":
                 part32, lo32 = part, lo_part
+        # ---- the two SyncBN exchange paths (peer-memory kernel | NCCL all-gather) fold the ranks in the same order: bit-equal ----
+        if comm.uses_peer_memory:
+            comm.set_peer_memory(False)
+            via_nccl = dcnr_b200.DCN_RecSys(N_USERS, N_ITEMS, CAT, N_NUM, P, precision="fp32")
+            lo_nccl = run(via_nccl, slice(b0, b1), True)
+            comm.set_peer_memory(True)
+            same = bool(torch.equal(lo_nccl, lo32))
+            D.allreduce_gradients(via_nccl.parameters_to_allreduce(), comm=comm, average=False)
+            out["syncbn_paths_grad_err"] = max(_err(pa.grad, pb.grad) for pa, pb in zip(via_nccl.parameters(), part32.parameters()))
+            for (n, ba), (_, bb) in zip(via_nccl.named_buffers(), part32.named_buffers()):
+                same = same and bool(torch.equal(ba, bb))
+            out["syncbn_paths_bit_equal"] = same
         st64 = {k: (v.double() if v.dtype.is_floating_point else v) for k, v in state.items()}
         ref, ref_g, _ = orc.forward_backward(st64, u, i, c, x.double(), grad_logits=gl.double())
         out["dp_vs_oracle_logits"] = _err(lo32.cpu(), ref[b0:b1])
@@ -158,3 +171,4 @@ def test_two_rank_parity():
         assert o["lookup_exact"] and o["shard_grad"] < 2e-6
         assert o["sharded_dcn"] < 1e-5, (o["sharded_dcn"], o["sharded_dcn_worst"])
         assert o["sharded_knn_exact"]
+        assert o.get("syncbn_paths_bit_equal", True) and o.get("syncbn_paths_grad_err", 0.0) < 1e-6
