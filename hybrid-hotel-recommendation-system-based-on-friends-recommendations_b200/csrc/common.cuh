@@ -95,8 +95,9 @@ void gemm_timer_before(cudaStream_t stream, double flops);
 void gemm_timer_after(cudaStream_t stream);
 int launch_sum_partials(const float *partials, int64_t n_partials, int64_t ld, const SegPtrs &seg,
                         cudaStream_t stream);
-// out[r*ldo + c] = sum_p partials[(p*rows + r)*cols_pad + c] for c < cols
+// out[r*ldo + c] = sum_p partials[(p*rows + r)*cols_pad + c] (+ u[r] * v[c] when both are given) for c < cols
 int launch_sum_partials_2d(const float *partials, int64_t n_partials, int32_t rows, int32_t cols_pad,
-                           int32_t cols, float *out, int64_t ldo, cudaStream_t stream, int64_t pitch = 0);   // pitch 0: dense
+                           int32_t cols, float *out, int64_t ldo, cudaStream_t stream, int64_t pitch = 0,   // pitch 0: dense
+                           const float *u = nullptr, const float *v = nullptr);
 
 }  // namespace dcnr

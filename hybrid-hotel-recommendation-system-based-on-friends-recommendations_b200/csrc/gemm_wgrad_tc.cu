@@ -103,6 +103,8 @@ struct Params {
     int32_t terms, stages, corr_sep, tmem_cols;
     int64_t rows_per_slab;     // multiple of BLOCK_K
     float *slabs;              // [n_slabs][n_out][k_in]
+    const float *center;       // optional [k_in]: subtracted from every X row before the split (TF32X3 only; the caller
+                               // adds colsum(dY) (x) center back -- see launch_linear_wgrad)
 };
 
 __global__ void __launch_bounds__(kThreads, 1)
@@ -206,6 +208,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
         const int tt = threadIdx.x - 64;                   // 0..127
         if (p.terms == 3) {
             const int n4 = (a_bytes + b_bytes) / 16;       // float4 of [A][B] (contiguous in the stage)
+            const int a4 = a_bytes / 16;
             int rs = 0; uint32_t rph = 0;
             for (int kb = 0; kb < num_kb; ++kb) {
                 const int s = rs;
@@ -215,7 +218,15 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * stage_bytes);
                 float4 *lo = hi + n4;
                 for (int i = tt; i < n4; i += 128) {
-                    const float4 v = hi[i];
+                    float4 v = hi[i];
+                    if (p.center != nullptr && i >= a4) {
+                        // X tile, SWIZZLE_128B_BASE32B: block of 32 columns = 32 batch rows x 128 B; the 32-byte chunk of a row
+                        // is XOR-ed with (row & 3).  float4 i of the tile -> its first column.
+                        const int o = i - a4, row = (o >> 3) & 31, c16 = o & 7;
+                        const int col = (o >> 8) * 32 + (((c16 >> 1) ^ (row & 3)) << 3) + ((c16 & 1) << 2);
+                        const float4 mu = __ldg(reinterpret_cast<const float4 *>(p.center + col));
+                        v.x -= mu.x; v.y -= mu.y; v.z -= mu.z; v.w -= mu.w;
+                    }
                     float4 h, l;
                     uint32_t u;
                     asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v.x)); h.x = __uint_as_float(u); l.x = v.x - h.x;
@@ -312,11 +323,13 @@ bool wgrad_tc_supported(int precision, int64_t lddy, int64_t ldx, int64_t m, int
     return m >= 1 && m <= 0x7fffff00LL;
 }
 
-// One slab per SM, but never more than kMaxSlabRows batch rows per slab: the tensor core's fp32 accumulate truncates
-// (profiles/r02_acc_probe.md), so the rounding error of a slab's partial product grows with the length of its accumulation
-// chain; 256 rows = 32 K-steps keeps a B = 65 536 weight gradient inside 2x the reference's own fp32 noise (896-row slabs
-// measured 1.4e-5 on initial_deep_layer.weight).  The slabs are summed in double, in slab order.
-constexpr int64_t kMaxSlabRows = 256;
+// Batch slabs of at most kMaxSlabRows rows.  The tensor core's fp32 accumulate truncates (profiles/r02_acc_probe.md), and tensor
+// memory bounds how many accumulation chains can run side by side (148 SMs x 512 columns = 74 chains per element of a 256 x 256
+// gradient, main + correction accumulators), so the only way to shorter chains is more CTAs per SM, one after the other.
+// Measured on the B = 65 536 gradients against float64 (worst weight gradient, profiles/r02_parity_65536.md): 886-row slabs
+// (one wave of CTAs) 1.1e-5, 256-row slabs (3.5 waves) 5.5e-6 -- the error goes with the square root of the chain length --
+// at 60 / 87 us per 65 536 x 256 x 256 gradient.  448 rows = two full waves at that batch.  Slabs are summed in double, in order.
+constexpr int64_t kMaxSlabRows = 448;
 int wgrad_tc_slabs(int64_t m, int32_t n) {
     const int64_t m_tiles = n / wg::BLOCK_M;
     const int64_t want = std::max<int64_t>(1, (int64_t)sm_count() / m_tiles);
@@ -326,7 +339,7 @@ int wgrad_tc_slabs(int64_t m, int32_t n) {
 
 // slabs: [wgrad_tc_slabs(m, n)][n][k] floats; the caller adds them in slab order
 int launch_wgrad_tc(int precision, const float *dy, int64_t lddy, const float *x, int64_t ldx, float *slabs, int64_t m,
-                    int32_t n, int32_t k, cudaStream_t stream) {
+                    int32_t n, int32_t k, cudaStream_t stream, const float *center) {
     using namespace wg;
     DCNR_REQUIRE(wgrad_tc_supported(precision, lddy, ldx, m, n, k), "shape not supported by the tcgen05 wgrad");
     DCNR_REQUIRE((((uintptr_t)dy | (uintptr_t)x | (uintptr_t)slabs) & 15) == 0, "operands must be 16-byte aligned");
@@ -338,6 +351,8 @@ int launch_wgrad_tc(int precision, const float *dy, int64_t lddy, const float *x
     const int n_slabs = wgrad_tc_slabs(m, n);
     p.rows_per_slab = std::min<int64_t>(kMaxSlabRows, round_up(ceil_div(m, n_slabs), BLOCK_K));
     p.slabs = slabs;
+    DCNR_REQUIRE(center == nullptr || (p.terms == 3 && ((uintptr_t)center & 15) == 0), "centred wgrad needs TF32X3 and an aligned vector");
+    p.center = center;
     const int stage_bytes = (p.terms == 3 ? 2 : 1) * (BLOCK_M + k) * BLOCK_K * 4;
     p.stages = std::max(1, std::min(4, (220 * 1024) / stage_bytes));
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;

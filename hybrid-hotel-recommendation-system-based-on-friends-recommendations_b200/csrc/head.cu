@@ -193,19 +193,58 @@ extern "C" int dcnr_check_ids(const dcnr_dims *dims, const dcnr_batch *batch, in
 // Used for the initial layer's bias gradient: db0 = colsum(dz1 W1 + dy2) = colsum(dz1) W1 + colsum(dy2) by linearity, so the
 // batch sum never runs over GEMM outputs (whose tensor-core rounding errors do not average out over a cancelling sum).
 namespace dcnr {
-__global__ void __launch_bounds__(256)
+// out[j] = base[j] + sum_n v[n] * W[n, j].  32 columns per CTA; the rows are dealt to 32 lanes-of-rows (thread ty takes rows
+// ty, ty + 32, ...), partial sums in double, folded in ty order: a fixed association, ~3 us for 256 x 256 (one thread per
+// column walking all rows was a 256-long dependent chain of L2 loads: 56 us).
+__global__ void __launch_bounds__(1024)
 k_vecmat_add(const float *__restrict__ v, const float *__restrict__ W, int64_t ldw, int32_t n_rows, int32_t n_cols,
              const float *__restrict__ base, float *__restrict__ out) {
-    const int j = blockIdx.x * blockDim.x + threadIdx.x;
-    if (j >= n_cols) return;
-    double acc = base != nullptr ? (double)base[j] : 0.0;
-    for (int n = 0; n < n_rows; ++n) acc += (double)__ldg(v + n) * (double)__ldg(W + (int64_t)n * ldw + j);
-    out[j] = (float)acc;
+    __shared__ double sh[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    double acc = 0.0;
+    if (j < n_cols)
+        for (int n = ty; n < n_rows; n += 32) acc += (double)__ldg(v + n) * (double)__ldg(W + (int64_t)n * ldw + j);
+    sh[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && j < n_cols) {
+        double t = base != nullptr ? (double)base[j] : 0.0;
+#pragma unroll
+        for (int y = 0; y < 32; ++y) t += sh[y][tx];
+        out[j] = (float)t;
+    }
 }
 
 int launch_vecmat_add(const float *v, const float *W, int64_t ldw, int32_t n_rows, int32_t n_cols, const float *base,
                       float *out, cudaStream_t stream) {
-    k_vecmat_add<<<(unsigned)ceil_div(n_cols, 256), 256, 0, stream>>>(v, W, ldw, n_rows, n_cols, base, out);
+    k_vecmat_add<<<(unsigned)ceil_div(n_cols, 32), 1024, 0, stream>>>(v, W, ldw, n_rows, n_cols, base, out);
+    DCNR_LAUNCHED();
+    return DCNR_OK;
+}
+
+// out[c] = mean over the first min(m, 2048) rows of a[:, c] (an ESTIMATE of the column mean for the centred weight gradient:
+// any vector works there, a close one removes the cancellation).  Same shape as k_vecmat_add.
+__global__ void __launch_bounds__(1024)
+k_col_mean_sample(const float *__restrict__ a, int64_t lda, int32_t rows, int32_t n, float *__restrict__ out) {
+    __shared__ double sh[32][33];
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int j = blockIdx.x * 32 + tx;
+    double acc = 0.0;
+    if (j < n)
+        for (int r = ty; r < rows; r += 32) acc += (double)__ldg(a + (int64_t)r * lda + j);
+    sh[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && j < n) {
+        double t = 0.0;
+#pragma unroll
+        for (int y = 0; y < 32; ++y) t += sh[y][tx];
+        out[j] = (float)(t / (double)rows);
+    }
+}
+
+int launch_col_mean_sample(const float *a, int64_t lda, int64_t m, int32_t n, float *out, cudaStream_t stream) {
+    const int32_t rows = (int32_t)std::min<int64_t>(m, 2048);
+    k_col_mean_sample<<<(unsigned)ceil_div(n, 32), 1024, 0, stream>>>(a, lda, rows, n, out);
     DCNR_LAUNCHED();
     return DCNR_OK;
 }

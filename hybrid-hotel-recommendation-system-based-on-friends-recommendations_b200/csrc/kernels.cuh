@@ -94,12 +94,17 @@ bool gemm_any_uses_tc(int precision, int64_t lda, int64_t ldc, int64_t m, int64_
 bool wgrad_tc_supported(int precision, int64_t lddy, int64_t ldx, int64_t m, int32_t n, int32_t k);
 int wgrad_tc_slabs(int64_t m, int32_t n);
 int launch_wgrad_tc(int precision, const float *dy, int64_t lddy, const float *x, int64_t ldx, float *slabs, int64_t m,
-                    int32_t n, int32_t k, cudaStream_t stream);
+                    int32_t n, int32_t k, cudaStream_t stream, const float *center = nullptr);
 int64_t wgrad_scratch_floats(int64_t m, int32_t n, int32_t k);
 // dW[n, 0:k_valid] (ld lddw) = dy^T x over k (padded) columns; db = column sums of dy (may be NULL)
+// center [k] + dy_colsum [n] (both or neither): the tensor-core path computes dy^T (x - center) + dy_colsum (x) center, which is
+// the same dW with far less cancellation when the columns of x have means that are large against their spread and dy sums to
+// ~0 over the batch (the layer after a BatchNorm backward); other paths ignore them.
 int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const float *x, int64_t ldx, float *dw,
                         int64_t lddw, float *db, int64_t m, int32_t n, int32_t k, int32_t k_valid, float *scratch,
-                        cudaStream_t stream);
+                        cudaStream_t stream, const float *center = nullptr, const float *dy_colsum = nullptr);
+// out[c] = mean of a[0:min(m, 2048), c]: a cheap estimate of the column means (one launch), n % 32 == 0
+int launch_col_mean_sample(const float *a, int64_t lda, int64_t m, int32_t n, float *out, cudaStream_t stream);
 
 // ---- fused eval tower (tower_eval.cu): initial layer + ResBlocks + deep half of the final dot in ONE persistent kernel ----
 bool tower_eval_supported(const dcnr_dims *d);                 // hidden 256, 1..4 ResBlocks, in_dim_pad <= 256

@@ -81,7 +81,7 @@ int64_t wgrad_scratch_floats(int64_t m, int32_t n, int32_t k) {
 
 int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const float *x, int64_t ldx, float *dw,
                         int64_t lddw, float *db, int64_t m, int32_t n, int32_t k, int32_t k_valid, float *scratch,
-                        cudaStream_t stream) {
+                        cudaStream_t stream, const float *center, const float *dy_colsum) {
     // dW[n_out, k_in] = sum_b dy[b, n_out] * x[b, k_in] : both operands have the reduction index as the row
     const int splits = wgrad_splits(m, n, k);
     float *slabs = scratch;                                           // [splits][n][k]
@@ -89,8 +89,10 @@ int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const floa
     precision = gemm_precision(precision);
     if (dw != nullptr && wgrad_tc_supported(precision, lddy, ldx, m, n, k)) {
         // tcgen05 path: MN-major operands straight from dy / x, one [n, k] partial per batch slab, slabs added in order
-        DCNR_TRY(launch_wgrad_tc(precision, dy, lddy, x, ldx, slabs, m, n, k, stream));
-        DCNR_TRY(launch_sum_partials_2d(slabs, wgrad_tc_slabs(m, n), n, k, k_valid, dw, lddw, stream));
+        const bool centred = center != nullptr && dy_colsum != nullptr && precision == DCNR_PREC_TF32X3;
+        DCNR_TRY(launch_wgrad_tc(precision, dy, lddy, x, ldx, slabs, m, n, k, stream, centred ? center : nullptr));
+        DCNR_TRY(launch_sum_partials_2d(slabs, wgrad_tc_slabs(m, n), n, k, k_valid, dw, lddw, stream, 0,
+                                        centred ? dy_colsum : nullptr, centred ? center : nullptr));
     } else if (dw != nullptr) {
         GemmEpilogue none{nullptr, nullptr, nullptr, 0, 0};
         if (splits == 1 && k_valid == k) {

@@ -86,7 +86,7 @@ struct TrainSaved {
 static bool dp_sparse_tables(const dcnr_dims *d) { return comm_world(d->comm) > 1 && d->dp_sparse_tables != 0; }
 
 struct BwdScratch {
-    float *ga, *gb, *gc, *dx0, *cross_partials, *wgrad, *bn, *wsplit, *vec_a, *vec_b;
+    float *ga, *gb, *gc, *dx0, *cross_partials, *wgrad, *bn, *wsplit, *vec_a, *vec_b, *vec_c;
     void *scatter;
     int64_t scatter_bytes;
     int64_t *pack_ids, *all_ids;       // [B][2] (user, item) of this rank / [world*B][2] of all ranks
@@ -104,6 +104,7 @@ struct BwdScratch {
         wsplit = a.take<float>(WeightOps::floats(d));
         vec_a = a.take<float>(H);
         vec_b = a.take<float>(H);
+        vec_c = a.take<float>(std::max<int64_t>(H, Dp));
         const int world = dp_sparse_tables(d) ? comm_world(d->comm) : 1;
         const int64_t cap = (world > 1 && d->dp_batch_cap > B) ? d->dp_batch_cap : B;    // rows per rank in the sparse exchange
         scatter_bytes = with_scatter ? scatter_scratch_bytes(2 * cap * world) : 0;      // user + item share one sort
@@ -362,8 +363,20 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
         float *db1 = (r == 0 && grads->b0 != nullptr && grads->res_b1[r] == nullptr) ? w.vec_a : grads->res_b1[r];
         DCNR_TRY(launch_bn_act_bwd(g3, H, s.d1[r], H, s.z1[r], H, mean1, rstd1, params->res_g1[r], post, g3, H, nullptr,
                                    0, grads->res_g1[r], grads->res_be1[r], db1, B, H, w.bn, st, dims->comm));
-        if (grads->res_w1[r])
-            DCNR_TRY(launch_linear_wgrad(prec, g3, H, s.h[r], H, grads->res_w1[r], H, nullptr, B, H, H, H, w.wgrad, st));
+        if (grads->res_w1[r]) {
+            // Block 0 reads h0 = x0 W0^T + b0, the one activation of the tower that no BatchNorm / ReLU has re-centred: its
+            // column means are several times its spread (5x on the synthetic states), and dz1 sums to ~0 over the batch, so
+            // dz1^T h0 cancels heavily.  The tensor-core kernel takes h0 - mu (mu = column means of a 2 048-row sample) and the
+            // exact rank-1 remainder colsum(dz1) (x) mu is added with the slabs: 4.7e-6 -> 6.9e-7 against float64 on the
+            // operands of a real step (profiles/r02_wgrad_centering.md).
+            const float *mu = nullptr;
+            if (r == 0 && db1 != nullptr && prec == DCNR_PREC_TF32X3) {
+                DCNR_TRY(launch_col_mean_sample(s.h[0], H, B, H, w.vec_c, st));
+                mu = w.vec_c;
+            }
+            DCNR_TRY(launch_linear_wgrad(prec, g3, H, s.h[r], H, grads->res_w1[r], H, nullptr, B, H, H, H, w.wgrad, st, mu,
+                                         mu != nullptr ? db1 : nullptr));
+        }
         GemmEpilogue idn{nullptr, nullptr, g, H, 0};                                                      // + dy2
         DCNR_TRY(gemm_any(prec, g3, H, true, params->res_w1[r], H, false, g2, H, B, H, H, 1, idn, st, wt.get(wt.w1[r])));
         std::swap(g, g2);
@@ -374,16 +387,26 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
     // runs over dy2 (elementwise products) instead of over GEMM outputs.  The tensor core's accumulate truncates toward zero
     // (profiles/r02_acc_probe.md), so a GEMM output carries a small error that is sign-correlated along the batch; a later
     // BatchNorm backward removes its column mean, but nothing does for the initial layer, where this cancellation-heavy sum
-    // collected it (3.4e-5 against a reference fp32 noise of 9e-6 at B = 4096).  The same rewrite of dW0 was tried and measured
-    // WORSE (1.6e-5 vs 1.3e-5 at B = 65 536: the error there is the weight-gradient GEMM's own), so dW0 keeps the direct form.
+    // collected it (3.4e-5 against a reference fp32 noise of 9e-6 at B = 4096).  (Rewriting dW0 = W1^T (dz1^T x0) + dy2^T x0 the
+    // same way was measured WORSE, 1.6e-5 vs 1.3e-5 at B = 65 536; dW0 is handled by centring x0, below.)
     const bool b0_split = grads->b0 != nullptr && R > 0;
-    if (grads->w0 || (grads->b0 && !b0_split))
-        DCNR_TRY(launch_linear_wgrad(prec, g, H, s.x0p, Dp, grads->w0, D, b0_split ? nullptr : grads->b0, B, H, Dp, D, w.wgrad, st));
     if (b0_split) {
         const float *db1 = grads->res_b1[0] != nullptr ? grads->res_b1[0] : w.vec_a;
         DCNR_TRY(launch_colsum(g2, H, B, H, w.vec_b, w.bn, st));
         DCNR_TRY(launch_vecmat_add(db1, params->res_w1[0], H, H, H, w.vec_b, grads->b0, st));
     }
+    // dW0 = g^T x0 collects the same batch-coherent error through the column means of x0 (the scaled numerics average 0.5):
+    // the tensor-core kernel takes x0 - mu and the rank-1 remainder uses the ACCURATE column sums of g from above,
+    // dW0 = g^T (x0 - mu) + db0 (x) mu -- identical in exact arithmetic, and the coherent part of g's error now meets a
+    // zero-mean operand (1.3e-5 -> see profiles/r02_parity_65536.md at B = 65 536).
+    const float *mu0 = nullptr;
+    if (b0_split && grads->w0 != nullptr && prec == DCNR_PREC_TF32X3) {
+        DCNR_TRY(launch_col_mean_sample(s.x0p, Dp, B, (int32_t)Dp, w.vec_c, st));
+        mu0 = w.vec_c;
+    }
+    if (grads->w0 || (grads->b0 && !b0_split))
+        DCNR_TRY(launch_linear_wgrad(prec, g, H, s.x0p, Dp, grads->w0, D, b0_split ? nullptr : grads->b0, B, H, Dp, D, w.wgrad, st,
+                                     mu0, mu0 != nullptr ? grads->b0 : nullptr));
     GemmEpilogue none{nullptr, nullptr, nullptr, 0, 0};
     DCNR_TRY(gemm_any(prec, g, H, true, s.w0p, Dp, false, w.dx0, Dp, B, Dp, H, 1, none, st, wt.get(wt.w0)));
     // cross network (recomputed from x0), accumulated onto dx0

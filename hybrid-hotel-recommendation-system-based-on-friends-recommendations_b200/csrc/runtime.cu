@@ -127,7 +127,8 @@ int launch_sum_partials(const float *partials, int64_t n_partials, int64_t ld, c
 // at B = 1 M) took 130 us.
 __global__ void __launch_bounds__(32 * kSumSlicesMax)
 k_sum_partials_2d(const float *__restrict__ partials, int64_t n_partials, int32_t rows, int32_t cols_pad, int32_t cols,
-                  float *__restrict__ out, int64_t ldo, int64_t pitch) {       // pitch: floats between consecutive partial tables
+                  float *__restrict__ out, int64_t ldo, int64_t pitch,         // pitch: floats between consecutive partial tables
+                  const float *__restrict__ u, const float *__restrict__ v) {  // optional rank-1 term u[r] * v[c]
     __shared__ double sh[kSumSlicesMax][33];
     const int kSumSlices = blockDim.x >> 5;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
@@ -155,17 +156,19 @@ k_sum_partials_2d(const float *__restrict__ partials, int64_t n_partials, int32_
             double t = sh[0][tx];
 #pragma unroll
             for (int y = 1; y < kSumSlices; ++y) t += sh[y][tx];
+            if (u != nullptr) t += (double)__ldg(u + r) * (double)__ldg(v + c);
             out[(int64_t)r * ldo + c] = (float)t;
         }
     }
 }
 
 int launch_sum_partials_2d(const float *partials, int64_t n_partials, int32_t rows, int32_t cols_pad,
-                           int32_t cols, float *out, int64_t ldo, cudaStream_t stream, int64_t pitch) {
+                           int32_t cols, float *out, int64_t ldo, cudaStream_t stream, int64_t pitch, const float *u,
+                           const float *v) {
     int64_t total = (int64_t)rows * cols_pad;
     if (pitch <= 0) pitch = total;
     k_sum_partials_2d<<<(unsigned)ceil_div(total, 32), 32 * sum_slices(n_partials), 0, stream>>>(partials, n_partials, rows, cols_pad,
-                                                                                   cols, out, ldo, pitch);
+                                                                                   cols, out, ldo, pitch, v != nullptr ? u : nullptr, v);
     DCNR_LAUNCHED();
     return DCNR_OK;
 }
