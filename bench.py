@@ -145,6 +145,28 @@ def time_steps(fn, steps, warmup, barrier):
     return ev[0].elapsed_time(ev[-1]) / 1e3       # seconds for exactly `steps` steps
 
 
+def bench_request_latency(model, dev):
+    """One ranking request (1 user x 500 candidates, main.py:320-325) through DCN_RecSys.eval(): device-resident inputs timed
+    with CUDA events back to back, and host inputs -> host scores by wall clock (H2D of 38 KB, 2 launches, D2H of 2 KB, sync)."""
+    import time
+    ru, ri, rc, rx = synth_requests(1, CANDIDATES, 99, dev)
+    with torch.no_grad():
+        dev_us = time_steps(lambda: model(ru, ri, rc, rx), 300, 30, lambda: None) / 300 * 1e6
+        hs = [t.cpu().pin_memory() for t in (ru, ri, rc, rx)]
+
+        def host_call():
+            return model(*(t.to(dev, non_blocking=True) for t in hs)).cpu()
+        for _ in range(30):
+            host_call()
+        t0 = time.perf_counter()
+        for _ in range(300):
+            host_call()
+        host_us = (time.perf_counter() - t0) / 300 * 1e6
+    return {"rows": CANDIDATES, "us_device_resident": dev_us, "us_host_to_host": host_us,
+            "what": "one request of 500 candidates through the module call; the reference's CPU forward of the same request takes "
+                    "2.55 ms (SURVEY 8a, a8)"}
+
+
 def load_reference():
     """The reference's own module (main.py: DCN_RecSys at main.py:93-127) from $REF_DIR or from baseline/_ref, the git-ignored
     copy __graft_entry__.build() makes in the build container and gpurun ships to the GPU box (the reference is a set of
@@ -318,7 +340,7 @@ def main():
     assert abs(float(hout.double().sum()) - checksum) <= 1e-6 * max(1.0, abs(checksum)) * 10, "e2e result differs"
 
     # ---- roofline of the dominant kernel ---------------------------------------------------------------------------------
-    # fp16x3 / bf16: the fused tower kernel (one launch per 1 Mi-row chunk: initial layer + 2R hidden layers + final dot);
+    # fp16x3 / bf16: the fused tower kernel (one launch per pass of up to 4 Mi rows: initial layer + 2R hidden layers + final dot);
     # other precisions: the per-layer dense GEMMs.  "isolated": the kernel alone on resident operands.
     M, H = min(rows, 1 << 20), P0["hidden_dim"]
     prec = C.PRECISIONS[args.precision]
@@ -335,7 +357,7 @@ def main():
         k_flops = M * (2.0 * dims.in_dim * H + 4 * 2.0 * H * H + 2.0 * H)
         del x0, tout
         kname = f"k_tower_eval (fused tower, tcgen05 kind::f16, {args.precision})"
-        what = ("one fused-tower launch per 1 Mi-row chunk (initial layer + four 256x256 layers + final dot, activations in TMEM); "
+        what = ("one fused-tower launch per pass of up to 4 Mi rows (initial layer + four 256x256 layers + final dot, activations in TMEM); "
                 "algorithmic flops = rows x (2*57*256 + 4*2*256*256 + 2*256)")
         iso_how = f"dcnr_tower_eval on {M} resident rows alone, 10 launches after 3 warm-ups (includes the weight-pack kernel)"
     else:
@@ -395,6 +417,7 @@ def main():
             roofline["traffic"] = t["dram_bytes_per_launch"]
             roofline["traffic_note"] = t["note"]
     if not args.skip_extras:
+        result["request_latency"] = bench_request_latency(model, dev)
         comm = None
         if world > 1:
             comm = dcnr_b200.distributed.Communicator()

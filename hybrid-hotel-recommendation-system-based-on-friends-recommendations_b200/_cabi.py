@@ -14,7 +14,8 @@ import torch
 MAX_CAT, MAX_RES, MAX_CROSS, PAD = 8, 8, 8, 32
 OK, ERR_INVALID, ERR_CUDA, ERR_WORKSPACE, ERR_INDEX = 0, -1, -2, -3, -4
 PRECISIONS = {"fp32": 0, "tf32x3": 1, "tf32": 2, "bf16": 3, "fp16x3": 4}
-ABI_VERSION = 3
+PRECISION_NAMES = {v: k for k, v in PRECISIONS.items()}
+ABI_VERSION = 4
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libdcnr_sm100a.so")
@@ -26,7 +27,15 @@ class Dims(Structure):
                 ("n_users", c_int64), ("n_items", c_int64), ("cat_rows", c_int64 * MAX_CAT),
                 ("cat_width", c_int32 * MAX_CAT), ("dropout_p", c_float), ("bn_eps", c_float),
                 ("bn_momentum", c_float), ("precision", c_int32), ("dp_sparse_tables", c_int32), ("dp_batch_cap", c_int64), ("dropout_step", c_void_p),
-                ("eval_flags", c_void_p), ("comm", c_void_p)]
+                ("eval_flags", c_void_p), ("tower_pack", c_void_p), ("comm", c_void_p)]
+
+
+def mark_mutated(tensors):
+    """Tell torch that kernels wrote these tensors through raw pointers (bumps ``Tensor._version``): autograd's saved-tensor
+    checks and the model's derived-weight caches key on it."""
+    ts = [t for t in tensors if t is not None]
+    if ts:
+        torch.autograd.graph.increment_version(ts)
 
 
 def _ptr_fields(spec):
@@ -107,6 +116,8 @@ _SIGS = {
                                 c_float, c_void_p, c_int64, c_void_p, c_int64, c_void_p, c_void_p, c_void_p, c_int64,
                                 c_int32, c_void_p, c_int64, c_void_p]),
     "dcnr_tower_eval_supported": (c_int, [POINTER(Dims)]),
+    "dcnr_tower_pack_bytes": (c_int64, [POINTER(Dims)]),
+    "dcnr_tower_prepare": (c_int, [POINTER(Dims), POINTER(Params), c_int32, c_void_p, c_int64, c_void_p]),
     "dcnr_tower_eval_workspace_bytes": (c_int64, [POINTER(Dims)]),
     "dcnr_tower_eval": (c_int, [POINTER(Dims), POINTER(Params), c_void_p, c_int64, c_void_p, c_void_p, c_int64, c_int32, c_int32,
                                 c_void_p, c_void_p, c_int64, c_void_p]),

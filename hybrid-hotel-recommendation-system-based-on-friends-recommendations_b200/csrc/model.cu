@@ -209,7 +209,11 @@ extern "C" int dcnr_forward_eval(const dcnr_dims *dims, const dcnr_params *param
     const CrossArgs ca = cross_args(dims, params);
     if (EvalWs::fused(dims)) {
         // gather + concat + cross network (K1), then ONE persistent kernel for the whole deep tower and the final dot
-        DCNR_TRY(launch_tower_prepare(dims, params, w.tower_pack, dims->precision, st));
+        const char *pack = static_cast<const char *>(dims->tower_pack);
+        if (pack == nullptr) {
+            DCNR_TRY(launch_tower_prepare(dims, params, w.tower_pack, dims->precision, st));
+            pack = w.tower_pack;
+        }
         for (int64_t r0 = 0; r0 < B; r0 += chunk) {
             const int64_t rows = std::min(chunk, B - r0);
             const dcnr_batch sb = slice_batch(dims, batch, r0, rows);
@@ -217,7 +221,7 @@ extern "C" int dcnr_forward_eval(const dcnr_dims *dims, const dcnr_params *param
             DCNR_TRY(make_gather_args(dims, params, &sb, &ga));
             DCNR_TRY(launch_embed_cross_fwd(&ga, nullptr, 0, rows, ca, Dp, w.x0p, Dp, nullptr, 0, params->wf + H,
                                             w.logit_cross, dims->eval_flags, st));
-            DCNR_TRY(launch_tower_eval(dims, w.x0p, Dp, w.logit_cross, params->bf, w.tower_pack, logits + r0, rows,
+            DCNR_TRY(launch_tower_eval(dims, w.x0p, Dp, w.logit_cross, params->bf, pack, logits + r0, rows,
                                        dims->eval_flags, dims->precision, 0, st));
         }
         return DCNR_OK;
@@ -437,6 +441,21 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
 }
 
 extern "C" int dcnr_tower_eval_supported(const dcnr_dims *dims) { return dims != nullptr && check_dims(dims) == DCNR_OK && tower_eval_supported(dims) ? 1 : 0; }
+
+extern "C" int64_t dcnr_tower_pack_bytes(const dcnr_dims *dims) {
+    if (dims == nullptr || !tower_eval_supported(dims)) return -1;
+    return tower_pack_bytes(dims);
+}
+
+extern "C" int dcnr_tower_prepare(const dcnr_dims *dims, const dcnr_params *params, int32_t precision, void *pack,
+                                  int64_t pack_bytes, dcnr_stream_t stream) {
+    DCNR_TRY(check_dims(dims));
+    DCNR_REQUIRE(params && pack, "null argument");
+    DCNR_REQUIRE(precision == DCNR_PREC_FP16X3 || precision == DCNR_PREC_BF16, "the fused tower runs FP16X3 or BF16");
+    DCNR_REQUIRE(tower_eval_supported(dims), "the fused tower needs hidden_dim 256 and 1..4 ResBlocks");
+    DCNR_REQUIRE(pack_bytes >= tower_pack_bytes(dims) && ((uintptr_t)pack & 255) == 0, "pack buffer too small or unaligned");
+    return launch_tower_prepare(dims, params, static_cast<char *>(pack), precision, as_stream(stream));
+}
 
 extern "C" int64_t dcnr_tower_eval_workspace_bytes(const dcnr_dims *dims) {
     if (dims == nullptr || !tower_eval_supported(dims)) return -1;

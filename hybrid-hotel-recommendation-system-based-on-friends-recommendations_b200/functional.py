@@ -210,6 +210,7 @@ class _BNActFn(Function):
         ws = _scratch(C.lib().dcnr_bn_scratch_bytes(m, n), z.device)
         C.check(C.lib().dcnr_bn_stats(C.ptr(z), n, m, n, eps, momentum, C.ptr(mean), C.ptr(rstd), C.ptr(running_mean),
                                       C.ptr(running_var), C.ptr(num_batches_tracked), C.ptr(ws), ws.numel(), C.stream()))
+        C.mark_mutated([t for t in (running_mean, running_var, num_batches_tracked) if t is not None])
         residual = None if residual is None else _f32c(residual)
         out = torch.empty_like(z)
         gamma, beta = _f32c(gamma), _f32c(beta)
@@ -282,3 +283,4 @@ def adam_step_(param, grad, exp_avg, exp_avg_sq, step, lr, betas=(0.9, 0.999), e
     assert param.is_contiguous() and grad.is_contiguous() and exp_avg.is_contiguous() and exp_avg_sq.is_contiguous()
     C.check(C.lib().dcnr_adam_step(C.ptr(param), C.ptr(grad), C.ptr(exp_avg), C.ptr(exp_avg_sq), param.numel(), lr,
                                    betas[0], betas[1], eps, weight_decay, 1 if decoupled else 0, int(step), C.stream()))
+    C.mark_mutated([param, exp_avg, exp_avg_sq])

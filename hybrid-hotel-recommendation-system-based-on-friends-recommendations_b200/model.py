@@ -116,6 +116,7 @@ class _DCNTrainFn(Function):
         mask = model._inject_drop_masks
         C.check(C.lib().dcnr_forward_train(dims, pstruct, batch, seed, C.ptr(mask), C.ptr(logits), C.ptr(saved),
                                            saved.numel(), C.stream()))
+        C.mark_mutated(model.buffers())       # the kernels updated the BatchNorm running statistics through raw pointers
         ctx.model, ctx.saved_ws, ctx.dims, ctx.pstruct = model, saved, dims, pstruct
         ctx.inputs = (user_ids, item_ids, cat_features, num_features)
         ctx.params = params
@@ -189,6 +190,7 @@ class DCN_RecSys(nn.Module):
         # calls check_eval_flags() once at the end.
         self.defer_eval_checks = False
         self._eval_flags = None
+        self._tower_pack = None             # (cache key, device buffer) of the fused tower's prepared weights
         self._inject_drop_masks = None      # uint8 [n_res, B, H] keep-mask for parity tests
 
     # ---- C-ABI marshalling -----------------------------------------------------------------
@@ -348,10 +350,28 @@ class DCN_RecSys(nn.Module):
             self._eval_flags = torch.zeros(4, dtype=torch.int32, device=dev)      # [0] flag bits, [1..2] diagnostics
         dims.eval_flags = C.ptr(self._eval_flags)
         pstruct = self._param_struct()
+        dims.tower_pack = self._tower_pack_ptr(dims, pstruct, dev)
         ws = torch.empty(C.lib().dcnr_workspace_bytes(dims, B, 0), dtype=torch.uint8, device=dev)
         logits = torch.empty(B, dtype=torch.float32, device=dev)
         C.check(C.lib().dcnr_forward_eval(dims, pstruct, batch, C.ptr(logits), C.ptr(ws), ws.numel(), C.stream()))
         return logits
+
+    def _tower_pack_ptr(self, dims, pstruct, dev):
+        """The fused tower's prepared weights (dcnr_tower_prepare), rebuilt only when a tensor it is made from changed: torch
+        bumps ``Tensor._version`` on every in-place update (optimizer step, load_state_dict, BatchNorm running statistics) and
+        ``.to()`` / ``.cuda()`` move the storage, so (data_ptr, _version) of those tensors is the cache key."""
+        if C.PRECISION_NAMES[dims.precision] not in ("fp16x3", "bf16") or not C.lib().dcnr_tower_eval_supported(dims):
+            return None
+        src = [self.initial_deep_layer.weight, self.initial_deep_layer.bias, self.final_linear.weight]
+        for blk in self.res_blocks:
+            for lin, bn in ((blk.layer1, blk.bn1), (blk.layer2, blk.bn2)):
+                src += [lin.weight, lin.bias, bn.weight, bn.bias, bn.running_mean, bn.running_var]
+        key = (dims.precision, float(dims.bn_eps), tuple((t.data_ptr(), t._version) for t in src))
+        if self._tower_pack is None or self._tower_pack[0] != key:
+            pack = torch.empty(C.lib().dcnr_tower_pack_bytes(dims), dtype=torch.uint8, device=dev)
+            C.check(C.lib().dcnr_tower_prepare(dims, pstruct, dims.precision, C.ptr(pack), pack.numel(), C.stream()))
+            self._tower_pack = (key, pack)
+        return C.ptr(self._tower_pack[1])
 
     def check_eval_flags(self) -> bool:
         """Read (and clear) the flag word of the eval() forwards since the last check.  Raises ``IndexError`` like

@@ -35,11 +35,12 @@ def sort_scored(scores: np.ndarray, item_ids):
 
 class RankingEngine:
     """Streams [rows] of (user, item, cat, num) HOST tensors through ``model`` (eval mode) and
-    returns the logits on the host.  Row chunks are double-buffered: chunk i+1 is copied
-    host->device on a copy stream while chunk i is scored; results go back device->host on the
+    returns the logits on the host.  Row chunks go through a ring of device buffers: chunks i+1, i+2 are
+    copied host->device on a copy stream while chunk i is scored (a third buffer absorbs the jitter of either side: copy and
+    compute take about the same time per chunk on a PCIe 5 host); results go back device->host on the
     compute stream.  Pinned host tensors make the copies asynchronous."""
 
-    def __init__(self, model, chunk_rows: int = 1 << 20, n_buffers: int = 2):
+    def __init__(self, model, chunk_rows: int = 1 << 20, n_buffers: int = 3):
         self.model = model
         self.dev = next(model.parameters()).device
         self.chunk_rows = int(chunk_rows)

@@ -13,6 +13,7 @@ from typing import Optional
 
 import torch
 
+from . import _cabi as C
 from . import functional as F_
 from .distributed import Communicator, allreduce_gradients, attach
 
@@ -93,6 +94,7 @@ class GraphedTrainStep:
         if self.graph is None:
             self.capture()
         self.graph.replay()
+        C.mark_mutated(self.model.buffers())                 # the replay updated the BatchNorm statistics behind torch's back
         for p, g in zip(self.params, self._grads):
             if p.grad is not g:
                 p.grad = g

@@ -28,7 +28,7 @@
 extern "C" {
 #endif
 
-#define DCNR_ABI_VERSION 3
+#define DCNR_ABI_VERSION 4
 #define DCNR_MAX_CAT 8     /* categorical tables (reference uses 2: city, hotel_type; train.py:290) */
 #define DCNR_MAX_RES 8     /* ResBlocks          (search space 1..4; train.py:183) */
 #define DCNR_MAX_CROSS 8   /* CrossLayers        (search space 1..6; train.py:182) */
@@ -93,6 +93,10 @@ typedef struct dcnr_dims {
     int32_t *eval_flags;        /* optional DEVICE int, OR-ed by dcnr_forward_eval (never cleared): bit 0 = an embedding id was out of
                                  * range (the row was read as row 0; torch raises IndexError), bit 1 = an activation left the
                                  * fp16 range of DCNR_PREC_FP16X3 (re-run the batch with DCNR_PREC_TF32X3).  NULL: not reported */
+    const void *tower_pack;     /* optional DEVICE buffer written by dcnr_tower_prepare for THESE parameters and this precision:
+                                 * dcnr_forward_eval then skips its per-call weight preparation (one launch less per call; it
+                                 * matters for single requests).  NULL: prepared in the workspace on every call.  The caller
+                                 * re-prepares after any parameter or running-statistics update */
     void *comm;                 /* data-parallel group (dcnr_comm_create) or NULL.  When set, train-mode BatchNorm
                                  * statistics and the BatchNorm backward reductions cover the batches of ALL ranks, so an
                                  * N-rank step equals the reference's single-device step on the concatenated batch */
@@ -294,6 +298,10 @@ int dcnr_bn_act_bwd(const float *g, int64_t ldg, const float *out, int64_t ldo, 
  * point at >= 3 ints. */
 int dcnr_tower_eval_supported(const dcnr_dims *dims);
 int64_t dcnr_tower_eval_workspace_bytes(const dcnr_dims *dims);
+/* The weight pack of the fused tower (pre-split fp16 / bf16 weights, folded BatchNorm scale / shift) for dcnr_dims.tower_pack. */
+int64_t dcnr_tower_pack_bytes(const dcnr_dims *dims);
+int dcnr_tower_prepare(const dcnr_dims *dims, const dcnr_params *params, int32_t precision, void *pack, int64_t pack_bytes,
+                       dcnr_stream_t stream);
 int dcnr_tower_eval(const dcnr_dims *dims, const dcnr_params *params, const float *x0, int64_t ldx0,
                     const float *logit_cross, float *logits, int64_t m, int32_t precision, int32_t options, int32_t *flags,
                     void *workspace, int64_t workspace_bytes, dcnr_stream_t stream);

@@ -30,7 +30,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(raw, n), f"{n} declared in include/dcnr.h but not exported"
     assert set(C.EXPORTS) == set(names), set(C.EXPORTS) ^ set(names)
-    assert C.lib().dcnr_abi_version() == C.ABI_VERSION == 3
+    assert C.lib().dcnr_abi_version() == C.ABI_VERSION == 4
 
 
 def test_ctypes_structs_match_header_sizes(tmp_path):

@@ -116,10 +116,47 @@ def test_whole_model_eval_uses_fused_tower(precision):
         out = m(u.cuda(), i.cuda(), c.cuda(), x.cuda())
     launches = C.launch_count()
     assert launches == 3, launches          # weight pack, gather + cross, fused tower
+    C.launch_count(reset=True)
+    with torch.no_grad():
+        again = m(u.cuda(), i.cuda(), c.cuda(), x.cuda())
+    assert C.launch_count() == 2            # the prepared weights are cached until a parameter changes
+    assert torch.equal(again, out)
     err = orc.max_abs_normalised(out.cpu(), ref)
     assert err < (TOL if precision == "fp16x3" else BF16_TOL), err
     if precision == "bf16":
         assert err > 1e-5                   # it really is the reduced-precision arithmetic (not an alias of a parity mode)
+
+
+def test_prepared_weights_follow_parameter_updates():
+    """The cached weight pack of the fused tower is rebuilt after in-place updates by torch (an optimizer step), by this
+    library's fused Adam, and after a training step of our kernels moved the BatchNorm running statistics."""
+    import dcnr_b200
+    from dcnr_b200 import functional as F_
+    params, st, nu, ni = _state()
+    B = 3000
+    u, i, c, x, y = synth_inputs(nu, ni, CAT, 11, B, seed=4)
+    args = (u.cuda(), i.cuda(), c.cuda(), x.cuda())
+    m = _model(params, st, nu, ni, "fp16x3")
+
+    def fresh_eval():
+        f = dcnr_b200.DCN_RecSys(nu, ni, CAT, 11, params, precision="fp16x3")
+        f.load_state_dict(m.state_dict())
+        f = f.cuda().eval()
+        with torch.no_grad():
+            return f(*args)
+
+    with torch.no_grad():
+        first = m(*args)
+        m.res_blocks[0].layer1.weight.mul_(1.5)                          # torch in-place update
+        assert torch.equal(m(*args), fresh_eval()) and not torch.equal(m(*args), first)
+        w = m.res_blocks[1].layer2.weight
+        F_.adam_step_(w, torch.ones_like(w), torch.zeros_like(w), torch.zeros_like(w), 1, 0.05)      # raw-pointer update
+        assert torch.equal(m(*args), fresh_eval())
+    m.train()
+    m(*args).sum().backward()                                            # moves the running statistics
+    m.eval()
+    with torch.no_grad():
+        assert torch.equal(m(*args), fresh_eval())
 
 
 def test_eval_reports_out_of_range_ids():
