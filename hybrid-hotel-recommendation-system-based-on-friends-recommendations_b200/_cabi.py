@@ -126,6 +126,10 @@ _SIGS = {
     "dcnr_knn_scratch_bytes": (c_int64, [c_int64, c_int32, c_int32, c_int32]),
     "dcnr_knn_topk": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p,
                               c_void_p, c_int64, c_void_p]),
+    "dcnr_knn_tc_supported": (c_int, [c_int64, c_int32, c_int32, c_int32]),
+    "dcnr_knn_tc_scratch_bytes": (c_int64, [c_int64, c_int32, c_int32, c_int32]),
+    "dcnr_knn_topk_tc": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_int32, c_int32, c_int64, c_void_p, c_void_p, c_void_p,
+                                 c_int64, c_void_p, c_void_p]),
     "dcnr_knn_merge": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p, c_void_p]),
     "dcnr_mmr_rerank": (c_int, [c_void_p, c_int64, c_int32, c_void_p, c_void_p, c_void_p, c_int32, c_float, c_int32, c_int32,
                                 c_void_p, c_void_p, c_void_p]),

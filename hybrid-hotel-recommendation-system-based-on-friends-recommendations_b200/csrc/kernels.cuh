@@ -106,6 +106,12 @@ int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const floa
 // out[c] = mean of a[0:min(m, 2048), c]: a cheap estimate of the column means (one launch), n % 32 == 0
 int launch_col_mean_sample(const float *a, int64_t lda, int64_t m, int32_t n, float *out, cudaStream_t stream);
 
+// ---- tensor-core shortlist + exact re-score top-k for query batches (topk_tc.cu) ----
+bool knn_tc_supported(int64_t n, int32_t d, int32_t n_queries, int32_t k);
+int64_t knn_tc_scratch_bytes(int64_t n, int32_t d, int32_t n_queries, int32_t k);
+int launch_knn_tc(const float *cat, int64_t n, int32_t d, const float *queries, int32_t n_queries, int32_t k, int64_t idx_base,
+                  float *dist_out, int64_t *idx_out, void *scratch, int64_t scratch_bytes, int32_t *status, cudaStream_t st);
+
 // ---- fused eval tower (tower_eval.cu): initial layer + ResBlocks + deep half of the final dot in ONE persistent kernel ----
 bool tower_eval_supported(const dcnr_dims *d);                 // hidden 256, 1..4 ResBlocks, in_dim_pad <= 256
 int64_t tower_pack_bytes(const dcnr_dims *d);

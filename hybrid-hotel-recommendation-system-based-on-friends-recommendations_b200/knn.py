@@ -30,6 +30,7 @@ class NearestNeighbors:
         self.device = torch.device(device) if device is not None else torch.device("cuda", torch.cuda.current_device()) \
             if torch.cuda.is_available() else None
         self.index_base = int(index_base)
+        self.tc_min_queries = 8             # query batches from this size on take the tensor-core shortlist path
         self._catalog_hat: Optional[torch.Tensor] = None
 
     # ---- fit ---------------------------------------------------------------------------------
@@ -66,6 +67,16 @@ class NearestNeighbors:
         with torch.cuda.device(Q.device):
             qhat = torch.empty_like(Q)
             C.check(C.lib().dcnr_knn_normalize(C.ptr(Q), C.ptr(qhat), nq, d, C.stream()))
+            # Query batches: tensor-core shortlist + exact re-score (same results bit for bit; csrc/topk_tc.cu).  The status
+            # word is read back once per call: a shortlist that overflowed (pathological duplicates) sends the batch down
+            # the exact streaming path below.
+            if nq >= self.tc_min_queries and C.lib().dcnr_knn_tc_supported(n, d, nq, k):
+                ws = torch.empty(C.lib().dcnr_knn_tc_scratch_bytes(n, d, nq, k), dtype=torch.uint8, device=Q.device)
+                status = torch.zeros(1, dtype=torch.int32, device=Q.device)
+                C.check(C.lib().dcnr_knn_topk_tc(C.ptr(self._catalog_hat), n, d, C.ptr(qhat), nq, k, self.index_base,
+                                                 C.ptr(dist), C.ptr(ind), C.ptr(ws), ws.numel(), C.ptr(status), C.stream()))
+                if int(status.item()) == 0:
+                    return dist, ind
             # k up to 256 per launch; query tiles of 1024 bound the scratch
             for q0 in range(0, nq, 1024):
                 q1 = min(nq, q0 + 1024)

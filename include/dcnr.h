@@ -329,6 +329,18 @@ int dcnr_knn_topk(const float *catalog_hat, int64_t n, int32_t d, const float *q
                   int32_t k, int64_t idx_base, float *dist_out, int64_t *idx_out, void *scratch,
                   int64_t scratch_bytes, dcnr_stream_t stream);
 
+/* The same result for a BATCH of queries, found with a tensor-core shortlist: tcgen05 kind::tf32 scores of every (row, query)
+ * pair decide which rows are re-scored with the exact arithmetic above (error bound 2e-3 on unit vectors, thresholds from exact
+ * top-k of row samples: no member of the true top-k can be dropped -- csrc/topk_tc.cu has the argument).  One catalog pass for
+ * up to 1 024 queries (d = 16).  Shapes: d in {16, 32, 64}, 2^18 <= n <= 2^24, k <= 256 (dcnr_knn_tc_supported).
+ * status: optional DEVICE int, OR-ed: bit 0 = a per-query shortlist overflowed (pathological duplicates; the outputs are
+ * then NOT valid and the caller re-runs the batch with dcnr_knn_topk). */
+int dcnr_knn_tc_supported(int64_t n, int32_t d, int32_t n_queries, int32_t k);
+int64_t dcnr_knn_tc_scratch_bytes(int64_t n, int32_t d, int32_t n_queries, int32_t k);
+int dcnr_knn_topk_tc(const float *catalog_hat, int64_t n, int32_t d, const float *queries_hat, int32_t n_queries,
+                     int32_t k, int64_t idx_base, float *dist_out, int64_t *idx_out, void *scratch,
+                     int64_t scratch_bytes, int32_t *status, dcnr_stream_t stream);
+
 /* Cross-shard merge: parts [n_parts, n_queries, k] (each row sorted, (inf,-1) padded) -> [n_queries, k]
  * in the same total order, so the result does not depend on the shard count. */
 int dcnr_knn_merge(const float *dist_parts, const int64_t *idx_parts, int32_t n_parts, int32_t n_queries,

@@ -96,3 +96,73 @@ def test_full_size_properties():
     # a brute-force check of the k-th distance: nothing outside the list is closer
     all_d = (1 - ehat @ ehat[rows[1]]).clamp_(0, 2)
     assert int((all_d < d[1, -1] - 1e-6).sum()) <= 201
+
+
+# ---- query batches: tensor-core shortlist + exact re-score (csrc/topk_tc.cu) ------------------------------------------------
+def _both_paths(E, Q, k, index_base=0):
+    """(tensor-core path, exact streaming path) results for the same fitted catalog."""
+    import dcnr_b200
+    model = dcnr_b200.NearestNeighbors(index_base=index_base).fit(E)
+    from dcnr_b200 import _cabi as C
+    assert C.lib().dcnr_knn_tc_supported(E.shape[0], E.shape[1], Q.shape[0], k)
+    tc = model.kneighbors_tensor(Q, k)
+    model.tc_min_queries = 1 << 30
+    exact = model.kneighbors_tensor(Q, k)
+    return tc, exact
+
+
+@pytest.mark.parametrize("n,d,nq,k", [(300_000, 16, 8, 11), (300_000, 16, 33, 201), (270_001, 32, 300, 51), (262_144, 64, 40, 256),
+                                      (1_000_000, 16, 1024, 201), (500_000, 64, 700, 16)])
+def test_batched_queries_bit_exact_with_the_streaming_path(n, d, nq, k):
+    g = torch.Generator(device="cuda").manual_seed(n + d + nq)
+    E = torch.randn(n, d, device="cuda", generator=g)
+    E[1000] = E[17].clone(); E[n - 1] = E[17].clone(); E[5] = 0.0                     # ties across tiles, a zero row
+    rows = torch.randint(0, n, (nq,), device="cuda", generator=g)
+    rows[0] = 17
+    Q = E[rows] + 0.05 * torch.randn(nq, d, device="cuda", generator=g)
+    Q[0] = E[17]
+    if nq > 2:
+        Q[1] = 0.0                                                    # a zero query: every distance is 1, order = index order
+        Q[2] = torch.randn(d, device="cuda", generator=g)             # a query far from everything
+    (td, ti), (ed, ei) = _both_paths(E, Q, k, index_base=7_000)
+    assert torch.equal(ti, ei)
+    assert torch.equal(td.view(torch.int32), ed.view(torch.int32))
+    assert int(ti[0, 0]) == 7_000 + 17 and int(ti[0, 1]) == 7_000 + 1000 and int(ti[0, 2]) == 7_000 + n - 1
+
+
+def test_batched_queries_against_oracle():
+    rng = np.random.default_rng(5)
+    n, d, nq, k = 280_000, 16, 12, 31
+    E = rng.standard_normal((n, d)).astype(np.float32)
+    Q = E[rng.integers(0, n, nq)] + (0.02 * rng.standard_normal((nq, d))).astype(np.float32)
+    ref_d, ref_i = knn_oracle.OracleNearestNeighbors().fit(E).kneighbors(Q, n_neighbors=k)
+    import dcnr_b200
+    model = dcnr_b200.NearestNeighbors().fit(E)
+    assert nq >= model.tc_min_queries
+    got_d, got_i = model.kneighbors(Q, n_neighbors=k)
+    assert np.array_equal(got_i, ref_i)
+    assert np.array_equal(got_d.view(np.uint32), ref_d.view(np.uint32))
+
+
+def test_shortlist_overflow_falls_back_to_the_streaming_path():
+    """60 000 copies of one vector: every copy passes the query's threshold, the per-query list overflows, the status word
+    sends the batch down the exact path -- the answer is still the first k copies in index order."""
+    g = torch.Generator(device="cuda").manual_seed(9)
+    n, d, k = 400_000, 16, 21
+    E = torch.randn(n, d, device="cuda", generator=g)
+    dup = torch.arange(1000, 400_000, 6, device="cuda")[:60_000]
+    E[dup] = E[3].clone()
+    Q = torch.cat([E[3:4], torch.randn(9, d, device="cuda", generator=g)])
+    from dcnr_b200 import _cabi as C
+    import dcnr_b200
+    model = dcnr_b200.NearestNeighbors().fit(E)
+    qhat = torch.nn.functional.normalize(Q)
+    ws = torch.empty(C.lib().dcnr_knn_tc_scratch_bytes(n, d, 10, k), dtype=torch.uint8, device="cuda")
+    status = torch.zeros(1, dtype=torch.int32, device="cuda")
+    dist = torch.empty(10, k, device="cuda"); ind = torch.empty(10, k, dtype=torch.int64, device="cuda")
+    C.check(C.lib().dcnr_knn_topk_tc(C.ptr(model._catalog_hat), n, d, C.ptr(qhat), 10, k, 0, C.ptr(dist), C.ptr(ind), C.ptr(ws),
+                                     ws.numel(), C.ptr(status), C.stream()))
+    assert int(status.item()) & 1
+    td, ti = model.kneighbors_tensor(Q, k)
+    expect = torch.cat([torch.tensor([3], device="cuda"), dup[: k - 1]])
+    assert torch.equal(ti[0], expect)
