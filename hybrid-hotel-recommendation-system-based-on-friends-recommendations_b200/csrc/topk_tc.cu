@@ -35,7 +35,9 @@ typedef unsigned long long u64;
 
 constexpr int BM = 128;                 // catalog rows per tile
 constexpr int NB = 256;                 // queries per MMA block (accumulator columns)
-constexpr int kThreads = 32 * 11;       // warp 0 TMA, warp 1 MMA, warps 2-9 score read-back, warp 10 flusher
+constexpr int kSelWarps = 16;           // score read-back warps: four per TMEM lane quadrant
+constexpr int kThreads = 32 * (3 + kSelWarps);      // warp 0 TMA, warp 1 MMA, warps 2-17 score read-back, warp 18 flusher
+constexpr int kMaxBuf = 8;              // accumulator slots in tensor memory (512 columns / slot width)
 constexpr int kRing = 4096;             // shared-memory ring of (query, row) survivors
 constexpr int kSampleRows = 8192;       // level 0
 constexpr int kListCap = 16384;         // survivors per query and level
@@ -47,10 +49,10 @@ constexpr int kMaxQueries = 1024;       // per launch (shared memory: d 16 -> 1 
 struct Params {
     int64_t n_rows, n_tiles, tile_stride;       // tile t covers rows [t * tile_stride * 128, + 128)
     int32_t d, kb_floats, nkb, nq, nqb, stages;
+    int32_t slot_cols, nbuf;                    // accumulator slot width (32 .. 256 columns) and count (2 .. kMaxBuf)
     const float *thr;                           // [nq] keep a row when its approximate score is >= thr
     uint32_t *lists;                            // [nq][kListCap]
     int32_t *counts;                            // [nq]
-    int32_t dbg;   // TEMP
 };
 
 __device__ __forceinline__ float exact_dist(const float *__restrict__ row, const float *__restrict__ q, int dv) {
@@ -196,25 +198,25 @@ k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
     uint8_t *cs = qs + (size_t)p.nqb * p.nkb * q_sub;                  // [stages][nkb][BM x KB]
     float *thr_s = reinterpret_cast<float *>(cs + (size_t)p.stages * p.nkb * c_sub);      // [nqb * NB]
     u64 *ring = reinterpret_cast<u64 *>(thr_s + p.nqb * NB);           // [kRing]
-    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + kRing);       // full[stages], empty[stages], accfull[2], accfree[2], qfull
-    uint32_t *ctl = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 5);        // head, tail, done, tmem slot
+    uint64_t *bars = reinterpret_cast<uint64_t *>(ring + kRing);       // full[stages], empty[stages], accfull[kMaxBuf], accfree[kMaxBuf], qfull
+    uint32_t *ctl = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 2 * kMaxBuf + 1);        // head, tail, done, tmem slot
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * p.stages, accfull0 = empty0 + 8 * p.stages,
-                   accfree0 = accfull0 + 16, qfull = accfree0 + 16;
+                   accfree0 = accfull0 + 8 * kMaxBuf, qfull = accfree0 + 8 * kMaxBuf;
     volatile uint32_t *head = ctl, *tail = ctl + 1, *done = ctl + 2;
     uint32_t *tmem_slot = ctl + 3;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (int i = threadIdx.x; i < kRing; i += kThreads) ring[i] = kEmpty;
-    for (int i = threadIdx.x; i < p.nqb * NB; i += kThreads) thr_s[i] = (i < p.nq && !((p.dbg & 1) && p.tile_stride == 1)) ? p.thr[i] : __int_as_float(0x7f800000);
+    for (int i = threadIdx.x; i < p.nqb * NB; i += kThreads) thr_s[i] = i < p.nq ? p.thr[i] : __int_as_float(0x7f800000);
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full0 + 8 * s, 1);
             mbar_init(empty0 + 8 * s, 1);
         }
-        mbar_init(accfull0, 1);
-        mbar_init(accfull0 + 8, 1);
-        mbar_init(accfree0, 8);
-        mbar_init(accfree0 + 8, 8);
+        for (int b = 0; b < kMaxBuf; ++b) {
+            mbar_init(accfull0 + 8 * b, 1);
+            mbar_init(accfree0 + 8 * b, kSelWarps);
+        }
         mbar_init(qfull, 1);
         ctl[0] = ctl[1] = ctl[2] = 0;
         mbar_init_fence();
@@ -251,12 +253,12 @@ k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
     } else if (warp == 1) {
         // ---------------- MMA issuer: every query block against the landed tile ----------------
         mbar_wait(qfull, 0);
-        int s = 0; uint32_t ph = 0, buf = 0, aph[2] = {0, 0};
+        int s = 0; uint32_t ph = 0, buf = 0, aph = 0;                   // aph: one phase bit per accumulator slot
         for (int64_t i = 0; i < my_tiles; ++i) {
             mbar_wait(full0 + 8 * s, ph);
             tc_fence_after();
             for (int qb = 0; qb < p.nqb; ++qb) {
-                mbar_wait(accfree0 + 8 * buf, aph[buf] ^ 1);
+                mbar_wait(accfree0 + 8 * buf, ((aph >> buf) & 1u) ^ 1u);
                 tc_fence_after();
                 if (elect_one()) {
                     const int ncols = min(NB, ((p.nq - qb * NB + 15) >> 4) << 4);
@@ -265,35 +267,37 @@ k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
                         const uint64_t da = smem_desc_kmajor(smem_u32(cs + (size_t)(s * p.nkb + kb) * c_sub), kbb);
                         const uint64_t db = smem_desc_kmajor(smem_u32(qs + (size_t)(qb * p.nkb + kb) * q_sub), kbb);
                         for (int ks = 0; ks < p.kb_floats / 8; ++ks)
-                            mma_tf32_ss(tmem_base + buf * NB, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc,
+                            mma_tf32_ss(tmem_base + buf * p.slot_cols, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc,
                                         (uint32_t)((kb | ks) != 0));
                     }
                     mma_commit<1>(accfull0 + 8 * buf);
                     if (qb == p.nqb - 1) mma_commit<1>(empty0 + 8 * s);
                 }
                 __syncwarp();
-                aph[buf] ^= 1u;
-                buf ^= 1u;
+                aph ^= 1u << buf;
+                if (++buf == (uint32_t)p.nbuf) buf = 0;
             }
             if (++s == p.stages) { s = 0; ph ^= 1u; }
         }
-    } else if (warp < 10) {
+    } else if (warp < 2 + kSelWarps) {
         // ---------------- score read-back: lane = catalog row, 32 queries per tcgen05.ld ----------------
-        const int quad = warp & 3, half = (warp - 2) >> 2;
-        uint32_t buf = 0, fph[2] = {0, 0};
+        // work item = (tile, query block, group of 32 queries); items are dealt round-robin to the four warps of a quadrant,
+        // so with few queries (one group per tile) the warps take alternate TILES
+        const int quad = warp & 3, part = (warp - 2) >> 2, nparts = kSelWarps / 4;
+        uint32_t buf = 0, fph = 0, item = 0;
         for (int64_t i = 0; i < my_tiles; ++i) {
             const int64_t t = blockIdx.x + i * gridDim.x;
             const int64_t row = t * p.tile_stride * BM + quad * 32 + lane;
             const bool valid = row < p.n_rows;
             for (int qb = 0; qb < p.nqb; ++qb) {
-                mbar_wait(accfull0 + 8 * buf, fph[buf]);
+                mbar_wait(accfull0 + 8 * buf, (fph >> buf) & 1u);
                 tc_fence_after();
                 const int ncols = min(NB, p.nq - qb * NB);
                 const int groups = (ncols + 31) >> 5;
-                for (int g = half; g < groups; g += 2) {
+                for (int g = 0; g < groups; ++g) {
+                    if ((int)((item + g) % nparts) != part) continue;
                     uint32_t r[32];
-                    if (!(p.dbg & 2)) tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * NB + g * 32, r);
-                    else { for (int j = 0; j < 32; ++j) r[j] = 0; }
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * p.slot_cols + g * 32, r);
                     const float4 *th = reinterpret_cast<const float4 *>(thr_s + qb * NB + g * 32);
                     // branch-free hit mask (bit j = query j of the group passes); the rare survivors are then walked in a
                     // COMPACT loop -- a 32-way unrolled "if hit then push" cost ~3 000 clk per entry in instruction fetch
@@ -323,8 +327,9 @@ k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(accfree0 + 8 * buf);
-                fph[buf] ^= 1u;
-                buf ^= 1u;
+                item += (uint32_t)groups;
+                fph ^= 1u << buf;
+                if (++buf == (uint32_t)p.nbuf) buf = 0;
             }
         }
         __syncwarp();
@@ -337,7 +342,7 @@ k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
             const uint32_t h = *head;
             uint32_t avail = h - t0;
             if (avail == 0) {
-                if (*done == 8u && *head == t0) break;
+                if (*done == (uint32_t)kSelWarps && *head == t0) break;
                 __nanosleep(100);
                 if (++idle > (1u << 26)) __trap();
                 continue;
@@ -492,9 +497,10 @@ int launch_knn_tc(const float *cat, int64_t n, int32_t d, const float *queries, 
         CUtensorMap tmQ;
         DCNR_TRY(make_map(&tmQ, qp, nq, d, kbf, NB));
         Params p{};
-        p.dbg = getenv("KT_DBG") ? atoi(getenv("KT_DBG")) : 0;
         p.n_rows = n; p.d = d; p.kb_floats = kbf; p.nkb = nkb; p.nq = nq; p.nqb = (int)ceil_div(nq, NB);
         p.thr = thr; p.lists = lists; p.counts = counts;
+        p.slot_cols = nq >= NB ? NB : (int)round_up(nq, 32);
+        p.nbuf = std::min(kMaxBuf, 512 / p.slot_cols);
         const size_t fixed = (size_t)p.nqb * nkb * NB * kbf * 4 + (size_t)p.nqb * NB * 4 + (size_t)kRing * 8 + 256 + 1024;
         p.stages = (int)std::max<int64_t>(2, std::min<int64_t>(6, ((int64_t)200 * 1024 - (int64_t)fixed) / ((int64_t)nkb * BM * kbf * 4)));
         const size_t smem = fixed + (size_t)p.stages * nkb * BM * kbf * 4;
