@@ -47,9 +47,11 @@ constexpr u64 kMaxKey = ~0ull;
 constexpr int kMaxQueries = 1024;       // per launch (shared memory: d 16 -> 1 024, d 32 -> 512, d 64 -> 256)
 
 struct Params {
-    int64_t n_rows, n_tiles, tile_stride;       // tile t covers rows [t * tile_stride * 128, + 128)
+    int64_t n_rows, n_tiles, tile_stride;       // tile t covers rows [t * tile_stride * 128 * sub, + 128 * sub)
     int32_t d, kb_floats, nkb, nq, nqb, stages;
-    int32_t slot_cols, nbuf;                    // accumulator slot width (32 .. 256 columns) and count (2 .. kMaxBuf)
+    int32_t slot_cols, nbuf;                    // accumulator slot width (32 .. 256 columns per sub-tile) and count (2 .. kMaxBuf)
+    int32_t sub;                                // 128-row sub-tiles per tile (4 / 2 for <= 32 / <= 64 queries: one barrier round
+                                                // then covers 512 / 256 rows and every read-back warp has work on every tile)
     const float *thr;                           // [nq] keep a row when its approximate score is >= thr
     uint32_t *lists;                            // [nq][kListCap]
     int32_t *counts;                            // [nq]
@@ -195,8 +197,8 @@ k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
     const int kbb = p.kb_floats * 4;                                   // row bytes of a K block: 64 or 128
     const int q_sub = NB * kbb, c_sub = BM * kbb;                      // one [256 x KB] query / [128 x KB] catalog sub-tile
     uint8_t *qs = smem;                                                // [nqb][nkb][NB x KB]
-    uint8_t *cs = qs + (size_t)p.nqb * p.nkb * q_sub;                  // [stages][nkb][BM x KB]
-    float *thr_s = reinterpret_cast<float *>(cs + (size_t)p.stages * p.nkb * c_sub);      // [nqb * NB]
+    uint8_t *cs = qs + (size_t)p.nqb * p.nkb * q_sub;                  // [stages][sub][nkb][BM x KB]
+    float *thr_s = reinterpret_cast<float *>(cs + (size_t)p.stages * p.sub * p.nkb * c_sub);      // [nqb * NB]
     u64 *ring = reinterpret_cast<u64 *>(thr_s + p.nqb * NB);           // [kRing]
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring + kRing);       // full[stages], empty[stages], accfull[kMaxBuf], accfree[kMaxBuf], qfull
     uint32_t *ctl = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 2 * kMaxBuf + 1);        // head, tail, done, tmem slot
@@ -242,10 +244,11 @@ k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
             const int64_t t = blockIdx.x + i * gridDim.x;
             mbar_wait(empty0 + 8 * s, ph ^ 1);
             if (elect_one()) {
-                mbar_expect_tx(full0 + 8 * s, (uint32_t)(p.nkb * c_sub));
-                for (int kb = 0; kb < p.nkb; ++kb)
-                    tma_load_2d(smem_u32(cs + (size_t)(s * p.nkb + kb) * c_sub), &tmC, kb * p.kb_floats,
-                                (int)(t * p.tile_stride * BM), full0 + 8 * s);
+                mbar_expect_tx(full0 + 8 * s, (uint32_t)(p.sub * p.nkb * c_sub));
+                for (int j = 0; j < p.sub; ++j)
+                    for (int kb = 0; kb < p.nkb; ++kb)
+                        tma_load_2d(smem_u32(cs + (size_t)((s * p.sub + j) * p.nkb + kb) * c_sub), &tmC, kb * p.kb_floats,
+                                    (int)((t * p.tile_stride * p.sub + j) * BM), full0 + 8 * s);
             }
             __syncwarp();
             if (++s == p.stages) { s = 0; ph ^= 1u; }
@@ -263,13 +266,14 @@ k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
                 if (elect_one()) {
                     const int ncols = min(NB, ((p.nq - qb * NB + 15) >> 4) << 4);
                     const uint32_t idesc = idesc_tf32(BM, ncols);
-                    for (int kb = 0; kb < p.nkb; ++kb) {
-                        const uint64_t da = smem_desc_kmajor(smem_u32(cs + (size_t)(s * p.nkb + kb) * c_sub), kbb);
-                        const uint64_t db = smem_desc_kmajor(smem_u32(qs + (size_t)(qb * p.nkb + kb) * q_sub), kbb);
-                        for (int ks = 0; ks < p.kb_floats / 8; ++ks)
-                            mma_tf32_ss(tmem_base + buf * p.slot_cols, da + (uint64_t)(ks * 2), db + (uint64_t)(ks * 2), idesc,
-                                        (uint32_t)((kb | ks) != 0));
-                    }
+                    for (int j = 0; j < p.sub; ++j)
+                        for (int kb = 0; kb < p.nkb; ++kb) {
+                            const uint64_t da = smem_desc_kmajor(smem_u32(cs + (size_t)((s * p.sub + j) * p.nkb + kb) * c_sub), kbb);
+                            const uint64_t db = smem_desc_kmajor(smem_u32(qs + (size_t)(qb * p.nkb + kb) * q_sub), kbb);
+                            for (int ks = 0; ks < p.kb_floats / 8; ++ks)
+                                mma_tf32_ss(tmem_base + (buf * p.sub + j) * p.slot_cols, da + (uint64_t)(ks * 2),
+                                            db + (uint64_t)(ks * 2), idesc, (uint32_t)((kb | ks) != 0));
+                        }
                     mma_commit<1>(accfull0 + 8 * buf);
                     if (qb == p.nqb - 1) mma_commit<1>(empty0 + 8 * s);
                 }
@@ -281,23 +285,25 @@ k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
         }
     } else if (warp < 2 + kSelWarps) {
         // ---------------- score read-back: lane = catalog row, 32 queries per tcgen05.ld ----------------
-        // work item = (tile, query block, group of 32 queries); items are dealt round-robin to the four warps of a quadrant,
-        // so with few queries (one group per tile) the warps take alternate TILES
+        // work item = (tile, query block, sub-tile, group of 32 queries); items are dealt round-robin to the four warps of a
+        // quadrant
         const int quad = warp & 3, part = (warp - 2) >> 2, nparts = kSelWarps / 4;
         uint32_t buf = 0, fph = 0, item = 0;
         for (int64_t i = 0; i < my_tiles; ++i) {
             const int64_t t = blockIdx.x + i * gridDim.x;
-            const int64_t row = t * p.tile_stride * BM + quad * 32 + lane;
-            const bool valid = row < p.n_rows;
+            const int64_t row0 = t * p.tile_stride * p.sub * BM + quad * 32 + lane;
             for (int qb = 0; qb < p.nqb; ++qb) {
                 mbar_wait(accfull0 + 8 * buf, (fph >> buf) & 1u);
                 tc_fence_after();
                 const int ncols = min(NB, p.nq - qb * NB);
                 const int groups = (ncols + 31) >> 5;
-                for (int g = 0; g < groups; ++g) {
-                    if ((int)((item + g) % nparts) != part) continue;
+                for (int w = 0; w < p.sub * groups; ++w) {
+                    if ((int)((item + w) % nparts) != part) continue;
+                    const int st = w / groups, g = w - st * groups;           // sub-tile, group of 32 queries
+                    const int64_t row = row0 + (int64_t)st * BM;
+                    const bool valid = row < p.n_rows;
                     uint32_t r[32];
-                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + buf * p.slot_cols + g * 32, r);
+                    tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (buf * p.sub + st) * p.slot_cols + g * 32, r);
                     const float4 *th = reinterpret_cast<const float4 *>(thr_s + qb * NB + g * 32);
                     // branch-free hit mask (bit j = query j of the group passes); the rare survivors are then walked in a
                     // COMPACT loop -- a 32-way unrolled "if hit then push" cost ~3 000 clk per entry in instruction fetch
@@ -327,7 +333,7 @@ k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(accfree0 + 8 * buf);
-                item += (uint32_t)groups;
+                item += (uint32_t)(p.sub * groups);
                 fph ^= 1u << buf;
                 if (++buf == (uint32_t)p.nbuf) buf = 0;
             }
@@ -500,16 +506,19 @@ int launch_knn_tc(const float *cat, int64_t n, int32_t d, const float *queries, 
         p.n_rows = n; p.d = d; p.kb_floats = kbf; p.nkb = nkb; p.nq = nq; p.nqb = (int)ceil_div(nq, NB);
         p.thr = thr; p.lists = lists; p.counts = counts;
         p.slot_cols = nq >= NB ? NB : (int)round_up(nq, 32);
-        p.nbuf = std::min(kMaxBuf, 512 / p.slot_cols);
         const size_t fixed = (size_t)p.nqb * nkb * NB * kbf * 4 + (size_t)p.nqb * NB * 4 + (size_t)kRing * 8 + 256 + 1024;
-        p.stages = (int)std::max<int64_t>(2, std::min<int64_t>(6, ((int64_t)200 * 1024 - (int64_t)fixed) / ((int64_t)nkb * BM * kbf * 4)));
-        const size_t smem = fixed + (size_t)p.stages * nkb * BM * kbf * 4;
+        p.sub = nq <= 32 ? 4 : (nq <= 64 ? 2 : 1);
+        while (p.sub > 1 && fixed + (size_t)3 * p.sub * nkb * BM * kbf * 4 > (size_t)200 * 1024) p.sub >>= 1;      // >= 3 stages
+        p.nbuf = std::min(kMaxBuf, 512 / (p.slot_cols * p.sub));
+        const int64_t stage_bytes = (int64_t)p.sub * nkb * BM * kbf * 4;
+        p.stages = (int)std::max<int64_t>(2, std::min<int64_t>(6, ((int64_t)200 * 1024 - (int64_t)fixed) / stage_bytes));
+        const size_t smem = fixed + (size_t)p.stages * stage_bytes;
         DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_knn_tc_scan, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         k_knn_tc_tau0<<<(unsigned)nq, 1024, tau_smem, st>>>(cat, n, d, qp, k, thr);
         DCNR_LAUNCHED();
         for (int level = 1; level <= 2; ++level) {
             p.tile_stride = level == 1 ? stride1 : 1;
-            p.n_tiles = ceil_div(tiles_all, p.tile_stride);
+            p.n_tiles = ceil_div(ceil_div(tiles_all, (int64_t)p.sub), p.tile_stride);
             DCNR_CUDA_CHECK(cudaMemsetAsync(counts, 0, (size_t)nq * 4, st));
             const unsigned grid = (unsigned)std::min<int64_t>(p.n_tiles, sm_count());
             k_knn_tc_scan<<<grid, kThreads, smem, st>>>(tmC, tmQ, p);
