@@ -145,6 +145,32 @@ def time_steps(fn, steps, warmup, barrier):
     return ev[0].elapsed_time(ev[-1]) / 1e3       # seconds for exactly `steps` steps
 
 
+def bind_to_gpu_numa_node(local):
+    """Best effort: pin this process to the CPUs of the NUMA node its GPU hangs off, BEFORE any pinned host buffer is
+    allocated, so the end-to-end copies do not cross the socket interconnect (8 ranks x 2.5 GB per step).  Returns the node or
+    None."""
+    try:
+        import subprocess
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if bus.startswith("00000000:"):
+            bus = bus[4:]                                   # sysfs uses a 4-digit PCI domain
+        node = int(open(f"/sys/bus/pci/devices/{bus}/numa_node").read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b_ = part.partition("-")
+            cpus.update(range(int(a), int(b_ or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
+
+
 def bench_request_latency(model, dev):
     """One ranking request (1 user x 500 candidates, main.py:320-325) through DCN_RecSys.eval(): device-resident inputs timed
     with CUDA events back to back, and host inputs -> host scores by wall clock (H2D of 38 KB, 2 launches, D2H of 2 KB, sync)."""
@@ -286,6 +312,7 @@ def main():
     rank, world = int(os.environ.get("RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a B200 (the product has no CPU path)"
+    numa_node = bind_to_gpu_numa_node(local)
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     dist = None
@@ -403,7 +430,8 @@ def main():
                                f"{args.requests} requests/step per GPU (BASELINE configs[1])",
                    "rows_per_step_per_gpu": rows, "tables": f"{N_USERS} users x {N_ITEMS} hotels",
                    "model": "emb16 hidden256 cross3 res2 (P0)", "l2": "inputs 2.5 GB per step > 126 MB L2, no flush needed",
-                   "parallelism": f"requests sharded x{world}, no data-path collective"},
+                   "parallelism": f"requests sharded x{world}, no data-path collective",
+                   "host_numa_node_of_rank0": numa_node},
         "e2e": {"value": e2e_value, "unit": "candidates/s", "h2d_bytes_per_step": rows * engine.bytes_per_row_h2d,
                 "d2h_bytes_per_step": rows * engine.bytes_per_row_d2h, "steps": e2e_steps,
                 "ms_per_step": e2e_secs / e2e_steps * 1e3},

@@ -729,14 +729,14 @@ static int block_n_for(int precision, int64_t n) { return pick_block_n(n, precis
 // warps -- 0.34 vs 0.43-0.54 ms per 1 M x 256 x 64), one otherwise (measured on the 256 x 256 layers: 0.83 vs 0.81 ms tf32x3,
 // 0.67 vs 0.62 ms tf32 -- the mainloop, not the epilogue, sets the pace there).  Also one when the tile has an odd number
 // of 32-column chunks.
-static int epi_groups_for(int block_n, int64_t k) {
+static int epi_groups_for(int block_n, int64_t k, int terms) {
     if (block_n <= 0 || (block_n / 32) % 2 != 0) return 1;
-    return k <= 64 ? 2 : 1;
+    return (k <= 64 || terms == 3) ? 2 : 1;
 }
 
 int gemm_tc_n_tiles(int64_t n, int precision, int64_t k) {      // partial row dots a FusedDot produces: column tiles x epilogue groups
     const int bn = tc::block_n_for(precision, n);
-    return bn > 0 ? (int)(n / bn) * epi_groups_for(bn, k) : 1;
+    return bn > 0 ? (int)(n / bn) * epi_groups_for(bn, k, precision == DCNR_PREC_TF32X3 ? 3 : 1) : 1;
 }
 
 bool gemm_tc_supported(int precision, bool a_kmajor, bool b_kmajor, int64_t lda, int64_t ldb, int64_t ldc, int64_t m,
@@ -786,7 +786,7 @@ int launch_gemm_tc(int precision, const float *A, int64_t lda, bool a_kmajor, co
     p.M = m; p.N_total = (int32_t)n; p.K = (int32_t)k;
     p.block_n = block_n_for(precision, n);
     p.terms = terms;
-    p.epi_groups = epi_groups_for(p.block_n, k);
+    p.epi_groups = epi_groups_for(p.block_n, k, terms);
     p.C = C; p.ldc = ldc; p.epi = epi;
     p.dot_w = dot_w; p.dot_out = dot_out;
     p.acc_cols = 32;
