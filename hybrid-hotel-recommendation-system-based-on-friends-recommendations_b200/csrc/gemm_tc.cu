@@ -726,9 +726,10 @@ static int block_n_for(int precision, int64_t n) { return pick_block_n(n, precis
 }  // namespace tc
 
 // Epilogue warp groups: two (eight warps) for short reductions (k <= 64: the initial layer is epilogue-bound with four
-// warps -- 0.34 vs 0.43-0.54 ms per 1 M x 256 x 64), one otherwise (measured on the 256 x 256 layers: 0.83 vs 0.81 ms tf32x3,
-// 0.67 vs 0.62 ms tf32 -- the mainloop, not the epilogue, sets the pace there).  Also one when the tile has an odd number
-// of 32-column chunks.
+// warps -- 0.34 vs 0.43-0.54 ms per 1 M x 256 x 64) and for TF32X3, whose accumulators are single-buffered since the
+// correction terms got their own (the epilogue is then on the critical path of every tile: 79 -> 69 us per
+// 65 536 x 256 x 256 layer, same-box A/B).  One group for single-pass TF32 (0.67 vs 0.62 ms: the mainloop sets the pace there)
+// and when the tile has an odd number of 32-column chunks.
 static int epi_groups_for(int block_n, int64_t k, int terms) {
     if (block_n <= 0 || (block_n / 32) % 2 != 0) return 1;
     return (k <= 64 || terms == 3) ? 2 : 1;

@@ -1,10 +1,14 @@
 #!/bin/bash
 L=hybrid-hotel-recommendation-system-based-on-friends-recommendations_b200/lib/libdcnr_sm100a.so
 for round in 1 2; do
-for v in epi4 epi8; do
+for v in a b; do
 cp build/ab/lib_$v.so $L
 echo "== $v"
 timeout 300 python scripts/train_probe.py tf32x3 30
-timeout 300 python scripts/gemm_probe.py tf32x3 65536 30 2>&1 | tail -2
 done
 done
+cp build/ab/lib_b.so $L
+timeout 600 python bench.py --steps 2 --warmup 3 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(json.dumps(d['kernels'])[:1500])"
+timeout 900 python -m pytest tests/test_gpu_model.py -m gpu -q -x 2>&1 | tail -2
