@@ -758,8 +758,7 @@ def bench_sharded(dev, world, rank, comm, barrier, max_over_ranks, precision, gl
 
 def bench_similarity(dev, pk, world=1, rank=0, barrier=lambda: None, max_over_ranks=lambda v: v, n=10_000_000, d=16, k=201):
     """BASELINE configs[3]: cosine top-201 over a 10 M x 16 catalog, query batches Q in {1, 8, 32, 1024}.
-    One GPU: 640 MB scan per catalog pass; hbm_frac = one catalog read / whole-call time (normalise + scan + merge),
-    replayed from a CUDA graph.  N > 1: the catalog is split into contiguous shards (10 M / N rows per GPU), every rank
+    One GPU: 640 MB scan per catalog pass; hbm_frac = one catalog read / whole-call time (normalise + scan + merge).  N > 1: the catalog is split into contiguous shards (10 M / N rows per GPU), every rank
     scans its shard, the (dist, idx) lists are all-gathered and merged in the contract order
     (distributed.ShardedNearestNeighbors); times are max over ranks, and rank 0 checks the Q = 32 answer bit for bit against
     the unsharded catalog on one GPU."""
@@ -771,20 +770,18 @@ def bench_similarity(dev, pk, world=1, rank=0, barrier=lambda: None, max_over_ra
     out = {}
     if world == 1:
         model = dcnr_b200.NearestNeighbors().fit(E)
+        from dcnr_b200 import _cabi as C
         for nq in (1, 8, 32, 1024):
             Q = E[qidx[:nq]].contiguous()
-            s = torch.cuda.Stream()
-            with torch.cuda.stream(s):
-                model.kneighbors_tensor(Q, k)
-                gr = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(gr, stream=s):
-                    model.kneighbors_tensor(Q, k)
-            torch.cuda.synchronize()
-            secs = time_steps(gr.replay, 10 if nq <= 32 else 3, 3 if nq <= 32 else 1, lambda: None) / (10 if nq <= 32 else 3)
-            passes = 1 if nq == 1 else (nq + 7) // 8
+            reps = 10 if nq <= 32 else 3
+            tc = nq >= model.tc_min_queries and bool(C.lib().dcnr_knn_tc_supported(n, d, nq, k))
+            secs = time_steps(lambda: model.kneighbors_tensor(Q, k), reps, 3, lambda: None) / reps
+            passes = 1 if (nq == 1 or tc) else (nq + 7) // 8
             out[f"q{nq}"] = {"ms": secs * 1e3, "pairs_per_s": nq * n / secs, "catalog_passes": passes,
-                             "hbm_frac": (n * d * 4) / secs / 1e9 / pk["hbm"],
-                             "hbm_frac_per_pass": passes * (n * d * 4) / secs / 1e9 / pk["hbm"]}
+                             "path": "tensor-core shortlist + exact re-score (dcnr_knn_topk_tc)" if tc else "exact streaming scan (dcnr_knn_topk)",
+                             "hbm_frac": (n * d * 4) / secs / 1e9 / pk["hbm"]}
+        out["how"] = ("whole kneighbors_tensor call (normalise + scan + select, incl. the status read-back of the tensor-core "
+                      "path), CUDA events over back-to-back calls")
         return {"metric": "similarity_query_candidate_pairs_per_s", "catalog": f"{n} x {d} f32", "k": k, **out}
     s0, s1 = shard_range(n, rank, world)
     snn = ShardedNearestNeighbors(n_neighbors=k).fit_shard(E[s0:s1].contiguous(), s0)

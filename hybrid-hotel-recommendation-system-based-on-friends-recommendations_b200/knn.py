@@ -70,7 +70,8 @@ class NearestNeighbors:
             # Query batches: tensor-core shortlist + exact re-score (same results bit for bit; csrc/topk_tc.cu).  The status
             # word is read back once per call: a shortlist that overflowed (pathological duplicates) sends the batch down
             # the exact streaming path below.
-            if nq >= self.tc_min_queries and C.lib().dcnr_knn_tc_supported(n, d, nq, k):
+            if (nq >= self.tc_min_queries and C.lib().dcnr_knn_tc_supported(n, d, nq, k)
+                    and not torch.cuda.is_current_stream_capturing()):      # the status read-back is a sync
                 ws = torch.empty(C.lib().dcnr_knn_tc_scratch_bytes(n, d, nq, k), dtype=torch.uint8, device=Q.device)
                 status = torch.zeros(1, dtype=torch.int32, device=Q.device)
                 C.check(C.lib().dcnr_knn_topk_tc(C.ptr(self._catalog_hat), n, d, C.ptr(qhat), nq, k, self.index_base,

@@ -22,4 +22,8 @@ timeout 300 python scripts/tower_probe.py 1048576 > $O/${TAG}_tower_probe_1m.log
 echo "ncu tower exit $?"
 (cd scripts && timeout 200 python k1_probe.py 4194304 2 > ../$O/${TAG}_k1_probe.log 2>&1 && timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_embed_cross_fwd -c 2 -f -o ../$O/prof_k1_${TAG} python k1_probe.py 4194304 2 > ../$O/ncu_k1.log 2>&1)
 echo "ncu k1 exit $?"
-ls -la $O | tail -20
+timeout 300 python scripts/knn_scan_probe.py 10000000 16 1024 > $O/${TAG}_knn_tc_probe_q1024.log 2>&1 \
+ && timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_knn_tc_scan -s 3 -c 1 -f -o $O/prof_knn_tc_${TAG} python scripts/knn_scan_probe.py 10000000 16 1024 > $O/ncu_knn_tc.log 2>&1
+echo "ncu knn exit $?"
+timeout 600 python scripts/knn_tc_probe.py 10000000 > $O/${TAG}_knn_tc_probe.log 2>&1; tail -24 $O/${TAG}_knn_tc_probe.log
+ls -la $O | tail -24

@@ -166,3 +166,25 @@ def test_shortlist_overflow_falls_back_to_the_streaming_path():
     td, ti = model.kneighbors_tensor(Q, k)
     expect = torch.cat([torch.tensor([3], device="cuda"), dup[: k - 1]])
     assert torch.equal(ti[0], expect)
+
+
+def test_kneighbors_inside_cuda_graph_capture():
+    """The tensor-core path reads a status word back (a sync), which a capturing stream cannot do: under capture the call
+    takes the exact streaming path, and the replayed graph gives the eager answer."""
+    import dcnr_b200
+    g = torch.Generator(device="cuda").manual_seed(3)
+    E = torch.randn(300_000, 16, device="cuda", generator=g)
+    Q = E[:32].contiguous()
+    model = dcnr_b200.NearestNeighbors().fit(E)
+    ed, ei = model.kneighbors_tensor(Q, 21)
+    s = torch.cuda.Stream()
+    with torch.cuda.stream(s):
+        model.tc_min_queries = 1 << 30
+        model.kneighbors_tensor(Q, 21)                 # warm the allocator on this stream
+        model.tc_min_queries = 8
+        gr = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(gr, stream=s):
+            gd, gi = model.kneighbors_tensor(Q, 21)
+    gr.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(gi, ei) and torch.equal(gd, ed)
