@@ -198,8 +198,13 @@ k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
     const int q_sub = NB * kbb, c_sub = BM * kbb;                      // one [256 x KB] query / [128 x KB] catalog sub-tile
     uint8_t *qs = smem;                                                // [nqb][nkb][NB x KB]
     uint8_t *cs = qs + (size_t)p.nqb * p.nkb * q_sub;                  // [stages][sub][nkb][BM x KB]
-    float *thr_s = reinterpret_cast<float *>(cs + (size_t)p.stages * p.sub * p.nkb * c_sub);      // [nqb * NB]
-    u64 *ring = reinterpret_cast<u64 *>(thr_s + p.nqb * NB);           // [kRing]
+    // The thresholds ride in the MMA: one extra K = 8 step multiplies a constant A block (columns 0, 1 = 1) with a per-query B block
+    // (columns 0, 1 = -thr_hi, -thr_lo; thr = hi + lo, both exact in tf32), so the accumulator holds s~ - thr and "keep this
+    // row" is its sign bit.  Both blocks are K-major with 32-byte rows (SWIZZLE_32B: the 16-byte half of a row is XOR-ed with
+    // bit 2 of the row index).
+    uint8_t *tb = cs + (size_t)p.stages * p.sub * p.nkb * c_sub;       // [nqb][NB x 32 B]
+    uint8_t *ta = tb + (size_t)p.nqb * NB * 32;                        // [BM x 32 B]
+    u64 *ring = reinterpret_cast<u64 *>(ta + BM * 32);                 // [kRing]
     uint64_t *bars = reinterpret_cast<uint64_t *>(ring + kRing);       // full[stages], empty[stages], accfull[kMaxBuf], accfree[kMaxBuf], qfull
     uint32_t *ctl = reinterpret_cast<uint32_t *>(bars + 2 * p.stages + 2 * kMaxBuf + 1);        // head, tail, done, tmem slot
     const uint32_t full0 = smem_u32(bars), empty0 = full0 + 8 * p.stages, accfull0 = empty0 + 8 * p.stages,
@@ -209,7 +214,25 @@ k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
     for (int i = threadIdx.x; i < kRing; i += kThreads) ring[i] = kEmpty;
-    for (int i = threadIdx.x; i < p.nqb * NB; i += kThreads) thr_s[i] = i < p.nq ? p.thr[i] : __int_as_float(0x7f800000);
+    for (int i = threadIdx.x; i < p.nqb * NB; i += kThreads) {         // row i of the threshold blocks (query i)
+        float hi = __int_as_float(0xff800000), lo = 0.f;               // no query: -inf, the sign bit is always set
+        if (i < p.nq) {
+            const float t = -p.thr[i];
+            hi = __uint_as_float(__float_as_uint(t) & 0xffffe000u);
+            lo = t - hi;
+        }
+        float4 *row = reinterpret_cast<float4 *>(tb + (size_t)i * 32);
+        const int sw = (i >> 2) & 1;
+        row[sw] = make_float4(hi, lo, 0.f, 0.f);
+        row[sw ^ 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    for (int i = threadIdx.x; i < BM; i += kThreads) {
+        float4 *row = reinterpret_cast<float4 *>(ta + (size_t)i * 32);
+        const int sw = (i >> 2) & 1;
+        row[sw] = make_float4(1.f, 1.f, 0.f, 0.f);
+        row[sw ^ 1] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    fence_proxy_async_smem();                                          // generic-proxy writes -> visible to the tensor core
     if (threadIdx.x == 0) {
         for (int s = 0; s < p.stages; ++s) {
             mbar_init(full0 + 8 * s, 1);
@@ -266,14 +289,18 @@ k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
                 if (elect_one()) {
                     const int ncols = min(NB, ((p.nq - qb * NB + 15) >> 4) << 4);
                     const uint32_t idesc = idesc_tf32(BM, ncols);
-                    for (int j = 0; j < p.sub; ++j)
+                    const uint64_t dta = smem_desc_kmajor(smem_u32(ta), 32);
+                    const uint64_t dtb = smem_desc_kmajor(smem_u32(tb + (size_t)qb * NB * 32), 32);
+                    for (int j = 0; j < p.sub; ++j) {
+                        mma_tf32_ss(tmem_base + (buf * p.sub + j) * p.slot_cols, dta, dtb, idesc, 0u);      // acc = -thr
                         for (int kb = 0; kb < p.nkb; ++kb) {
                             const uint64_t da = smem_desc_kmajor(smem_u32(cs + (size_t)((s * p.sub + j) * p.nkb + kb) * c_sub), kbb);
                             const uint64_t db = smem_desc_kmajor(smem_u32(qs + (size_t)(qb * p.nkb + kb) * q_sub), kbb);
                             for (int ks = 0; ks < p.kb_floats / 8; ++ks)
                                 mma_tf32_ss(tmem_base + (buf * p.sub + j) * p.slot_cols, da + (uint64_t)(ks * 2),
-                                            db + (uint64_t)(ks * 2), idesc, (uint32_t)((kb | ks) != 0));
+                                            db + (uint64_t)(ks * 2), idesc, 1u);
                         }
+                    }
                     mma_commit<1>(accfull0 + 8 * buf);
                     if (qb == p.nqb - 1) mma_commit<1>(empty0 + 8 * s);
                 }
@@ -304,18 +331,18 @@ k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ C
                     const bool valid = row < p.n_rows;
                     uint32_t r[32];
                     tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (buf * p.sub + st) * p.slot_cols + g * 32, r);
-                    const float4 *th = reinterpret_cast<const float4 *>(thr_s + qb * NB + g * 32);
-                    // branch-free hit mask (bit j = query j of the group passes); the rare survivors are then walked in a
-                    // COMPACT loop -- a 32-way unrolled "if hit then push" cost ~3 000 clk per entry in instruction fetch
-                    uint32_t mask = 0;
+                    // the accumulator holds s~ - thr: a row survives for query j iff the sign bit of r[j] is clear.  Fast
+                    // path: AND of all 32 words (16 LOP3) -- sign bit still set means no survivor in this group
+                    uint32_t all = r[0];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        const float4 tv = th[j];
-                        mask |= (__uint_as_float(r[4 * j]) >= tv.x ? 1u : 0u) << (4 * j);
-                        mask |= (__uint_as_float(r[4 * j + 1]) >= tv.y ? 1u : 0u) << (4 * j + 1);
-                        mask |= (__uint_as_float(r[4 * j + 2]) >= tv.z ? 1u : 0u) << (4 * j + 2);
-                        mask |= (__uint_as_float(r[4 * j + 3]) >= tv.w ? 1u : 0u) << (4 * j + 3);
+                    for (int j = 1; j < 32; ++j) all &= r[j];
+                    uint32_t mask = 0;
+                    if ((int32_t)all >= 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) mask |= ((~r[j]) >> 31) << j;
                     }
+                    const int nvalid = ncols - g * 32;                        // queries of this group that exist (columns past the
+                    if (nvalid < 32) mask &= (1u << nvalid) - 1u;             // MMA's N hold stale tensor-memory contents)
                     if (!valid) mask = 0;
                     while (mask != 0) {
                         const int j = __ffs(mask) - 1;
@@ -506,7 +533,7 @@ int launch_knn_tc(const float *cat, int64_t n, int32_t d, const float *queries, 
         p.n_rows = n; p.d = d; p.kb_floats = kbf; p.nkb = nkb; p.nq = nq; p.nqb = (int)ceil_div(nq, NB);
         p.thr = thr; p.lists = lists; p.counts = counts;
         p.slot_cols = nq >= NB ? NB : (int)round_up(nq, 32);
-        const size_t fixed = (size_t)p.nqb * nkb * NB * kbf * 4 + (size_t)p.nqb * NB * 4 + (size_t)kRing * 8 + 256 + 1024;
+        const size_t fixed = (size_t)p.nqb * nkb * NB * kbf * 4 + (size_t)p.nqb * NB * 32 + (size_t)BM * 32 + (size_t)kRing * 8 + 256 + 1024;
         p.sub = nq <= 32 ? 4 : (nq <= 64 ? 2 : 1);
         while (p.sub > 1 && fixed + (size_t)3 * p.sub * nkb * BM * kbf * 4 > (size_t)200 * 1024) p.sub >>= 1;      // >= 3 stages
         p.nbuf = std::min(kMaxBuf, 512 / (p.slot_cols * p.sub));
