@@ -222,7 +222,7 @@ int launch_vecmat_add(const float *v, const float *W, int64_t ldw, int32_t n_row
     return DCNR_OK;
 }
 
-// out[c] = mean over the first min(m, 2048) rows of a[:, c] (an ESTIMATE of the column mean for the centred weight gradient:
+// out[c] = mean over the first min(m, 512) rows of a[:, c] (an ESTIMATE of the column mean for the centred weight gradient:
 // any vector works there, a close one removes the cancellation).  Same shape as k_vecmat_add.
 __global__ void __launch_bounds__(1024)
 k_col_mean_sample(const float *__restrict__ a, int64_t lda, int32_t rows, int32_t n, float *__restrict__ out) {
@@ -243,7 +243,7 @@ k_col_mean_sample(const float *__restrict__ a, int64_t lda, int32_t rows, int32_
 }
 
 int launch_col_mean_sample(const float *a, int64_t lda, int64_t m, int32_t n, float *out, cudaStream_t stream) {
-    const int32_t rows = (int32_t)std::min<int64_t>(m, 2048);
+    const int32_t rows = (int32_t)std::min<int64_t>(m, 512);
     k_col_mean_sample<<<(unsigned)ceil_div(n, 32), 1024, 0, stream>>>(a, lda, rows, n, out);
     DCNR_LAUNCHED();
     return DCNR_OK;

@@ -103,7 +103,7 @@ int64_t wgrad_scratch_floats(int64_t m, int32_t n, int32_t k);
 int launch_linear_wgrad(int precision, const float *dy, int64_t lddy, const float *x, int64_t ldx, float *dw,
                         int64_t lddw, float *db, int64_t m, int32_t n, int32_t k, int32_t k_valid, float *scratch,
                         cudaStream_t stream, const float *center = nullptr, const float *dy_colsum = nullptr);
-// out[c] = mean of a[0:min(m, 2048), c]: a cheap estimate of the column means (one launch), n % 32 == 0
+// out[c] = mean of a[0:min(m, 512), c]: a cheap estimate of the column means (one launch), n % 32 == 0
 int launch_col_mean_sample(const float *a, int64_t lda, int64_t m, int32_t n, float *out, cudaStream_t stream);
 
 // ---- tensor-core shortlist + exact re-score top-k for query batches (topk_tc.cu) ----

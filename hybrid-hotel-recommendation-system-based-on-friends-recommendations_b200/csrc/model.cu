@@ -370,7 +370,7 @@ extern "C" int dcnr_backward(const dcnr_dims *dims, const dcnr_params *params, c
         if (grads->res_w1[r]) {
             // Block 0 reads h0 = x0 W0^T + b0, the one activation of the tower that no BatchNorm / ReLU has re-centred: its
             // column means are several times its spread (5x on the synthetic states), and dz1 sums to ~0 over the batch, so
-            // dz1^T h0 cancels heavily.  The tensor-core kernel takes h0 - mu (mu = column means of a 2 048-row sample) and the
+            // dz1^T h0 cancels heavily.  The tensor-core kernel takes h0 - mu (mu = column means of a 512-row sample) and the
             // exact rank-1 remainder colsum(dz1) (x) mu is added with the slabs: 4.7e-6 -> 6.9e-7 against float64 on the
             // operands of a real step (profiles/r02_wgrad_centering.md).
             const float *mu = nullptr;

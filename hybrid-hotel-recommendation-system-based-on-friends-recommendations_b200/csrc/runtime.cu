@@ -162,11 +162,59 @@ k_sum_partials_2d(const float *__restrict__ partials, int64_t n_partials, int32_
     }
 }
 
+// float4 form of k_sum_partials_2d for cols_pad % 4 == 0 (the weight-gradient slabs: ~150 tables of 256 KB): a CTA folds 128
+// consecutive elements, so the grid is four times smaller and every load is 16 bytes -- same slices, same order of additions.
+__global__ void __launch_bounds__(32 * kSumSlicesMax)
+k_sum_partials_2d_v4(const float *__restrict__ partials, int64_t n_partials, int32_t rows, int32_t cols_pad, int32_t cols,
+                     float *__restrict__ out, int64_t ldo, int64_t pitch, const float *__restrict__ u,
+                     const float *__restrict__ v) {
+    __shared__ double sh[kSumSlicesMax][32][5];
+    const int kSumSlices = blockDim.x >> 5;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int64_t e = ((int64_t)blockIdx.x * 32 + tx) * 4;
+    const int64_t total = (int64_t)rows * cols_pad;
+    const int64_t per = (n_partials + kSumSlices - 1) / kSumSlices;
+    const int64_t p0 = min(n_partials, ty * per), p1 = min(n_partials, p0 + per);
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+    if (e < total) {
+        int64_t p = p0;
+        for (; p + 4 <= p1; p += 4) {
+            float4 w[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) w[j] = ldg4(partials + (p + j) * pitch + e);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { a0 += (double)w[j].x; a1 += (double)w[j].y; a2 += (double)w[j].z; a3 += (double)w[j].w; }
+        }
+        for (; p < p1; ++p) {
+            const float4 w = ldg4(partials + p * pitch + e);
+            a0 += (double)w.x; a1 += (double)w.y; a2 += (double)w.z; a3 += (double)w.w;
+        }
+    }
+    sh[ty][tx][0] = a0; sh[ty][tx][1] = a1; sh[ty][tx][2] = a2; sh[ty][tx][3] = a3;
+    __syncthreads();
+    if (ty < 4 && e < total) {                         // warp `ty` finishes component `ty` of the 32 float4
+        const int64_t ee = e + ty;
+        const int r = (int)(ee / cols_pad), c = (int)(ee % cols_pad);
+        if (c < cols) {
+            double t = sh[0][tx][ty];
+            for (int y = 1; y < kSumSlices; ++y) t += sh[y][tx][ty];
+            if (u != nullptr) t += (double)__ldg(u + r) * (double)__ldg(v + c);
+            out[(int64_t)r * ldo + c] = (float)t;
+        }
+    }
+}
+
 int launch_sum_partials_2d(const float *partials, int64_t n_partials, int32_t rows, int32_t cols_pad,
                            int32_t cols, float *out, int64_t ldo, cudaStream_t stream, int64_t pitch, const float *u,
                            const float *v) {
     int64_t total = (int64_t)rows * cols_pad;
     if (pitch <= 0) pitch = total;
+    if (cols_pad % 4 == 0 && pitch % 4 == 0 && ((uintptr_t)partials & 15) == 0 && n_partials >= 8) {
+        k_sum_partials_2d_v4<<<(unsigned)ceil_div(total, 128), 32 * sum_slices(n_partials), 0, stream>>>(
+            partials, n_partials, rows, cols_pad, cols, out, ldo, pitch, v != nullptr ? u : nullptr, v);
+        DCNR_LAUNCHED();
+        return DCNR_OK;
+    }
     k_sum_partials_2d<<<(unsigned)ceil_div(total, 32), 32 * sum_slices(n_partials), 0, stream>>>(partials, n_partials, rows, cols_pad,
                                                                                    cols, out, ldo, pitch, v != nullptr ? u : nullptr, v);
     DCNR_LAUNCHED();
