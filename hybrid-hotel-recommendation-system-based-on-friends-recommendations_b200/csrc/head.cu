@@ -56,8 +56,9 @@ int launch_combine_logits(const float *parts, int n_parts, int64_t m, const floa
     return DCNR_OK;
 }
 
+constexpr int kTB = 1024;     // threads per 256-row chunk of the backward pass (occupancy at the training batch, like bn.cu)
 // dh[b,:] = dlogit[b] * w ;  partial[chunk][c] = sum_b dlogit[b]*a[b,c] ;  partial[chunk][n] = sum_b dlogit[b]
-__global__ void __launch_bounds__(kT)
+__global__ void __launch_bounds__(kTB)
 k_rowdot_bwd(const float *__restrict__ dlogit, const float *__restrict__ a, int64_t lda, const float *__restrict__ w,
              float *__restrict__ dh, int64_t lddh, int64_t m, int n, int tx_n, int ty_n, float *__restrict__ partials) {
     extern __shared__ __align__(16) float sm[];   // [ty_n][n + 4]
@@ -80,7 +81,7 @@ k_rowdot_bwd(const float *__restrict__ dlogit, const float *__restrict__ a, int6
         if (q == 0) sm[(size_t)ty * np + n] = sd;
     }
     __syncthreads();
-    for (int c = threadIdx.x; c <= n; c += kT) {
+    for (int c = threadIdx.x; c <= n; c += kTB) {
         float s = 0.f;
         for (int t = 0; t < ty_n; ++t) s += sm[(size_t)t * np + c];
         partials[(int64_t)blockIdx.x * np + c] = s;
@@ -93,12 +94,12 @@ int launch_rowdot_bwd(const float *dlogit, const float *a, int64_t lda, const fl
     if (m <= 0) return DCNR_OK;
     const int64_t chunks = ceil_div(m, kChunkRows);
     int tx_n = 8;
-    while (tx_n < n / 4 && tx_n < kT) tx_n <<= 1;
-    const int ty_n = kT / tx_n;
+    while (tx_n < n / 4 && tx_n < kTB) tx_n <<= 1;
+    const int ty_n = kTB / tx_n;
     const size_t smem = (size_t)ty_n * (n + 4) * sizeof(float);
     if (smem > 48 * 1024)
         DCNR_CUDA_CHECK(cudaFuncSetAttribute(k_rowdot_bwd, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_rowdot_bwd<<<(unsigned)chunks, kT, smem, stream>>>(dlogit, a, lda, w, dh, lddh, m, n, tx_n, ty_n, scratch);
+    k_rowdot_bwd<<<(unsigned)chunks, kTB, smem, stream>>>(dlogit, a, lda, w, dh, lddh, m, n, tx_n, ty_n, scratch);
     DCNR_LAUNCHED();
     SegPtrs seg;
     memset(&seg, 0, sizeof(seg));
