@@ -198,6 +198,45 @@ def exchange_lookup(comm, shard: torch.Tensor, ids: torch.Tensor, gather_rows=_g
     return rows, dict(order=order, ids_here=ids_here, send_rows=send_rows, recv_rows=recv_rows)
 
 
+def exchange_lookup_multi(comm, shards, ids_list, gather_rows=_gather_rows_device):
+    """``exchange_lookup`` for several tables of the same width in ONE exchange: one owner sort, one count all-gather (one
+    host sync), one all-to-all of ids and one of rows for all tables together -- the user and the item lookup of a step cost
+    the collectives of one.  Segment layout of every message: for peer p the ids of table 0, then table 1, ...
+    Returns ([rows of table t in batch order], plan)."""
+    world, rank, T = comm.world, comm.rank, len(shards)
+    dev = ids_list[0].device
+    keys, locals_ = [], []
+    for t, ids in enumerate(ids_list):
+        owner, local = owner_of(ids, world)
+        keys.append(owner * T + t)
+        locals_.append(local)
+    key, local = torch.cat(keys), torch.cat(locals_)
+    order = torch.sort(key, stable=True).indices
+    counts = torch.bincount(key, minlength=world * T)
+    matrix = (comm.allgather(counts).cpu() if world > 1 else counts.reshape(1, -1).cpu()).reshape(world, world, T)
+    send_seg = matrix[rank]                                   # [peer, table]: ids this rank asks peer p for
+    recv_seg = matrix[:, rank, :]                             # [peer, table]: ids peer p asks this rank for
+    send_rows = [int(v) for v in send_seg.sum(1)]
+    recv_rows = [int(v) for v in recv_seg.sum(1)]
+    ids_sorted = local[order].contiguous()
+    ids_here = comm.alltoallv(ids_sorted, send_rows, recv_rows) if world > 1 else ids_sorted
+    # which table each received id belongs to: segments (peer 0: t0, t1, ...), (peer 1: ...)
+    # (all sizes are known on the host from `matrix`: no further sync)
+    n_here = int(recv_seg.sum())
+    table_here = torch.repeat_interleave(torch.arange(T, device=dev).repeat(world), recv_seg.reshape(-1).to(dev),
+                                         output_size=n_here)
+    pos = list(torch.split(torch.sort(table_here, stable=True).indices, [int(v) for v in recv_seg.sum(0)]))
+    rows_here = torch.empty((ids_here.numel(), shards[0].shape[1]), dtype=shards[0].dtype, device=dev)
+    for t in range(T):
+        rows_here[pos[t]] = gather_rows(shards[t], ids_here[pos[t]].contiguous())
+    rows_sorted = comm.alltoallv(rows_here, recv_rows, send_rows) if world > 1 else rows_here
+    rows = torch.empty_like(rows_sorted)
+    rows[order] = rows_sorted                                 # back to (table, batch) order
+    sizes = [ids.numel() for ids in ids_list]
+    return list(torch.split(rows, sizes)), dict(order=order, ids_here=ids_here, pos=pos, send_rows=send_rows, recv_rows=recv_rows,
+                                                sizes=sizes)
+
+
 class _LookupFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, table: "RowShardedTable", shard: torch.Tensor, ids: torch.Tensor):
@@ -222,6 +261,51 @@ class _LookupFn(torch.autograd.Function):
         C.check(C.lib().dcnr_scatter_rows(C.ptr(ctx.ids_here), n, ctx.shard_shape[0], ctx.shard_shape[1], C.ptr(g_here),
                                           ctx.shard_shape[1], C.ptr(grad_shard), C.ptr(ws), ws.numel(), C.stream()))
         return None, grad_shard, None
+
+
+class _LookupMultiFn(torch.autograd.Function):
+    """Two (or more) row-sharded tables through one exchange: inputs (tables tuple, shard_0, ids_0, shard_1, ids_1, ...)."""
+
+    @staticmethod
+    def forward(ctx, tables, *args):
+        shards, ids_list = list(args[0::2]), list(args[1::2])
+        comm = tables[0].comm
+        rows, plan = exchange_lookup_multi(comm, shards, ids_list)
+        ctx.tables, ctx.plan, ctx.shapes = tables, plan, [tuple(s.shape) for s in shards]
+        dim, rank = shards[0].shape[1], comm.rank
+        moved = ((sum(plan["send_rows"]) - plan["send_rows"][rank]) * 8 + (sum(plan["recv_rows"]) - plan["recv_rows"][rank]) * dim * 4)
+        for t in tables:
+            t.last_exchange_bytes = moved // len(tables)
+        return tuple(rows)
+
+    @staticmethod
+    def backward(ctx, *grad_rows):
+        from . import _cabi as C
+        from .functional import _scratch
+        plan, comm = ctx.plan, ctx.tables[0].comm
+        g = torch.cat([gr.contiguous() for gr in grad_rows])
+        g_sorted = g[plan["order"]].contiguous()
+        g_here = comm.alltoallv(g_sorted, plan["send_rows"], plan["recv_rows"]) if comm.world > 1 else g_sorted
+        out = [None]
+        for t, table in enumerate(ctx.tables):
+            shape = ctx.shapes[t]
+            ids_t = plan["ids_here"][plan["pos"][t]].contiguous()
+            g_t = g_here[plan["pos"][t]].contiguous()
+            grad_shard = torch.empty(shape, dtype=torch.float32, device=g.device)
+            n = ids_t.numel()
+            ws = _scratch(table.scatter_scratch_bytes(n), g.device)
+            C.check(C.lib().dcnr_scatter_rows(C.ptr(ids_t), n, shape[0], shape[1], C.ptr(g_t), shape[1], C.ptr(grad_shard),
+                                              C.ptr(ws), ws.numel(), C.stream()))
+            out += [grad_shard, None]
+        return tuple(out)
+
+
+def lookup_tables(tables, ids_list):
+    """Rows of several ``RowShardedTable`` s (same width, same communicator) through one fused exchange."""
+    args = []
+    for table, ids in zip(tables, ids_list):
+        args += [table.weight, ids.reshape(-1).to(torch.int64).contiguous()]
+    return _LookupMultiFn.apply(tuple(tables), *args)
 
 
 class RowShardedTable(torch.nn.Module):
@@ -273,7 +357,8 @@ class RowShardedDCN(torch.nn.Module):
         attach(self.core, comm)
 
     def forward(self, user_ids, item_ids, cat_features, num_features):
-        return self.core.forward_rows(self.user_table(user_ids), self.item_table(item_ids), cat_features, num_features)
+        user_rows, item_rows = lookup_tables([self.user_table, self.item_table], [user_ids, item_ids])      # one exchange
+        return self.core.forward_rows(user_rows, item_rows, cat_features, num_features)
 
     def dense_parameters(self):
         skip = {id(self.core.user_embedding.weight), id(self.core.item_embedding.weight)}

@@ -117,6 +117,24 @@ def _exchange_job(rank, world):
     return ok_rows and ok_plan and ok_local
 
 
+def _exchange_multi_job(rank, world):
+    torch.manual_seed(1)
+    full = [torch.randn(1001, 8), torch.randn(257, 8)]            # two tables, odd row counts
+    shards = [f[rank::world].contiguous() for f in full]
+    g = torch.Generator().manual_seed(11 + rank)
+    ids = [torch.cat([torch.randint(0, 1001, (200 + 13 * rank,), generator=g), torch.tensor([0, 1000, 1000])]),
+           torch.cat([torch.randint(0, 257, (90 + 5 * rank,), generator=g), torch.tensor([256, 0])])]
+    rows, plan = D.exchange_lookup_multi(_GlooComm(), shards, ids, gather_rows=lambda s, i: s[i])
+    ok = all(bool(torch.equal(r, f[i])) for r, f, i in zip(rows, full, ids))
+    ok = ok and sum(plan["send_rows"]) == sum(i.numel() for i in ids)
+    return ok
+
+
+def test_fused_two_table_exchange_returns_the_right_rows():
+    assert all(_run(_exchange_multi_job))
+    assert all(_run(_exchange_multi_job, world=3))
+
+
 def test_row_sharded_exchange_returns_the_right_rows_in_batch_order():
     assert all(_run(_exchange_job))
     assert all(_run(_exchange_job, world=3))
