@@ -205,6 +205,16 @@ def exchange_lookup_multi(comm, shards, ids_list, gather_rows=_gather_rows_devic
     Returns ([rows of table t in batch order], plan)."""
     world, rank, T = comm.world, comm.rank, len(shards)
     dev = ids_list[0].device
+    if world == 1:                                            # every row is local: no sort, no exchange
+        sizes = [ids.numel() for ids in ids_list]
+        ids_here = torch.cat(ids_list)
+        bounds = [0]
+        for n in sizes:
+            bounds.append(bounds[-1] + n)
+        pos = [torch.arange(bounds[t], bounds[t + 1], device=dev) for t in range(T)]
+        rows = [gather_rows(shards[t], ids_list[t].contiguous()) for t in range(T)]
+        return rows, dict(order=None, ids_here=ids_here, pos=pos, send_rows=[ids_here.numel()], recv_rows=[ids_here.numel()],
+                          sizes=sizes)
     keys, locals_ = [], []
     for t, ids in enumerate(ids_list):
         owner, local = owner_of(ids, world)
@@ -284,8 +294,11 @@ class _LookupMultiFn(torch.autograd.Function):
         from .functional import _scratch
         plan, comm = ctx.plan, ctx.tables[0].comm
         g = torch.cat([gr.contiguous() for gr in grad_rows])
-        g_sorted = g[plan["order"]].contiguous()
-        g_here = comm.alltoallv(g_sorted, plan["send_rows"], plan["recv_rows"]) if comm.world > 1 else g_sorted
+        if plan["order"] is None:                             # single rank
+            g_here = g
+        else:
+            g_sorted = g[plan["order"]].contiguous()
+            g_here = comm.alltoallv(g_sorted, plan["send_rows"], plan["recv_rows"])
         out = [None]
         for t, table in enumerate(ctx.tables):
             shape = ctx.shapes[t]
