@@ -69,8 +69,15 @@ class RankingEngine:
         deferred, self.model.defer_eval_checks = self.model.defer_eval_checks, True     # one flag read-back per score()
         for b in self.bufs:
             b["free"].record(compute)
-        for i, r0 in enumerate(range(0, n, self.chunk_rows)):
-            r1 = min(n, r0 + self.chunk_rows)
+        # chunk schedule: the first chunks are short (1/8, 1/4, 1/2 of a chunk) so that scoring starts after a 0.2 ms copy
+        # instead of a 1.5 ms one; from then on the copy of chunk i + 1 hides behind the scoring of chunk i
+        bounds, r0, ramp = [], 0, 8
+        while r0 < n:
+            step = max(1, self.chunk_rows // ramp)
+            bounds.append((r0, min(n, r0 + step)))
+            r0 += step
+            ramp = max(1, ramp // 2)
+        for i, (r0, r1) in enumerate(bounds):
             rows = r1 - r0
             b = self.bufs[i % len(self.bufs)]
             with torch.cuda.stream(self.copy_stream):
