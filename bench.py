@@ -171,6 +171,27 @@ def bind_to_gpu_numa_node(local):
         return None
 
 
+def bench_bf16_mode(model, u, i, c, x, parity_logits, rows=8192 * CANDIDATES):
+    """The stated-tolerance bf16 mode of the fused tower (bf16 operands, one MMA per product) on the first `rows` candidates of
+    the headline workload: throughput, and how far its logits are from the parity mode's on the same inputs.  Reported beside the
+    headline, never as the headline."""
+    rows = min(rows, u.numel())
+    args = (u[:rows], i[:rows], c[:rows], x[:rows])
+    prec, model.precision = model.precision, "bf16"
+    try:
+        with torch.no_grad():
+            secs = time_steps(lambda: model(*args), 5, 2, lambda: None) / 5
+            out = model(*args)
+    finally:
+        model.precision = prec
+    ref = parity_logits[:rows].double()
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    return {"value": rows / secs, "unit": "candidates/s", "rows": rows, "ms": secs * 1e3,
+            "logits_max_abs_normalised_vs_parity_mode": err,
+            "what": "DCN_RecSys(precision='bf16'): the fused tower with bf16 operands and one tcgen05 MMA per product, fp32 accumulate "
+                    "and epilogue; a stated-tolerance mode (tests assert <= 3e-2 against the float64 oracle), not the default"}
+
+
 def bench_request_latency(model, dev):
     """One ranking request (1 user x 500 candidates, main.py:320-325) through DCN_RecSys.eval(): device-resident inputs timed
     with CUDA events back to back, and host inputs -> host scores by wall clock (H2D of 38 KB, 2 launches, D2H of 2 KB, sync)."""
@@ -446,6 +467,8 @@ def main():
             roofline["traffic_note"] = t["note"]
     if not args.skip_extras:
         result["request_latency"] = bench_request_latency(model, dev)
+        if world == 1 and args.precision == "fp16x3":
+            result["bf16_mode"] = bench_bf16_mode(model, u, i, c, x, out_dev["logits"])
         comm = None
         if world > 1:
             comm = dcnr_b200.distributed.Communicator()
