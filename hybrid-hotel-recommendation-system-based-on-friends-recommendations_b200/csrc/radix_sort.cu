@@ -13,6 +13,8 @@
 //                    shared-memory copy of the tile; the tile is then written out linearly, so consecutive threads write
 //                    consecutive addresses of the same digit's run (32 keys per digit and tile on average: coalesced).
 // Order inside a digit is (tile, warp, round, lane) = input order, i.e. every pass is stable.
+#include <cooperative_groups.h>
+
 #include "kernels.cuh"
 
 namespace dcnr {
@@ -222,7 +224,139 @@ k_radix_scatter(const uint32_t *__restrict__ keys, const uint32_t *__restrict__ 
     }
 }
 
+// Small inputs (<= one tile per SM): ALL passes in ONE cooperative launch.  A pass is count -> publish the tile's digit totals ->
+// grid.sync -> every CTA derives its own output bases from the [digit][tile] table (radix threads x n_tiles loads: no separate
+// scan) -> rank -> write-out -> grid.sync.  Nine launches (hist, scan, scatter per pass) become one; the training step's
+// 131 072 keys sort in ~45 us instead of ~110.  Loads of data written earlier in the same kernel bypass L1 (__ldcg).
+__global__ void __launch_bounds__(kThreads)
+k_radix_sort_coop(uint32_t *k0, uint32_t *v0, uint32_t *k1, uint32_t *v1, int64_t n, int end_bit, int passes, int n_tiles,
+                  uint32_t *counts) {
+    cooperative_groups::grid_group grid = cooperative_groups::this_grid();
+    __shared__ uint32_t cur[kWarps * kMaxRadix];
+    __shared__ uint32_t lbase[kMaxRadix], gbase[kMaxRadix];
+    __shared__ uint32_t skey[kTile], sval[kTile];
+    __shared__ uint32_t wsum[kWarps];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t lt = (1u << lane) - 1u;
+    const int64_t tile0 = (int64_t)blockIdx.x * kTile;
+    const int64_t base = tile0 + (int64_t)warp * (kRounds * 32) + lane;
+    const int tile_n = (int)max((int64_t)0, min((int64_t)kTile, n - tile0));
+    const uint32_t *kin = k0, *vin = v0;
+    uint32_t *kout = k1, *vout = v1;
+    int shift = 0;
+    for (int p = 0; p < passes; ++p) {
+        const int bits = (end_bit - shift + (passes - p) - 1) / (passes - p);
+        const int radix = 1 << bits;
+        const uint32_t mask = (uint32_t)radix - 1u;
+        for (int d = threadIdx.x; d < kWarps * radix; d += kThreads) cur[d] = 0u;
+        __syncthreads();
+        uint32_t k[kRounds], v[kRounds];
+        uint32_t *mine = cur + warp * radix;
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+            const int64_t i = base + r * 32;
+            const bool ok = i < n;
+            k[r] = ok ? __ldcg(kin + i) : 0u;
+            v[r] = ok ? __ldcg(vin + i) : 0u;
+            const uint32_t d = ok ? ((k[r] >> shift) & mask) : (0x80000000u | (uint32_t)lane);
+            const uint32_t m = __match_any_sync(0xffffffffu, d);
+            if (ok && (m & lt) == 0u) mine[d] += (uint32_t)__popc(m);
+            __syncwarp();
+        }
+        __syncthreads();
+        const int d = threadIdx.x;
+        uint32_t tot = 0;
+        if (d < radix) {
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) tot += cur[w * radix + d];
+            counts[(int64_t)d * n_tiles + blockIdx.x] = tot;
+        }
+        // tile-local exclusive scan of tot over the digits (positions inside the sorted tile)
+        uint32_t incl = tot;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= o) incl += t;
+        }
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        uint32_t woff = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w)
+            if (w < warp) woff += wsum[w];
+        if (d < radix) {
+            uint32_t run = woff + incl - tot;
+            lbase[d] = run;
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) {
+                const uint32_t c = cur[w * radix + d];
+                cur[w * radix + d] = run;
+                run += c;
+            }
+        }
+        __threadfence();
+        grid.sync();                                                   // every tile's digit totals are published
+        // global base of digit d for this tile = (keys with a smaller digit, all tiles) + (digit d in earlier tiles)
+        uint32_t total = 0, before = 0;
+        if (d < radix) {
+            for (int t = 0; t < n_tiles; ++t) {
+                const uint32_t c = __ldcg(counts + (int64_t)d * n_tiles + t);
+                total += c;
+                if (t < (int)blockIdx.x) before += c;
+            }
+        }
+        uint32_t gincl = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t t = __shfl_up_sync(0xffffffffu, gincl, o);
+            if (lane >= o) gincl += t;
+        }
+        __syncthreads();                                               // wsum reuse
+        if (lane == 31) wsum[warp] = gincl;
+        __syncthreads();
+        uint32_t goff = 0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w)
+            if (w < warp) goff += wsum[w];
+        if (d < radix) gbase[d] = goff + gincl - total + before;
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < kRounds; ++r) {
+            const int64_t i = base + r * 32;
+            const bool ok = i < n;
+            const uint32_t dg = ok ? ((k[r] >> shift) & mask) : (0x80000000u | (uint32_t)lane);
+            const uint32_t m = __match_any_sync(0xffffffffu, dg);
+            uint32_t pos = 0u;
+            if (ok) pos = mine[dg] + (uint32_t)__popc(m & lt);
+            __syncwarp();
+            if (ok && (m & lt) == 0u) mine[dg] += (uint32_t)__popc(m);
+            __syncwarp();
+            if (ok) {
+                skey[pos] = k[r];
+                sval[pos] = v[r];
+            }
+        }
+        __syncthreads();
+        for (int j = threadIdx.x; j < tile_n; j += kThreads) {
+            const uint32_t key = skey[j];
+            const uint32_t dg = (key >> shift) & mask;
+            const uint32_t pos = gbase[dg] + ((uint32_t)j - lbase[dg]);
+            kout[pos] = key;
+            vout[pos] = sval[j];
+        }
+        shift += bits;
+        const uint32_t *tk = kin, *tv = vin;
+        kin = kout; vin = vout;
+        kout = const_cast<uint32_t *>(tk); vout = const_cast<uint32_t *>(tv);
+        if (p + 1 < passes) {
+            __threadfence();
+            grid.sync();                                               // the pass's output is complete before it is read
+        }
+    }
+}
+
 }  // namespace rs
+
 
 int64_t radix_sort_scratch_bytes(int64_t n) {
     const int64_t n_tiles = ceil_div(std::max<int64_t>(n, 1), rs::kTile);
@@ -240,6 +374,20 @@ int launch_radix_sort_pairs(uint32_t *k0, uint32_t *v0, uint32_t *k1, uint32_t *
     if (n <= 1 || end_bit <= 0) return DCNR_OK;
     const int passes = (end_bit + kMaxBits - 1) / kMaxBits;
     const int64_t n_tiles = ceil_div(n, kTile);
+    if (n_tiles <= sm_count()) {                                       // one cooperative launch for all passes
+        int per_sm = 0;
+        DCNR_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_radix_sort_coop, kThreads, 0));
+        if ((int64_t)per_sm * sm_count() >= n_tiles) {
+            int nt = (int)n_tiles, eb = end_bit, ps = passes;
+            uint32_t *cnt = reinterpret_cast<uint32_t *>(scratch);
+            void *args[] = {&k0, &v0, &k1, &v1, &n, &eb, &ps, &nt, &cnt};
+            DCNR_CUDA_CHECK(cudaLaunchCooperativeKernel(reinterpret_cast<void *>(k_radix_sort_coop), dim3((unsigned)n_tiles),
+                                                        dim3(kThreads), args, 0, stream));
+            DCNR_LAUNCHED();
+            if (passes & 1) { *k_out = k1; *v_out = v1; }
+            return DCNR_OK;
+        }
+    }
     uint32_t *counts = reinterpret_cast<uint32_t *>(scratch);
     uint32_t *sums = reinterpret_cast<uint32_t *>(reinterpret_cast<char *>(scratch) + round_up((int64_t)kMaxRadix * n_tiles * 4, 256));
     int shift = 0;
