@@ -301,7 +301,7 @@ extern "C" int dcnr_forward_train(const dcnr_dims *dims, const dcnr_params *para
     DCNR_TRY(make_gather_args(dims, params, batch, &ga));
     const CrossArgs ca = cross_args(dims, params);
     DCNR_TRY(launch_embed_cross_fwd(&ga, nullptr, 0, B, ca, Dp, s.x0p, Dp, nullptr, 0, params->wf + H, s.logit_cross,
-                                    nullptr, st));
+                                    dims->eval_flags, st));
     GemmEpilogue e0{nullptr, params->b0, nullptr, 0, 0};
     DCNR_TRY(gemm_any(prec, s.x0p, Dp, true, s.w0p, Dp, true, s.h[0], H, B, H, Dp, 1, e0, st, wo.get(wo.w0)));
     for (int r = 0; r < dims->n_res; ++r) {

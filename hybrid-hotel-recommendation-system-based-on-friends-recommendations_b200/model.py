@@ -203,6 +203,8 @@ class DCN_RecSys(nn.Module):
         for i, (r, w) in enumerate(zip(s["cat_rows"], s["cat_width"])):
             d.cat_rows[i], d.cat_width[i] = r, w
         d.dropout_p = s["dropout"] if self.training else 0.0
+        if self._eval_flags is not None:        # train-mode forwards record out-of-range ids here too; read by the next
+            d.eval_flags = C.ptr(self._eval_flags)      # eval() forward or by check_eval_flags() (e.g. once per epoch)
         blk = self.res_blocks[0] if len(self.res_blocks) else None
         d.bn_eps = blk.bn1.eps if blk is not None else 1e-5
         d.bn_momentum = blk.bn1.momentum if blk is not None else 0.1
@@ -323,6 +325,7 @@ class DCN_RecSys(nn.Module):
             flag = torch.zeros(1, dtype=torch.int32, device=user_ids.device)
             C.check(C.lib().dcnr_check_ids(dims, batch, C.ptr(flag), C.stream()))
         if self.training:
+            self._flags(user_ids.device)
             if B == 1 and len(self.res_blocks) > 0 and dims.comm is None:
                 raise ValueError(f"Expected more than 1 value per channel when training, got input size "
                                  f"torch.Size([1, {self._shape['hidden']}])")
@@ -345,10 +348,13 @@ class DCN_RecSys(nn.Module):
                     raise RuntimeError("unexpected range flag from the tf32x3 path")
         return logits.squeeze()       # [B]; 0-d when B == 1, like train.py:170
 
-    def _eval_call(self, dims, batch, B, dev):
+    def _flags(self, dev):
         if self._eval_flags is None or self._eval_flags.device != dev:
             self._eval_flags = torch.zeros(4, dtype=torch.int32, device=dev)      # [0] flag bits, [1..2] diagnostics
-        dims.eval_flags = C.ptr(self._eval_flags)
+        return self._eval_flags
+
+    def _eval_call(self, dims, batch, B, dev):
+        dims.eval_flags = C.ptr(self._flags(dev))
         pstruct = self._param_struct()
         dims.tower_pack = self._tower_pack_ptr(dims, pstruct, dev)
         ws = torch.empty(C.lib().dcnr_workspace_bytes(dims, B, 0), dtype=torch.uint8, device=dev)

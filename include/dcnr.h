@@ -90,7 +90,7 @@ typedef struct dcnr_dims {
     uint64_t *dropout_step;     /* optional DEVICE counter: its value is added to dropout_seed and every dcnr_forward_train
                                  * increments it, so a captured CUDA graph of the training step draws a fresh dropout mask
                                  * on every replay (NULL: the seed argument alone decides the mask) */
-    int32_t *eval_flags;        /* optional DEVICE int, OR-ed by dcnr_forward_eval (never cleared): bit 0 = an embedding id was out of
+    int32_t *eval_flags;        /* optional DEVICE int, OR-ed by dcnr_forward_eval and dcnr_forward_train (never cleared): bit 0 = an embedding id was out of
                                  * range (the row was read as row 0; torch raises IndexError), bit 1 = an activation left the
                                  * fp16 range of DCNR_PREC_FP16X3 (re-run the batch with DCNR_PREC_TF32X3).  NULL: not reported */
     const void *tower_pack;     /* optional DEVICE buffer written by dcnr_tower_prepare for THESE parameters and this precision:

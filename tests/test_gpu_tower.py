@@ -170,6 +170,13 @@ def test_eval_reports_out_of_range_ids():
     u[7] = 0
     with torch.no_grad():
         m(u.cuda(), i.cuda(), c.cuda(), x.cuda())       # the flag was cleared: the next call is clean
+    # train-mode forwards record the same flag (no read-back per step); check_eval_flags() raises at the caller's pace
+    m.train()
+    i[3] = ni + 1
+    m(u.cuda(), i.cuda(), c.cuda(), x.cuda())
+    with pytest.raises(IndexError):
+        m.check_eval_flags()
+    assert m.check_eval_flags() is False
 
 
 def test_fp16_range_overflow_falls_back_to_tf32x3():
