@@ -5,7 +5,7 @@
 // oracle/knn_oracle.c bit for bit (sequential-fma fp32 scores, dist = clip(1 - sim, 0, 2), order (dist, index) ascending):
 // the tensor core only decides WHICH rows get the exact treatment.
 //
-//   scan    k_knn_tc_scan: persistent, one CTA per SM.  A 128-row catalog tile lands by TMA (fp32, K-major, 64- or 128-byte
+//   scan    k_knn_tc_scan: persistent, one CTA per SM.  A 128-row catalog tile lands by TMA (fp32, K-major, 32- / 64- / 128-byte
 //           swizzle), the queries (up to 1 024, resident in shared memory as the B operand) are multiplied block by block
 //           with tcgen05.mma kind::tf32 (M = 128 rows, N <= 256 queries, K = 8 per instruction) into a double-buffered
 //           TMEM accumulator.  Eight warps read the scores back (tcgen05.ld, 32 queries per instruction) and compare them
@@ -194,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 k_knn_tc_scan(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmQ, Params p) {
     extern __shared__ __align__(1024) uint8_t smem_scan[];
     uint8_t *smem = smem_scan + ((1024u - (smem_u32(smem_scan) & 1023u)) & 1023u);
-    const int kbb = p.kb_floats * 4;                                   // row bytes of a K block: 64 or 128
+    const int kbb = p.kb_floats * 4;                                   // row bytes of a K block: 32, 64 or 128
     const int q_sub = NB * kbb, c_sub = BM * kbb;                      // one [256 x KB] query / [128 x KB] catalog sub-tile
     uint8_t *qs = smem;                                                // [nqb][nkb][NB x KB]
     uint8_t *cs = qs + (size_t)p.nqb * p.nkb * q_sub;                  // [stages][sub][nkb][BM x KB]
@@ -480,7 +480,8 @@ static int make_map(CUtensorMap *tm, const float *base, int64_t rows, int d, int
     cuuint32_t box[2] = {(cuuint32_t)kb_floats, (cuuint32_t)box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, kb_floats == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    kb_floats == 32 ? CU_TENSOR_MAP_SWIZZLE_128B : (kb_floats == 16 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B),
                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         set_error("cuTensorMapEncodeTiled failed (%d): rows %lld d %d", (int)r, (long long)rows, d);
@@ -489,12 +490,16 @@ static int make_map(CUtensorMap *tm, const float *base, int64_t rows, int d, int
     return DCNR_OK;
 }
 
-static int queries_per_launch(int d) { return d == 16 ? 1024 : (d == 32 ? 512 : 256); }
+// queries resident in shared memory per launch (64-96 KB of operand blocks)
+static int queries_per_launch(int d) { return d <= 24 ? 1024 : (d <= 48 ? 512 : 256); }
+// K block = the widest of 32 / 16 / 8 floats (128- / 64- / 32-byte swizzle) that divides d: 16 -> 16, 24 -> 8, 32 -> 32, 48 -> 16
+static int k_block_floats(int d) { return d % 32 == 0 ? 32 : (d % 16 == 0 ? 16 : 8); }
 
 }  // namespace kt
 
 bool knn_tc_supported(int64_t n, int32_t d, int32_t n_queries, int32_t k) {
-    return (d == 16 || d == 32 || d == 64) && n >= (1 << 18) && n <= (1 << 24) && n_queries >= 1 && k >= 1 && k <= 256;
+    return (d == 16 || d == 24 || d == 32 || d == 48 || d == 64) && n >= (1 << 18) && n <= (1 << 24) && n_queries >= 1 && k >= 1 &&
+           k <= 256;
 }
 
 int64_t knn_tc_scratch_bytes(int64_t n, int32_t d, int32_t n_queries, int32_t k) {
@@ -515,7 +520,7 @@ int launch_knn_tc(const float *cat, int64_t n, int32_t d, const float *queries, 
     uint32_t *lists = ar.take<uint32_t>((int64_t)std::min(n_queries, qmax) * kListCap);
     int32_t *counts = ar.take<int32_t>(std::min(n_queries, qmax));
     float *thr = ar.take<float>(std::min(n_queries, qmax));
-    const int kbf = d == 16 ? 16 : 32, nkb = d / kbf;
+    const int kbf = k_block_floats(d), nkb = d / kbf;
     const int64_t tiles_all = ceil_div(n, (int64_t)BM);
     const int64_t stride1 = std::max<int64_t>(32, ceil_div(n, (int64_t)(1 << 18)));
     CUtensorMap tmC;

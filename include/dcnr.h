@@ -332,7 +332,8 @@ int dcnr_knn_topk(const float *catalog_hat, int64_t n, int32_t d, const float *q
 /* The same result for a BATCH of queries, found with a tensor-core shortlist: tcgen05 kind::tf32 scores of every (row, query)
  * pair decide which rows are re-scored with the exact arithmetic above (error bound 2e-3 on unit vectors, thresholds from exact
  * top-k of row samples: no member of the true top-k can be dropped -- csrc/topk_tc.cu has the argument).  One catalog pass for
- * up to 1 024 queries (d = 16).  Shapes: d in {16, 32, 64}, 2^18 <= n <= 2^24, k <= 256 (dcnr_knn_tc_supported).
+ * up to 1 024 queries (d = 16).  Shapes: d in {16, 24, 32, 48, 64} (the reference's emb_dim search space, train.py:180), 2^18 <= n <= 2^24, k <= 256
+ * (dcnr_knn_tc_supported).
  * status: optional DEVICE int, OR-ed: bit 0 = a per-query shortlist overflowed (pathological duplicates; the outputs are
  * then NOT valid and the caller re-runs the batch with dcnr_knn_topk). */
 int dcnr_knn_tc_supported(int64_t n, int32_t d, int32_t n_queries, int32_t k);

@@ -113,7 +113,8 @@ def _both_paths(E, Q, k, index_base=0):
 
 @pytest.mark.parametrize("n,d,nq,k", [(300_000, 16, 8, 11), (300_000, 16, 33, 201), (270_001, 32, 300, 51), (262_144, 64, 40, 256),
                                       (1_000_000, 16, 1024, 201), (500_000, 64, 700, 16), (300_000, 64, 20, 33), (300_000, 32, 64, 100),
-                                      (300_000, 32, 1100, 11)])            # more queries than one launch holds (512 at d = 32)
+                                      (300_000, 32, 1100, 11),             # more queries than one launch holds (512 at d = 32)
+                                      (300_000, 24, 50, 21), (280_000, 48, 9, 64)])     # 8- and 16-float K blocks
 def test_batched_queries_bit_exact_with_the_streaming_path(n, d, nq, k):
     g = torch.Generator(device="cuda").manual_seed(n + d + nq)
     E = torch.randn(n, d, device="cuda", generator=g)
