@@ -142,6 +142,49 @@ __global__ void k_bn_stats_finalize(const double *__restrict__ gmean, const doub
     }
 }
 
+// Levels 1 and 2 in ONE launch for batches of up to 32 groups (B <= 131 072) on a single rank: thread (column, group) folds the
+// group's 16 chunks exactly like k_bn_stats_merge1, the column's thread of group 0 then folds the groups in order exactly like
+// k_bn_stats_finalize -- same association, bit-identical statistics, one launch instead of two per BatchNorm.
+__global__ void __launch_bounds__(1024)
+k_bn_stats_merge_finalize(const double *__restrict__ pmean, const double *__restrict__ pm2, int64_t chunks, int64_t m, int n,
+                          int groups, float eps, float momentum, float *__restrict__ mean_out, float *__restrict__ rstd_out,
+                          float *running_mean, float *running_var, int64_t *nbt) {
+    __shared__ double smean[32][33], sm2[32][33], scnt[32];
+    const int tx = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int c = blockIdx.x * 32 + tx;
+    if (g < groups && c < n) {
+        const int64_t k0 = (int64_t)g * kMergeFan, k1 = min(chunks, k0 + kMergeFan);
+        double vm[kMergeFan], v2[kMergeFan];
+#pragma unroll
+        for (int j = 0; j < kMergeFan; ++j) {
+            vm[j] = k0 + j < k1 ? pmean[(k0 + j) * n + c] : 0.0;
+            v2[j] = k0 + j < k1 ? pm2[(k0 + j) * n + c] : 0.0;
+        }
+        Moments acc{0.0, 0.0, 0.0};
+#pragma unroll
+        for (int j = 0; j < kMergeFan; ++j)
+            if (k0 + j < k1)
+                merge_moments(acc, Moments{(double)min((int64_t)kChunkRows, m - (k0 + j) * kChunkRows), vm[j], v2[j]});
+        smean[g][tx] = acc.mean;
+        sm2[g][tx] = acc.m2;
+        if (tx == 0) scnt[g] = acc.n;
+    }
+    __syncthreads();
+    if (g != 0 || c >= n) return;
+    if (c == 0 && nbt != nullptr) *nbt += 1;
+    Moments acc{0.0, 0.0, 0.0};
+    for (int k = 0; k < groups; ++k) merge_moments(acc, Moments{scnt[k], smean[k][tx], sm2[k][tx]});
+    const double cnt = acc.n;
+    const double var_b = acc.m2 / cnt;
+    mean_out[c] = (float)acc.mean;
+    rstd_out[c] = (float)(1.0 / sqrt(var_b + (double)eps));
+    if (running_mean != nullptr) {
+        const double var_u = cnt > 1.0 ? acc.m2 / (cnt - 1.0) : var_b;
+        running_mean[c] = (float)((1.0 - (double)momentum) * (double)running_mean[c] + (double)momentum * acc.mean);
+        running_var[c] = (float)((1.0 - (double)momentum) * (double)running_var[c] + (double)momentum * var_u);
+    }
+}
+
 // SyncBN forward over peer memory: ONE CTA folds this rank's groups, exchanges (mean | M2 | count) with every rank through the
 // NVLink-mapped staging slots, folds the ranks in rank order (identical on every rank) and emits mean / rstd / running
 // statistics -- the pack kernel, the NCCL all-gather and the fold kernel of the NCCL path in a single launch.
@@ -239,6 +282,12 @@ int launch_bn_stats(const float *z, int64_t ldz, int64_t m, int32_t n, float eps
     k_bn_stats_partial<<<(unsigned)chunks, kT, smem, stream>>>(z, ldz, m, n, cm.tx_n, cm.ty_n, pmean, pm2);
     DCNR_LAUNCHED();
     const int64_t groups = ceil_div(chunks, kMergeFan);
+    if (comm_world(comm) <= 1 && groups <= 32) {
+        k_bn_stats_merge_finalize<<<(unsigned)ceil_div(n, 32), (unsigned)(32 * groups), 0, stream>>>(
+            pmean, pm2, chunks, m, n, (int)groups, eps, momentum, mean, rstd, running_mean, running_var, nbt);
+        DCNR_LAUNCHED();
+        return DCNR_OK;
+    }
     double *gmean = pm2 + chunks * n, *gm2 = gmean + groups * n, *gcnt = gm2 + groups * n;
     dim3 g1((unsigned)groups, (unsigned)ceil_div(n, 128));
     k_bn_stats_merge1<<<g1, 128, 0, stream>>>(pmean, pm2, chunks, m, n, gmean, gm2, gcnt);
