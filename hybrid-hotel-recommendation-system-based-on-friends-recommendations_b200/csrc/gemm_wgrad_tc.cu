@@ -24,7 +24,8 @@ namespace wg {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;                 // batch rows per k-block
-constexpr int kThreads = 192;               // warp 0 TMA, warp 1 MMA, warps 2-5 split + epilogue
+constexpr int kSplitWarps = 8;               // warps that split the landed tiles (the k-block cadence was split-bound with four)
+constexpr int kThreads = 64 + 32 * kSplitWarps;     // warp 0 TMA, warp 1 MMA, warps 2-9 split, warps 2-5 also the epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
@@ -130,7 +131,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     if (threadIdx.x == 0) {
         for (int s = 0; s < stages; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(ready0 + 8 * s, 4);
+            mbar_init(ready0 + 8 * s, kSplitWarps);
             mbar_init(empty0 + 8 * s, 1);
         }
         mbar_init(done0, 1);
@@ -217,7 +218,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 mbar_wait(full0 + 8 * s, ph);
                 float4 *hi = reinterpret_cast<float4 *>(smem + (size_t)s * stage_bytes);
                 float4 *lo = hi + n4;
-                for (int i = tt; i < n4; i += 128) {
+                for (int i = tt; i < n4; i += 32 * kSplitWarps) {
                     float4 v = hi[i];
                     if (p.center != nullptr && i >= a4) {
                         // X tile, SWIZZLE_128B_BASE32B: block of 32 columns = 32 batch rows x 128 B; the 32-byte chunk of a row
@@ -241,7 +242,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                 if (lane == 0) mbar_arrive(ready0 + 8 * s);
             }
         }
-        // epilogue: lane = one row of the [128 x k_in] partial product; each lane writes whole 128-byte lines
+        // epilogue (warps 2-5): lane = one row of the [128 x k_in] partial product; each lane writes whole 128-byte lines
+        if (warp < 6) {
         mbar_wait(done0, 0);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int quad = warp & 3;
@@ -268,6 +270,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     st4(orow + c0 + j, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]),
                                                    __uint_as_float(r[j + 3])));
             }
+        }
         }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");

@@ -8,4 +8,4 @@ timeout 300 python scripts/train_probe.py tf32x3 30
 done
 done
 cp build/ab/lib_b.so $L
-timeout 900 python -m pytest tests/test_gpu_model.py -m gpu -q -x 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_gpu_model.py tests/test_gpu_gemm.py tests/test_gpu_cross_v2.py -m gpu -q -x 2>&1 | tail -2
