@@ -24,7 +24,7 @@ namespace wg {
 
 constexpr int BLOCK_M = 128;
 constexpr int BLOCK_K = 32;                 // batch rows per k-block
-constexpr int kSplitWarps = 8;               // warps that split the landed tiles (the k-block cadence was split-bound with four)
+constexpr int kSplitWarps = 16;              // warps that split the landed tiles (the k-block cadence was split-bound with four)
 constexpr int kThreads = 64 + 32 * kSplitWarps;     // warp 0 TMA, warp 1 MMA, warps 2-9 split, warps 2-5 also the epilogue
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
