@@ -236,8 +236,23 @@ class DCN_RecSys(nn.Module):
         return ps
 
     def _param_struct(self) -> C.Params:
-        p = C.Params()
+        # the ctypes struct of 35 device pointers is rebuilt only when a storage moved (a single ranking request is ~100 us of
+        # GPU time: marshalling must not cost as much)
         ps = self._ordered_params()
+        bufs = []
+        for blk in self.res_blocks:
+            for bn in (blk.bn1, blk.bn2):
+                bufs += [bn.running_mean, bn.running_var, bn.num_batches_tracked]
+        key = tuple(t.data_ptr() for t in ps) + tuple(t.data_ptr() for t in bufs)
+        cached = getattr(self, "_pstruct_cache", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        p = self._build_param_struct(ps)
+        self._pstruct_cache = (key, p)
+        return p
+
+    def _build_param_struct(self, ps) -> C.Params:
+        p = C.Params()
         for t in ps:
             if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
                 raise RuntimeError("DCN_RecSys parameters must be contiguous float32 CUDA tensors "
