@@ -98,11 +98,12 @@ def make_state(seed=42):
     return orc.make_state(N_USERS, N_ITEMS, CAT_DIMS, N_NUM, P0, seed=seed, emb_scale=0.1, randomize_bn=True)
 
 
-def synth_state_device(dev, seed=42):
-    """Same shapes as make_state but generated on the device (1 M x 16 tables)."""
+def synth_module(n_users=N_USERS, n_items=N_ITEMS, params=None, seed=42):
+    """A 'trained-like' DCN_RecSys (SURVEY.md 8d: embeddings x0.1, randomised BatchNorm affine / running statistics) on the CPU;
+    the product arm's own initialiser (nothing from oracle/ on this path)."""
     import dcnr_b200
     torch.manual_seed(seed)
-    m = dcnr_b200.DCN_RecSys(N_USERS, N_ITEMS, CAT_DIMS, N_NUM, P0)
+    m = dcnr_b200.DCN_RecSys(n_users, n_items, CAT_DIMS, N_NUM, dict(P0 if params is None else params))
     g = torch.Generator().manual_seed(seed)
     with torch.no_grad():
         for e in [m.user_embedding, m.item_embedding, *m.cat_embeddings]:
@@ -113,7 +114,12 @@ def synth_state_device(dev, seed=42):
                 bn.bias.copy_(torch.randn(bn.bias.shape, generator=g) * 0.2)
                 bn.running_mean.copy_(torch.randn(bn.bias.shape, generator=g) * 0.3)
                 bn.running_var.copy_(0.5 + torch.rand(bn.bias.shape, generator=g))
-    return m.to(dev)
+    return m
+
+
+def synth_state_device(dev, seed=42):
+    """The P0 model of the headline workload (1 M x 100 K tables) on the device."""
+    return synth_module(seed=seed).to(dev)
 
 
 def synth_requests(n_req, n_cand, seed, device):
@@ -666,9 +672,8 @@ def sharded_parity_vs_single_device(dev, world, rank, comm, barrier, precision, 
     off: logits of rank 0's slice, its table shards' gradients (rows rank 0 owns) and the dense gradients."""
     import dcnr_b200
     from dcnr_b200.distributed import RowShardedDCN, allreduce_gradients, attach, shard_range
-    from oracle import dcnr_oracle as orc          # initialiser of a seeded state only
     params = dict(P0); params["dropout"] = 0.0
-    state = orc.make_state(rows, rows // 4, CAT_DIMS, N_NUM, params, seed=3, emb_scale=0.1, randomize_bn=True)
+    state = synth_module(rows, rows // 4, params, seed=3).state_dict()
     GB = per_rank * world
     g = torch.Generator().manual_seed(17)
     u = torch.randint(0, rows, (GB,), generator=g).to(dev); i = torch.randint(0, rows // 4, (GB,), generator=g).to(dev)

@@ -1,13 +1,13 @@
 """Weight-gradient error of the tensor-core kernel on the REAL operands of a training step (dz and the layer input X captured from
 the reference class run in float64 on the GPU), plain and with X centred per column:
     dW = dz^T X = dz^T (X - mean) + colsum(dz) (x) mean
-Usage: python scripts/wgrad_real_probe.py [B]"""
+Usage: python tests/tools/wgrad_real_probe.py [B]"""
 import os
 import sys
 
 import torch
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import dcnr_b200  # noqa: E402,F401
