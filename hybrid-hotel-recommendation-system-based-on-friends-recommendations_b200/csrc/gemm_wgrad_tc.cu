@@ -23,7 +23,8 @@ namespace dcnr {
 namespace wg {
 
 constexpr int BLOCK_M = 128;
-constexpr int BLOCK_K = 32;                 // batch rows per k-block
+constexpr int BLOCK_K = 16;                 // batch rows per k-block (32-row blocks left room for two stages only: hi + lo copies of both
+                                            // tiles are 96 KB at k_in = 256; 16 rows = four stages, step 2.022 -> 2.004 ms)
 constexpr int kSplitWarps = 16;              // warps that split the landed tiles (the k-block cadence was split-bound with four)
 constexpr int kThreads = 64 + 32 * kSplitWarps;     // warp 0 TMA, warp 1 MMA, warps 2-9 split, warps 2-5 also the epilogue
 
@@ -114,7 +115,7 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
     // 1024-byte alignment by OFFSETTING the __shared__ array: a round trip through uintptr_t loses the address space and
     // every shared-memory access below became a generic LD / ST (the split and the epilogue ran 3-4x slower)
     uint8_t *smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    const int a_bytes = BLOCK_M * BLOCK_K * 4;                 // 16 KB: 4 blocks of [32 rows x 128 B]
+    const int a_bytes = BLOCK_M * BLOCK_K * 4;                 // 4 blocks of [BLOCK_K rows x 128 B]
     const int b_bytes = p.k_in * BLOCK_K * 4;                  // k_in / 32 blocks
     const int stage_bytes = (p.terms == 3 ? 2 : 1) * (a_bytes + b_bytes);      // [A hi][B hi]([A lo][B lo])
     const int stages = p.stages;
@@ -223,8 +224,8 @@ k_wgrad_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUte
                     if (p.center != nullptr && i >= a4) {
                         // X tile, SWIZZLE_128B_BASE32B: block of 32 columns = 32 batch rows x 128 B; the 32-byte chunk of a row
                         // is XOR-ed with (row & 3).  float4 i of the tile -> its first column.
-                        const int o = i - a4, row = (o >> 3) & 31, c16 = o & 7;
-                        const int col = (o >> 8) * 32 + (((c16 >> 1) ^ (row & 3)) << 3) + ((c16 & 1) << 2);
+                        const int o = i - a4, row = (o >> 3) % BLOCK_K, c16 = o & 7;
+                        const int col = (o / (BLOCK_K * 8)) * 32 + (((c16 >> 1) ^ (row & 3)) << 3) + ((c16 & 1) << 2);
                         const float4 mu = __ldg(reinterpret_cast<const float4 *>(p.center + col));
                         v.x -= mu.x; v.y -= mu.y; v.z -= mu.z; v.w -= mu.w;
                     }
@@ -357,7 +358,7 @@ int launch_wgrad_tc(int precision, const float *dy, int64_t lddy, const float *x
     DCNR_REQUIRE(center == nullptr || (p.terms == 3 && ((uintptr_t)center & 15) == 0), "centred wgrad needs TF32X3 and an aligned vector");
     p.center = center;
     const int stage_bytes = (p.terms == 3 ? 2 : 1) * (BLOCK_M + k) * BLOCK_K * 4;
-    p.stages = std::max(1, std::min(4, (220 * 1024) / stage_bytes));
+    p.stages = std::max(1, std::min(6, (220 * 1024) / stage_bytes));
     const size_t smem = (size_t)p.stages * stage_bytes + 1024 + 256;
     CUtensorMap tmA, tmB;
     DCNR_TRY(make_map_mn(&tmA, dy, m, n, lddy, BLOCK_M / 32));
